@@ -1,0 +1,109 @@
+/*
+ * sparenet_b200.h -- C ABI of libsparenet_b200.so: the SpareNet per-batch point-cloud hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary: each entry point replaces one pybind function of the reference's CUDA
+ * extensions; the reference-side Python wrappers (torch.autograd.Function / nn.Module, mirrored under
+ * sparenet_b200/dropin/) bind these through ctypes.
+ *
+ * Conventions
+ *   - plain device pointers + sizes, no torch types.  fp32 contiguous AoS clouds [B,N,3]; int32 indices.
+ *   - the caller owns every buffer, including scratch ("workspace"); the library never allocates, frees or
+ *     keeps state between calls.  Query scratch sizes with snb_<op>_workspace_bytes().
+ *   - stream-explicit: `stream` is a cudaStream_t (0 = legacy default stream); the device is the current one.
+ *     No host synchronisation, no host reads of device memory: every call is CUDA-graph capturable.
+ *   - return value: 0 = ok, < 0 = invalid argument (SNB_E*), > 0 = cudaError_t of the failed launch.
+ *     snb_strerror() turns any of them into text.  (The reference printf()s and continues, chamfer.cu:166-169,
+ *     emd_cuda.cu:276-280, or exit(-1)s, MDS_cuda.cu:15-24.)
+ */
+#ifndef SPARENET_B200_H
+#define SPARENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_OK 0
+#define SNB_EINVAL (-1)     /* null/negative/inconsistent argument */
+#define SNB_ELIMIT (-2)     /* shape outside the op's documented limits */
+#define SNB_EWORKSPACE (-3) /* workspace too small */
+#define SNB_EALIGN (-4)     /* pointer alignment */
+
+int snb_version(void);
+const char* snb_strerror(int code);
+
+/* ---- Chamfer --------------------------------------------------------------------------------------
+ * replaces chamfer.forward / chamfer.backward (cuda/chamfer_dist/chamfer_cuda.cpp:12-42, chamfer.cu:147-229)
+ * and cd.forward_cuda / cd.backward_cuda (cuda/chamfer_distance/chamfer_distance.cpp:26-55,
+ * chamfer_distance.cu:139-155,189-209).
+ * dist1[b,i] = min_j |xyz1[b,i]-xyz2[b,j]|^2, idx1 = smallest argmin; dist2/idx2 the other direction.
+ * Outputs are fully written (no pre-zeroing needed).  Gradient buffers are fully written too. */
+int snb_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int N, int M,
+                    float* dist1, float* dist2, int* idx1, int* idx2, void* stream);
+int snb_chamfer_bwd(const float* xyz1, const float* xyz2, int B, int N, int M,
+                    const int* idx1, const int* idx2, const float* grad_dist1, const float* grad_dist2,
+                    float* grad_xyz1, float* grad_xyz2, void* stream);
+
+/* ---- EMD (auction) ---------------------------------------------------------------------------------
+ * replaces emd.forward / emd.backward (cuda/emd/emd.cpp:6-28, emd_cuda.cu:228-316).  n == m, n % 1024 == 0,
+ * B <= 512 (emd_cuda.cu:236-249 -> SNB_ELIMIT).  The 12 scratch tensors the reference allocates in Python
+ * (emd_module.py:43-54) become one caller-owned workspace.  dist = squared distance to the assigned point. */
+size_t snb_emd_workspace_bytes(int B, int N);
+int snb_emd_fwd(const float* xyz1, const float* xyz2, int B, int N, float eps, int iters,
+                float* dist, int* assignment, void* workspace, size_t workspace_bytes, void* stream);
+int snb_emd_bwd(const float* xyz1, const float* xyz2, int B, int N, const float* grad_dist,
+                const int* assignment, float* grad_xyz1, void* stream);
+
+/* ---- Expansion penalty (per-primitive MST) ------------------------------------------------------------
+ * replaces expansion_penalty.forward / .backward (cuda/expansion_penalty/expansion_penalty.cpp:4-22,
+ * expansion_penalty_cuda.cu:151-198).  primitive_size: power of two, 2..512, dividing N (the reference's tree
+ * reductions are only complete for powers of two).  The 2 x B*N*512 global scratch
+ * (expansion_penalty_module.py:33-34) shrinks to B*N/p floats.  mean_mst_length is already divided by N/p. */
+size_t snb_expansion_workspace_bytes(int B, int N, int primitive_size);
+int snb_expansion_fwd(const float* xyz, int B, int N, int primitive_size, float alpha,
+                      float* dist, int* assignment, float* mean_mst_length,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int snb_expansion_bwd(const float* xyz, int B, int N, const float* grad_dist, const int* assignment,
+                      float* grad_xyz, void* stream);
+
+/* ---- Minimum-density sampling + gather ---------------------------------------------------------------
+ * replaces MDS.minimum_density_sampling / gather_points / gather_points_grad (cuda/MDS/MDS.cpp:54-135,
+ * MDS_cuda.cu:29-271).  xyz [B,n,3], idx [B,m] int32; features [B,C,n]. */
+size_t snb_mds_workspace_bytes(int B, int n, int m);
+int snb_mds_sample(const float* xyz, int B, int n, int m, const float* mean_mst_length, int* idx,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int snb_gather_fwd(const float* features, const int* idx, int B, int C, int n, int m, float* out, void* stream);
+int snb_gather_bwd(const float* grad_out, const int* idx, int B, int C, int n, int m, float* grad_features, void* stream);
+
+/* ---- p2i (point -> image splat) ----------------------------------------------------------------------
+ * replaces ext.p2i_{max,sum}_{forward,backward}_gpu (cuda/p2i_op/ext.cpp:8-15, p2i_max.h:145-232,
+ * p2i_sum.h:133-214).  points [npoints,2] (row, col) in PIXEL space, features [npoints,C], batch_inds [npoints],
+ * background/out [B,C,H,W]; kernel_kind 0 = cosine.  is_double selects float64 buffers (gradcheck path).
+ * max: out = max(background, max f*w); ids = lowest point id attaining it, -1 where the background stands.
+ * workspace: snb_p2i_workspace_bytes (zero-size allowed for sum). */
+size_t snb_p2i_workspace_bytes(int B, int C, int H, int W, int is_double);
+int snb_p2i_max_fwd(const void* points, const void* features, const int* batch_inds, const void* background,
+                    int npoints, int B, int C, int H, int W, int kernel_kind, double radius, int is_double,
+                    void* out, int* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+int snb_p2i_max_bwd(const void* grad_out, const int* out_ids, const void* points, const void* features,
+                    int npoints, int B, int C, int H, int W, int kernel_kind, double radius, int is_double,
+                    void* grad_points, void* grad_features, void* grad_background, void* stream);
+int snb_p2i_sum_fwd(const void* points, const void* features, const int* batch_inds, const void* background,
+                    int npoints, int B, int C, int H, int W, int kernel_kind, double radius, int is_double,
+                    void* out, void* stream);
+int snb_p2i_sum_bwd(const void* grad_out, const void* points, const void* features, const int* batch_inds,
+                    int npoints, int B, int C, int H, int W, int kernel_kind, double radius, int is_double,
+                    void* grad_points, void* grad_features, void* stream);
+
+/* ---- kNN (replaces the un-vendored knn_cuda.KNN used by models/sparenet_generator.py:852-877) -------
+ * x [B,C,N] channel-major features; idx [B,N,k] int32 = the k nearest points (self included) by exact fp32
+ * squared distance, ascending; ties by smaller index.  k <= 32. */
+size_t snb_knn_workspace_bytes(int B, int N);
+int snb_knn(const float* x, int B, int C, int N, int k, int* idx, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARENET_B200_H */

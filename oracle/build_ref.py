@@ -1,0 +1,99 @@
+"""Build recipe for the *real* reference extensions -> oracle/_ref/ (TEST INFRASTRUCTURE ONLY).
+
+Compiles the reference's own CUDA extensions from the sources where they lie under
+/root/reference/cuda/** for sm_100a with torch.utils.cpp_extension (the same JIT route the
+reference itself uses in cuda/chamfer_distance/chamfer_distance.py:8-15 and
+cuda/p2i_op/__init__.py:11-19; its setup.py files pass no arch flags, cuda/emd/setup.py:4-8).
+Nothing from /root/reference is copied into the repository: only the built pybind `.so`
+files land in oracle/_ref/ (git-ignored, NOT gpurun-ignored, so they travel to the GPU box).
+
+The single shim: cuda/p2i_op uses `points.type()` inside AT_DISPATCH_FLOATING_TYPES
+(p2i_max.h:177,218; p2i_sum.h:162,201), which torch 2.11 rejects; a build-time copy in a
+temporary directory replaces those 4 tokens with `points.scalar_type()`.
+
+Run here (no GPU needed; nvcc cross-compiles):   python oracle/build_ref.py [names...]
+On the GPU box /root/reference does not exist; tests load the prebuilt .so via `load_ref`.
+"""
+import importlib.util
+import os
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF = "/root/reference/cuda"
+
+# name -> (source dir, files, extra cuda flags).  Names are the TORCH_EXTENSION_NAMEs the
+# reference's own Python wrappers import.
+EXTS = {
+    "cd": ("chamfer_distance", ["chamfer_distance.cpp", "chamfer_distance.cu"], []),
+    "chamfer": ("chamfer_dist", ["chamfer_cuda.cpp", "chamfer.cu"], []),
+    "emd": ("emd", ["emd.cpp", "emd_cuda.cu"], []),
+    "expansion_penalty": ("expansion_penalty", ["expansion_penalty.cpp", "expansion_penalty_cuda.cu"], []),
+    "MDS": ("MDS", ["MDS.cpp", "MDS_cuda.cu"], []),
+    "ext": ("p2i_op", ["ext.cpp", "p2i_sum.cu", "p2i_max.cu"], ["--expt-extended-lambda", "-O3"]),
+    "gridding": ("gridding", ["gridding_cuda.cpp", "gridding.cu", "gridding_reverse.cu"], []),
+}
+
+
+def build(names=None, verbose=False):
+    os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
+    os.environ.setdefault("MAX_JOBS", "8")
+    from torch.utils.cpp_extension import load
+
+    os.makedirs(OUT, exist_ok=True)
+    built = []
+    for name in names or EXTS:
+        sub, files, cuflags = EXTS[name]
+        dst = os.path.join(OUT, name + ".so")
+        if os.path.exists(dst):
+            built.append(dst)
+            continue
+        srcdir = os.path.join(REF, sub)
+        if not os.path.isdir(srcdir):
+            print(f"[build_ref] {srcdir} absent (GPU box?) - skipping {name}")
+            continue
+        tmp = tempfile.mkdtemp(prefix=f"snb_ref_{name}_")
+        try:
+            if name == "ext":  # the 4-token shim, applied to a throw-away copy
+                shim = os.path.join(tmp, "src")
+                shutil.copytree(srcdir, shim)
+                for h in ("p2i_max.h", "p2i_sum.h"):
+                    p = os.path.join(shim, h)
+                    s = open(p).read().replace("points.type()", "points.scalar_type()")
+                    open(p, "w").write(s)
+                srcdir = shim
+            bdir = os.path.join(tmp, "build")
+            os.makedirs(bdir)
+            load(name=name, sources=[os.path.join(srcdir, f) for f in files],
+                 extra_cuda_cflags=cuflags + ["-lineinfo"], build_directory=bdir, verbose=verbose)
+            shutil.copy(os.path.join(bdir, name + ".so"), dst)
+            built.append(dst)
+            print(f"[build_ref] built {dst}")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return built
+
+
+def available(name):
+    return os.path.exists(os.path.join(OUT, name + ".so"))
+
+
+def load_ref(name):
+    """Import a prebuilt reference extension from oracle/_ref/ (needs `import torch` first)."""
+    import torch  # noqa: F401  (libtorch symbols must be loaded before the pybind module)
+    path = os.path.join(OUT, name + ".so")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    if name in sys.modules and getattr(sys.modules[name], "__file__", None) == path:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules[name] = mod
+    return mod
+
+
+if __name__ == "__main__":
+    build(sys.argv[1:] or None, verbose=False)

@@ -1,0 +1,77 @@
+"""ctypes binding of libsparenet_b200.so (the C ABI declared in include/sparenet_b200.h).
+
+There is no CPU fallback and no PyTorch re-implementation behind these calls: if the shared library is
+missing the import fails loudly, and every op raises on a non-zero return code.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsparenet_b200.so")
+
+c_int, c_float, c_double, c_size_t, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p
+P = c_void_p
+
+# name -> (restype, argtypes); must list every symbol of include/sparenet_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "snb_version": (c_int, []),
+    "snb_strerror": (ctypes.c_char_p, [c_int]),
+    "snb_chamfer_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P]),
+    "snb_chamfer_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "snb_emd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "snb_emd_fwd": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P, P, c_size_t, P]),
+    "snb_emd_bwd": (c_int, [P, P, c_int, c_int, P, P, P, P]),
+    "snb_expansion_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "snb_expansion_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, P, P, P, c_size_t, P]),
+    "snb_expansion_bwd": (c_int, [P, c_int, c_int, P, P, P, P]),
+    "snb_mds_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "snb_mds_sample": (c_int, [P, c_int, c_int, c_int, P, P, P, c_size_t, P]),
+    "snb_gather_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "snb_gather_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "snb_p2i_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "snb_p2i_max_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P, P, c_size_t, P]),
+    "snb_p2i_max_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P, P, P]),
+    "snb_p2i_sum_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P]),
+    "snb_p2i_sum_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P, P]),
+    "snb_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "snb_knn": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
+}
+
+_lib = None
+
+
+class SnbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building nothing: run `python -m sparenet_b200.build` or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m sparenet_b200.build` (nvcc, sm_100a). "
+                "sparenet_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().snb_strerror(rc).decode()
+        raise SnbError(f"{what} failed: {msg} (code {rc})")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

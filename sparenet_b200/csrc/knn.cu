@@ -1,0 +1,167 @@
+// knn.cu -- k nearest neighbours in feature space for the EdgeConv encoder, sm_100a.
+//
+// Replaces the un-vendored third-party knn_cuda.KNN(k, transpose_mode=True) call of
+// models/sparenet_generator.py:852-877 (KNN_CUDA 0.2 wheel, setup_env.sh:5; brute force, fp32).  Contract
+// (SURVEY.md 9.6): for every point the k points with the smallest squared feature distance, itself
+// included; downstream only consumes the SET (max over k, BN/SE statistics are permutation invariant).
+// Defined arithmetic: d(i,j) = sum_c (x[c,j]-x[c,i])^2 accumulated with FMAs in ascending c, fp32;
+// ordering (d, j) lexicographic, i.e. ties go to the smaller index.
+//
+// Two kernels: (1) a register-tiled 128x128 SIMT distance kernel on the channel-major [B,C,N] layout the
+// encoder already uses (coalesced loads, 8x8 outputs per thread, direct-difference form -- the
+// |a|^2+|b|^2-2ab GEMM form would lose the exact ordering to cancellation); (2) a warp-per-row top-k.
+#include "common.cuh"
+
+namespace snb {
+
+constexpr int KNN_BT = 128;  // block tile (rows = cols)
+constexpr int KNN_KT = 16;   // channels per smem stage
+constexpr int KNN_MAXK = 32;
+
+__global__ void __launch_bounds__(256) knn_dist_kernel(const float* __restrict__ x, int C, int N, float* __restrict__ D) {
+  __shared__ __align__(16) float sa[KNN_KT][KNN_BT];
+  __shared__ __align__(16) float sb[KNN_KT][KNN_BT];
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * KNN_BT, j0 = blockIdx.x * KNN_BT;
+  const float* __restrict__ xb = x + (size_t)b * C * N;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 8 x 8 outputs each
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[r][c] = 0.f;
+
+  for (int c0 = 0; c0 < C; c0 += KNN_KT) {
+    // stage KNN_KT channels x 128 points for rows and columns (coalesced along N)
+    for (int e = threadIdx.x; e < KNN_KT * KNN_BT; e += 256) {
+      const int cc = e / KNN_BT, p = e % KNN_BT;
+      const int c = c0 + cc;
+      const int ia = i0 + p, jb = j0 + p;
+      sa[cc][p] = (c < C && ia < N) ? xb[(size_t)c * N + ia] : 0.f;
+      sb[cc][p] = (c < C && jb < N) ? xb[(size_t)c * N + jb] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < KNN_KT; cc++) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sa[cc][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sa[cc][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sb[cc][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sb[cc][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const float d = __fsub_rn(bv[c], av[r]);
+          acc[r][c] = __fmaf_rn(d, d, acc[r][c]);
+        }
+    }
+    __syncthreads();
+  }
+  float* __restrict__ Db = D + (size_t)b * N * N;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int i = i0 + ty * 8 + r;
+    if (i >= N) continue;
+    const int j = j0 + tx * 8;
+    if (j + 7 < N && ((N & 3) == 0)) {
+      *reinterpret_cast<float4*>(&Db[(size_t)i * N + j]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      *reinterpret_cast<float4*>(&Db[(size_t)i * N + j + 4]) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        if (j + c < N) Db[(size_t)i * N + j + c] = acc[r][c];
+    }
+  }
+}
+
+// warp per query row: per-lane sorted top-K over a strided scan, then K rounds of warp arg-min to merge.
+template <int K>
+__global__ void __launch_bounds__(256) knn_topk_kernel(const float* __restrict__ D, int N, size_t rows, int k, int* __restrict__ idx) {
+  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* __restrict__ d = D + row * N;
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int t = 0; t < K; t++) {
+    bd[t] = __int_as_float(0x7f800000);
+    bi[t] = 0x7fffffff;
+  }
+  for (int j = lane; j < N; j += 32) {
+    float v = d[j];
+    int vi = j;
+    if (v < bd[K - 1]) {  // within a lane j ascends, so strict '<' keeps the smaller index on ties
+      bool ins = false;
+#pragma unroll
+      for (int t = 0; t < K; t++) {
+        if (ins || v < bd[t]) {  // insert, then shift every later entry down by one
+          ins = true;
+          const float tv = bd[t];
+          const int ti = bi[t];
+          bd[t] = v;
+          bi[t] = vi;
+          v = tv;
+          vi = ti;
+        }
+      }
+    }
+  }
+  int* out = idx + row * k;
+  for (int t = 0; t < k; t++) {
+    float hv = bd[0];
+    int hi = bi[0];
+    float mv = hv;
+    int mi = hi;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (ov < mv || (ov == mv && oi < mi)) {
+        mv = ov;
+        mi = oi;
+      }
+    }
+    if (lane == 0) out[t] = mi;
+    if (hi == mi && hv == mv) {  // the owning lane pops its head
+#pragma unroll
+      for (int u = 0; u + 1 < K; u++) {
+        bd[u] = bd[u + 1];
+        bi[u] = bi[u + 1];
+      }
+      bd[K - 1] = __int_as_float(0x7f800000);
+      bi[K - 1] = 0x7fffffff;
+    }
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+SNB_API size_t snb_knn_workspace_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return sizeof(float) * (size_t)B * N * N;
+}
+
+SNB_API int snb_knn(const float* x, int B, int C, int N, int k, int* idx, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || C <= 0 || N < 0 || k <= 0) return SNB_EINVAL;
+  if (k > KNN_MAXK || k > N || B > 65535) return SNB_ELIMIT;
+  if (B == 0 || N == 0) return SNB_OK;
+  if (!workspace || workspace_bytes < snb_knn_workspace_bytes(B, N)) return SNB_EWORKSPACE;
+  if (((uintptr_t)workspace & 15) != 0) return SNB_EALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* D = (float*)workspace;
+  const int nt = (N + KNN_BT - 1) / KNN_BT;
+  knn_dist_kernel<<<dim3(nt, nt, B), 256, 0, s>>>(x, C, N, D);
+  SNB_LAUNCH_CHECK();
+  const size_t rows = (size_t)B * N;
+  const unsigned g = (unsigned)((rows * 32 + 255) / 256);
+  if (k <= 8) knn_topk_kernel<8><<<g, 256, 0, s>>>(D, N, rows, k, idx);
+  else if (k <= 16) knn_topk_kernel<16><<<g, 256, 0, s>>>(D, N, rows, k, idx);
+  else knn_topk_kernel<32><<<g, 256, 0, s>>>(D, N, rows, k, idx);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

@@ -1,0 +1,215 @@
+// mds.cu -- minimum-density sampling + gather_points (fwd/bwd), sm_100a.
+//
+// Replaces minimum_density_sampling_kernel / gather_points[_grad]_kernel (cuda/MDS/MDS_cuda.cu:29-211).
+// Contract: t = (float)(5.0*mml*mml); idx[0] = 0; each of the m-1 dependent rounds adds
+// w = expf(-d/t) (d = fma(dz,dz,fma(dx,dx,dy*dy)), d* = x_k - x_old; IEEE divide, accurate expf; doubled for
+// k >= 8192) to every point's accumulated density and picks the arg-min; ties: lower (k % block_size), then
+// lower k, with block_size = min(1024, 2^floor(log2 n)).  Chosen points are parked at 1e9.
+//   The reference accumulates as (float)((double)temp + (double)w): for one addition of two floats, double
+//   rounding through fp64 is innocuous (53 >= 2*24+2), so a plain fp32 add is bit-identical.
+//
+// Design: the m-1 rounds are a latency chain, so the only lever is the time of ONE round.  A thread-block
+// CLUSTER (up to 8 CTAs = 8 SMs) owns one sample; every point (xyz + density) lives in registers for the
+// whole kernel; a round is: register update -> packed (density,key) u64 warp arg-min by shuffles -> one
+// DSMEM store per warp into every CTA of the cluster -> ONE cluster barrier -> local 64-entry reduce.
+// No global or shared-memory traffic for `temp`, no block barriers (the reference does 11 per round).
+#include <math.h>
+#include "common.cuh"
+
+namespace snb {
+
+constexpr int MDS_THREADS = 512;
+constexpr int MDS_WARPS = MDS_THREADS / 32;
+constexpr int MDS_MAX_CLUSTER = 8;
+constexpr unsigned long long MDS_NONE = 0xffffffffffffffffull;
+
+template <int PT>
+__global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
+                                                                      const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
+                                                                      int bs_mask) {
+  __shared__ __align__(16) unsigned long long slots[2][MDS_MAX_CLUSTER * MDS_WARPS];
+  const uint32_t cs = cluster_nctarank();
+  const uint32_t rank = cluster_ctarank();
+  const int b = blockIdx.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  dataset += (size_t)b * n * 3;
+  idxs += (size_t)b * m;
+
+  const int chunk = (n + cs - 1) / cs;
+  const int kbeg = rank * chunk;
+  const int kend = (kbeg + chunk) < n ? (kbeg + chunk) : n;
+
+  float x[PT], y[PT], z[PT], temp[PT];
+#pragma unroll
+  for (int i = 0; i < PT; i++) {
+    const int k = kbeg + tid + i * MDS_THREADS;
+    const bool ok = k < kend;
+    x[i] = ok ? dataset[k * 3 + 0] : 0.f;
+    y[i] = ok ? dataset[k * 3 + 1] : 0.f;
+    z[i] = ok ? dataset[k * 3 + 2] : 0.f;
+    temp[i] = ok ? (k == 0 ? 1e9f : 0.f) : 2e9f;  // out-of-range slots can never win
+  }
+  const float mml = mean_mst_length[b];
+  const float t = (float)(5.0 * (double)mml * (double)mml);
+
+  if (rank == 0 && tid == 0) idxs[0] = 0;
+  int old = 0;
+  float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];
+
+  // everybody's slots must exist before the first remote store
+  cluster_sync_all();
+
+  const uint32_t slot_base = smem_u32(&slots[0][0]);
+  for (int j = 1; j < m; j++) {
+    unsigned long long best = MDS_NONE;
+#pragma unroll
+    for (int i = 0; i < PT; i++) {
+      const int k = kbeg + tid + i * MDS_THREADS;
+      const float d = sqdist3(__fsub_rn(x[i], x1), __fsub_rn(y[i], y1), __fsub_rn(z[i], z1));
+      float w = expf(__fdiv_rn(-d, t));
+      if (k >= 8192) w = __fmul_rn(w, 2.0f);
+      const float v = __fadd_rn(temp[i], w);
+      temp[i] = v;
+      const unsigned key = ((unsigned)(k & bs_mask) << 21) | (unsigned)k;
+      const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key;
+      if (v < 1e9f && p < best) best = p;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    const int par = j & 1;
+    if (lane < (int)cs) {  // lane r publishes this warp's candidate into CTA r
+      const uint32_t local = slot_base + (uint32_t)((par * MDS_MAX_CLUSTER * MDS_WARPS + rank * MDS_WARPS + warp) * 8);
+      st_cluster_u64(mapa_shared(local, (uint32_t)lane), best);
+    }
+    cluster_sync_all();
+    // reduce cs*MDS_WARPS candidates (<= 128): each lane takes up to 4
+    unsigned long long g = MDS_NONE;
+    const int total = cs * MDS_WARPS;
+    for (int e = lane; e < total; e += 32) {
+      const unsigned long long c = slots[par][e];  // entries [0, cs*MDS_WARPS) are contiguous by (rank, warp)
+      g = c < g ? c : g;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, g, o);
+      g = other < g ? other : g;
+    }
+    old = (g == MDS_NONE) ? 0 : (int)((unsigned)g & 0x1fffffu);
+    if (rank == 0 && tid == 0) idxs[j] = old;
+    // park the chosen point (the owner thread finds it among its registers)
+    {
+      const int rel = old - kbeg - tid;
+      if (old >= kbeg && old < kend && rel >= 0 && (rel % MDS_THREADS) == 0) {
+        const int slot = rel / MDS_THREADS;
+#pragma unroll
+        for (int i = 0; i < PT; i++)
+          if (i == slot) temp[i] = 1e9f;
+      }
+    }
+    x1 = __ldg(&dataset[old * 3 + 0]);
+    y1 = __ldg(&dataset[old * 3 + 1]);
+    z1 = __ldg(&dataset[old * 3 + 2]);
+  }
+  // no CTA may exit while a peer can still store into its shared memory
+  cluster_sync_all();
+}
+
+// ---- gather_points: out[b,c,j] = f[b,c,idx[b,j]]; backward scatters with atomics (the reference's
+// non-atomic '+=' (MDS_cuda.cu:63-65) is only correct for unique indices; RED.ADD is correct always) -----
+__global__ void __launch_bounds__(256) gather_fwd_kernel(const float* __restrict__ f, const int* __restrict__ idx, int C, int n, int m,
+                                                          float* __restrict__ out) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  out[((size_t)b * C + c) * m + j] = f[((size_t)b * C + c) * n + idx[(size_t)b * m + j]];
+}
+__global__ void __launch_bounds__(256) gather_bwd_kernel(const float* __restrict__ g, const int* __restrict__ idx, int C, int n, int m,
+                                                          float* __restrict__ gf) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  atomicAdd(&gf[((size_t)b * C + c) * n + idx[(size_t)b * m + j]], g[((size_t)b * C + c) * m + j]);
+}
+
+template <int PT>
+static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, int* idx, int cs, int bs_mask, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * cs));
+  cfg.blockDim = dim3(MDS_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<PT>, xyz, n, m, mml, idx, bs_mask);
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+SNB_API size_t snb_mds_workspace_bytes(int B, int n, int m) {
+  (void)B; (void)n; (void)m;
+  return 0;  // densities live in registers; kept in the ABI for the out-of-register fallback
+}
+
+SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* mean_mst_length, int* idx, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (B < 0 || n <= 0 || m < 0) return SNB_EINVAL;
+  if (B == 0 || m == 0) return SNB_OK;
+  if (n >= (1 << 21)) return SNB_ELIMIT;
+  cudaStream_t s = (cudaStream_t)stream;
+  int bs = 1;
+  while (bs * 2 <= n && bs < 1024) bs *= 2;  // opt_n_threads(n), MDS_cuda.cu:8-12
+  // cluster size: as many SMs per sample as the batch leaves free (<= 8, power of two)
+  int cs = 1;
+  while (cs * 2 <= MDS_MAX_CLUSTER && B * cs * 2 <= kNumSMs) cs *= 2;
+  int pt = (((n + cs - 1) / cs) + MDS_THREADS - 1) / MDS_THREADS;
+  while (pt > 24 && cs < MDS_MAX_CLUSTER) {  // too many points for the register file: widen the cluster
+    cs *= 2;
+    pt = (((n + cs - 1) / cs) + MDS_THREADS - 1) / MDS_THREADS;
+  }
+  int rc;
+  if (pt <= 2) rc = mds_launch<2>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  else if (pt <= 4) rc = mds_launch<4>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  else if (pt <= 6) rc = mds_launch<6>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  else if (pt <= 9) rc = mds_launch<9>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  else if (pt <= 12) rc = mds_launch<12>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  else if (pt <= 18) rc = mds_launch<18>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  else if (pt <= 24) rc = mds_launch<24>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  else return SNB_ELIMIT;  // n > 8*512*24 = 98304 points per sample
+  if (rc != 0) return rc;
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_gather_fwd(const float* features, const int* idx, int B, int C, int n, int m, float* out, void* stream) {
+  if (B < 0 || C < 0 || n < 0 || m < 0) return SNB_EINVAL;
+  if (B == 0 || C == 0 || m == 0) return SNB_OK;
+  if (B > 65535 || C > 65535) return SNB_ELIMIT;
+  dim3 grid((m + 255) / 256, C, B);
+  gather_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(features, idx, C, n, m, out);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_gather_bwd(const float* grad_out, const int* idx, int B, int C, int n, int m, float* grad_features, void* stream) {
+  if (B < 0 || C < 0 || n < 0 || m < 0) return SNB_EINVAL;
+  if (B == 0 || C == 0 || n == 0) return SNB_OK;
+  if (B > 65535 || C > 65535) return SNB_ELIMIT;
+  cudaStream_t s = (cudaStream_t)stream;
+  SNB_CUDA(cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)B * C * n, s));
+  if (m == 0) return SNB_OK;
+  dim3 grid((m + 255) / 256, C, B);
+  gather_bwd_kernel<<<grid, 256, 0, s>>>(grad_out, idx, C, n, m, grad_features);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

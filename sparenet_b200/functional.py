@@ -1,0 +1,220 @@
+"""Raw (non-autograd) host wrappers: torch CUDA tensors in, C-ABI call, torch CUDA tensors out.
+
+PyTorch is plumbing here: it owns device memory (outputs and scratch come from its caching allocator) and
+the current stream.  All arithmetic happens in libsparenet_b200.so; there is no fallback path.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _cuda_f32(t, name):
+    if not t.is_cuda:
+        raise SnbValueError(f"{name} must be a CUDA tensor (sparenet_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise SnbValueError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _cuda_i32(t, name):
+    if not t.is_cuda or t.dtype != torch.int32:
+        raise SnbValueError(f"{name} must be a CUDA int32 tensor")
+    return t.contiguous()
+
+
+class SnbValueError(ValueError):
+    pass
+
+
+def _ws(nbytes, device):
+    # 16-byte aligned scratch from the caching allocator (allocations are 512-byte aligned)
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------- Chamfer
+def chamfer_forward(xyz1, xyz2):
+    xyz1, xyz2 = _cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2")
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
+        raise SnbValueError("chamfer: expected [B,N,3] and [B,M,3]")
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    dev = xyz1.device
+    d1 = torch.empty(B, N, device=dev)
+    d2 = torch.empty(B, M, device=dev)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
+    i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().snb_chamfer_fwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), stream_ptr()), "chamfer_fwd")
+    return d1, d2, i1, i2
+
+
+def chamfer_backward(xyz1, xyz2, idx1, idx2, g1, g2):
+    xyz1, xyz2 = _cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2")
+    g1, g2 = _cuda_f32(g1, "grad_dist1"), _cuda_f32(g2, "grad_dist2")
+    idx1, idx2 = _cuda_i32(idx1, "idx1"), _cuda_i32(idx2, "idx2")
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    gx1, gx2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    with torch.cuda.device(xyz1.device):
+        check(_lib.load().snb_chamfer_bwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(idx1), ptr(idx2), ptr(g1), ptr(g2), ptr(gx1), ptr(gx2),
+                                          stream_ptr()), "chamfer_bwd")
+    return gx1, gx2
+
+
+# ----------------------------------------------------------------------------- EMD
+def emd_forward(xyz1, xyz2, eps, iters):
+    xyz1, xyz2 = _cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2")
+    B, N, _ = xyz1.shape
+    dev = xyz1.device
+    dist = torch.empty(B, N, device=dev)
+    ass = torch.empty(B, N, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.snb_emd_workspace_bytes(B, N)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        check(lib.snb_emd_fwd(ptr(xyz1), ptr(xyz2), B, N, float(eps), int(iters), ptr(dist), ptr(ass), ptr(ws), nbytes, stream_ptr()), "emd_fwd")
+    return dist, ass
+
+
+def emd_backward(xyz1, xyz2, grad_dist, assignment):
+    xyz1, xyz2, grad_dist = _cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2"), _cuda_f32(grad_dist, "grad_dist")
+    assignment = _cuda_i32(assignment, "assignment")
+    B, N, _ = xyz1.shape
+    g = torch.empty_like(xyz1)
+    with torch.cuda.device(xyz1.device):
+        check(_lib.load().snb_emd_bwd(ptr(xyz1), ptr(xyz2), B, N, ptr(grad_dist), ptr(assignment), ptr(g), stream_ptr()), "emd_bwd")
+    return g
+
+
+# ----------------------------------------------------------------------------- expansion penalty
+def expansion_forward(xyz, primitive_size, alpha):
+    xyz = _cuda_f32(xyz, "xyz")
+    B, N, _ = xyz.shape
+    dev = xyz.device
+    dist = torch.empty(B, N, device=dev)
+    ass = torch.empty(B, N, dtype=torch.int32, device=dev)
+    mml = torch.empty(B, device=dev)
+    lib = _lib.load()
+    nbytes = lib.snb_expansion_workspace_bytes(B, N, int(primitive_size))
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        check(lib.snb_expansion_fwd(ptr(xyz), B, N, int(primitive_size), float(alpha), ptr(dist), ptr(ass), ptr(mml), ptr(ws), nbytes,
+                                    stream_ptr()), "expansion_fwd")
+    return dist, ass, mml
+
+
+def expansion_backward(xyz, grad_dist, assignment):
+    xyz, grad_dist, assignment = _cuda_f32(xyz, "xyz"), _cuda_f32(grad_dist, "grad_dist"), _cuda_i32(assignment, "assignment")
+    B, N, _ = xyz.shape
+    g = torch.empty_like(xyz)
+    with torch.cuda.device(xyz.device):
+        check(_lib.load().snb_expansion_bwd(ptr(xyz), B, N, ptr(grad_dist), ptr(assignment), ptr(g), stream_ptr()), "expansion_bwd")
+    return g
+
+
+# ----------------------------------------------------------------------------- MDS + gather
+def mds_sample(xyz, npoint, mean_mst_length):
+    xyz, mml = _cuda_f32(xyz, "xyz"), _cuda_f32(mean_mst_length, "mean_mst_length")
+    B, n, _ = xyz.shape
+    idx = torch.empty(B, int(npoint), dtype=torch.int32, device=xyz.device)
+    lib = _lib.load()
+    nbytes = lib.snb_mds_workspace_bytes(B, n, int(npoint))
+    ws = _ws(nbytes, xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(lib.snb_mds_sample(ptr(xyz), B, n, int(npoint), ptr(mml), ptr(idx), ptr(ws), nbytes, stream_ptr()), "mds_sample")
+    return idx
+
+
+def gather_forward(features, idx):
+    features, idx = _cuda_f32(features, "features"), _cuda_i32(idx, "idx")
+    B, C, n = features.shape
+    m = idx.shape[1]
+    out = torch.empty(B, C, m, device=features.device)
+    with torch.cuda.device(features.device):
+        check(_lib.load().snb_gather_fwd(ptr(features), ptr(idx), B, C, n, m, ptr(out), stream_ptr()), "gather_fwd")
+    return out
+
+
+def gather_backward(grad_out, idx, n):
+    grad_out, idx = _cuda_f32(grad_out, "grad_out"), _cuda_i32(idx, "idx")
+    B, C, m = grad_out.shape
+    g = torch.empty(B, C, int(n), device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(_lib.load().snb_gather_bwd(ptr(grad_out), ptr(idx), B, C, int(n), m, ptr(g), stream_ptr()), "gather_bwd")
+    return g
+
+
+# ----------------------------------------------------------------------------- p2i
+def _p2i_dtype(points):
+    if not points.is_cuda:
+        raise SnbValueError("p2i: tensors must live on a CUDA device")
+    if points.dtype not in (torch.float32, torch.float64):
+        raise SnbValueError(f"p2i: float32 or float64 expected, got {points.dtype}")
+    return 1 if points.dtype == torch.float64 else 0
+
+
+def p2i_max_forward(points, feat, batch_inds, background, kernel_kind, radius):
+    dbl = _p2i_dtype(points)
+    points, feat, background = points.contiguous(), feat.to(points.dtype).contiguous(), background.to(points.dtype).contiguous()
+    binds = _cuda_i32(batch_inds, "batch_inds")
+    B, C, H, W = background.shape
+    out = torch.empty_like(background)
+    ids = torch.empty(B, C, H, W, dtype=torch.int32, device=points.device)
+    lib = _lib.load()
+    nbytes = lib.snb_p2i_workspace_bytes(B, C, H, W, dbl)
+    ws = _ws(nbytes, points.device)
+    with torch.cuda.device(points.device):
+        check(lib.snb_p2i_max_fwd(ptr(points), ptr(feat), ptr(binds), ptr(background), points.shape[0], B, C, H, W, int(kernel_kind),
+                                  float(radius), dbl, ptr(out), ptr(ids), ptr(ws), nbytes, stream_ptr()), "p2i_max_fwd")
+    return out, ids
+
+
+def p2i_max_backward(grad_out, ids, points, feat, kernel_kind, radius):
+    dbl = _p2i_dtype(points)
+    grad_out, points, feat = grad_out.to(points.dtype).contiguous(), points.contiguous(), feat.to(points.dtype).contiguous()
+    ids = _cuda_i32(ids, "out_point_ids")
+    B, C, H, W = grad_out.shape
+    gp, gf, gb = torch.empty_like(points), torch.empty_like(feat), torch.empty_like(grad_out)
+    with torch.cuda.device(points.device):
+        check(_lib.load().snb_p2i_max_bwd(ptr(grad_out), ptr(ids), ptr(points), ptr(feat), points.shape[0], B, C, H, W, int(kernel_kind),
+                                          float(radius), dbl, ptr(gp), ptr(gf), ptr(gb), stream_ptr()), "p2i_max_bwd")
+    return gp, gf, gb
+
+
+def p2i_sum_forward(points, feat, batch_inds, background, kernel_kind, radius):
+    dbl = _p2i_dtype(points)
+    points, feat, background = points.contiguous(), feat.to(points.dtype).contiguous(), background.to(points.dtype).contiguous()
+    binds = _cuda_i32(batch_inds, "batch_inds")
+    B, C, H, W = background.shape
+    out = torch.empty_like(background)
+    with torch.cuda.device(points.device):
+        check(_lib.load().snb_p2i_sum_fwd(ptr(points), ptr(feat), ptr(binds), ptr(background), points.shape[0], B, C, H, W, int(kernel_kind),
+                                          float(radius), dbl, ptr(out), stream_ptr()), "p2i_sum_fwd")
+    return out
+
+
+def p2i_sum_backward(grad_out, points, feat, batch_inds, kernel_kind, radius):
+    dbl = _p2i_dtype(points)
+    grad_out, points, feat = grad_out.to(points.dtype).contiguous(), points.contiguous(), feat.to(points.dtype).contiguous()
+    binds = _cuda_i32(batch_inds, "batch_inds")
+    B, C, H, W = grad_out.shape
+    gp, gf = torch.empty_like(points), torch.empty_like(feat)
+    with torch.cuda.device(points.device):
+        check(_lib.load().snb_p2i_sum_bwd(ptr(grad_out), ptr(points), ptr(feat), ptr(binds), points.shape[0], B, C, H, W, int(kernel_kind),
+                                          float(radius), dbl, ptr(gp), ptr(gf), stream_ptr()), "p2i_sum_bwd")
+    return gp, gf
+
+
+# ----------------------------------------------------------------------------- kNN
+def knn_indices(x, k):
+    """x: [B, C, N] float32 (channel-major, as the encoder holds it) -> idx [B, N, k] int32."""
+    x = _cuda_f32(x, "x")
+    B, C, N = x.shape
+    idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    nbytes = lib.snb_knn_workspace_bytes(B, N)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        check(lib.snb_knn(ptr(x), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn")
+    return idx
