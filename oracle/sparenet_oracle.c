@@ -309,8 +309,11 @@ ORC_API void orc_expansion_bwd(const float *xyz, int B, int N, const float *gdis
 /* ------------------------------------------------------------------------------------------
  * Minimum-density sampling  (cuda/MDS/MDS_cuda.cu:91-211, MDS.cpp:114-135)
  * t = (float)(5.0*mml*mml); per round temp[k] = (float)((double)temp[k] + w or 2w), w=expf(-d/t);
- * argmin tie key = (k % block_size, k) (thread-strided scan :123-133 then lower-tid-wins tree :81-87),
- * block_size = min(1024, 2^floor(log2 n)) (:8-12).  temp[old]=1e9 is applied before the next round.
+ * argmin ties: inside a thread the first k of its stride wins (:123-133); across threads the smem tournament
+ * (:81-87,139-198) lets slot t absorb slot t+s for s = bs/2..1 with the lower slot winning ties, so among equal
+ * values the thread with the smallest BIT-REVERSED tid wins: tie key = (bitrev(k % bs), k),
+ * bs = min(1024, 2^floor(log2 n)) (:8-12).  (Pinned against the reference extension on the GPU: with all-zero
+ * densities it samples 0, 1024, 512, 1536, 256, ...)  temp[old]=1e9 is applied before the next round.
  * NOTE: host expf is not bit-identical to CUDA's expf, so index parity with the GPU holds only
  * up to near-ties; orc_mds_check below verifies a GPU-produced sequence step by step instead.
  * ---------------------------------------------------------------------------------------- */
@@ -318,6 +321,12 @@ static int mds_block_size(int n) {
   int bs = 1;
   while (bs * 2 <= n && bs < 1024) bs *= 2;
   return bs;
+}
+
+static inline int mds_lane_key(int k, int bs) { /* bit-reversed (k % bs) over log2(bs) bits */
+  int t = k % bs, r = 0;
+  for (int b = 1; b < bs; b <<= 1) { r = (r << 1) | (t & 1); t >>= 1; }
+  return r;
 }
 
 static inline float mds_w(const float *xyz, int k, float x1, float y1, float z1, float t) {
@@ -343,7 +352,7 @@ ORC_API void orc_mds(const float *xyz, int B, int n, int m, const float *mml, in
         const float w = mds_w(p, k, x1, y1, z1, t);
         temp[k] = (float)((double)temp[k] + (k < 8192 ? (double)w : (double)w * 2.0));
         const float v = temp[k];
-        const int lane = k % bs;
+        const int lane = mds_lane_key(k, bs);
         /* strict '<' inside a thread (first k of the stride wins), lower tid wins across threads;
          * threads that saw nothing below 1e9 report (1e9, index 0) */
         if (v < 1e9f && (v < best || (v == best && lane < bestlane))) { best = v; besti = k; bestlane = lane; }
@@ -373,7 +382,7 @@ ORC_API int orc_mds_check(const float *xyz, int n, int m, float mml, const int *
       const float w = mds_w(xyz, k, x1, y1, z1, t);
       temp[k] = (float)((double)temp[k] + (k < 8192 ? (double)w : (double)w * 2.0));
       const float v = temp[k];
-      const int lane = k % bs;
+      const int lane = mds_lane_key(k, bs);
       if (v < 1e9f && (v < best || (v == best && lane < bestlane))) { best = v; besti = k; bestlane = lane; }
     }
     const int c = idxs[j];
@@ -404,7 +413,8 @@ ORC_API void orc_gather_bwd(const float *gout, const int *idx, int B, int C, int
 
 /* ------------------------------------------------------------------------------------------
  * p2i  (cuda/p2i_op/p2i_max.h:7-143, p2i_sum.h:7-131, utility.h:82-100), float and double.
- * r = sqrt(fma(dx,dx,dy*dy)) (nvcc contracts utility.h:93; checked in the SASS of oracle/_ref/ext.so).
+ * Footprint loops (utility.h:90-99, x outer): nvcc hoists dx*dx and fuses dy: r = sqrt(fma(dy,dy,dx*dx));
+ * the per-pixel max-backward (p2i_max.h:109-110) contracts to fma(dx,dx,dy*dy) (SASS of oracle/_ref/ext.so).
  * points are already in pixel space (the (p+1)/2*(H-1) map lives in Python, __init__.py:116-121).
  * max: out = max(background, max_p f*w), ids = lowest point id attaining a value strictly above the
  * background (the reference's winner on exact ties is whichever thread locked first).
@@ -424,7 +434,7 @@ ORC_API void orc_gather_bwd(const float *gout, const int *idx, int B, int C, int
       for (int x = x0; x <= x1; x++)                                                                            \
         for (int y = y0; y <= y1; y++) {                                                                        \
           const T dx = (T)x - px, dy = (T)y - py;                                                               \
-          const T r = SQRT(FMA(dx, dx, dy * dy));                                                                  \
+          const T r = SQRT(FMA(dy, dy, dx * dx));                                                                  \
           if (!(r <= radius)) continue;                                                                         \
           const T w = (T)(cos((double)r * M_PI / (double)radius) * 0.5 + 0.5);                                  \
           for (int c = 0; c < C; c++) {                                                                         \
@@ -472,7 +482,7 @@ ORC_API void orc_gather_bwd(const float *gout, const int *idx, int B, int C, int
       for (int x = x0; x <= x1; x++)                                                                            \
         for (int y = y0; y <= y1; y++) {                                                                        \
           const T dx = (T)x - px, dy = (T)y - py;                                                               \
-          const T r = SQRT(FMA(dx, dx, dy * dy));                                                                  \
+          const T r = SQRT(FMA(dy, dy, dx * dx));                                                                  \
           if (!(r <= radius)) continue;                                                                         \
           const T w = (T)(cos((double)r * M_PI / (double)radius) * 0.5 + 0.5);                                  \
           for (int c = 0; c < C; c++) out[(((size_t)b * C + c) * H + y) * W + x] += w * feat[(size_t)p * C + c]; \
@@ -492,7 +502,7 @@ ORC_API void orc_gather_bwd(const float *gout, const int *idx, int B, int C, int
       for (int x = x0; x <= x1; x++)                                                                            \
         for (int y = y0; y <= y1; y++) {                                                                        \
           const T dx = (T)x - px, dy = (T)y - py;                                                               \
-          const T r = SQRT(FMA(dx, dx, dy * dy));                                                                  \
+          const T r = SQRT(FMA(dy, dy, dx * dx));                                                                  \
           if (!(r <= radius)) continue;                                                                         \
           const T w = (T)(cos((double)r * M_PI / (double)radius) * 0.5 + 0.5);                                  \
           const T rr = r > (T)1e-10 ? r : (T)1e-10;                                                             \

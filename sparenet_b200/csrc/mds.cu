@@ -3,8 +3,11 @@
 // Replaces minimum_density_sampling_kernel / gather_points[_grad]_kernel (cuda/MDS/MDS_cuda.cu:29-211).
 // Contract: t = (float)(5.0*mml*mml); idx[0] = 0; each of the m-1 dependent rounds adds
 // w = expf(-d/t) (d = fma(dz,dz,fma(dx,dx,dy*dy)), d* = x_k - x_old; IEEE divide, accurate expf; doubled for
-// k >= 8192) to every point's accumulated density and picks the arg-min; ties: lower (k % block_size), then
-// lower k, with block_size = min(1024, 2^floor(log2 n)).  Chosen points are parked at 1e9.
+// k >= 8192) to every point's accumulated density and picks the arg-min.  Ties follow the reference's reduction
+// exactly: inside a thread the first k of its stride (k = tid, tid+bs, ...), across threads the smem tournament
+// (MDS_cuda.cu:81-87,139-198: slot t absorbs slot t+s for s = bs/2..1, lower slot wins ties), whose winner among
+// equals is the thread with the smallest BIT-REVERSED tid.  So the tie key is (bitrev(k % bs), k),
+// bs = min(1024, 2^floor(log2 n)) -- verified against the reference extension on the GPU.  Chosen points park at 1e9.
 //   The reference accumulates as (float)((double)temp + (double)w): for one addition of two floats, double
 //   rounding through fp64 is innocuous (53 >= 2*24+2), so a plain fp32 add is bit-identical.
 //
@@ -26,7 +29,7 @@ constexpr unsigned long long MDS_NONE = 0xffffffffffffffffull;
 template <int PT>
 __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
                                                                       const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
-                                                                      int bs_mask) {
+                                                                      int bs_mask, int bs_log2) {
   __shared__ __align__(16) unsigned long long slots[2][MDS_MAX_CLUSTER * MDS_WARPS];
   const uint32_t cs = cluster_nctarank();
   const uint32_t rank = cluster_ctarank();
@@ -70,7 +73,8 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
       if (k >= 8192) w = __fmul_rn(w, 2.0f);
       const float v = __fadd_rn(temp[i], w);
       temp[i] = v;
-      const unsigned key = ((unsigned)(k & bs_mask) << 21) | (unsigned)k;
+      const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
+      const unsigned key = (rev << 21) | (unsigned)k;
       const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key;
       if (v < 1e9f && p < best) best = p;
     }
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float* __restrict
 }
 
 template <int PT>
-static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, int* idx, int cs, int bs_mask, cudaStream_t s) {
+static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, int* idx, int cs, int bs_mask, int bs_log2, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cs));
   cfg.blockDim = dim3(MDS_THREADS);
@@ -148,7 +152,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<PT>, xyz, n, m, mml, idx, bs_mask);
+  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<PT>, xyz, n, m, mml, idx, bs_mask, bs_log2);
 }
 
 }  // namespace snb
@@ -168,7 +172,8 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   if (n >= (1 << 21)) return SNB_ELIMIT;
   cudaStream_t s = (cudaStream_t)stream;
   int bs = 1;
-  while (bs * 2 <= n && bs < 1024) bs *= 2;  // opt_n_threads(n), MDS_cuda.cu:8-12
+  int lg = 0;
+  while (bs * 2 <= n && bs < 1024) { bs *= 2; lg++; }  // opt_n_threads(n), MDS_cuda.cu:8-12
   // cluster size: as many SMs per sample as the batch leaves free (<= 8, power of two)
   int cs = 1;
   while (cs * 2 <= MDS_MAX_CLUSTER && B * cs * 2 <= kNumSMs) cs *= 2;
@@ -178,13 +183,13 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
     pt = (((n + cs - 1) / cs) + MDS_THREADS - 1) / MDS_THREADS;
   }
   int rc;
-  if (pt <= 2) rc = mds_launch<2>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
-  else if (pt <= 4) rc = mds_launch<4>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
-  else if (pt <= 6) rc = mds_launch<6>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
-  else if (pt <= 9) rc = mds_launch<9>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
-  else if (pt <= 12) rc = mds_launch<12>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
-  else if (pt <= 18) rc = mds_launch<18>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
-  else if (pt <= 24) rc = mds_launch<24>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, s);
+  if (pt <= 2) rc = mds_launch<2>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
+  else if (pt <= 4) rc = mds_launch<4>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
+  else if (pt <= 6) rc = mds_launch<6>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
+  else if (pt <= 9) rc = mds_launch<9>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
+  else if (pt <= 12) rc = mds_launch<12>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
+  else if (pt <= 18) rc = mds_launch<18>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
+  else if (pt <= 24) rc = mds_launch<24>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
   else return SNB_ELIMIT;  // n > 8*512*24 = 98304 points per sample
   if (rc != 0) return rc;
   SNB_LAUNCH_CHECK();

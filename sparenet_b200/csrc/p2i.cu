@@ -2,7 +2,7 @@
 //
 // Replaces p2i_{max,sum}_{forward,backward}_kernel (cuda/p2i_op/p2i_max.h:7-143, p2i_sum.h:7-131,
 // footprint utility.h:82-100, launcher common.h:95-128).  Contract:
-//   footprint: integer pixels in [clamp(floor(p-R)), clamp(ceil(p+R))]^2 with r = sqrt(fma(dx,dx,dy*dy)) <= R,
+//   footprint: integer pixels in [clamp(floor(p-R)), clamp(ceil(p+R))]^2 with r = sqrt(fma(dy,dy,dx*dx)) <= R,
 //   weight  w = (T)(cos((double)r*pi/(double)R)*0.5+0.5)  (fp64 math even for T=float, p2i_max.h:48),
 //   max:  out = max(background, max f*w) with strict '<' (p2i_max.h:56), ids = winner (lowest point id on ties),
 //   sum:  out = background + sum f*w.
@@ -84,11 +84,12 @@ __global__ void __launch_bounds__(256) p2i_max_splat_f32(const float* __restrict
     const int xo = t / fp.bh;
     const int x = fp.x0 + xo, y = fp.y0 + (t - xo * fp.bh);
     const float dx = (float)x - px, dy = (float)y - py;
-    const float r = sqrtf(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const float r = sqrtf(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));  // x is the outer loop of utility.h:90-99: dx*dx is hoisted, dy fused
     if (!(r <= radius)) continue;
-    // fp32 upper bound of w = cos^2(pi r / 2R):  relative error of the approximation < 1e-5, padded to 1e-4
-    const float ch = __cosf(r * inv2r);
-    const float w_hi = ch * ch * 1.0001f + 1e-7f;
+    // fp32 upper bound of w = cos^2(pi r / 2R): __cosf is within 2^-21.4 absolute on [0, pi/2] and the argument
+    // within ~2e-7, so |cos| + 2e-6 bounds the true half-angle cosine; squared and padded by 1e-4 relative.
+    const float ch = fabsf(__cosf(r * inv2r)) + 2e-6f;
+    const float w_hi = ch * ch * 1.0001f;
     float w = -1.f;  // exact weight, computed lazily
     for (int c = 0; c < C; c++) {
       const float f = feat[(size_t)p * C + c];
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256) p2i_max_splat_f64(const double* __restric
     const int xo = t / fp.bh;
     const int x = fp.x0 + xo, y = fp.y0 + (t - xo * fp.bh);
     const double dx = (double)x - px, dy = (double)y - py;
-    const double r = sqrt(__fma_rn(dx, dx, __dmul_rn(dy, dy)));
+    const double r = sqrt(__fma_rn(dy, dy, __dmul_rn(dx, dx)));
     if (!(r <= radius)) continue;
     const double w = p2i_weight<double>(r, radius);
     for (int c = 0; c < C; c++) {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) p2i_sum_fwd_kernel(const T* __restrict__ 
     const int xo = t / fp.bh;
     const int x = fp.x0 + xo, y = fp.y0 + (t - xo * fp.bh);
     const T dx = (T)x - px, dy = (T)y - py;
-    const T r = P2I<T>::sqrt_(P2I<T>::fma_(dx, dx, P2I<T>::mul_(dy, dy)));
+    const T r = P2I<T>::sqrt_(P2I<T>::fma_(dy, dy, P2I<T>::mul_(dx, dx)));
     if (!(r <= radius)) continue;
     const T w = p2i_weight<T>(r, radius);
     for (int c = 0; c < C; c++) atomicAdd(&out[(((size_t)b * C + c) * H + y) * W + x], w * feat[(size_t)p * C + c]);
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) p2i_sum_bwd_kernel(const T* __restrict__ 
       const int xo = t / fp.bh;
       const int x = fp.x0 + xo, y = fp.y0 + (t - xo * fp.bh);
       const T dx = (T)x - px, dy = (T)y - py;
-      const T r = P2I<T>::sqrt_(P2I<T>::fma_(dx, dx, P2I<T>::mul_(dy, dy)));
+      const T r = P2I<T>::sqrt_(P2I<T>::fma_(dy, dy, P2I<T>::mul_(dx, dx)));
       if (!(r <= radius)) continue;
       const T w = p2i_weight<T>(r, radius);
       const T g = gout[(((size_t)b * C + c) * H + y) * W + x];

@@ -403,7 +403,8 @@ def test_p2i_dropin_gradcheck_fp64(cuda):
             pts = (torch.rand(2, 2, dtype=torch.float64, device=cuda) * 1.2 - 0.6).requires_grad_()
             feat = torch.rand(2, 2, dtype=torch.float64, device=cuda).requires_grad_()
             binds = torch.zeros(2, dtype=torch.int32, device=cuda)
-            bg = torch.zeros(1, 2, 8, 8, dtype=torch.float64, device=cuda).requires_grad_()
+            # background well below every splatted value: max() has no kink within the finite-difference step
+            bg = torch.full((1, 2, 8, 8), -0.5, dtype=torch.float64, device=cuda).requires_grad_()
             assert torch.autograd.gradcheck(lambda p, f, b: p2i(p, f, binds, b, 3.0, "cos", reduce), (pts, feat, bg), eps=1e-6, atol=1e-5)
     with pytest.raises(RuntimeError):
         p2i(pts, feat, binds, bg, 3.0, "cos", "mean")
