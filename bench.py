@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric  : point-clouds/sec (completions/s)
+workload: configs[1] "SpareNet generator + CD loss, synthetic ShapeNet B=32 2048->16384 pts, 1xB200": one step =
+          generator forward (EdgeConv encoder, 32 folding decoders, 2 x [expansion penalty, MDS, gather, PointNetRes])
+          + 3 x ChamferDistanceMean + 0.1*loss_mst + 0.5*consistency CD (runners/sparenet_runner.py:84-105)
+          + backward + Adam(lr 1e-4, betas (0, 0.9)) step.  fp32 parameters/activations; dense 1x1 convs on tensor cores
+          in TF32 (what cuDNN does for the reference's convs by default).  Synthetic data, seeded random-init weights
+          (utils/model_init.py:137-159).
+N > 1   : one process per GPU (torchrun), batch sharded by sample (local B=32 per rank, weak scaling), NCCL gradient
+          all-reduce over NVLink -- the only collective the path has.
+--impl reference : the CPU restatement of the same step (oracle/: C kernels + plain PyTorch generator) on the box's
+          host cores, on a bounded sample (B=2) of the same workload.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_OUT, N_PARTIAL, N_PRIM, LOCAL_B = 16384, 2048, 32, 32
+METRIC, UNIT = "point-clouds/sec", "completions/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=LOCAL_B, help="local batch per GPU (default: BASELINE config)")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_factory(batch):
+    """The reference's step restated on the CPU (oracle/): generator_ref + oracle Chamfer.  Returns (step_fn, describe)."""
+    import oracle
+    from oracle import generator_ref as G
+
+    class ChamferCPU(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, a, b):
+            d1, d2, i1, i2 = oracle.chamfer_fwd(a.detach().contiguous(), b.detach().contiguous())
+            ctx.save_for_backward(a.detach(), b.detach(), i1, i2)
+            return d1, d2
+
+        @staticmethod
+        def backward(ctx, g1, g2):
+            a, b, i1, i2 = ctx.saved_tensors
+            return oracle.chamfer_bwd(a.contiguous(), b.contiguous(), i1, i2, g1.contiguous(), g2.contiguous())
+
+    torch.manual_seed(0)
+    net = G.SpareNetGenerator(n_primitives=N_PRIM, hide_size=4096, bottleneck_size=4096, num_points=N_OUT).train()
+    net.apply(G.init_weights)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9))
+    g = torch.Generator().manual_seed(1)
+    partial = torch.rand(batch, N_PARTIAL, 3, generator=g) - 0.5
+    gt = torch.rand(batch, N_OUT, 3, generator=torch.Generator().manual_seed(2)) - 0.5
+
+    def cd_mean(a, b):
+        d1, d2 = ChamferCPU.apply(a, b)
+        return d1.mean() + d2.mean()
+
+    def step():
+        coarse, middle, refine, loss_mst = net({"partial_cloud": partial})
+        loss = cd_mean(coarse, gt) + cd_mean(middle, gt) + cd_mean(refine, gt) + loss_mst.mean() * 0.1
+        d1, _ = ChamferCPU.apply(refine, gt)
+        loss = loss + d1.mean() * 0.5
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    step = cpu_step_factory(args.cpu_batch)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    k = max(1, min(args.steps, 2))
+    for _ in range(k):
+        step()
+    dt = (time.perf_counter() - t0) / k
+    val = args.cpu_batch / dt
+    sample = f"B={args.cpu_batch} of the B=32 step (same N: {N_PARTIAL}->{N_OUT} pts, all losses, Adam), {k} timed step(s)"
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": min(args.warmup, 1),
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": "configs[1]: SpareNet generator + CD loss, B=32 2048->16384 pts (CPU: bounded sample)", "cpu_batch": args.cpu_batch,
+                       "n_out": N_OUT, "n_partial": N_PARTIAL, "n_primitives": N_PRIM},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "omp_threads": oracle.num_threads()},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for i, n in enumerate(names) if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+def build_gpu(args, dev, rank):
+    import sparenet_b200
+    sys.path.insert(0, sparenet_b200.dropin_path())
+    from sparenet_b200.dropin.cuda.chamfer_distance import ChamferDistance, ChamferDistanceMean
+    from sparenet_b200.dropin.models.sparenet_generator import SpareNetGenerator
+    from oracle.generator_ref import init_weights  # initialisation recipe only (utils/model_init.py:137-159), no compute
+
+    torch.backends.cuda.matmul.allow_tf32 = True       # the reference's cuDNN convs run TF32 by default on this class of GPU
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(0)
+    net = SpareNetGenerator(n_primitives=N_PRIM, hide_size=4096, bottleneck_size=4096, num_points=N_OUT, use_SElayer=True,
+                            use_AdaIn="share", encode="Residualnet")
+    net.apply(init_weights)
+    net = net.to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9))
+    cd_mean, cd = ChamferDistanceMean(), ChamferDistance()
+    B = args.batch
+    gp = torch.Generator().manual_seed(1 + 100 * rank)
+    gg = torch.Generator().manual_seed(2 + 100 * rank)
+    h_partial = (torch.rand(B, N_PARTIAL, 3, generator=gp) - 0.5).pin_memory()
+    h_gt = (torch.rand(B, N_OUT, 3, generator=gg) - 0.5).pin_memory()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    params = [p for p in net.parameters()]
+
+    def step(partial, gt):
+        coarse, middle, refine, loss_mst = net({"partial_cloud": partial})
+        loss = cd_mean(coarse, gt).mean() + cd_mean(middle, gt).mean() + cd_mean(refine, gt).mean() + loss_mst.mean() * 0.1
+        d1, _ = cd(refine, gt)
+        loss = loss + torch.mean(d1).mean() * 0.5
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            import torch.distributed as dist
+            grads = [p.grad for p in params if p.grad is not None]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(flat)
+            flat.div_(world)
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
+        opt.step()
+        return loss
+
+    return step, h_partial, h_gt
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sparenet_b200 has no CPU path (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from sparenet_b200 import functional as F_
+
+    step, h_partial, h_gt = build_gpu(args, dev, rank)
+    partial, gt = h_partial.to(dev), h_gt.to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(partial, gt)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs ------------------------------------------------------------------
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank) if rank == 0 else None
+    F_.LAUNCHES["count"] = 0
+    F_.PROFILE = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(partial, gt)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof, F_.PROFILE = F_.PROFILE, None
+    launches = F_.LAUNCHES["count"] // max(args.steps, 1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- timed region 2: end to end through the public modules with HOST buffers ----------------------------------
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    last = None
+    for _ in range(args.steps):
+        p = h_partial.to(dev, non_blocking=True)
+        g = h_gt.to(dev, non_blocking=True)
+        last = step(p, g).item()            # device -> host read of the step's loss
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    Bg = args.batch * world
+    value = Bg * args.steps / (ms / 1e3)
+    e2e_val = Bg * args.steps / (ms_e2e / 1e3)
+    # ---- roofline of the dominant kernel (largest share of the step among our kernels) ----------------------------
+    per_op = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in prof.items()}
+    tot_op = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in prof.items()}
+    dom = max(tot_op, key=tot_op.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    B = args.batch
+    n_mds = N_OUT + N_PARTIAL
+    alg_bytes = {  # algorithmic (compulsory) bytes per launch, SURVEY.md 8(d)
+        "mds_sample": B * (12 * n_mds + 4 * N_OUT),
+        "chamfer_fwd": B * (N_OUT + N_OUT) * (12 + 8),
+        "chamfer_bwd": B * (N_OUT + N_OUT) * (12 + 4 + 4 + 12),
+        "knn": None, "expansion_fwd": B * N_OUT * (12 + 8), "gather_fwd": B * 4 * N_OUT * 8, "gather_bwd": B * 4 * N_OUT * 8,
+        "expansion_bwd": B * N_OUT * (12 + 4 + 4 + 12),
+    }
+    ab = alg_bytes.get(dom)
+    roof = {"kernel": dom, "bound": "hbm", "achieved": (ab / (per_op[dom] * 1e-3) / 1e9) if ab else None, "peak": hbm_peak, "unit": "GB/s",
+            "frac": (ab / (per_op[dom] * 1e-3) / 1e9 / hbm_peak) if ab else None, "traffic": None, "peak_source": peak_src,
+            "ms_per_launch": per_op[dom], "share_of_step": tot_op[dom] / (ms / args.steps),
+            "note": "mds_sample is a 16383-round dependent chain (latency bound by construction): the HBM fraction of its compulsory bytes is "
+                    "reported as asked; rounds/s is the meaningful figure" if dom == "mds_sample" else "",
+            "rounds_per_s": ((N_OUT - 1) / (per_op[dom] * 1e-3)) if dom == "mds_sample" else None,
+            "ops_ms_per_step": {k: round(v, 3) for k, v in sorted(tot_op.items(), key=lambda kv: -kv[1])}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core GEMMs)",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: SpareNet generator + CD loss, synthetic ShapeNet B=32 2048->16384 pts", "local_batch": args.batch,
+                       "global_batch": Bg, "n_out": N_OUT, "n_partial": N_PARTIAL, "n_primitives": N_PRIM, "k": 8,
+                       "losses": "3xChamferDistanceMean + 0.1*expansion + 0.5*consistency CD, Adam step", "parallelism": f"dp{world}",
+                       "l2": "working set per step (GBs of activations) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h_partial.numel() + h_gt.numel()) * 4, "d2h_bytes_per_step": 4, "last_loss": last},
+            "roofline": roof}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        cstep = cpu_step_factory(args.cpu_batch)
+        t0 = time.perf_counter()
+        cstep()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": args.cpu_batch / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"one step at B={args.cpu_batch} (same point counts and losses), oracle C kernels + plain PyTorch generator"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -44,8 +44,8 @@ static inline float sqdist(float dx, float dy, float dz) {
  * dist[i] = min_j s(i,j), idx[i] = smallest j attaining it (strict '<' everywhere: :47,:137).
  * d* = ref_j - query_i.
  * ---------------------------------------------------------------------------------------- */
-static void nn_search(int n, const float *q, int m, const float *r, float *dist, int *idx) {
-  for (int i = 0; i < n; i++) {
+static void nn_search(int i0, int i1, const float *q, int m, const float *r, float *dist, int *idx) {
+  for (int i = i0; i < i1; i++) {
     const float x = q[i * 3], y = q[i * 3 + 1], z = q[i * 3 + 2];
     float best = 0.f;
     int bi = 0;
@@ -60,12 +60,19 @@ static void nn_search(int n, const float *q, int m, const float *r, float *dist,
 
 ORC_API void orc_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                              float *dist1, float *dist2, int *idx1, int *idx2) {
-#pragma omp parallel for schedule(dynamic)
-  for (int t = 0; t < 2 * B; t++) {
-    const int b = t >> 1;
-    if (t & 1) nn_search(M, xyz2 + (size_t)b * M * 3, N, xyz1 + (size_t)b * N * 3, dist2 + (size_t)b * M, idx2 + (size_t)b * M);
-    else       nn_search(N, xyz1 + (size_t)b * N * 3, M, xyz2 + (size_t)b * M * 3, dist1 + (size_t)b * N, idx1 + (size_t)b * N);
-  }
+  const int CH = 256; /* query chunk: lets every host thread work even for a single sample */
+  const int nmax = N > M ? N : M;
+  const int nch = (nmax + CH - 1) / CH;
+#pragma omp parallel for collapse(2) schedule(dynamic)
+  for (int t = 0; t < 2 * B; t++)
+    for (int c = 0; c < nch; c++) {
+      const int b = t >> 1;
+      const int nq = (t & 1) ? M : N;
+      const int i0 = c * CH, i1 = (i0 + CH) < nq ? (i0 + CH) : nq;
+      if (i0 >= nq) continue;
+      if (t & 1) nn_search(i0, i1, xyz2 + (size_t)b * M * 3, N, xyz1 + (size_t)b * N * 3, dist2 + (size_t)b * M, idx2 + (size_t)b * M);
+      else       nn_search(i0, i1, xyz1 + (size_t)b * N * 3, M, xyz2 + (size_t)b * M * 3, dist1 + (size_t)b * N, idx1 + (size_t)b * N);
+    }
 }
 
 /* chamfer.cu:173-201 (two launches :215-222).  g = grad*2; t = g*(x1-x2);
@@ -334,9 +341,30 @@ static inline float mds_w(const float *xyz, int k, float x1, float y1, float z1,
   return expf(-d / t);
 }
 
+/* one round over the point range [k0,k1): accumulate densities, return the range's best (value, index, lane key) */
+static inline void mds_round_range(const float *p, float *temp, int k0, int k1, int bs, float x1, float y1, float z1, float t,
+                                   float *obest, int *obesti, int *obestlane) {
+  float best = 1e9f; int besti = 0, bestlane = 0x7fffffff;
+  for (int k = k0; k < k1; k++) {
+    const float w = mds_w(p, k, x1, y1, z1, t);
+    temp[k] = (float)((double)temp[k] + (k < 8192 ? (double)w : (double)w * 2.0));
+    const float v = temp[k];
+    const int lane = mds_lane_key(k, bs);
+    /* strict '<' inside a thread (first k of the stride wins), tournament order across threads;
+     * a range that saw nothing below 1e9 reports (1e9, index 0) */
+    if (v < 1e9f && (v < best || (v == best && lane < bestlane))) { best = v; besti = k; bestlane = lane; }
+  }
+  *obest = best; *obesti = besti; *obestlane = bestlane;
+}
+
 ORC_API void orc_mds(const float *xyz, int B, int n, int m, const float *mml, int *idxs) {
   if (m <= 0) return;
-#pragma omp parallel for schedule(dynamic)
+  int nth = 1;
+#ifdef _OPENMP
+  nth = omp_get_max_threads();
+#endif
+  const int inner = (B < nth && n >= 4096); /* few samples: spread every round's point loop over the host threads */
+#pragma omp parallel for schedule(dynamic) if (!inner)
   for (int b = 0; b < B; b++) {
     const float *p = xyz + (size_t)b * n * 3;
     int *out = idxs + (size_t)b * m;
@@ -345,22 +373,23 @@ ORC_API void orc_mds(const float *xyz, int B, int n, int m, const float *mml, in
     const float t = (float)(5.0 * (double)mml[b] * (double)mml[b]);
     int old = 0;
     out[0] = 0; temp[0] = 1e9f;
+    const int nparts = inner ? nth : 1;
+    float *pb = (float *)malloc(sizeof(float) * nparts);
+    int *pi = (int *)malloc(sizeof(int) * nparts), *pl = (int *)malloc(sizeof(int) * nparts);
     for (int j = 1; j < m; j++) {
       const float x1 = p[old * 3], y1 = p[old * 3 + 1], z1 = p[old * 3 + 2];
-      float best = 1e9f; int besti = 0, bestlane = 0;
-      for (int k = 0; k < n; k++) {
-        const float w = mds_w(p, k, x1, y1, z1, t);
-        temp[k] = (float)((double)temp[k] + (k < 8192 ? (double)w : (double)w * 2.0));
-        const float v = temp[k];
-        const int lane = mds_lane_key(k, bs);
-        /* strict '<' inside a thread (first k of the stride wins), lower tid wins across threads;
-         * threads that saw nothing below 1e9 report (1e9, index 0) */
-        if (v < 1e9f && (v < best || (v == best && lane < bestlane))) { best = v; besti = k; bestlane = lane; }
+#pragma omp parallel for schedule(static) if (inner)
+      for (int part = 0; part < nparts; part++) {
+        const int k0 = (int)((long long)n * part / nparts), k1 = (int)((long long)n * (part + 1) / nparts);
+        mds_round_range(p, temp, k0, k1, bs, x1, y1, z1, t, &pb[part], &pi[part], &pl[part]);
       }
+      float best = 1e9f; int besti = 0, bestlane = 0x7fffffff;
+      for (int part = 0; part < nparts; part++) /* (value, lane key, k) lexicographic; parts hold ascending k */
+        if (pb[part] < 1e9f && (pb[part] < best || (pb[part] == best && pl[part] < bestlane))) { best = pb[part]; besti = pi[part]; bestlane = pl[part]; }
       old = besti;
       out[j] = old; temp[old] = 1e9f;
     }
-    free(temp);
+    free(temp); free(pb); free(pi); free(pl);
   }
 }
 

@@ -1,0 +1,390 @@
+"""Drop-in for the reference's models/sparenet_generator.py: SpareNetGenerator (style-based generator with the
+channel-attentive EdgeConv encoder, 32 AdaIN-modulated folding decoders and the residual refiner).
+
+Same constructor signature, same forward contract -- forward({"partial_cloud": [B,Np,3]}) ->
+(coarse, middle, refine, loss_mst), all [B,N,3] (reference :63-82) -- and IDENTICAL state_dict keys
+(encoder.feat_extractor.conv1.weight, decoder.decoder.{i}.dec.conv2.weight, decoder.mlp.{0,2}.*, refine.residual.*,
+the unused top-level conv1 (:43) and the AdaIN dummy buffers (:932-933)), so reference checkpoints load unchanged.
+
+The math is re-associated rather than translated (every identity is exact in real arithmetic and
+checked against the plain restatement in tests/):
+  * EdgeConv: W.[x_j - x_i ; x_i] = W_a x_j + (W_b - W_a) x_i, so the 1x1 conv runs per POINT (k x fewer flops, no
+    [B,2C,N,k] tensor); max_k LeakyReLU(SE(BN(u))) = LeakyReLU(s.BN(max_k u or min_k u by sign of gamma)); the kNN is
+    the sm_100a kernel behind snb_knn.
+  * Decoder: all 32 primitives advance together as batched GEMMs ([P,Cout,Cin] x [P,Cin,B*512]); the conv bias in
+    front of AdaIN cancels; BN batch statistics and the SE squeeze after AdaIN are closed-form in the style
+    parameters, so AdaIN o BN o SE o ReLU collapses to one per-(primitive,sample,channel) scale/shift + ReLU.
+  * Refiner: max over points of BN(conv3) needs only per-(b,c) max/min + channel statistics; conv4 on
+    [global ; pointfeat] splits into a per-sample GEMV plus a 64-channel GEMM.  Expansion penalty, MDS and gather
+    are the sm_100a kernels (snb_expansion_*, snb_mds_sample, snb_gather_*).
+Only the shipped configuration is served (configs/sparenet.yaml:18-24): encode="Residualnet", use_AdaIn="share",
+use_SElayer=True; anything else raises.  CUDA only: there is no CPU path.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from sparenet_b200 import functional as F_
+from sparenet_b200.dropin.cuda.MDS import MDS_module
+from sparenet_b200.dropin.cuda.expansion_penalty import expansion_penalty_module as expansion
+
+EPS = 1e-5
+MOMENTUM = 0.1
+
+
+# ------------------------------------------------------------------------------------------ parameter holders
+class SELayer(nn.Module):  # reference :741-764
+    def __init__(self, channel, reduction=16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(inplace=True),
+                                nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
+
+    def gate(self, squeeze):  # squeeze: [..., C] -> sigmoid gate [..., C]
+        return self.fc(squeeze)
+
+    def forward(self, x):
+        b, c = x.shape[:2]
+        return x * self.fc(x.reshape(b, c, -1).mean(-1)).view(b, c, *([1] * (x.dim() - 2)))
+
+
+class SELayer1D(SELayer):  # reference :767-790
+    def __init__(self, channel, reduction=16):
+        super().__init__(channel, reduction)
+        self.avg_pool = nn.AdaptiveAvgPool1d(1)
+
+
+def _bn_apply_stats(bn, mean, var_biased, count):
+    """Training-mode bookkeeping of nn.BatchNorm (running stats with the unbiased variance, counter)."""
+    if bn.training and bn.track_running_stats:
+        with torch.no_grad():
+            m = bn.momentum if bn.momentum is not None else MOMENTUM
+            bn.running_mean.mul_(1 - m).add_(mean.detach(), alpha=m)
+            bn.running_var.mul_(1 - m).add_(var_biased.detach() * (count / max(count - 1, 1)), alpha=m)
+            bn.num_batches_tracked.add_(1)
+
+
+def _bn_stats(bn, x, dims):
+    """(mean, biased var) the layer normalises with: batch statistics in train mode, running ones in eval."""
+    if bn.training:
+        var, mean = torch.var_mean(x, dim=dims, unbiased=False)
+        count = x.numel() // mean.numel()
+        _bn_apply_stats(bn, mean, var, count)
+        return mean, var
+    return bn.running_mean, bn.running_var
+
+
+def knn(x, k: int):
+    """Reference :852-877.  x [B,C,N] -> idx [B,N,k] int64 (self included); exact fp32 brute force on the GPU."""
+    return F_.knn_indices(x.contiguous(), k).long()
+
+
+def get_graph_feature(x, k: int = 20, idx=None):
+    """Reference :880-906, kept for API parity (the encoder below never materialises this tensor)."""
+    B, C, N = x.shape
+    if idx is None:
+        idx = knn(x, k)
+    nb = torch.gather(x.unsqueeze(2).expand(-1, -1, N, -1), 3, idx.unsqueeze(1).expand(-1, C, -1, -1))  # [B,C,N,k]
+    ctr = x.unsqueeze(-1).expand(-1, -1, -1, idx.size(-1))
+    return torch.cat((nb - ctr, ctr), dim=1).contiguous()
+
+
+class EdgeConvResFeat(nn.Module):  # reference :123-242
+    def __init__(self, num_point: int = 16382, use_SElayer: bool = False, k: int = 8, hide_size: int = 2048, output_size: int = 4096):
+        super().__init__()
+        if not use_SElayer:
+            raise NotImplementedError("sparenet_b200 serves the shipped configuration only (use_selayer: true)")
+        self.use_SElayer, self.k, self.hide_size, self.output_size = use_SElayer, k, hide_size, output_size
+        h = hide_size
+        self.conv1 = nn.Conv2d(6, h // 16, kernel_size=1, bias=False)
+        self.conv2 = nn.Conv2d(h // 8, h // 16, kernel_size=1, bias=False)
+        self.conv3 = nn.Conv2d(h // 8, h // 8, kernel_size=1, bias=False)
+        self.conv4 = nn.Conv2d(h // 4, h // 4, kernel_size=1, bias=False)
+        self.conv5 = nn.Conv1d(h // 2, output_size // 2, kernel_size=1, bias=False)
+        self.relu1, self.relu2, self.relu3, self.relu4, self.relu5 = (nn.LeakyReLU(negative_slope=0.2) for _ in range(5))
+        self.se1, self.se2, self.se3, self.se4 = SELayer(h // 16), SELayer(h // 16), SELayer(h // 8), SELayer(h // 4)
+        self.bn1, self.bn2, self.bn3, self.bn4 = nn.BatchNorm2d(h // 16), nn.BatchNorm2d(h // 16), nn.BatchNorm2d(h // 8), nn.BatchNorm2d(h // 4)
+        self.bn5 = nn.BatchNorm1d(output_size // 2)
+        self.resconv1 = nn.Conv1d(h // 16, h // 16, kernel_size=1, bias=False)
+        self.resconv2 = nn.Conv1d(h // 16, h // 8, kernel_size=1, bias=False)
+        self.resconv3 = nn.Conv1d(h // 8, h // 4, kernel_size=1, bias=False)
+
+    def _edge_block(self, x, conv, bn, se, res=None):
+        """max_k LeakyReLU(SE(BN(conv([x_j - x_i ; x_i]))))  (+ residual 1x1 conv of x), x [B,C,N] -> [B,Cout,N]."""
+        B, C, N = x.shape
+        k = self.k
+        idx = knn(x, k)                                            # [B,N,k]
+        W = conv.weight.view(conv.out_channels, 2 * C)
+        Wa, Wb = W[:, :C], W[:, C:]
+        Wcat = torch.cat((Wa, Wb - Wa) if res is None else (Wa, Wb - Wa, res.weight.view(res.out_channels, C)), 0)
+        y = torch.matmul(Wcat, x)                                  # one per-point GEMM: [B, 2Cout(+Cres), N]
+        Co = conv.out_channels
+        a, c = y[:, :Co], y[:, Co:2 * Co]
+        u = torch.gather(a, 2, idx.reshape(B, 1, N * k).expand(-1, Co, -1)).view(B, Co, N, k) + c.unsqueeze(-1)
+        mean, var = _bn_stats(bn, u, (0, 2, 3))
+        inv = torch.rsqrt(var + bn.eps)
+        g, beta = bn.weight, bn.bias
+        scale = (g * inv).view(1, Co, 1)
+        shift = (beta - g * inv * mean).view(1, Co, 1)
+        gate = se.gate(u.mean(dim=(2, 3)) * scale.squeeze(-1) + shift.squeeze(-1)).unsqueeze(-1)   # [B,Co,1], in (0,1)
+        ustar = torch.where((g > 0).view(1, Co, 1), u.amax(-1), u.amin(-1))                            # monotone through BN.SE.LReLU
+        out = F.leaky_relu(gate * (ustar * scale + shift), 0.2)
+        if res is not None:
+            out = out + y[:, 2 * Co:]
+        return out
+
+    def forward(self, x):
+        B = x.size(0)
+        x1 = self._edge_block(x, self.conv1, self.bn1, self.se1)
+        x2 = self._edge_block(x1, self.conv2, self.bn2, self.se2, self.resconv1)
+        x3 = self._edge_block(x2, self.conv3, self.bn3, self.se3, self.resconv2)
+        x4 = self._edge_block(x3, self.conv4, self.bn4, self.se4, self.resconv3)
+        h = torch.matmul(self.conv5.weight.squeeze(-1), torch.cat((x1, x2, x3, x4), dim=1))
+        mean, var = _bn_stats(self.bn5, h, (0, 2))
+        scale = self.bn5.weight * torch.rsqrt(var + self.bn5.eps)
+        h = F.leaky_relu(h * scale.view(1, -1, 1) + (self.bn5.bias - scale * mean).view(1, -1, 1), 0.2)
+        return torch.cat((h.amax(2), h.mean(2)), 1).view(B, self.output_size)
+
+
+class PointNetfeat(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError('encode="Pointfeat" is not part of the shipped configuration (configs/sparenet.yaml:21)')
+
+
+class SpareNetEncode(nn.Module):  # reference :85-120
+    def __init__(self, bottleneck_size=4096, use_SElayer=False, encode="Pointfeat", hide_size=4096):
+        super().__init__()
+        if encode != "Residualnet":
+            raise NotImplementedError('sparenet_b200 serves encode="Residualnet" only (configs/sparenet.yaml:21)')
+        self.feat_extractor = EdgeConvResFeat(use_SElayer=use_SElayer, k=8, output_size=hide_size, hide_size=4096)
+        self.linear = nn.Linear(hide_size, bottleneck_size)
+        self.bn = nn.BatchNorm1d(bottleneck_size)
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        return self.relu(self.bn(self.linear(self.feat_extractor(x))))
+
+
+class AdaptiveInstanceNorm1d(nn.Module):  # reference :909-959 (buffers only; the math is folded into SpareNetDecode)
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = None
+        self.bias = None
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+
+    def __repr__(self):
+        return self.__class__.__name__ + "(" + str(self.num_features) + ")"
+
+
+class GridDecoder(nn.Module):  # reference :962-1062 (parameter holder)
+    def __init__(self, input_dim: int = 2, bottleneck_size: int = 1026, use_SElayer: bool = False, use_sine: bool = False):
+        super().__init__()
+        if use_sine or not use_SElayer:
+            raise NotImplementedError("sparenet_b200 serves the shipped configuration only (SE layers, no sine)")
+        bs = bottleneck_size
+        self.bottleneck_size, self.input_dim, self.use_SElayer, self.use_sine = bs, input_dim, use_SElayer, use_sine
+        self.conv1 = nn.Conv1d(input_dim, bs, 1)
+        self.conv2 = nn.Conv1d(bs, bs // 2, 1)
+        self.conv3 = nn.Conv1d(bs // 2, bs // 4, 1)
+        self.conv4 = nn.Conv1d(bs // 4, 3, 1)
+        self.th = nn.Tanh()
+        self.adain1, self.adain2, self.adain3 = AdaptiveInstanceNorm1d(bs), AdaptiveInstanceNorm1d(bs // 2), AdaptiveInstanceNorm1d(bs // 4)
+        self.bn1, self.bn2, self.bn3 = nn.BatchNorm1d(bs), nn.BatchNorm1d(bs // 2), nn.BatchNorm1d(bs // 4)
+        self.se1, self.se2, self.se3 = SELayer1D(bs), SELayer1D(bs // 2), SELayer1D(bs // 4)
+
+
+class StyleBasedAdaIn(nn.Module):  # reference :394-422 (parameter holder)
+    def __init__(self, input_dim: int = 1026, style_dim: int = 1024, bottleneck_size: int = 1026, use_SElayer: bool = False):
+        super().__init__()
+        self.bottleneck_size, self.input_dim, self.style_dim = bottleneck_size, input_dim, style_dim
+        self.dec = GridDecoder(input_dim, bottleneck_size, use_SElayer=use_SElayer)
+
+
+def grid_generation(num_points, nb_primitives):
+    """Reference :793-812: the same 2^floor x 2^ceil lattice on [0,1]^2 for every primitive (list of lists)."""
+    per = num_points / nb_primitives
+    gx = 2 ** math.floor(math.log2(per) / 2) - 1
+    gy = 2 ** math.ceil(math.log2(per) / 2) - 1
+    vertices = [[i / gx, j / gy] for i in range(int(gx + 1)) for j in range(int(gy + 1))]
+    return [vertices for _ in range(nb_primitives)]
+
+
+def get_num_adain_params(model):  # reference :815-828
+    return sum(2 * m.num_features for m in model.modules() if m.__class__.__name__ == "AdaptiveInstanceNorm1d")
+
+
+class SpareNetDecode(nn.Module):  # reference :289-391
+    def __init__(self, num_points: int = 16382, n_primitives: int = 32, bottleneck_size: int = 4096, use_AdaIn: str = "no_use",
+                 use_SElayer: bool = False):
+        super().__init__()
+        if use_AdaIn != "share":
+            raise NotImplementedError('sparenet_b200 serves use_AdaIn="share" only (configs/sparenet.yaml:22)')
+        self.use_AdaIn, self.num_points, self.n_primitives, self.bottleneck_size = use_AdaIn, num_points, n_primitives, bottleneck_size
+        self.grid = grid_generation(num_points, n_primitives)
+        self.decoder = nn.ModuleList([StyleBasedAdaIn(input_dim=2, style_dim=bottleneck_size, use_SElayer=use_SElayer) for _ in range(n_primitives)])
+        self.mlp = nn.Sequential(nn.Linear(bottleneck_size, bottleneck_size), nn.ReLU(),
+                                 nn.Linear(bottleneck_size, get_num_adain_params(self.decoder[0])))
+        g = (torch.tensor(self.grid[0], dtype=torch.float32) - 0.5) * 2      # :357-362, identical for every primitive and sample
+        self.register_buffer("_grid_t", g.t().contiguous(), persistent=False)  # [2, pts]
+
+    # ---- stacked views of the 32 primitives' parameters -----------------------------------------------------
+    def _stack(self, getter):
+        return torch.stack([getter(d.dec) for d in self.decoder])
+
+    def _bn_se(self, layer, wsty, bsty, v):
+        """Closed-form BN statistics + SE gate after AdaIN.  wsty/bsty [B,C] style scale/shift (shared by all
+        primitives), v [P,C,B] or [P,C,1] = variance of the instance-normalised activations (= s2/(s2+eps)).
+        Returns A, D [P,C,B] with AdaIN.BN.SE(x_hat) = A * x_hat + D."""
+        P = self.n_primitives
+        bns = [getattr(d.dec, f"bn{layer}") for d in self.decoder]
+        ses = [getattr(d.dec, f"se{layer}") for d in self.decoder]
+        gam = torch.stack([b.weight for b in bns]).unsqueeze(-1)              # [P,C,1]
+        bet = torch.stack([b.bias for b in bns]).unsqueeze(-1)
+        wt, bt = wsty.t().unsqueeze(0), bsty.t().unsqueeze(0)                 # [1,C,B]
+        if self.training:
+            mu = bt.mean(-1, keepdim=True).expand(P, -1, -1)                  # x_hat has zero mean over the points
+            var = (wt * wt * v + bt * bt).mean(-1, keepdim=True) - mu * mu
+            n = wsty.size(0) * (self.num_points // self.n_primitives)
+            with torch.no_grad():
+                for p, b in enumerate(bns):
+                    b.running_mean.mul_(1 - MOMENTUM).add_(mu[p, :, 0], alpha=MOMENTUM)
+                    b.running_var.mul_(1 - MOMENTUM).add_(var[p, :, 0] * (n / max(n - 1, 1)), alpha=MOMENTUM)
+                    b.num_batches_tracked.add_(1)
+        else:
+            mu = torch.stack([b.running_mean for b in bns]).unsqueeze(-1)
+            var = torch.stack([b.running_var for b in bns]).unsqueeze(-1)
+        inv = torch.rsqrt(var + EPS)
+        squeeze = gam * (bt - mu) * inv + bet                                 # [P,C,B]: mean over points of BN(AdaIN(.))
+        w1 = torch.stack([s.fc[0].weight for s in ses])                       # [P,C/16,C]
+        w2 = torch.stack([s.fc[2].weight for s in ses])                       # [P,C,C/16]
+        gate = torch.sigmoid(torch.bmm(w2, torch.relu(torch.bmm(w1, squeeze))))   # [P,C,B]
+        A = gate * gam * inv * wt
+        D = gate * (gam * inv * (bt - mu) + bet)
+        return A, D
+
+    def forward(self, style, partial_x):
+        B, P = style.size(0), self.n_primitives
+        npts = self._grid_t.size(1)
+        params = self.mlp(style)                                              # [B, 2*(1026+513+256)]
+        sizes = [self.decoder[0].dec.adain1.num_features, self.decoder[0].dec.adain2.num_features, self.decoder[0].dec.adain3.num_features]
+        sty, off = [], 0
+        for nf in sizes:                                                      # assign_adain_params :831-849: [mean(=bias) | std(=weight)]
+            sty.append((params[:, off + nf:off + 2 * nf], params[:, off:off + nf]))
+            off += 2 * nf
+        # layer 1: the input lattice is constant, so the instance-normalised activations are batch independent
+        W1 = self._stack(lambda d: d.conv1.weight.squeeze(-1))                # [P,1026,2] (bias cancels under instance norm)
+        h = torch.matmul(W1, self._grid_t)                                    # [P,1026,pts]
+        var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
+        xhat = (h - mean) * torch.rsqrt(var + EPS)
+        A, D = self._bn_se(1, sty[0][0], sty[0][1], var / (var + EPS))
+        x = torch.relu(A.unsqueeze(-1) * xhat.unsqueeze(2) + D.unsqueeze(-1))  # [P,1026,B,pts]
+        for layer, name in ((2, "conv2"), (3, "conv3")):
+            W = self._stack(lambda d: getattr(d, name).weight.squeeze(-1))    # [P,Cout,Cin]
+            h = torch.bmm(W, x.reshape(P, x.size(1), B * npts)).view(P, -1, B, npts)
+            var, mean = torch.var_mean(h, dim=3, unbiased=False)              # per (primitive, channel, sample)
+            rstd = torch.rsqrt(var + EPS)
+            A, D = self._bn_se(layer, sty[layer - 1][0], sty[layer - 1][1], var / (var + EPS))
+            sc = A * rstd
+            x = torch.relu(sc.unsqueeze(-1) * h + (D - sc * mean).unsqueeze(-1))
+        W4 = self._stack(lambda d: d.conv4.weight.squeeze(-1))                # [P,3,256]
+        b4 = self._stack(lambda d: d.conv4.bias).view(P, 3, 1)
+        out = torch.tanh(torch.bmm(W4, x.reshape(P, x.size(1), B * npts)) + b4).view(P, 3, B, npts)
+        return out.permute(2, 1, 0, 3).reshape(B, 3, P * npts).contiguous()   # primitive i owns points [512 i, 512 (i+1))
+
+
+def assign_adain_params(adain_params, model):
+    """Reference :831-849, kept for API parity (SpareNetDecode slices the style vector itself)."""
+    for m in model.modules():
+        if m.__class__.__name__ == "AdaptiveInstanceNorm1d":
+            m.bias = adain_params[:, :m.num_features].contiguous().view(-1)
+            m.weight = adain_params[:, m.num_features:2 * m.num_features].contiguous().view(-1)
+            if adain_params.size(1) > 2 * m.num_features:
+                adain_params = adain_params[:, 2 * m.num_features:]
+
+
+class PointNetRes(nn.Module):  # reference :582-646
+    def __init__(self, use_SElayer: bool = False):
+        super().__init__()
+        if not use_SElayer:
+            raise NotImplementedError("sparenet_b200 serves the shipped configuration only (use_selayer: true)")
+        self.conv1, self.conv2, self.conv3 = nn.Conv1d(4, 64, 1), nn.Conv1d(64, 128, 1), nn.Conv1d(128, 1024, 1)
+        self.conv4, self.conv5, self.conv6, self.conv7 = nn.Conv1d(1088, 512, 1), nn.Conv1d(512, 256, 1), nn.Conv1d(256, 128, 1), nn.Conv1d(128, 3, 1)
+        self.use_SElayer = use_SElayer
+        self.se1, self.se2, self.se4, self.se5, self.se6 = SELayer1D(64), SELayer1D(128), SELayer1D(512), SELayer1D(256), SELayer1D(128)
+        self.bn1, self.bn2, self.bn3 = nn.BatchNorm1d(64), nn.BatchNorm1d(128), nn.BatchNorm1d(1024)
+        self.bn4, self.bn5, self.bn6, self.bn7 = nn.BatchNorm1d(512), nn.BatchNorm1d(256), nn.BatchNorm1d(128), nn.BatchNorm1d(3)
+        self.th = nn.Tanh()
+
+    @staticmethod
+    def _bn_se_relu(h, bn, se):
+        """relu(SE(BN(h))) as one per-(sample,channel) scale/shift: h [B,C,N]."""
+        mean, var = _bn_stats(bn, h, (0, 2))
+        inv = torch.rsqrt(var + bn.eps)
+        scale, shift = bn.weight * inv, bn.bias - bn.weight * inv * mean      # [C]
+        gate = se.gate(h.mean(2) * scale + shift)                              # [B,C]
+        return torch.relu(h * (gate * scale).unsqueeze(-1) + (gate * shift).unsqueeze(-1))
+
+    def forward(self, x):
+        x = self._bn_se_relu(torch.matmul(self.conv1.weight.squeeze(-1), x) + self.conv1.bias.view(1, -1, 1), self.bn1, self.se1)
+        pointfeat = x
+        x = self._bn_se_relu(torch.matmul(self.conv2.weight.squeeze(-1), x) + self.conv2.bias.view(1, -1, 1), self.bn2, self.se2)
+        h3 = torch.matmul(self.conv3.weight.squeeze(-1), x) + self.conv3.bias.view(1, -1, 1)   # [B,1024,N]
+        mean, var = _bn_stats(self.bn3, h3, (0, 2))
+        inv = torch.rsqrt(var + self.bn3.eps)
+        g3 = self.bn3.weight
+        hstar = torch.where((g3 > 0).view(1, -1), h3.amax(2), h3.amin(2))     # max_N BN(h3) only needs max/min of h3
+        glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
+        W4 = self.conv4.weight.squeeze(-1)
+        h4 = torch.matmul(W4[:, 1024:], pointfeat) + (torch.matmul(glob, W4[:, :1024].t()) + self.conv4.bias).unsqueeze(-1)
+        x = self._bn_se_relu(h4, self.bn4, self.se4)
+        x = self._bn_se_relu(torch.matmul(self.conv5.weight.squeeze(-1), x) + self.conv5.bias.view(1, -1, 1), self.bn5, self.se5)
+        x = self._bn_se_relu(torch.matmul(self.conv6.weight.squeeze(-1), x) + self.conv6.bias.view(1, -1, 1), self.bn6, self.se6)
+        return self.th(torch.matmul(self.conv7.weight.squeeze(-1), x) + self.conv7.bias.view(1, -1, 1))
+
+
+class SpareNetRefine(nn.Module):  # reference :530-579
+    def __init__(self, n_primitives: int = 32, num_points: int = 16382, use_SElayer: bool = False):
+        super().__init__()
+        self.num_points, self.n_primitives = num_points, n_primitives
+        self.expansion = expansion.expansionPenaltyModule()
+        self.edgeres = False
+        self.residual = PointNetRes(use_SElayer=use_SElayer)
+
+    def forward(self, inps, partial, coarse):
+        dist, _, mean_mst_dis = self.expansion(coarse, self.num_points // self.n_primitives, 1.5)
+        loss_mst = torch.mean(dist)
+        B, _, n_out = inps.shape
+        n_in = partial.shape[2]
+        base = torch.cat((torch.cat((inps, inps.new_zeros(B, 1, n_out)), 1), torch.cat((partial, partial.new_ones(B, 1, n_in)), 1)), 2)
+        xyz = torch.cat((coarse, partial.transpose(1, 2)), 1).contiguous()    # == base[:, 0:3].transpose(1, 2)
+        resampled_idx = MDS_module.minimum_density_sample(xyz.detach(), coarse.shape[1], mean_mst_dis)
+        base = MDS_module.gather_operation(base.contiguous(), resampled_idx)
+        delta = self.residual(base)
+        outs = base[:, 0:3, :] + delta
+        return outs.transpose(2, 1).contiguous(), loss_mst
+
+
+class SpareNetGenerator(nn.Module):  # reference :12-82
+    def __init__(self, n_primitives: int = 32, hide_size: int = 4096, bottleneck_size: int = 4096, num_points: int = 16382,
+                 use_SElayer: bool = False, use_AdaIn: str = "no_use", encode: str = "Pointfeat"):
+        super().__init__()
+        self.num_points, self.bottleneck_size, self.n_primitives = num_points, bottleneck_size, n_primitives
+        self.use_AdaIn, self.hide_size = use_AdaIn, hide_size
+        self.conv1 = nn.Conv1d(3, 64, 1)
+        self.encoder = SpareNetEncode(hide_size=hide_size, bottleneck_size=bottleneck_size, use_SElayer=use_SElayer, encode=encode)
+        self.decoder = SpareNetDecode(num_points=num_points, n_primitives=n_primitives, bottleneck_size=bottleneck_size,
+                                      use_AdaIn=use_AdaIn, use_SElayer=use_SElayer)
+        self.refine = SpareNetRefine(num_points=num_points, n_primitives=n_primitives, use_SElayer=use_SElayer)
+
+    def forward(self, data):
+        partial = data["partial_cloud"].transpose(1, 2).contiguous()         # [B,3,Np]
+        style = self.encoder(partial)
+        outs = self.decoder(style, partial)                                   # [B,3,N]
+        coarse = outs.transpose(1, 2).contiguous()
+        middle, loss_mst = self.refine(outs, partial, coarse)
+        refine, _ = self.refine(middle.transpose(1, 2).contiguous(), partial, middle)
+        return coarse, middle, refine, loss_mst

@@ -27,6 +27,31 @@ class SnbValueError(ValueError):
     pass
 
 
+# ---- instrumentation: kernel-launch counter (bench.py's gpu_launches) and optional per-op CUDA-event timing --------
+LAUNCHES = {"count": 0}
+PROFILE = None  # set to a dict {op: [(start_event, end_event), ...]} by bench.py to time ops on the current stream
+
+
+class _op:
+    """Counts the kernels a C-ABI call launches and, when PROFILE is set, brackets it with CUDA events."""
+    def __init__(self, name, launches):
+        self.name, self.launches = name, launches
+
+    def __enter__(self):
+        LAUNCHES["count"] += self.launches
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            PROFILE.setdefault(self.name, []).append((self.a, b))
+        return False
+
+
 def _ws(nbytes, device):
     # 16-byte aligned scratch from the caching allocator (allocations are 512-byte aligned)
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
@@ -44,7 +69,7 @@ def chamfer_forward(xyz1, xyz2):
     d2 = torch.empty(B, M, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
     i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _op("chamfer_fwd", 1):
         check(_lib.load().snb_chamfer_fwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), stream_ptr()), "chamfer_fwd")
     return d1, d2, i1, i2
 
@@ -56,7 +81,7 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, g1, g2):
     B, N, _ = xyz1.shape
     M = xyz2.shape[1]
     gx1, gx2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
-    with torch.cuda.device(xyz1.device):
+    with torch.cuda.device(xyz1.device), _op("chamfer_bwd", 2):
         check(_lib.load().snb_chamfer_bwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(idx1), ptr(idx2), ptr(g1), ptr(g2), ptr(gx1), ptr(gx2),
                                           stream_ptr()), "chamfer_bwd")
     return gx1, gx2
@@ -72,7 +97,7 @@ def emd_forward(xyz1, xyz2, eps, iters):
     lib = _lib.load()
     nbytes = lib.snb_emd_workspace_bytes(B, N)
     ws = _ws(nbytes, dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _op("emd_fwd", 1):
         check(lib.snb_emd_fwd(ptr(xyz1), ptr(xyz2), B, N, float(eps), int(iters), ptr(dist), ptr(ass), ptr(ws), nbytes, stream_ptr()), "emd_fwd")
     return dist, ass
 
@@ -82,7 +107,7 @@ def emd_backward(xyz1, xyz2, grad_dist, assignment):
     assignment = _cuda_i32(assignment, "assignment")
     B, N, _ = xyz1.shape
     g = torch.empty_like(xyz1)
-    with torch.cuda.device(xyz1.device):
+    with torch.cuda.device(xyz1.device), _op("emd_bwd", 1):
         check(_lib.load().snb_emd_bwd(ptr(xyz1), ptr(xyz2), B, N, ptr(grad_dist), ptr(assignment), ptr(g), stream_ptr()), "emd_bwd")
     return g
 
@@ -98,7 +123,7 @@ def expansion_forward(xyz, primitive_size, alpha):
     lib = _lib.load()
     nbytes = lib.snb_expansion_workspace_bytes(B, N, int(primitive_size))
     ws = _ws(nbytes, dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _op("expansion_fwd", 2):
         check(lib.snb_expansion_fwd(ptr(xyz), B, N, int(primitive_size), float(alpha), ptr(dist), ptr(ass), ptr(mml), ptr(ws), nbytes,
                                     stream_ptr()), "expansion_fwd")
     return dist, ass, mml
@@ -108,7 +133,7 @@ def expansion_backward(xyz, grad_dist, assignment):
     xyz, grad_dist, assignment = _cuda_f32(xyz, "xyz"), _cuda_f32(grad_dist, "grad_dist"), _cuda_i32(assignment, "assignment")
     B, N, _ = xyz.shape
     g = torch.empty_like(xyz)
-    with torch.cuda.device(xyz.device):
+    with torch.cuda.device(xyz.device), _op("expansion_bwd", 1):
         check(_lib.load().snb_expansion_bwd(ptr(xyz), B, N, ptr(grad_dist), ptr(assignment), ptr(g), stream_ptr()), "expansion_bwd")
     return g
 
@@ -121,7 +146,7 @@ def mds_sample(xyz, npoint, mean_mst_length):
     lib = _lib.load()
     nbytes = lib.snb_mds_workspace_bytes(B, n, int(npoint))
     ws = _ws(nbytes, xyz.device)
-    with torch.cuda.device(xyz.device):
+    with torch.cuda.device(xyz.device), _op("mds_sample", 1):
         check(lib.snb_mds_sample(ptr(xyz), B, n, int(npoint), ptr(mml), ptr(idx), ptr(ws), nbytes, stream_ptr()), "mds_sample")
     return idx
 
@@ -131,7 +156,7 @@ def gather_forward(features, idx):
     B, C, n = features.shape
     m = idx.shape[1]
     out = torch.empty(B, C, m, device=features.device)
-    with torch.cuda.device(features.device):
+    with torch.cuda.device(features.device), _op("gather_fwd", 1):
         check(_lib.load().snb_gather_fwd(ptr(features), ptr(idx), B, C, n, m, ptr(out), stream_ptr()), "gather_fwd")
     return out
 
@@ -140,7 +165,7 @@ def gather_backward(grad_out, idx, n):
     grad_out, idx = _cuda_f32(grad_out, "grad_out"), _cuda_i32(idx, "idx")
     B, C, m = grad_out.shape
     g = torch.empty(B, C, int(n), device=grad_out.device)
-    with torch.cuda.device(grad_out.device):
+    with torch.cuda.device(grad_out.device), _op("gather_bwd", 1):
         check(_lib.load().snb_gather_bwd(ptr(grad_out), ptr(idx), B, C, int(n), m, ptr(g), stream_ptr()), "gather_bwd")
     return g
 
@@ -164,7 +189,7 @@ def p2i_max_forward(points, feat, batch_inds, background, kernel_kind, radius):
     lib = _lib.load()
     nbytes = lib.snb_p2i_workspace_bytes(B, C, H, W, dbl)
     ws = _ws(nbytes, points.device)
-    with torch.cuda.device(points.device):
+    with torch.cuda.device(points.device), _op("p2i_max_fwd", 3):
         check(lib.snb_p2i_max_fwd(ptr(points), ptr(feat), ptr(binds), ptr(background), points.shape[0], B, C, H, W, int(kernel_kind),
                                   float(radius), dbl, ptr(out), ptr(ids), ptr(ws), nbytes, stream_ptr()), "p2i_max_fwd")
     return out, ids
@@ -176,7 +201,7 @@ def p2i_max_backward(grad_out, ids, points, feat, kernel_kind, radius):
     ids = _cuda_i32(ids, "out_point_ids")
     B, C, H, W = grad_out.shape
     gp, gf, gb = torch.empty_like(points), torch.empty_like(feat), torch.empty_like(grad_out)
-    with torch.cuda.device(points.device):
+    with torch.cuda.device(points.device), _op("p2i_max_bwd", 1):
         check(_lib.load().snb_p2i_max_bwd(ptr(grad_out), ptr(ids), ptr(points), ptr(feat), points.shape[0], B, C, H, W, int(kernel_kind),
                                           float(radius), dbl, ptr(gp), ptr(gf), ptr(gb), stream_ptr()), "p2i_max_bwd")
     return gp, gf, gb
@@ -188,7 +213,7 @@ def p2i_sum_forward(points, feat, batch_inds, background, kernel_kind, radius):
     binds = _cuda_i32(batch_inds, "batch_inds")
     B, C, H, W = background.shape
     out = torch.empty_like(background)
-    with torch.cuda.device(points.device):
+    with torch.cuda.device(points.device), _op("p2i_sum_fwd", 1):
         check(_lib.load().snb_p2i_sum_fwd(ptr(points), ptr(feat), ptr(binds), ptr(background), points.shape[0], B, C, H, W, int(kernel_kind),
                                           float(radius), dbl, ptr(out), stream_ptr()), "p2i_sum_fwd")
     return out
@@ -200,7 +225,7 @@ def p2i_sum_backward(grad_out, points, feat, batch_inds, kernel_kind, radius):
     binds = _cuda_i32(batch_inds, "batch_inds")
     B, C, H, W = grad_out.shape
     gp, gf = torch.empty_like(points), torch.empty_like(feat)
-    with torch.cuda.device(points.device):
+    with torch.cuda.device(points.device), _op("p2i_sum_bwd", 1):
         check(_lib.load().snb_p2i_sum_bwd(ptr(grad_out), ptr(points), ptr(feat), ptr(binds), points.shape[0], B, C, H, W, int(kernel_kind),
                                           float(radius), dbl, ptr(gp), ptr(gf), stream_ptr()), "p2i_sum_bwd")
     return gp, gf
@@ -215,6 +240,6 @@ def knn_indices(x, k):
     lib = _lib.load()
     nbytes = lib.snb_knn_workspace_bytes(B, N)
     ws = _ws(nbytes, x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _op("knn", 2):
         check(lib.snb_knn(ptr(x), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn")
     return idx

@@ -1,0 +1,76 @@
+"""ComputeDepthMaps drop-in vs goldens produced by the REAL reference utils/p2i_utils.py
+(tests/golden/make_golden_depthmaps.py).  The CPU test checks the host math (matrices, projection, depth feature) with
+the splat monkeypatched to the oracle (test only); the GPU test runs the real kernels through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "depthmaps_ref.npz"))
+
+
+def _cpu_p2i(points, point_features, batch_inds, background, kernel_radius, kernel_kind_str="cos", reduce="sum"):
+    h, w = background.shape[2:]
+    pts = (points + 1) / 2 * torch.tensor([h - 1, w - 1], dtype=points.dtype).view(1, 2)
+    return oracle.p2i_max_fwd(pts.contiguous(), point_features.contiguous(), batch_inds, background, float(kernel_radius))[0]
+
+
+@pytest.mark.parametrize("proj", ["orthorgonal", "perspective"])
+def test_view_matrices_and_host_math_cpu(monkeypatch, proj):
+    from sparenet_b200.dropin.utils import p2i_utils as U
+    monkeypatch.setattr(U, "p2i", _cpu_p2i)
+    r = U.ComputeDepthMaps(projection=proj, eyepos_scale=1.0, image_size=32).float()
+    pre = torch.cat(r.pre_matrix_list, 0)
+    assert torch.allclose(pre, torch.from_numpy(GOLD[f"{proj}_pre"]), rtol=1e-6, atol=1e-7)
+    assert "_pre_matrix" in r.state_dict() and torch.equal(r.state_dict()["_pre_matrix"], pre[-1:])
+    data = torch.from_numpy(GOLD["data"])
+    for view in (0, 5):
+        out = r(data, view_id=view, radius_list=[3.0, 5.0])
+        ref = torch.from_numpy(GOLD[f"{proj}_v{view}"])
+        assert out.shape == ref.shape
+        # fp32 re-association of the 4x4 product moves pixel coordinates by ~1e-6: compare away from footprint edges
+        close = torch.isclose(out, ref, rtol=1e-4, atol=1e-4)
+        assert close.float().mean().item() > 0.999
+    assert r(data, view_id=8) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("proj", ["orthorgonal", "perspective"])
+def test_depthmaps_gpu_vs_reference_golden(cuda, proj):
+    from sparenet_b200.dropin.utils import p2i_utils as U
+    r = U.ComputeDepthMaps(projection=proj, eyepos_scale=1.0, image_size=32).float().to(cuda)
+    data = torch.from_numpy(GOLD["data"]).to(cuda).requires_grad_()
+    for view in (0, 5):
+        out = r(data, view_id=view, radius_list=[3.0, 5.0])
+        ref = torch.from_numpy(GOLD[f"{proj}_v{view}"]).to(cuda)
+        close = torch.isclose(out, ref, rtol=1e-4, atol=1e-4)       # <= 1e-5 rel away from footprint edges (see above)
+        assert close.float().mean().item() > 0.999
+    out.mean().backward()
+    assert torch.isfinite(data.grad).all() and data.grad.abs().sum() > 0
+
+
+@pytest.mark.gpu
+def test_depthmaps_gradient_matches_autograd_through_oracle_formula(cuda):
+    """d(depth)/d(data) through pos_ij AND through the min/max-normalised feature, against fp64 finite differences of
+    the same pipeline built from the float64 p2i kernels."""
+    from sparenet_b200.dropin.utils import p2i_utils as U
+    torch.manual_seed(7)
+    r = U.ComputeDepthMaps("orthorgonal", 1.0, 16).double().to(cuda)
+    data = ((torch.rand(1, 12, 3, dtype=torch.float64) - 0.5) * 0.8).to(cuda).requires_grad_()
+    w = torch.rand(1, 1, 16, 16, dtype=torch.float64, device=cuda)
+    loss = (r(data, view_id=3, radius_list=[4.0]) * w).sum()
+    g, = torch.autograd.grad(loss, data)
+    eps = 1e-6
+    num = torch.zeros_like(data)
+    flat = data.detach().clone().view(-1)
+    for i in range(flat.numel()):
+        p, m = flat.clone(), flat.clone()
+        p[i] += eps
+        m[i] -= eps
+        lp = (r(p.view_as(data), view_id=3, radius_list=[4.0]) * w).sum()
+        lm = (r(m.view_as(data), view_id=3, radius_list=[4.0]) * w).sum()
+        num.view(-1)[i] = (lp - lm) / (2 * eps)
+    assert torch.allclose(g, num, rtol=1e-3, atol=1e-5 * num.abs().max().item()), (g - num).abs().max()

@@ -1,0 +1,109 @@
+"""GPU parity of the drop-in generator (fused algebra + sm_100a point ops) against the plain restatement
+(oracle/generator_ref.py, itself pinned to the real reference classes) with the SAME state_dict."""
+import pytest
+import torch
+
+from oracle import generator_ref as G
+
+pytestmark = pytest.mark.gpu
+
+
+class GpuOps:
+    """Point ops for the restatement on the GPU: our kernels, so only the dense algebra differs between the two models."""
+    @staticmethod
+    def knn(x, k):
+        from sparenet_b200 import functional as F_
+        return F_.knn_indices(x.contiguous(), k).long()
+
+    @staticmethod
+    def expansion(xyz, p, alpha):
+        from sparenet_b200.dropin.cuda.expansion_penalty.expansion_penalty_module import expansionPenaltyModule
+        return expansionPenaltyModule()(xyz, p, alpha)
+
+    @staticmethod
+    def mds(xyz, m, mml):
+        from sparenet_b200 import functional as F_
+        return F_.mds_sample(xyz.contiguous(), m, mml.contiguous())
+
+    @staticmethod
+    def gather(f, idx):
+        from sparenet_b200.dropin.cuda.MDS.MDS_module import gather_operation
+        return gather_operation(f.contiguous(), idx)
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = a, b
+
+
+def test_generator_matches_restatement(cuda):
+    from sparenet_b200.dropin.models import sparenet_generator as M
+    kw = dict(n_primitives=8, hide_size=256, bottleneck_size=256, num_points=8 * 512)
+    ref = G.SpareNetGenerator(ops=GpuOps, **kw)
+    torch.manual_seed(0)
+    ref.apply(G.init_weights)
+    ref = ref.to(cuda).train()
+    mine = M.SpareNetGenerator(use_SElayer=True, use_AdaIn="share", encode="Residualnet", **kw).to(cuda).train()
+    assert sorted(mine.state_dict()) == sorted(ref.state_dict())
+    mine.load_state_dict(ref.state_dict())
+    torch.manual_seed(1)
+    data = {"partial_cloud": (torch.rand(4, 1024, 3, device=cuda) - 0.5)}
+    c1, m1, r1, l1 = ref(data)
+    c2, m2, r2, l2 = mine(data)
+    assert torch.allclose(c1, c2, rtol=1e-3, atol=1e-5), (c1 - c2).abs().max()
+    assert abs(l1.item() - l2.item()) <= 1e-4 * abs(l1.item()) + 1e-8
+    # running statistics advanced identically (sample a few)
+    b1, b2 = dict(ref.named_buffers()), dict(mine.named_buffers())
+    for k in ("encoder.feat_extractor.bn3.running_var", "decoder.decoder.5.dec.bn2.running_mean", "refine.residual.bn4.running_var",
+              "encoder.bn.running_mean", "decoder.decoder.0.dec.bn1.num_batches_tracked"):
+        assert torch.allclose(b1[k].float(), b2[k].float(), rtol=2e-3, atol=1e-6), k
+    (r2.mean() + l2).backward()
+    assert all(torch.isfinite(p.grad).all() for p in mine.parameters() if p.grad is not None)
+
+
+def test_refiner_matches_restatement_given_same_inputs(cuda):
+    from sparenet_b200.dropin.models import sparenet_generator as M
+    ref = G.SpareNetRefine(n_primitives=4, num_points=2048, ops=GpuOps).to(cuda).train()
+    torch.manual_seed(2)
+    ref.apply(G.init_weights)
+    mine = M.SpareNetRefine(n_primitives=4, num_points=2048, use_SElayer=True).to(cuda).train()
+    mine.load_state_dict(ref.state_dict())
+    coarse = (torch.rand(3, 2048, 3, device=cuda) - 0.5) * 0.8
+    partial = (torch.rand(3, 3, 512, device=cuda) - 0.5)
+    c1, c2 = coarse.clone().requires_grad_(), coarse.clone().requires_grad_()
+    o1, l1 = ref(c1.transpose(1, 2).contiguous(), partial, c1)
+    o2, l2 = mine(c2.transpose(1, 2).contiguous(), partial, c2)
+    assert torch.equal(l1, l2)
+    assert torch.allclose(o1, o2, rtol=1e-3, atol=1e-5), (o1 - o2).abs().max()
+    w = torch.randn_like(o1)
+    ((o1 * w).sum() + l1).backward()
+    ((o2 * w).sum() + l2).backward()
+    assert torch.allclose(c1.grad, c2.grad, rtol=5e-3, atol=1e-4 * c1.grad.abs().max().item())
+
+
+def test_training_step_runs_and_learns(cuda):
+    """A few Adam steps of the BASELINE config-2 loss at reduced size: the loss must go down."""
+    from sparenet_b200.dropin.cuda.chamfer_distance import ChamferDistance, ChamferDistanceMean
+    from sparenet_b200.dropin.models import sparenet_generator as M
+    torch.manual_seed(0)
+    net = M.SpareNetGenerator(n_primitives=8, hide_size=256, bottleneck_size=256, num_points=4096, use_SElayer=True, use_AdaIn="share",
+                              encode="Residualnet")
+    net.apply(G.init_weights)
+    net = net.to(cuda).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.0, 0.9))
+    gt = torch.rand(4, 4096, 3, device=cuda) - 0.5
+    partial = gt[:, :1024].contiguous()
+    cdm, cd = ChamferDistanceMean(), ChamferDistance()
+    losses = []
+    for _ in range(6):
+        coarse, middle, refine, lm = net({"partial_cloud": partial})
+        loss = cdm(coarse, gt) + cdm(middle, gt) + cdm(refine, gt) + lm * 0.1 + cd(refine, gt)[0].mean() * 0.5
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(map(lambda v: v == v, losses)) and losses[-1] < losses[0]
