@@ -157,10 +157,17 @@ def test_emd_vs_reference_extension(cuda):
     ours = (ass == ra1).float().mean().item()
     e_ref1, e_ref2, e_ours = rd1.sqrt().mean().item(), rd2.sqrt().mean().item(), dist.sqrt().mean().item()
     print(f"[emd] ref-vs-ref identical={ref_self:.6f} ours-vs-ref identical={ours:.6f} emd ref={e_ref1:.7f}/{e_ref2:.7f} ours={e_ours:.7f}")
+    # tools/diag2.py (crafted duplicate bidders) shows the reference's GetMax winner is scheduling dependent: lower lane
+    # inside a warp, otherwise whichever warp/block stores last -- no index rule reproduces it.  Our rule (largest index)
+    # therefore departs from it on a few bids per round; the loss value agrees to ~1e-5 and >99% of matches coincide.
     band = max(abs(e_ref1 - e_ref2), 1e-5 * e_ref1)
-    assert abs(e_ours - e_ref1) <= 10 * band + 1e-4 * e_ref1
-    if ref_self == 1.0:
-        assert ours >= 0.999
+    assert abs(e_ours - e_ref1) <= 10 * band + 5e-5 * e_ref1
+    assert ours >= 0.99
+    # rounds before the first in-window conflict are bit-identical to the reference
+    for it in (1, 2):
+        rd, ra = refcalls.emd_fwd(ext, x, y, 0.005, it)
+        d, a = F_.emd_forward(x, y, 0.005, it)
+        assert torch.equal(a, ra) and torch.equal(d, rd)
 
 
 def test_emd_full_size_properties(cuda):
