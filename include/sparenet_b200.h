@@ -103,6 +103,32 @@ int snb_p2i_sum_bwd(const void* grad_out, const void* points, const void* featur
 size_t snb_knn_workspace_bytes(int B, int N);
 int snb_knn(const float* x, int B, int C, int N, int k, int* idx, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- EdgeConv neighbourhood reduction (models/sparenet_generator.py:188-242,880-906) -----------------------
+ * With conv([x_j - x_i ; x_i]) = a_j + c_i (a = W_a x, c = (W_b - W_a) x, per-point GEMMs done by the caller) this
+ * produces everything the block needs from u[b,ch,i,m] = a[b,ch,idx[b,i,m]] + c[b,ch,i] without forming it:
+ * umax/umin [B,C,N] = max_m / min_m u, the winning neighbour slots (uint8), S1/S2 [B,C] = sum u, sum u^2 (fp64).
+ * a, c, umax, umin are channel-major [B,C,N]; idx [B,N,k] int32, k <= 32.  _bwd is the exact adjoint. */
+int snb_edge_reduce_fwd(const float* a, const float* c, const int* idx, int B, int C, int N, int k,
+                        float* umax, float* umin, unsigned char* slot_max, unsigned char* slot_min,
+                        double* S1, double* S2, void* stream);
+int snb_edge_reduce_bwd(const float* a, const float* c, const int* idx, const unsigned char* slot_max,
+                        const unsigned char* slot_min, const float* g_umax, const float* g_umin,
+                        const double* gS1, const double* gS2, int B, int C, int N, int k,
+                        float* ga, float* gc, void* stream);
+
+/* ---- row-wise tails of the folded normalisation stacks (models/sparenet_generator.py:618-646,1053-1061) ----
+ * h [R,L] contiguous rows.  row_stats: mean / biased variance per row.  row_affine_act:
+ * y[r,:] = leaky_relu(h[r / in_div,:] * scale[r] + shift[r], slope) (slope 0 = ReLU); _bwd returns gh [R/in_div, L],
+ * gscale [R], gshift [R].  row_minmax: per-row max/min and their first positions. */
+int snb_row_stats(const float* h, long long R, int L, float* mean, float* var, void* stream);
+int snb_row_stats_bwd(const float* h, const float* mean, const float* gmean, const float* gvar, long long R, int L,
+                      float* gh, void* stream);
+int snb_row_affine_act_fwd(const float* h, const float* scale, const float* shift, long long R, int L, int in_div,
+                           float slope, float* y, void* stream);
+int snb_row_affine_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, long long R, int L,
+                           int in_div, float slope, float* gh, float* gscale, float* gshift, void* stream);
+int snb_row_minmax(const float* h, long long R, int L, float* vmax, float* vmin, int* imax, int* imin, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,13 @@ SIGNATURES = {
     "snb_p2i_sum_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P, P]),
     "snb_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "snb_knn": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
+    "snb_edge_reduce_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "snb_edge_reduce_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "snb_row_stats": (c_int, [P, ctypes.c_longlong, c_int, P, P, P]),
+    "snb_row_stats_bwd": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, P, P]),
+    "snb_row_affine_act_fwd": (c_int, [P, P, P, ctypes.c_longlong, c_int, c_int, c_float, P, P]),
+    "snb_row_affine_act_bwd": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, c_int, c_float, P, P, P, P]),
+    "snb_row_minmax": (c_int, [P, ctypes.c_longlong, c_int, P, P, P, P, P]),
 }
 
 _lib = None

@@ -1,0 +1,151 @@
+// edge.cu -- fused EdgeConv neighbourhood reduction (forward + backward), sm_100a.
+//
+// Replaces, together with snb_knn, the get_graph_feature -> Conv2d -> BatchNorm2d -> SE -> LeakyReLU -> max_k chain of the
+// reference's EdgeConvResFeat (models/sparenet_generator.py:188-242,880-906) WITHOUT ever forming its [B,2C,N,k] /
+// [B,C',N,k] tensors.  With W = [W_a | W_b]:  conv([x_j - x_i ; x_i]) = a_j + c_i,  a = W_a x,  c = (W_b - W_a) x  (per-point
+// GEMMs, done by the caller).  Everything the rest of the block needs from u[b,ch,i,m] = a[b,ch,idx[b,i,m]] + c[b,ch,i] is
+//     umax/umin[b,ch,i] = max_m / min_m u      (max_k commutes with the monotone BN.SE.LeakyReLU tail, sign of gamma picks one)
+//     S1[b,ch] = sum_{i,m} u,  S2[b,ch] = sum_{i,m} u^2     (BatchNorm2d batch statistics and the SE squeeze)
+// which this kernel produces in one pass over a and c.  The backward kernel is the exact adjoint.
+//
+// Layout: a, c, umax, umin [B,C,N] channel-major (what the encoder already holds), idx [B,N,k] int32.
+// One CTA per (sample, channel) row: the row of `a` (N floats) is staged in shared memory, so the k gathers per point are
+// shared-memory reads; idx is read coalesced and re-used by all C channel-CTAs of a sample out of L2.
+#include "common.cuh"
+
+namespace snb {
+
+constexpr int EDGE_THREADS = 256;
+constexpr int EDGE_MAXK = 32;
+
+__device__ __forceinline__ double block_sum_double(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double t = (threadIdx.x < EDGE_THREADS / 32) ? red[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_fwd_kernel(const float* __restrict__ a, const float* __restrict__ c,
+                                                                        const int* __restrict__ idx, int C, int N, int k,
+                                                                        float* __restrict__ umax, float* __restrict__ umin,
+                                                                        unsigned char* __restrict__ smax, unsigned char* __restrict__ smin,
+                                                                        double* __restrict__ S1, double* __restrict__ S2) {
+  extern __shared__ float arow[];
+  __shared__ double red[EDGE_THREADS / 32];
+  const int ch = blockIdx.x, b = blockIdx.y;
+  const size_t row = ((size_t)b * C + ch) * N;
+  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) arow[i] = a[row + i];
+  __syncthreads();
+  const int* __restrict__ ib = idx + (size_t)b * N * k;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) {
+    const float ci = c[row + i];
+    float mx = -3.4e38f, mn = 3.4e38f, sa = 0.f, sq = 0.f;
+    int ax = 0, an = 0;
+    for (int m = 0; m < k; m++) {
+      const float v = arow[ib[(size_t)i * k + m]];
+      sa += v;
+      sq = __fmaf_rn(v, v, sq);
+      if (v > mx) { mx = v; ax = m; }   // first maximum / minimum wins, like torch.max over dim=-1 on CUDA is free to
+      if (v < mn) { mn = v; an = m; }
+    }
+    umax[row + i] = mx + ci;
+    umin[row + i] = mn + ci;
+    smax[row + i] = (unsigned char)ax;
+    smin[row + i] = (unsigned char)an;
+    // sum_m (a_j + c)   and   sum_m (a_j + c)^2 = sum a_j^2 + 2 c sum a_j + k c^2
+    s1 += (double)sa + (double)k * (double)ci;
+    s2 += (double)sq + 2.0 * (double)ci * (double)sa + (double)k * (double)ci * (double)ci;
+  }
+  const double t1 = block_sum_double(s1, red);
+  const double t2 = block_sum_double(s2, red);
+  if (threadIdx.x == 0) {
+    S1[(size_t)b * C + ch] = t1;
+    S2[(size_t)b * C + ch] = t2;
+  }
+}
+
+// adjoint:  gc_i = gmax_i + gmin_i + k gS1 + 2 gS2 (sum_m a_jm + k c_i)
+//           ga_j = sum_{(i,m): idx[i,m] = j} [ gS1 + 2 gS2 (a_j + c_i) + [m = smax_i] gmax_i + [m = smin_i] gmin_i ]
+__global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_bwd_kernel(const float* __restrict__ a, const float* __restrict__ c,
+                                                                        const int* __restrict__ idx, const unsigned char* __restrict__ smax,
+                                                                        const unsigned char* __restrict__ smin, const float* __restrict__ gmax,
+                                                                        const float* __restrict__ gmin, const double* __restrict__ gS1,
+                                                                        const double* __restrict__ gS2, int C, int N, int k,
+                                                                        float* __restrict__ ga, float* __restrict__ gc) {
+  extern __shared__ float sm[];
+  float* arow = sm;
+  float* grow = sm + N;
+  const int ch = blockIdx.x, b = blockIdx.y;
+  const size_t row = ((size_t)b * C + ch) * N;
+  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) {
+    arow[i] = a[row + i];
+    grow[i] = 0.f;
+  }
+  __syncthreads();
+  const float g1 = (float)gS1[(size_t)b * C + ch];
+  const float g2 = 2.f * (float)gS2[(size_t)b * C + ch];
+  const int* __restrict__ ib = idx + (size_t)b * N * k;
+  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) {
+    const float ci = c[row + i];
+    const float gx = gmax[row + i], gn = gmin[row + i];
+    const int ax = smax[row + i], an = smin[row + i];
+    float sa = 0.f;
+    for (int m = 0; m < k; m++) {
+      const int j = ib[(size_t)i * k + m];
+      const float v = arow[j];
+      sa += v;
+      float g = __fmaf_rn(g2, v + ci, g1);
+      if (m == ax) g += gx;
+      if (m == an) g += gn;
+      atomicAdd(&grow[j], g);
+    }
+    gc[row + i] = gx + gn + (float)k * g1 + g2 * (sa + (float)k * ci);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) ga[row + i] = grow[i];
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+static int edge_check(int B, int C, int N, int k) {
+  if (B < 0 || C < 0 || N < 0 || k <= 0) return SNB_EINVAL;
+  if (k > EDGE_MAXK || k > 255 || B > 65535 || (size_t)N * 8 > 200 * 1024) return SNB_ELIMIT;
+  return SNB_OK;
+}
+
+SNB_API int snb_edge_reduce_fwd(const float* a, const float* c, const int* idx, int B, int C, int N, int k, float* umax, float* umin,
+                                unsigned char* slot_max, unsigned char* slot_min, double* S1, double* S2, void* stream) {
+  int rc = edge_check(B, C, N, k);
+  if (rc) return rc;
+  if (B == 0 || C == 0 || N == 0) return SNB_OK;
+  const size_t smem = (size_t)N * sizeof(float);
+  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_reduce_fwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, C, N, k, umax, umin, slot_max, slot_min, S1, S2);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_edge_reduce_bwd(const float* a, const float* c, const int* idx, const unsigned char* slot_max, const unsigned char* slot_min,
+                                const float* g_umax, const float* g_umin, const double* gS1, const double* gS2, int B, int C, int N, int k,
+                                float* ga, float* gc, void* stream) {
+  int rc = edge_check(B, C, N, k);
+  if (rc) return rc;
+  if (B == 0 || C == 0 || N == 0) return SNB_OK;
+  const size_t smem = (size_t)N * 2 * sizeof(float);
+  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_reduce_bwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, slot_max, slot_min, g_umax, g_umin, gS1, gS2, C, N, k,
+                                                                                  ga, gc);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

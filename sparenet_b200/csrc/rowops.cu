@@ -1,0 +1,278 @@
+// rowops.cu -- row-wise statistics and fused per-row affine + (leaky-)ReLU, forward and backward, sm_100a.
+//
+// These are the memory-bound tails of every dense layer of the generator once the normalisation algebra is folded
+// (SURVEY.md 9.6): AdaIN o BatchNorm o SE o ReLU after a decoder conv (models/sparenet_generator.py:1053-1061), and
+// BatchNorm o SE o ReLU in PointNetRes / conv5 of the encoder (:618-646, :234-236), all collapse to
+//        y[r, :] = act( h[r, :] * scale[r] + shift[r] )          with one (scale, shift) per ROW r = (primitive, channel, sample)
+// plus the row statistics (mean, biased variance) that the closed-form scale/shift are computed from.
+// HBM-bound by construction: each kernel touches every element once with 128-bit accesses; one warp owns a row so the
+// reductions are shuffle-only.  `in_div` lets several output rows share one input row (decoder layer 1: the folded
+// lattice activations do not depend on the sample).
+#include "common.cuh"
+
+namespace snb {
+
+constexpr int ROW_THREADS = 256;  // 8 warps = 8 rows per CTA
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// mean / biased variance per row; sums are shifted by the row's first element so E[x^2]-E[x]^2 does not cancel
+__global__ void __launch_bounds__(ROW_THREADS) row_stats_kernel(const float* __restrict__ h, long long R, int L, float* __restrict__ mean,
+                                                                 float* __restrict__ var) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* __restrict__ p = h + r * L;
+  const float x0 = p[0];
+  float s = 0.f, q = 0.f;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i];
+      const float a = v.x - x0, b = v.y - x0, c = v.z - x0, d = v.w - x0;
+      s += (a + b) + (c + d);
+      q = __fmaf_rn(a, a, __fmaf_rn(b, b, __fmaf_rn(c, c, __fmaf_rn(d, d, q))));
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) {
+      const float a = p[i] - x0;
+      s += a;
+      q = __fmaf_rn(a, a, q);
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const float m = s / (float)L;
+    mean[r] = x0 + m;
+    var[r] = fmaxf(q / (float)L - m * m, 0.f);
+  }
+}
+
+// gh[r,l] = gmean[r]/L + gvar[r] * 2 (h[r,l] - mean[r]) / L      (adjoint of row_stats)
+__global__ void __launch_bounds__(ROW_THREADS) row_stats_bwd_kernel(const float* __restrict__ h, const float* __restrict__ mean,
+                                                                     const float* __restrict__ gmean, const float* __restrict__ gvar, long long R,
+                                                                     int L, float* __restrict__ gh) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float invL = 1.f / (float)L;
+  const float a = gmean[r] * invL, b = 2.f * gvar[r] * invL, m = mean[r];
+  const float* __restrict__ p = h + r * L;
+  float* __restrict__ g = gh + r * L;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    float4* __restrict__ g4 = reinterpret_cast<float4*>(g);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i];
+      g4[i] = make_float4(__fmaf_rn(b, v.x - m, a), __fmaf_rn(b, v.y - m, a), __fmaf_rn(b, v.z - m, a), __fmaf_rn(b, v.w - m, a));
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) g[i] = __fmaf_rn(b, p[i] - m, a);
+  }
+}
+
+__device__ __forceinline__ float act(float z, float slope) { return z > 0.f ? z : z * slope; }
+
+// y[r,:] = act(h[r / in_div, :] * scale[r] + shift[r])
+__global__ void __launch_bounds__(ROW_THREADS) row_affine_act_fwd_kernel(const float* __restrict__ h, const float* __restrict__ scale,
+                                                                          const float* __restrict__ shift, long long R, int L, int in_div,
+                                                                          float slope, float* __restrict__ y) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float sc = scale[r], sh = shift[r];
+  const float* __restrict__ p = h + (r / in_div) * L;
+  float* __restrict__ o = y + r * L;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    float4* __restrict__ o4 = reinterpret_cast<float4*>(o);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i];
+      o4[i] = make_float4(act(__fmaf_rn(v.x, sc, sh), slope), act(__fmaf_rn(v.y, sc, sh), slope), act(__fmaf_rn(v.z, sc, sh), slope),
+                          act(__fmaf_rn(v.w, sc, sh), slope));
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) o[i] = act(__fmaf_rn(p[i], sc, sh), slope);
+  }
+}
+
+// One warp per INPUT row: loops over the in_div output rows that share it.
+//   d = gy * act'(z),  gh[rin,:] = sum_rows d * scale[r],  gscale[r] = sum_l d * h,  gshift[r] = sum_l d
+__global__ void __launch_bounds__(ROW_THREADS) row_affine_act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ h,
+                                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                          long long Rin, int L, int in_div, float slope, float* __restrict__ gh,
+                                                                          float* __restrict__ gscale, float* __restrict__ gshift) {
+  const long long rin = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (rin >= Rin) return;
+  const float* __restrict__ p = h + rin * L;
+  float* __restrict__ g = gh + rin * L;
+  if (in_div == 1) {
+    const float sc = scale[rin], sh = shift[rin];
+    const float* __restrict__ q = gy + rin * L;
+    float as = 0.f, ab = 0.f;
+    if ((L & 3) == 0) {
+      const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+      const float4* __restrict__ q4 = reinterpret_cast<const float4*>(q);
+      float4* __restrict__ g4 = reinterpret_cast<float4*>(g);
+      for (int i = lane; i < (L >> 2); i += 32) {
+        const float4 v = p4[i], w = q4[i];
+        const float d0 = __fmaf_rn(v.x, sc, sh) > 0.f ? w.x : w.x * slope;
+        const float d1 = __fmaf_rn(v.y, sc, sh) > 0.f ? w.y : w.y * slope;
+        const float d2 = __fmaf_rn(v.z, sc, sh) > 0.f ? w.z : w.z * slope;
+        const float d3 = __fmaf_rn(v.w, sc, sh) > 0.f ? w.w : w.w * slope;
+        g4[i] = make_float4(d0 * sc, d1 * sc, d2 * sc, d3 * sc);
+        as = __fmaf_rn(d0, v.x, __fmaf_rn(d1, v.y, __fmaf_rn(d2, v.z, __fmaf_rn(d3, v.w, as))));
+        ab += (d0 + d1) + (d2 + d3);
+      }
+    } else {
+      for (int i = lane; i < L; i += 32) {
+        const float v = p[i], w = q[i];
+        const float d = __fmaf_rn(v, sc, sh) > 0.f ? w : w * slope;
+        g[i] = d * sc;
+        as = __fmaf_rn(d, v, as);
+        ab += d;
+      }
+    }
+    as = warp_sum(as);
+    ab = warp_sum(ab);
+    if (lane == 0) {
+      gscale[rin] = as;
+      gshift[rin] = ab;
+    }
+    return;
+  }
+  // shared-input variant: element-major so gh accumulates in registers across the in_div rows
+  for (int i0 = lane; i0 < L; i0 += 32 * 4) {
+    float hv[4], acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + 32 * u;
+      hv[u] = i < L ? p[i] : 0.f;
+      acc[u] = 0.f;
+    }
+    for (int s = 0; s < in_div; s++) {
+      const long long r = rin * in_div + s;
+      const float sc = scale[r], sh = shift[r];
+      const float* __restrict__ q = gy + r * L;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + 32 * u;
+        if (i < L) {
+          const float w = q[i];
+          const float d = __fmaf_rn(hv[u], sc, sh) > 0.f ? w : w * slope;
+          acc[u] = __fmaf_rn(d, sc, acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + 32 * u;
+      if (i < L) g[i] = acc[u];
+    }
+  }
+  for (int s = 0; s < in_div; s++) {
+    const long long r = rin * in_div + s;
+    const float sc = scale[r], sh = shift[r];
+    const float* __restrict__ q = gy + r * L;
+    float as = 0.f, ab = 0.f;
+    for (int i = lane; i < L; i += 32) {
+      const float v = p[i], w = q[i];
+      const float d = __fmaf_rn(v, sc, sh) > 0.f ? w : w * slope;
+      as = __fmaf_rn(d, v, as);
+      ab += d;
+    }
+    as = warp_sum(as);
+    ab = warp_sum(ab);
+    if (lane == 0) {
+      gscale[r] = as;
+      gshift[r] = ab;
+    }
+  }
+}
+
+// max / min / argmax / argmin per row (PointNetRes global feature: max over points commutes with the monotone BN)
+__global__ void __launch_bounds__(ROW_THREADS) row_minmax_kernel(const float* __restrict__ h, long long R, int L, float* __restrict__ vmax,
+                                                                  float* __restrict__ vmin, int* __restrict__ imax, int* __restrict__ imin) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* __restrict__ p = h + r * L;
+  float mx = -3.4e38f, mn = 3.4e38f;
+  int ax = 0, an = 0;
+  for (int i = lane; i < L; i += 32) {
+    const float v = p[i];
+    if (v > mx) { mx = v; ax = i; }
+    if (v < mn) { mn = v; an = i; }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o), omn = __shfl_xor_sync(0xffffffffu, mn, o);
+    const int oax = __shfl_xor_sync(0xffffffffu, ax, o), oan = __shfl_xor_sync(0xffffffffu, an, o);
+    if (omx > mx || (omx == mx && oax < ax)) { mx = omx; ax = oax; }
+    if (omn < mn || (omn == mn && oan < an)) { mn = omn; an = oan; }
+  }
+  if (lane == 0) {
+    vmax[r] = mx; vmin[r] = mn; imax[r] = ax; imin[r] = an;
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+static inline unsigned row_grid(long long R) { return (unsigned)((R + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32)); }
+
+SNB_API int snb_row_stats(const float* h, long long R, int L, float* mean, float* var, void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_stats_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, R, L, mean, var);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_stats_bwd(const float* h, const float* mean, const float* gmean, const float* gvar, long long R, int L, float* gh,
+                              void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_stats_bwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, mean, gmean, gvar, R, L, gh);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_affine_act_fwd(const float* h, const float* scale, const float* shift, long long R, int L, int in_div, float slope,
+                                   float* y, void* stream) {
+  if (R < 0 || L <= 0 || in_div <= 0 || (R % in_div) != 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_affine_act_fwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, scale, shift, R, L, in_div, slope, y);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_affine_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, long long R, int L, int in_div,
+                                   float slope, float* gh, float* gscale, float* gshift, void* stream) {
+  if (R < 0 || L <= 0 || in_div <= 0 || (R % in_div) != 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_affine_act_bwd_kernel<<<row_grid(R / in_div), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, R / in_div, L, in_div, slope, gh,
+                                                                                          gscale, gshift);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_minmax(const float* h, long long R, int L, float* vmax, float* vmin, int* imax, int* imin, void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_minmax_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, R, L, vmax, vmin, imax, imin);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

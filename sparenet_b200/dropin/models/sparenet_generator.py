@@ -27,6 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from sparenet_b200 import functional as F_
+from sparenet_b200 import fused
 from sparenet_b200.dropin.cuda.MDS import MDS_module
 from sparenet_b200.dropin.cuda.expansion_penalty import expansion_penalty_module as expansion
 
@@ -76,6 +77,19 @@ def _bn_stats(bn, x, dims):
     return bn.running_mean, bn.running_var
 
 
+def _channel_stats(bn, h):
+    """BatchNorm1d statistics of h [B,C,N] from one fused row pass: per-(b,c) mean/var -> per-channel mean / biased var.
+    Returns (mean [C], var [C], row_mean [B,C]); running statistics are advanced in train mode."""
+    m_bc, v_bc = fused.row_stats(h)
+    if bn.training:
+        mean = m_bc.mean(0)
+        dm = m_bc - mean
+        var = v_bc.mean(0) + (dm * dm).mean(0)              # within-row + between-row variance: no cancellation
+        _bn_apply_stats(bn, mean, var, h.size(0) * h.size(2))
+        return mean, var, m_bc
+    return bn.running_mean, bn.running_var, m_bc
+
+
 def knn(x, k: int):
     """Reference :852-877.  x [B,C,N] -> idx [B,N,k] int64 (self included); exact fp32 brute force on the GPU."""
     return F_.knn_indices(x.contiguous(), k).long()
@@ -115,22 +129,28 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         """max_k LeakyReLU(SE(BN(conv([x_j - x_i ; x_i]))))  (+ residual 1x1 conv of x), x [B,C,N] -> [B,Cout,N]."""
         B, C, N = x.shape
         k = self.k
-        idx = knn(x, k)                                            # [B,N,k]
+        idx = F_.knn_indices(x.contiguous(), k)                    # [B,N,k] int32, sm_100a brute force (snb_knn)
         W = conv.weight.view(conv.out_channels, 2 * C)
         Wa, Wb = W[:, :C], W[:, C:]
         Wcat = torch.cat((Wa, Wb - Wa) if res is None else (Wa, Wb - Wa, res.weight.view(res.out_channels, C)), 0)
         y = torch.matmul(Wcat, x)                                  # one per-point GEMM: [B, 2Cout(+Cres), N]
         Co = conv.out_channels
-        a, c = y[:, :Co], y[:, Co:2 * Co]
-        u = torch.gather(a, 2, idx.reshape(B, 1, N * k).expand(-1, Co, -1)).view(B, Co, N, k) + c.unsqueeze(-1)
-        mean, var = _bn_stats(bn, u, (0, 2, 3))
-        inv = torch.rsqrt(var + bn.eps)
+        # u[b,c,i,m] = a[b,c,idx[b,i,m]] + c[b,c,i] is never formed: the fused kernel returns its max/min over m and its moments
+        umax, umin, S1, S2 = fused.edge_reduce(y[:, :Co], y[:, Co:2 * Co], idx)
+        n = B * N * k
+        if bn.training:
+            mean64 = S1.sum(0) / n
+            var64 = (S2.sum(0) / n - mean64 * mean64).clamp_min(0)
+            mean, var = mean64.to(x.dtype), var64.to(x.dtype)
+            _bn_apply_stats(bn, mean, var, n)
+        else:
+            mean, var = bn.running_mean, bn.running_var
         g, beta = bn.weight, bn.bias
-        scale = (g * inv).view(1, Co, 1)
-        shift = (beta - g * inv * mean).view(1, Co, 1)
-        gate = se.gate(u.mean(dim=(2, 3)) * scale.squeeze(-1) + shift.squeeze(-1)).unsqueeze(-1)   # [B,Co,1], in (0,1)
-        ustar = torch.where((g > 0).view(1, Co, 1), u.amax(-1), u.amin(-1))                            # monotone through BN.SE.LReLU
-        out = F.leaky_relu(gate * (ustar * scale + shift), 0.2)
+        scale = g * torch.rsqrt(var + bn.eps)                      # [Co]
+        shift = beta - scale * mean
+        gate = se.gate((S1 / (N * k)).to(x.dtype) * scale + shift)  # [B,Co] in (0,1): SE squeeze = mean_{N,k} BN(u)
+        ustar = torch.where((g > 0).view(1, Co, 1), umax, umin)    # max_k commutes with the monotone BN.SE.LeakyReLU tail
+        out = fused.row_affine_act(ustar, gate * scale, gate * shift, slope=0.2)
         if res is not None:
             out = out + y[:, 2 * Co:]
         return out
@@ -142,9 +162,9 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         x3 = self._edge_block(x2, self.conv3, self.bn3, self.se3, self.resconv2)
         x4 = self._edge_block(x3, self.conv4, self.bn4, self.se4, self.resconv3)
         h = torch.matmul(self.conv5.weight.squeeze(-1), torch.cat((x1, x2, x3, x4), dim=1))
-        mean, var = _bn_stats(self.bn5, h, (0, 2))
+        mean, var, _ = _channel_stats(self.bn5, h)
         scale = self.bn5.weight * torch.rsqrt(var + self.bn5.eps)
-        h = F.leaky_relu(h * scale.view(1, -1, 1) + (self.bn5.bias - scale * mean).view(1, -1, 1), 0.2)
+        h = fused.row_affine_act(h, scale.expand(B, -1), (self.bn5.bias - scale * mean).expand(B, -1), slope=0.2)
         return torch.cat((h.amax(2), h.mean(2)), 1).view(B, self.output_size)
 
 
@@ -249,11 +269,13 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             mu = bt.mean(-1, keepdim=True).expand(P, -1, -1)                  # x_hat has zero mean over the points
             var = (wt * wt * v + bt * bt).mean(-1, keepdim=True) - mu * mu
             n = wsty.size(0) * (self.num_points // self.n_primitives)
-            with torch.no_grad():
-                for p, b in enumerate(bns):
-                    b.running_mean.mul_(1 - MOMENTUM).add_(mu[p, :, 0], alpha=MOMENTUM)
-                    b.running_var.mul_(1 - MOMENTUM).add_(var[p, :, 0] * (n / max(n - 1, 1)), alpha=MOMENTUM)
-                    b.num_batches_tracked.add_(1)
+            with torch.no_grad():                                             # 32 primitives' running statistics in 5 launches
+                rms, rvs = [b.running_mean for b in bns], [b.running_var for b in bns]
+                torch._foreach_mul_(rms, 1 - MOMENTUM)
+                torch._foreach_add_(rms, list(mu[:, :, 0].detach().unbind(0)), alpha=MOMENTUM)
+                torch._foreach_mul_(rvs, 1 - MOMENTUM)
+                torch._foreach_add_(rvs, list((var[:, :, 0].detach() * (n / max(n - 1, 1))).unbind(0)), alpha=MOMENTUM)
+                torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
         else:
             mu = torch.stack([b.running_mean for b in bns]).unsqueeze(-1)
             var = torch.stack([b.running_var for b in bns]).unsqueeze(-1)
@@ -276,23 +298,38 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             sty.append((params[:, off + nf:off + 2 * nf], params[:, off:off + nf]))
             off += 2 * nf
         # layer 1: the input lattice is constant, so the instance-normalised activations are batch independent
+        # Channel counts are padded to multiples of 8 (1026 -> 1032, 513 -> 520) with all-zero channels so every GEMM
+        # operand row is 16-byte aligned for the tensor-core kernels; padded channels stay exactly zero end to end.
+        def pad8(n):
+            return (n + 7) // 8 * 8
+
+        def padc(t, cp):                                                      # zero-pad dim 1 of a small tensor
+            return t if t.size(1) == cp else F.pad(t, (0, 0) * (t.dim() - 2) + (0, cp - t.size(1)))
+
+        C1 = sizes[0]
         W1 = self._stack(lambda d: d.conv1.weight.squeeze(-1))                # [P,1026,2] (bias cancels under instance norm)
-        h = torch.matmul(W1, self._grid_t)                                    # [P,1026,pts]
+        h = torch.matmul(W1, self._grid_t)                                    # [P,1026,pts], batch independent
         var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
         xhat = (h - mean) * torch.rsqrt(var + EPS)
         A, D = self._bn_se(1, sty[0][0], sty[0][1], var / (var + EPS))
-        x = torch.relu(A.unsqueeze(-1) * xhat.unsqueeze(2) + D.unsqueeze(-1))  # [P,1026,B,pts]
+        cp = pad8(C1)
+        x = fused.row_affine_act(padc(xhat, cp), padc(A, cp), padc(D, cp), in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D)
+        cin = C1
         for layer, name in ((2, "conv2"), (3, "conv3")):
             W = self._stack(lambda d: getattr(d, name).weight.squeeze(-1))    # [P,Cout,Cin]
-            h = torch.bmm(W, x.reshape(P, x.size(1), B * npts)).view(P, -1, B, npts)
-            var, mean = torch.var_mean(h, dim=3, unbiased=False)              # per (primitive, channel, sample)
+            cout = W.size(1)
+            cop = pad8(cout)
+            Wp = F.pad(W, (0, cp - cin, 0, cop - cout))                       # zero rows / columns for the padded channels
+            h = torch.bmm(Wp, x.view(P, cp, B * npts)).view(P, cop, B, npts)
+            mean, var = fused.row_stats(h)                                    # per (primitive, channel, sample)
             rstd = torch.rsqrt(var + EPS)
-            A, D = self._bn_se(layer, sty[layer - 1][0], sty[layer - 1][1], var / (var + EPS))
-            sc = A * rstd
-            x = torch.relu(sc.unsqueeze(-1) * h + (D - sc * mean).unsqueeze(-1))
-        W4 = self._stack(lambda d: d.conv4.weight.squeeze(-1))                # [P,3,256]
+            A, D = self._bn_se(layer, sty[layer - 1][0], sty[layer - 1][1], (var / (var + EPS))[:, :cout])
+            sc = padc(A, cop) * rstd
+            x = fused.row_affine_act(h, sc, padc(D, cop) - sc * mean)
+            cin, cp = cout, cop
+        W4 = F.pad(self._stack(lambda d: d.conv4.weight.squeeze(-1)), (0, cp - cin))   # [P,3,256]
         b4 = self._stack(lambda d: d.conv4.bias).view(P, 3, 1)
-        out = torch.tanh(torch.bmm(W4, x.reshape(P, x.size(1), B * npts)) + b4).view(P, 3, B, npts)
+        out = torch.tanh(torch.bmm(W4, x.view(P, cp, B * npts)) + b4).view(P, 3, B, npts)
         return out.permute(2, 1, 0, 3).reshape(B, 3, P * npts).contiguous()   # primitive i owns points [512 i, 512 (i+1))
 
 
@@ -322,21 +359,22 @@ class PointNetRes(nn.Module):  # reference :582-646
     @staticmethod
     def _bn_se_relu(h, bn, se):
         """relu(SE(BN(h))) as one per-(sample,channel) scale/shift: h [B,C,N]."""
-        mean, var = _bn_stats(bn, h, (0, 2))
+        mean, var, m_bc = _channel_stats(bn, h)
         inv = torch.rsqrt(var + bn.eps)
         scale, shift = bn.weight * inv, bn.bias - bn.weight * inv * mean      # [C]
-        gate = se.gate(h.mean(2) * scale + shift)                              # [B,C]
-        return torch.relu(h * (gate * scale).unsqueeze(-1) + (gate * shift).unsqueeze(-1))
+        gate = se.gate(m_bc * scale + shift)                                   # [B,C]: SE squeeze = mean over points of BN(h)
+        return fused.row_affine_act(h, gate * scale, gate * shift)
 
     def forward(self, x):
         x = self._bn_se_relu(torch.matmul(self.conv1.weight.squeeze(-1), x) + self.conv1.bias.view(1, -1, 1), self.bn1, self.se1)
         pointfeat = x
         x = self._bn_se_relu(torch.matmul(self.conv2.weight.squeeze(-1), x) + self.conv2.bias.view(1, -1, 1), self.bn2, self.se2)
         h3 = torch.matmul(self.conv3.weight.squeeze(-1), x) + self.conv3.bias.view(1, -1, 1)   # [B,1024,N]
-        mean, var = _bn_stats(self.bn3, h3, (0, 2))
+        mean, var, _ = _channel_stats(self.bn3, h3)
         inv = torch.rsqrt(var + self.bn3.eps)
         g3 = self.bn3.weight
-        hstar = torch.where((g3 > 0).view(1, -1), h3.amax(2), h3.amin(2))     # max_N BN(h3) only needs max/min of h3
+        hmax, hmin = fused.row_minmax(h3)
+        hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin)                 # max_N BN(h3) only needs max/min of h3
         glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
         W4 = self.conv4.weight.squeeze(-1)
         h4 = torch.matmul(W4[:, 1024:], pointfeat) + (torch.matmul(glob, W4[:, :1024].t()) + self.conv4.bias).unsqueeze(-1)

@@ -1,0 +1,37 @@
+"""Plain PyTorch definitions of the fused generator kernels (sparenet_b200/fused.py) -- TEST INFRASTRUCTURE ONLY.
+They specify what snb_edge_reduce_* / snb_row_* must compute: used (a) to monkeypatch the kernels away so the
+generator algebra can be verified on CPU, (b) as the fp32/fp64 reference the CUDA kernels are compared with on the GPU."""
+import torch
+import torch.nn.functional as F
+
+
+def edge_reduce(a, c, idx):
+    B, C, N = a.shape
+    k = idx.shape[2]
+    u = torch.gather(a, 2, idx.long().reshape(B, 1, N * k).expand(-1, C, -1)).view(B, C, N, k) + c.unsqueeze(-1)
+    ud = u.double()
+    return u.amax(-1), u.amin(-1), ud.sum((2, 3)), (ud * ud).sum((2, 3))
+
+
+def row_stats(h):
+    var, mean = torch.var_mean(h, dim=-1, unbiased=False)
+    return mean, var
+
+
+def row_affine_act(h, scale, shift, slope=0.0, in_div=1, out_shape=None):
+    L = h.shape[-1]
+    hin = h.reshape(-1, L)
+    if in_div > 1:
+        hin = hin.repeat_interleave(in_div, 0)
+    y = F.leaky_relu(hin * scale.reshape(-1, 1) + shift.reshape(-1, 1), slope)
+    return y.view(tuple(out_shape) if out_shape is not None else h.shape)
+
+
+def row_minmax(h):
+    return h.amax(-1), h.amin(-1)
+
+
+def patch(monkeypatch):
+    from sparenet_b200 import fused
+    for name in ("edge_reduce", "row_stats", "row_affine_act", "row_minmax"):
+        monkeypatch.setattr(fused, name, globals()[name])

@@ -23,6 +23,8 @@ def cpu_point_ops(monkeypatch):
     monkeypatch.setattr(F_, "mds_sample", lambda xyz, m, mml: oracle.mds(xyz.contiguous(), m, mml.contiguous()))
     monkeypatch.setattr(F_, "gather_forward", lambda f, idx: oracle.gather_fwd(f.contiguous(), idx))
     monkeypatch.setattr(F_, "gather_backward", lambda g, idx, n: oracle.gather_bwd(g.contiguous(), idx, n))
+    from tests import fused_ref
+    fused_ref.patch(monkeypatch)        # the fused CUDA kernels -> their plain PyTorch definitions (test only)
     import sparenet_b200.dropin.cuda.expansion_penalty.expansion_penalty_module as E
     monkeypatch.setattr(E.torch.Tensor, "cuda", lambda self, *a, **k: self)   # the wrapper forces .cuda() like the reference
     yield

@@ -1,0 +1,82 @@
+"""GPU tests of the fused generator kernels (snb_edge_reduce_*, snb_row_*) through their autograd Functions, against the
+plain PyTorch definitions in tests/fused_ref.py evaluated in float64.  Floating point: <= 1e-5 relative."""
+import pytest
+import torch
+
+from tests import fused_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rtol=1e-5, atol=1e-6):
+    b = b.to(a.dtype)
+    return torch.allclose(a, b, rtol=rtol, atol=atol * (b.abs().max().item() + 1e-30))
+
+
+@pytest.mark.parametrize("B,C,N,k", [(2, 5, 300, 8), (3, 64, 2048, 8), (1, 16, 97, 3), (2, 8, 4096, 16)])
+def test_edge_reduce_forward_backward(cuda, B, C, N, k):
+    from sparenet_b200 import fused
+    torch.manual_seed(B * 1000 + N)
+    a = torch.randn(B, C, N, device=cuda)
+    c = torch.randn(B, C, N, device=cuda)
+    idx = torch.stack([torch.stack([torch.randperm(N, device=cuda)[:k] for _ in range(N)]) for _ in range(B)]).int()
+    a1, c1 = a.clone().requires_grad_(), c.clone().requires_grad_()
+    a2, c2 = a.double().requires_grad_(), c.double().requires_grad_()
+    o1 = fused.edge_reduce(a1, c1, idx)
+    o2 = R.edge_reduce(a2, c2, idx)
+    assert torch.equal(o1[0], o2[0].float()) and torch.equal(o1[1], o2[1].float())      # max/min of fp32 sums: exact
+    assert _close(o1[2], o2[2], 1e-6) and _close(o1[3], o2[3], 1e-6)
+    w = [torch.randn_like(t) for t in o1]
+    sum((x * y).sum() for x, y in zip(o1, w)).backward()
+    sum((x * y.double()).sum() for x, y in zip(o2, w)).backward()
+    assert _close(a1.grad, a2.grad, 2e-5, 1e-5) and _close(c1.grad, c2.grad, 2e-5, 1e-5)
+
+
+@pytest.mark.parametrize("shape", [(4, 7, 512), (3, 5, 2048), (2, 3, 333), (1, 2, 16384), (6, 1)])
+def test_row_stats_forward_backward(cuda, shape):
+    from sparenet_b200 import fused
+    torch.manual_seed(sum(shape))
+    h = torch.randn(*shape, device=cuda) * 0.3 + 5.0            # large mean / small spread: the cancellation-prone case
+    h1, h2 = h.clone().requires_grad_(), h.double().requires_grad_()
+    m1, v1 = fused.row_stats(h1)
+    m2, v2 = R.row_stats(h2)
+    assert _close(m1, m2, 1e-6) and _close(v1, v2, 1e-5)
+    wm, wv = torch.randn_like(m1), torch.randn_like(v1)
+    ((m1 * wm).sum() + (v1 * wv).sum()).backward()
+    ((m2 * wm.double()).sum() + (v2 * wv.double()).sum()).backward()
+    assert _close(h1.grad, h2.grad, 1e-5, 1e-6)
+
+
+@pytest.mark.parametrize("rows,L,in_div,slope", [((4, 6), 512, 1, 0.0), ((3, 5), 2048, 1, 0.2), ((2, 9), 333, 1, 0.0),
+                                                ((3, 4), 512, 5, 0.0), ((2, 3), 100, 4, 0.2)])
+def test_row_affine_act_forward_backward(cuda, rows, L, in_div, slope):
+    from sparenet_b200 import fused
+    torch.manual_seed(L + in_div)
+    h = torch.randn(*rows, L, device=cuda)
+    R_out = rows[0] * rows[1] * in_div
+    sc = torch.randn(R_out, device=cuda)
+    sh = torch.randn(R_out, device=cuda) * 0.5
+    out_shape = (*rows, in_div, L) if in_div > 1 else (*rows, L)
+    t1 = [t.clone().requires_grad_() for t in (h, sc, sh)]
+    t2 = [t.double().requires_grad_() for t in (h, sc, sh)]
+    y1 = fused.row_affine_act(t1[0], t1[1], t1[2], slope=slope, in_div=in_div, out_shape=out_shape)
+    y2 = R.row_affine_act(t2[0], t2[1], t2[2], slope=slope, in_div=in_div, out_shape=out_shape)
+    assert y1.shape == y2.shape and _close(y1, y2, 1e-6)
+    w = torch.randn_like(y1)
+    (y1 * w).sum().backward()
+    (y2 * w.double()).sum().backward()
+    for a, b in zip(t1, t2):
+        assert _close(a.grad, b.grad, 2e-5, 2e-6)
+
+
+def test_row_minmax(cuda):
+    from sparenet_b200 import fused
+    torch.manual_seed(3)
+    h = torch.randn(5, 33, 1000, device=cuda)
+    h[0, 0, 10] = h[0, 0, 500] = 9.0                            # tie: the first position takes the gradient
+    h1 = h.clone().requires_grad_()
+    vmax, vmin = fused.row_minmax(h1)
+    assert torch.equal(vmax, h.amax(-1)) and torch.equal(vmin, h.amin(-1))
+    (vmax.sum() + 2 * vmin.sum()).backward()
+    assert h1.grad[0, 0, 10] == 1 and h1.grad[0, 0, 500] == 0
+    assert h1.grad.sum().item() == pytest.approx(3 * 5 * 33)
