@@ -165,7 +165,7 @@ def build_gpu(args, dev, rank):
                             use_AdaIn="share", encode="Residualnet")
     net.apply(init_weights)
     net = net.to(dev).train()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9), fused=True)
     cd_mean, cd = ChamferDistanceMean(), ChamferDistance()
     B = args.batch
     gp = torch.Generator().manual_seed(1 + 100 * rank)

@@ -7,6 +7,7 @@
 // Defined arithmetic: d(i,j) = sum_c (x[c,j]-x[c,i])^2 accumulated with FMAs in ascending c, fp32;
 // ordering (d, j) lexicographic, i.e. ties go to the smaller index.
 //
+// The matrix is symmetric bit for bit, so only upper-triangular tiles are evaluated and mirrored.
 // Two kernels: (1) a register-tiled 128x128 SIMT distance kernel on the channel-major [B,C,N] layout the
 // encoder already uses (coalesced loads, 8x8 outputs per thread, direct-difference form -- the
 // |a|^2+|b|^2-2ab GEMM form would lose the exact ordering to cancellation); (2) a warp-per-row top-k.
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(256) knn_dist_kernel(const float* __restrict__
   __shared__ __align__(16) float sa[KNN_KT][KNN_BT];
   __shared__ __align__(16) float sb[KNN_KT][KNN_BT];
   const int b = blockIdx.z;
+  if (blockIdx.x < blockIdx.y) return;  // d(i,j) == d(j,i) bit for bit ((-t)^2 == t^2): only upper-triangular tiles compute
   const int i0 = blockIdx.y * KNN_BT, j0 = blockIdx.x * KNN_BT;
   const float* __restrict__ xb = x + (size_t)b * C * N;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 8 x 8 outputs each
@@ -72,6 +74,22 @@ __global__ void __launch_bounds__(256) knn_dist_kernel(const float* __restrict__
 #pragma unroll
       for (int c = 0; c < 8; c++)
         if (j + c < N) Db[(size_t)i * N + j + c] = acc[r][c];
+    }
+  }
+  if (blockIdx.x == blockIdx.y) return;
+  // mirror tile: D[j0+.., i0+..] = acc^T; for a fixed column c the 8 rows r are contiguous in memory
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int j = j0 + tx * 8 + c;
+    if (j >= N) continue;
+    const int i = i0 + ty * 8;
+    if (i + 7 < N && ((N & 3) == 0)) {
+      *reinterpret_cast<float4*>(&Db[(size_t)j * N + i]) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      *reinterpret_cast<float4*>(&Db[(size_t)j * N + i + 4]) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (i + r < N) Db[(size_t)j * N + i + r] = acc[r][c];
     }
   }
 }

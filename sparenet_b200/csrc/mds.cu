@@ -13,9 +13,11 @@
 //
 // Design: the m-1 rounds are a latency chain, so the only lever is the time of ONE round.  A thread-block
 // CLUSTER (up to 8 CTAs = 8 SMs) owns one sample; every point (xyz + density) lives in registers for the
-// whole kernel; a round is: register update -> packed (density,key) u64 warp arg-min by shuffles -> one
-// DSMEM store per warp into every CTA of the cluster -> ONE cluster barrier -> local 64-entry reduce.
-// No global or shared-memory traffic for `temp`, no block barriers (the reference does 11 per round).
+// whole kernel; a round is: register update -> packed (density,key) u64 warp arg-min by shuffles -> each warp
+// pushes its candidate (+ coordinates) into every CTA of the cluster with st.async, which also completes tx-bytes
+// on the peer's mbarrier -> every warp waits on its own CTA's mbarrier and reduces the <= 128 candidates.
+// No global/shared traffic for `temp`, no block barrier, no barrier.cluster and no global load inside the loop
+// (the reference does 11 block barriers and a global read-modify-write of `temp` per round).
 #include <math.h>
 #include "common.cuh"
 
@@ -26,11 +28,28 @@ constexpr int MDS_WARPS = MDS_THREADS / 32;
 constexpr int MDS_MAX_CLUSTER = 8;
 constexpr unsigned long long MDS_NONE = 0xffffffffffffffffull;
 
+// DSMEM message of one warp for one round: packed (density bits, tie key) + the candidate's coordinates.
+// st.async writes the payload into the peer CTA's shared memory AND completes the same number of tx-bytes on the
+// peer's mbarrier, so data and "it arrived" are one instruction; nobody executes barrier.cluster inside the loop.
+__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, unsigned long long v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(v), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4f32(uint32_t remote_addr, float a, float b, float c, float d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(remote_addr), "f"(a),
+               "f"(b), "f"(c), "f"(d), "r"(remote_bar)
+               : "memory");
+}
+
+constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_WARPS;  // 128 candidate slots per parity
+
 template <int PT>
 __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
                                                                       const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
                                                                       int bs_mask, int bs_log2) {
-  __shared__ __align__(16) unsigned long long slots[2][MDS_MAX_CLUSTER * MDS_WARPS];
+  __shared__ __align__(16) unsigned long long packs[2][MDS_SLOTS];
+  __shared__ __align__(16) float4 coords[2][MDS_SLOTS];
+  __shared__ __align__(8) uint64_t bars[2];
   const uint32_t cs = cluster_nctarank();
   const uint32_t rank = cluster_ctarank();
   const int b = blockIdx.x / cs;
@@ -50,21 +69,39 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
     x[i] = ok ? dataset[k * 3 + 0] : 0.f;
     y[i] = ok ? dataset[k * 3 + 1] : 0.f;
     z[i] = ok ? dataset[k * 3 + 2] : 0.f;
-    temp[i] = ok ? (k == 0 ? 1e9f : 0.f) : 2e9f;  // out-of-range slots can never win
+    temp[i] = ok ? (k == 0 ? 1e9f : 0.f) : 2e9f;  // out-of-range slots sit above every real density: they can never win
   }
   const float mml = mean_mst_length[b];
   const float t = (float)(5.0 * (double)mml * (double)mml);
 
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
   if (rank == 0 && tid == 0) idxs[0] = 0;
-  int old = 0;
   float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];
-
-  // everybody's slots must exist before the first remote store
+  // peers must see initialised barriers before the first remote complete_tx
   cluster_sync_all();
 
-  const uint32_t slot_base = smem_u32(&slots[0][0]);
+  // per-lane remote addresses (lane r < cs talks to CTA r): this warp's slot in both parities + the two barriers
+  const uint32_t my_slot = rank * MDS_WARPS + warp;
+  uint32_t r_pack[2], r_coord[2], r_bar[2];
+#pragma unroll
+  for (int par = 0; par < 2; par++) {
+    const uint32_t dst = lane < (int)cs ? (uint32_t)lane : 0u;
+    r_pack[par] = mapa_shared(smem_u32(&packs[par][my_slot]), dst);
+    r_coord[par] = mapa_shared(smem_u32(&coords[par][my_slot]), dst);
+    r_bar[par] = mapa_shared(smem_u32(&bars[par]), dst);
+  }
+  const uint32_t round_bytes = cs * MDS_WARPS * 24u;
+  const int total = cs * MDS_WARPS;
+
   for (int j = 1; j < m; j++) {
+    const int par = j & 1;
+    if (tid == 0) mbar_expect_tx(&bars[par], round_bytes);  // arm this round's phase (the single expected arrival)
     unsigned long long best = MDS_NONE;
+    int bi = 0;
 #pragma unroll
     for (int i = 0; i < PT; i++) {
       const int k = kbeg + tid + i * MDS_THREADS;
@@ -74,34 +111,62 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
       const float v = __fadd_rn(temp[i], w);
       temp[i] = v;
       const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
-      const unsigned key = (rev << 21) | (unsigned)k;
-      const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key;
-      if (v < 1e9f && p < best) best = p;
+      const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | ((rev << 21) | (unsigned)k);
+      if (p < best) {  // densities are >= 0, so the u64 order is (density, tie key) lexicographic; parked points hold 1e9
+        best = p;
+        bi = i;
+      }
     }
+    unsigned long long wbest = best;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other < best ? other : best;
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
+      wbest = other < wbest ? other : wbest;
     }
-    const int par = j & 1;
-    if (lane < (int)cs) {  // lane r publishes this warp's candidate into CTA r
-      const uint32_t local = slot_base + (uint32_t)((par * MDS_MAX_CLUSTER * MDS_WARPS + rank * MDS_WARPS + warp) * 8);
-      st_cluster_u64(mapa_shared(local, (uint32_t)lane), best);
+    // the lane that owns the warp's candidate supplies its coordinates
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+    for (int i = 0; i < PT; i++)
+      if (i == bi) { cx = x[i]; cy = y[i]; cz = z[i]; }
+    const int owner = __ffs(__ballot_sync(0xffffffffu, best == wbest)) - 1;
+    cx = __shfl_sync(0xffffffffu, cx, owner);
+    cy = __shfl_sync(0xffffffffu, cy, owner);
+    cz = __shfl_sync(0xffffffffu, cz, owner);
+    if (lane < (int)cs) {
+      st_async_b64(r_pack[par], wbest, r_bar[par]);
+      st_async_v4f32(r_coord[par], cx, cy, cz, 0.f, r_bar[par]);
     }
-    cluster_sync_all();
-    // reduce cs*MDS_WARPS candidates (<= 128): each lane takes up to 4
-    unsigned long long g = MDS_NONE;
-    const int total = cs * MDS_WARPS;
-    for (int e = lane; e < total; e += 32) {
-      const unsigned long long c = slots[par][e];  // entries [0, cs*MDS_WARPS) are contiguous by (rank, warp)
-      g = c < g ? c : g;
+    mbar_wait_cluster(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);  // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
+    // every warp reduces the cs*16 candidates redundantly (<= 128: up to 4 per lane)
+    unsigned long long c[4], g = MDS_NONE;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = lane + 32 * q;
+      c[q] = e < total ? packs[par][e] : MDS_NONE;
+      g = c[q] < g ? c[q] : g;
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, g, o);
       g = other < g ? other : g;
     }
-    old = (g == MDS_NONE) ? 0 : (int)((unsigned)g & 0x1fffffu);
+    int wq = -1;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (c[q] == g && wq < 0) wq = q;
+    const int src = __ffs(__ballot_sync(0xffffffffu, wq >= 0)) - 1;
+    float4 wc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == src) wc = coords[par][lane + 32 * wq];
+    x1 = __shfl_sync(0xffffffffu, wc.x, src);
+    y1 = __shfl_sync(0xffffffffu, wc.y, src);
+    z1 = __shfl_sync(0xffffffffu, wc.z, src);
+    int old = (int)((unsigned)g & 0x1fffffu);
+    if ((unsigned)(g >> 32) >= 0x4e6e6b28u) {  // >= 1e9f: every point is parked -> the reference returns index 0 (MDS_cuda.cu:121-133)
+      old = 0;
+      x1 = __ldg(&dataset[0]);
+      y1 = __ldg(&dataset[1]);
+      z1 = __ldg(&dataset[2]);
+    }
     if (rank == 0 && tid == 0) idxs[j] = old;
     // park the chosen point (the owner thread finds it among its registers)
     {
@@ -113,11 +178,8 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
           if (i == slot) temp[i] = 1e9f;
       }
     }
-    x1 = __ldg(&dataset[old * 3 + 0]);
-    y1 = __ldg(&dataset[old * 3 + 1]);
-    z1 = __ldg(&dataset[old * 3 + 2]);
   }
-  // no CTA may exit while a peer can still store into its shared memory
+  // no CTA may exit while a peer can still write into its shared memory
   cluster_sync_all();
 }
 

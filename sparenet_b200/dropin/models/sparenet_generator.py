@@ -77,10 +77,13 @@ def _bn_stats(bn, x, dims):
     return bn.running_mean, bn.running_var
 
 
-def _channel_stats(bn, h):
-    """BatchNorm1d statistics of h [B,C,N] from one fused row pass: per-(b,c) mean/var -> per-channel mean / biased var.
+def _channel_stats(bn, h, row_bias=None):
+    """BatchNorm1d statistics of (h + row_bias) for h [B,C,N] from one fused row pass: per-(b,c) mean/var -> per-channel
+    mean / biased var.  row_bias ([C] or [B,C]) is constant along N, so it only shifts the row means.
     Returns (mean [C], var [C], row_mean [B,C]); running statistics are advanced in train mode."""
     m_bc, v_bc = fused.row_stats(h)
+    if row_bias is not None:
+        m_bc = m_bc + row_bias
     if bn.training:
         mean = m_bc.mean(0)
         dm = m_bc - mean
@@ -132,11 +135,11 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         idx = F_.knn_indices(x.contiguous(), k)                    # [B,N,k] int32, sm_100a brute force (snb_knn)
         W = conv.weight.view(conv.out_channels, 2 * C)
         Wa, Wb = W[:, :C], W[:, C:]
-        Wcat = torch.cat((Wa, Wb - Wa) if res is None else (Wa, Wb - Wa, res.weight.view(res.out_channels, C)), 0)
-        y = torch.matmul(Wcat, x)                                  # one per-point GEMM: [B, 2Cout(+Cres), N]
         Co = conv.out_channels
+        a = F.conv1d(x, Wa.unsqueeze(-1))                          # per-POINT 1x1 convs (k x fewer flops than per edge)
+        c = F.conv1d(x, (Wb - Wa).unsqueeze(-1))
         # u[b,c,i,m] = a[b,c,idx[b,i,m]] + c[b,c,i] is never formed: the fused kernel returns its max/min over m and its moments
-        umax, umin, S1, S2 = fused.edge_reduce(y[:, :Co], y[:, Co:2 * Co], idx)
+        umax, umin, S1, S2 = fused.edge_reduce(a, c, idx)
         n = B * N * k
         if bn.training:
             mean64 = S1.sum(0) / n
@@ -152,7 +155,7 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         ustar = torch.where((g > 0).view(1, Co, 1), umax, umin)    # max_k commutes with the monotone BN.SE.LeakyReLU tail
         out = fused.row_affine_act(ustar, gate * scale, gate * shift, slope=0.2)
         if res is not None:
-            out = out + y[:, 2 * Co:]
+            out = out + res(x)
         return out
 
     def forward(self, x):
@@ -161,7 +164,7 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         x2 = self._edge_block(x1, self.conv2, self.bn2, self.se2, self.resconv1)
         x3 = self._edge_block(x2, self.conv3, self.bn3, self.se3, self.resconv2)
         x4 = self._edge_block(x3, self.conv4, self.bn4, self.se4, self.resconv3)
-        h = torch.matmul(self.conv5.weight.squeeze(-1), torch.cat((x1, x2, x3, x4), dim=1))
+        h = self.conv5(torch.cat((x1, x2, x3, x4), dim=1))
         mean, var, _ = _channel_stats(self.bn5, h)
         scale = self.bn5.weight * torch.rsqrt(var + self.bn5.eps)
         h = fused.row_affine_act(h, scale.expand(B, -1), (self.bn5.bias - scale * mean).expand(B, -1), slope=0.2)
@@ -357,31 +360,34 @@ class PointNetRes(nn.Module):  # reference :582-646
         self.th = nn.Tanh()
 
     @staticmethod
-    def _bn_se_relu(h, bn, se):
-        """relu(SE(BN(h))) as one per-(sample,channel) scale/shift: h [B,C,N]."""
-        mean, var, m_bc = _channel_stats(bn, h)
+    def _bn_se_relu(h, bn, se, row_bias):
+        """relu(SE(BN(h + row_bias))) as ONE per-(sample,channel) scale/shift over h [B,C,N]; row_bias ([C] conv bias or
+        [B,C]) is never added to the activations: it only shifts the statistics and folds into the shift."""
+        mean, var, m_bc = _channel_stats(bn, h, row_bias)
         inv = torch.rsqrt(var + bn.eps)
         scale, shift = bn.weight * inv, bn.bias - bn.weight * inv * mean      # [C]
-        gate = se.gate(m_bc * scale + shift)                                   # [B,C]: SE squeeze = mean over points of BN(h)
-        return fused.row_affine_act(h, gate * scale, gate * shift)
+        gate = se.gate(m_bc * scale + shift)                                   # [B,C]: SE squeeze = mean over points of BN(.)
+        gs = gate * scale
+        return fused.row_affine_act(h, gs, gate * shift + row_bias * gs)
 
     def forward(self, x):
-        x = self._bn_se_relu(torch.matmul(self.conv1.weight.squeeze(-1), x) + self.conv1.bias.view(1, -1, 1), self.bn1, self.se1)
+        B = x.size(0)
+        x = self._bn_se_relu(F.conv1d(x, self.conv1.weight), self.bn1, self.se1, self.conv1.bias)
         pointfeat = x
-        x = self._bn_se_relu(torch.matmul(self.conv2.weight.squeeze(-1), x) + self.conv2.bias.view(1, -1, 1), self.bn2, self.se2)
-        h3 = torch.matmul(self.conv3.weight.squeeze(-1), x) + self.conv3.bias.view(1, -1, 1)   # [B,1024,N]
-        mean, var, _ = _channel_stats(self.bn3, h3)
+        x = self._bn_se_relu(F.conv1d(x, self.conv2.weight), self.bn2, self.se2, self.conv2.bias)
+        h3 = F.conv1d(x, self.conv3.weight)                                    # [B,1024,N]; the bias is folded below
+        mean, var, _ = _channel_stats(self.bn3, h3, self.conv3.bias)
         inv = torch.rsqrt(var + self.bn3.eps)
         g3 = self.bn3.weight
         hmax, hmin = fused.row_minmax(h3)
-        hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin)                 # max_N BN(h3) only needs max/min of h3
+        hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin) + self.conv3.bias   # max_N BN(h3) only needs max/min of h3
         glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
-        W4 = self.conv4.weight.squeeze(-1)
-        h4 = torch.matmul(W4[:, 1024:], pointfeat) + (torch.matmul(glob, W4[:, :1024].t()) + self.conv4.bias).unsqueeze(-1)
-        x = self._bn_se_relu(h4, self.bn4, self.se4)
-        x = self._bn_se_relu(torch.matmul(self.conv5.weight.squeeze(-1), x) + self.conv5.bias.view(1, -1, 1), self.bn5, self.se5)
-        x = self._bn_se_relu(torch.matmul(self.conv6.weight.squeeze(-1), x) + self.conv6.bias.view(1, -1, 1), self.bn6, self.se6)
-        return self.th(torch.matmul(self.conv7.weight.squeeze(-1), x) + self.conv7.bias.view(1, -1, 1))
+        W4 = self.conv4.weight
+        pb = F.linear(glob, W4[:, :1024, 0], self.conv4.bias)                 # [B,512]: the broadcast global half of conv4
+        x = self._bn_se_relu(F.conv1d(pointfeat, W4[:, 1024:].contiguous()), self.bn4, self.se4, pb)
+        x = self._bn_se_relu(F.conv1d(x, self.conv5.weight), self.bn5, self.se5, self.conv5.bias)
+        x = self._bn_se_relu(F.conv1d(x, self.conv6.weight), self.bn6, self.se6, self.conv6.bias)
+        return self.th(self.conv7(x))
 
 
 class SpareNetRefine(nn.Module):  # reference :530-579

@@ -58,6 +58,9 @@ def _ws(nbytes, device):
 
 
 # ----------------------------------------------------------------------------- Chamfer
+_CHAMFER_MEMO = {}
+
+
 def chamfer_forward(xyz1, xyz2):
     xyz1, xyz2 = _cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2")
     if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
@@ -65,12 +68,22 @@ def chamfer_forward(xyz1, xyz2):
     B, N, _ = xyz1.shape
     M = xyz2.shape[1]
     dev = xyz1.device
+    # The training loss evaluates Chamfer(refine, gt) twice in a row (ChamferDistanceMean, then the consistency term,
+    # runners/sparenet_runner.py:87,103): a one-entry memo on the very same, unmodified tensors skips the second N x M search.
+    # The entry keeps references to its inputs, so their storage cannot be recycled while it is alive.
+    c = _CHAMFER_MEMO
+    key = (xyz1.data_ptr(), xyz1._version, tuple(xyz1.shape), xyz2.data_ptr(), xyz2._version, tuple(xyz2.shape),
+           torch.cuda.current_stream(dev).cuda_stream)
+    if c.get("key") == key:
+        return tuple(t.detach() for t in c["out"])     # fresh aliases: each autograd node owns its output objects
     d1 = torch.empty(B, N, device=dev)
     d2 = torch.empty(B, M, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
     i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev), _op("chamfer_fwd", 1):
         check(_lib.load().snb_chamfer_fwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), stream_ptr()), "chamfer_fwd")
+    c.clear()
+    c.update(key=key, keep=(xyz1, xyz2), out=(d1, d2, i1, i2))
     return d1, d2, i1, i2
 
 

@@ -29,7 +29,10 @@ def test_edge_reduce_forward_backward(cuda, B, C, N, k):
     w = [torch.randn_like(t) for t in o1]
     sum((x * y).sum() for x, y in zip(o1, w)).backward()
     sum((x * y.double()).sum() for x, y in zip(o2, w)).backward()
-    assert _close(a1.grad, a2.grad, 2e-5, 1e-5) and _close(c1.grad, c2.grad, 2e-5, 1e-5)
+    ea = (a1.grad.double() - a2.grad).abs().max().item() / a2.grad.abs().max().item()
+    ec = (c1.grad.double() - c2.grad).abs().max().item() / c2.grad.abs().max().item()
+    print(f"[edge_reduce] B={B} C={C} N={N} k={k}: max grad err / scale  a={ea:.2e} c={ec:.2e}")
+    assert ea < 1e-5 and ec < 1e-5      # fp32 accumulation of ~k terms per point against float64
 
 
 @pytest.mark.parametrize("shape", [(4, 7, 512), (3, 5, 2048), (2, 3, 333), (1, 2, 16384), (6, 1)])
