@@ -43,48 +43,38 @@ __device__ __forceinline__ void st_async_v4f32(uint32_t remote_addr, float a, fl
 
 constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_WARPS;  // 128 candidate slots per parity
 
-template <int PT>
-__global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
-                                                                      const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
-                                                                      int bs_mask, int bs_log2) {
-  __shared__ __align__(16) unsigned long long packs[2][MDS_SLOTS];
-  __shared__ __align__(16) float4 coords[2][MDS_SLOTS];
-  __shared__ __align__(8) uint64_t bars[2];
-  const uint32_t cs = cluster_nctarank();
-  const uint32_t rank = cluster_ctarank();
-  const int b = blockIdx.x / cs;
+// The round loop is issue bound (4 warps per scheduler, every instruction counts), so it is written to the bone:
+//   * -d/t with the loop-invariant divisor t becomes Markstein's 3-instruction correctly-rounded division
+//     (q = RN(d*r), rem = fma(-q,t,d) exact, q' = fma(rem,r,q) with r = RN(1/t)); the IEEE result is identical to
+//     div.rn whenever t's significand is not all ones and the quotient is a normal number -- outside the normal
+//     range expf(q') is exactly 1 or 0 either way; an all-ones significand falls back to div.rn (FAST_DIV=false).
+//   * the x2 weight of points k >= 8192 is a per-slot register factor folded into one FMA (2w is exact),
+//   * tie keys are per-slot registers, candidates are compared as packed u64 (density bits, key),
+//   * candidate coordinates come from a shared-memory copy of the CTA's own points, and only the warp that owns
+//     the winner runs the register-select chain that parks it.
+template <int PT, bool FAST_DIV>
+__device__ __forceinline__ void mds_rounds(const float* __restrict__ dataset, int m, int* __restrict__ idxs, float t, int kbeg, int kend,
+                                           int bs_mask, int bs_log2, uint32_t cs, uint32_t rank, unsigned long long (*packs)[MDS_SLOTS],
+                                           float4 (*coords)[MDS_SLOTS], uint64_t* bars, const float* sxyz) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  dataset += (size_t)b * n * 3;
-  idxs += (size_t)b * m;
-
-  const int chunk = (n + cs - 1) / cs;
-  const int kbeg = rank * chunk;
-  const int kend = (kbeg + chunk) < n ? (kbeg + chunk) : n;
-
-  float x[PT], y[PT], z[PT], temp[PT];
+  float x[PT], y[PT], z[PT], temp[PT], fac[PT];
+  unsigned key[PT];
 #pragma unroll
   for (int i = 0; i < PT; i++) {
     const int k = kbeg + tid + i * MDS_THREADS;
     const bool ok = k < kend;
-    x[i] = ok ? dataset[k * 3 + 0] : 0.f;
-    y[i] = ok ? dataset[k * 3 + 1] : 0.f;
-    z[i] = ok ? dataset[k * 3 + 2] : 0.f;
+    x[i] = ok ? sxyz[(k - kbeg) * 3 + 0] : 0.f;
+    y[i] = ok ? sxyz[(k - kbeg) * 3 + 1] : 0.f;
+    z[i] = ok ? sxyz[(k - kbeg) * 3 + 2] : 0.f;
     temp[i] = ok ? (k == 0 ? 1e9f : 0.f) : 2e9f;  // out-of-range slots sit above every real density: they can never win
+    fac[i] = k < 8192 ? 1.0f : 2.0f;
+    const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
+    key[i] = (rev << 21) | (unsigned)k;
   }
-  const float mml = mean_mst_length[b];
-  const float t = (float)(5.0 * (double)mml * (double)mml);
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_mbar_init();
-  }
-  if (rank == 0 && tid == 0) idxs[0] = 0;
+  const float r = __frcp_rn(t);
   float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];
-  // peers must see initialised barriers before the first remote complete_tx
-  cluster_sync_all();
 
-  // per-lane remote addresses (lane r < cs talks to CTA r): this warp's slot in both parities + the two barriers
+  // per-lane remote addresses (lane q < cs talks to CTA q): this warp's slot in both parities + the two barriers
   const uint32_t my_slot = rank * MDS_WARPS + warp;
   uint32_t r_pack[2], r_coord[2], r_bar[2];
 #pragma unroll
@@ -96,26 +86,26 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
   }
   const uint32_t round_bytes = cs * MDS_WARPS * 24u;
   const int total = cs * MDS_WARPS;
+  const int wbeg = kbeg + warp * 32;  // this warp owns points k with ((k - kbeg) % 512) / 32 == warp
 
   for (int j = 1; j < m; j++) {
     const int par = j & 1;
     if (tid == 0) mbar_expect_tx(&bars[par], round_bytes);  // arm this round's phase (the single expected arrival)
     unsigned long long best = MDS_NONE;
-    int bi = 0;
 #pragma unroll
     for (int i = 0; i < PT; i++) {
-      const int k = kbeg + tid + i * MDS_THREADS;
       const float d = sqdist3(__fsub_rn(x[i], x1), __fsub_rn(y[i], y1), __fsub_rn(z[i], z1));
-      float w = expf(__fdiv_rn(-d, t));
-      if (k >= 8192) w = __fmul_rn(w, 2.0f);
-      const float v = __fadd_rn(temp[i], w);
-      temp[i] = v;
-      const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
-      const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | ((rev << 21) | (unsigned)k);
-      if (p < best) {  // densities are >= 0, so the u64 order is (density, tie key) lexicographic; parked points hold 1e9
-        best = p;
-        bi = i;
+      float q;
+      if (FAST_DIV) {
+        const float q0 = __fmul_rn(d, r);
+        q = __fmaf_rn(__fmaf_rn(-q0, t, d), r, q0);  // == div.rn(d, t) (see above)
+      } else {
+        q = __fdiv_rn(d, t);
       }
+      const float v = __fmaf_rn(expf(-q), fac[i], temp[i]);  // temp + w or temp + 2w (2w exact): one rounding, as the reference
+      temp[i] = v;
+      const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key[i];
+      best = p < best ? p : best;  // densities are >= 0: u64 order == (density, tie key); parked points hold 1e9
     }
     unsigned long long wbest = best;
 #pragma unroll
@@ -123,43 +113,36 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
       wbest = other < wbest ? other : wbest;
     }
-    // the lane that owns the warp's candidate supplies its coordinates
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-#pragma unroll
-    for (int i = 0; i < PT; i++)
-      if (i == bi) { cx = x[i]; cy = y[i]; cz = z[i]; }
-    const int owner = __ffs(__ballot_sync(0xffffffffu, best == wbest)) - 1;
-    cx = __shfl_sync(0xffffffffu, cx, owner);
-    cy = __shfl_sync(0xffffffffu, cy, owner);
-    cz = __shfl_sync(0xffffffffu, cz, owner);
     if (lane < (int)cs) {
+      const int kc = (int)((unsigned)wbest & 0x1fffffu) - kbeg;  // the warp's candidate is one of this CTA's points
+      const int kk = (kc >= 0 && kc < kend - kbeg) ? kc : 0;
       st_async_b64(r_pack[par], wbest, r_bar[par]);
-      st_async_v4f32(r_coord[par], cx, cy, cz, 0.f, r_bar[par]);
+      st_async_v4f32(r_coord[par], sxyz[kk * 3 + 0], sxyz[kk * 3 + 1], sxyz[kk * 3 + 2], 0.f, r_bar[par]);
     }
     mbar_wait_cluster(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);  // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
     // every warp reduces the cs*16 candidates redundantly (<= 128: up to 4 per lane)
     unsigned long long c[4], g = MDS_NONE;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int e = lane + 32 * q;
-      c[q] = e < total ? packs[par][e] : MDS_NONE;
-      g = c[q] < g ? c[q] : g;
+    for (int qd = 0; qd < 4; qd++) {
+      const int e = lane + 32 * qd;
+      c[qd] = e < total ? packs[par][e] : MDS_NONE;
+      g = c[qd] < g ? c[qd] : g;
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, g, o);
       g = other < g ? other : g;
     }
-    int wq = -1;
+    int we = -1;
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-      if (c[q] == g && wq < 0) wq = q;
-    const int src = __ffs(__ballot_sync(0xffffffffu, wq >= 0)) - 1;
-    float4 wc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane == src) wc = coords[par][lane + 32 * wq];
-    x1 = __shfl_sync(0xffffffffu, wc.x, src);
-    y1 = __shfl_sync(0xffffffffu, wc.y, src);
-    z1 = __shfl_sync(0xffffffffu, wc.z, src);
+    for (int qd = 3; qd >= 0; qd--)
+      if (c[qd] == g) we = lane + 32 * qd;
+    const int src = __ffs(__ballot_sync(0xffffffffu, we >= 0)) - 1;
+    we = __shfl_sync(0xffffffffu, we, src);
+    const float4 wc = coords[par][we];  // broadcast read
+    x1 = wc.x;
+    y1 = wc.y;
+    z1 = wc.z;
     int old = (int)((unsigned)g & 0x1fffffu);
     if ((unsigned)(g >> 32) >= 0x4e6e6b28u) {  // >= 1e9f: every point is parked -> the reference returns index 0 (MDS_cuda.cu:121-133)
       old = 0;
@@ -168,10 +151,10 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
       z1 = __ldg(&dataset[2]);
     }
     if (rank == 0 && tid == 0) idxs[j] = old;
-    // park the chosen point (the owner thread finds it among its registers)
-    {
-      const int rel = old - kbeg - tid;
-      if (old >= kbeg && old < kend && rel >= 0 && (rel % MDS_THREADS) == 0) {
+    // park the chosen point: only the warp that owns it runs the select chain
+    const int rel = old - wbeg;
+    if (old >= kbeg && old < kend && rel >= 0 && ((rel % MDS_THREADS) < 32)) {
+      if ((rel % MDS_THREADS) == lane) {
         const int slot = rel / MDS_THREADS;
 #pragma unroll
         for (int i = 0; i < PT; i++)
@@ -179,8 +162,41 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
       }
     }
   }
-  // no CTA may exit while a peer can still write into its shared memory
-  cluster_sync_all();
+}
+
+template <int PT>
+__global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
+                                                                      const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
+                                                                      int bs_mask, int bs_log2) {
+  __shared__ __align__(16) unsigned long long packs[2][MDS_SLOTS];
+  __shared__ __align__(16) float4 coords[2][MDS_SLOTS];
+  __shared__ __align__(8) uint64_t bars[2];
+  extern __shared__ __align__(16) float sxyz[];  // this CTA's points, AoS
+  const uint32_t cs = cluster_nctarank();
+  const uint32_t rank = cluster_ctarank();
+  const int b = blockIdx.x / cs;
+  const int tid = threadIdx.x;
+  dataset += (size_t)b * n * 3;
+  idxs += (size_t)b * m;
+  const int chunk = (n + cs - 1) / cs;
+  const int kbeg = rank * chunk;
+  const int kend = (kbeg + chunk) < n ? (kbeg + chunk) : n;
+  for (int i = tid; i < (kend - kbeg) * 3; i += MDS_THREADS) sxyz[i] = dataset[(size_t)kbeg * 3 + i];
+  const float mml = mean_mst_length[b];
+  const float t = (float)(5.0 * (double)mml * (double)mml);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (rank == 0 && tid == 0) idxs[0] = 0;
+  __syncthreads();
+  cluster_sync_all();  // peers must see initialised barriers before the first remote complete_tx
+  const unsigned tb = __float_as_uint(t);
+  const bool fast = ((tb & 0x7fffffu) != 0x7fffffu) && ((tb >> 23) & 0xffu) > 1u && ((tb >> 23) & 0xffu) < 254u && !(tb >> 31);
+  if (fast) mds_rounds<PT, true>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
+  else mds_rounds<PT, false>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
+  cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 // ---- gather_points: out[b,c,j] = f[b,c,idx[b,j]]; backward scatters with atomics (the reference's
@@ -205,7 +221,10 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cs));
   cfg.blockDim = dim3(MDS_THREADS);
-  cfg.dynamicSmemBytes = 0;
+  const size_t smem = (size_t)((n + cs - 1) / cs) * 3 * sizeof(float);
+  cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ea != cudaSuccess) return (int)ea;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

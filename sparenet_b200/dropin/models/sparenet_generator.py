@@ -93,6 +93,15 @@ def _channel_stats(bn, h, row_bias=None):
     return bn.running_mean, bn.running_var, m_bc
 
 
+def _pconv(x, W):
+    """1x1 convolution y[b] = W x[b] for x [B,Cin,N], W [Cout,Cin(,1)].  Thin layers (<= 8 channels on either side) go through
+    a batched GEMM: cuDNN's weight-gradient kernel for them is a slow direct kernel; everything else is a cuDNN 1x1 conv."""
+    W2 = W.reshape(W.size(0), -1)
+    if min(W2.shape) <= 8:
+        return torch.bmm(W2.unsqueeze(0).expand(x.size(0), -1, -1), x)
+    return F.conv1d(x, W2.unsqueeze(-1))
+
+
 def knn(x, k: int):
     """Reference :852-877.  x [B,C,N] -> idx [B,N,k] int64 (self included); exact fp32 brute force on the GPU."""
     return F_.knn_indices(x.contiguous(), k).long()
@@ -136,8 +145,8 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         W = conv.weight.view(conv.out_channels, 2 * C)
         Wa, Wb = W[:, :C], W[:, C:]
         Co = conv.out_channels
-        a = F.conv1d(x, Wa.unsqueeze(-1))                          # per-POINT 1x1 convs (k x fewer flops than per edge)
-        c = F.conv1d(x, (Wb - Wa).unsqueeze(-1))
+        a = _pconv(x, Wa)                                          # per-POINT 1x1 convs (k x fewer flops than per edge)
+        c = _pconv(x, Wb - Wa)
         # u[b,c,i,m] = a[b,c,idx[b,i,m]] + c[b,c,i] is never formed: the fused kernel returns its max/min over m and its moments
         umax, umin, S1, S2 = fused.edge_reduce(a, c, idx)
         n = B * N * k
@@ -372,7 +381,7 @@ class PointNetRes(nn.Module):  # reference :582-646
 
     def forward(self, x):
         B = x.size(0)
-        x = self._bn_se_relu(F.conv1d(x, self.conv1.weight), self.bn1, self.se1, self.conv1.bias)
+        x = self._bn_se_relu(_pconv(x, self.conv1.weight), self.bn1, self.se1, self.conv1.bias)
         pointfeat = x
         x = self._bn_se_relu(F.conv1d(x, self.conv2.weight), self.bn2, self.se2, self.conv2.bias)
         h3 = F.conv1d(x, self.conv3.weight)                                    # [B,1024,N]; the bias is folded below
@@ -387,7 +396,7 @@ class PointNetRes(nn.Module):  # reference :582-646
         x = self._bn_se_relu(F.conv1d(pointfeat, W4[:, 1024:].contiguous()), self.bn4, self.se4, pb)
         x = self._bn_se_relu(F.conv1d(x, self.conv5.weight), self.bn5, self.se5, self.conv5.bias)
         x = self._bn_se_relu(F.conv1d(x, self.conv6.weight), self.bn6, self.se6, self.conv6.bias)
-        return self.th(self.conv7(x))
+        return self.th(_pconv(x, self.conv7.weight) + self.conv7.bias.view(1, -1, 1))
 
 
 class SpareNetRefine(nn.Module):  # reference :530-579
