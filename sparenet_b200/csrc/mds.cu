@@ -23,8 +23,7 @@
 
 namespace snb {
 
-constexpr int MDS_THREADS = 512;
-constexpr int MDS_WARPS = MDS_THREADS / 32;
+constexpr int MDS_MAX_WARPS = 16;  // warps per CTA: 8 (256 threads, the default) or 16
 constexpr int MDS_MAX_CLUSTER = 8;
 constexpr unsigned long long MDS_NONE = 0xffffffffffffffffull;
 
@@ -41,7 +40,7 @@ __device__ __forceinline__ void st_async_v4f32(uint32_t remote_addr, float a, fl
                : "memory");
 }
 
-constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_WARPS;  // 128 candidate slots per parity
+constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_MAX_WARPS;  // up to 128 candidate slots per parity
 
 // The round loop is issue bound (4 warps per scheduler, every instruction counts), so it is written to the bone:
 //   * -d/t with the loop-invariant divisor t becomes Markstein's 3-instruction correctly-rounded division
@@ -52,10 +51,14 @@ constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_WARPS;  // 128 candidate slots p
 //   * tie keys are per-slot registers, candidates are compared as packed u64 (density bits, key),
 //   * candidate coordinates come from a shared-memory copy of the CTA's own points, and only the warp that owns
 //     the winner runs the register-select chain that parks it.
-template <int PT, bool FAST_DIV>
+//   * few, fat warps: the per-round tail (two shuffle reductions, the exchange, parking) costs ~200 instructions per
+//     WARP, so 256 threads x 18 points beat 512 x 9 (2 warps per scheduler instead of 4, same points per SM).
+template <int MDS_THREADS, int PT, bool FAST_DIV>
 __device__ __forceinline__ void mds_rounds(const float* __restrict__ dataset, int m, int* __restrict__ idxs, float t, int kbeg, int kend,
                                            int bs_mask, int bs_log2, uint32_t cs, uint32_t rank, unsigned long long (*packs)[MDS_SLOTS],
                                            float4 (*coords)[MDS_SLOTS], uint64_t* bars, const float* sxyz) {
+  constexpr int MDS_WARPS = MDS_THREADS / 32;
+  constexpr int NQ = (MDS_MAX_CLUSTER * MDS_WARPS + 31) / 32;  // candidate entries per lane in the final reduce
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float x[PT], y[PT], z[PT], temp[PT], fac[PT];
   unsigned key[PT];
@@ -121,9 +124,9 @@ __device__ __forceinline__ void mds_rounds(const float* __restrict__ dataset, in
     }
     mbar_wait_cluster(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);  // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
     // every warp reduces the cs*16 candidates redundantly (<= 128: up to 4 per lane)
-    unsigned long long c[4], g = MDS_NONE;
+    unsigned long long c[NQ], g = MDS_NONE;
 #pragma unroll
-    for (int qd = 0; qd < 4; qd++) {
+    for (int qd = 0; qd < NQ; qd++) {
       const int e = lane + 32 * qd;
       c[qd] = e < total ? packs[par][e] : MDS_NONE;
       g = c[qd] < g ? c[qd] : g;
@@ -135,7 +138,7 @@ __device__ __forceinline__ void mds_rounds(const float* __restrict__ dataset, in
     }
     int we = -1;
 #pragma unroll
-    for (int qd = 3; qd >= 0; qd--)
+    for (int qd = NQ - 1; qd >= 0; qd--)
       if (c[qd] == g) we = lane + 32 * qd;
     const int src = __ffs(__ballot_sync(0xffffffffu, we >= 0)) - 1;
     we = __shfl_sync(0xffffffffu, we, src);
@@ -164,7 +167,7 @@ __device__ __forceinline__ void mds_rounds(const float* __restrict__ dataset, in
   }
 }
 
-template <int PT>
+template <int MDS_THREADS, int PT>
 __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
                                                                       const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
                                                                       int bs_mask, int bs_log2) {
@@ -194,8 +197,8 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
   cluster_sync_all();  // peers must see initialised barriers before the first remote complete_tx
   const unsigned tb = __float_as_uint(t);
   const bool fast = ((tb & 0x7fffffu) != 0x7fffffu) && ((tb >> 23) & 0xffu) > 1u && ((tb >> 23) & 0xffu) < 254u && !(tb >> 31);
-  if (fast) mds_rounds<PT, true>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
-  else mds_rounds<PT, false>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
+  if (fast) mds_rounds<MDS_THREADS, PT, true>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
+  else mds_rounds<MDS_THREADS, PT, false>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
   cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
 }
 
@@ -216,13 +219,13 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float* __restrict
   atomicAdd(&gf[((size_t)b * C + c) * n + idx[(size_t)b * m + j]], g[((size_t)b * C + c) * m + j]);
 }
 
-template <int PT>
+template <int MDS_THREADS, int PT>
 static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, int* idx, int cs, int bs_mask, int bs_log2, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cs));
   cfg.blockDim = dim3(MDS_THREADS);
   const size_t smem = (size_t)((n + cs - 1) / cs) * 3 * sizeof(float);
-  cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<MDS_THREADS, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea != cudaSuccess) return (int)ea;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -233,7 +236,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<PT>, xyz, n, m, mml, idx, bs_mask, bs_log2);
+  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<MDS_THREADS, PT>, xyz, n, m, mml, idx, bs_mask, bs_log2);
 }
 
 }  // namespace snb
@@ -258,20 +261,25 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   // cluster size: as many SMs per sample as the batch leaves free (<= 8, power of two)
   int cs = 1;
   while (cs * 2 <= MDS_MAX_CLUSTER && B * cs * 2 <= kNumSMs) cs *= 2;
-  int pt = (((n + cs - 1) / cs) + MDS_THREADS - 1) / MDS_THREADS;
-  while (pt > 24 && cs < MDS_MAX_CLUSTER) {  // too many points for the register file: widen the cluster
+  int per = (n + cs - 1) / cs;  // points per CTA
+  while (per > 512 * 24 && cs < MDS_MAX_CLUSTER) {  // too many points for the register file: widen the cluster
     cs *= 2;
-    pt = (((n + cs - 1) / cs) + MDS_THREADS - 1) / MDS_THREADS;
+    per = (n + cs - 1) / cs;
   }
   int rc;
-  if (pt <= 2) rc = mds_launch<2>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
-  else if (pt <= 4) rc = mds_launch<4>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
-  else if (pt <= 6) rc = mds_launch<6>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
-  else if (pt <= 9) rc = mds_launch<9>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
-  else if (pt <= 12) rc = mds_launch<12>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
-  else if (pt <= 18) rc = mds_launch<18>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
-  else if (pt <= 24) rc = mds_launch<24>(xyz, B, n, m, mean_mst_length, idx, cs, bs - 1, lg, s);
+  const int bm = bs - 1;
+#define MDS_GO(T, P) rc = mds_launch<T, P>(xyz, B, n, m, mean_mst_length, idx, cs, bm, lg, s)
+  if (per <= 256 * 2) MDS_GO(256, 2);
+  else if (per <= 256 * 4) MDS_GO(256, 4);
+  else if (per <= 256 * 6) MDS_GO(256, 6);
+  else if (per <= 256 * 9) MDS_GO(256, 9);
+  else if (per <= 256 * 12) MDS_GO(256, 12);
+  else if (per <= 256 * 18) MDS_GO(256, 18);
+  else if (per <= 512 * 12) MDS_GO(512, 12);
+  else if (per <= 512 * 18) MDS_GO(512, 18);
+  else if (per <= 512 * 24) MDS_GO(512, 24);
   else return SNB_ELIMIT;  // n > 8*512*24 = 98304 points per sample
+#undef MDS_GO
   if (rc != 0) return rc;
   SNB_LAUNCH_CHECK();
   return SNB_OK;
