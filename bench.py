@@ -183,13 +183,8 @@ def build_gpu(args, dev, rank):
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:
-            import torch.distributed as dist
-            grads = [p.grad for p in params if p.grad is not None]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat)
-            flat.div_(world)
-            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                g.copy_(f)
+            from sparenet_b200.dist import allreduce_gradients
+            allreduce_gradients(params, world)      # the path's only collective: NCCL all-reduce of the gradients over NVLink
         opt.step()
         return loss
 

@@ -129,6 +129,19 @@ int snb_row_affine_act_bwd(const float* gy, const float* h, const float* scale, 
                            int in_div, float slope, float* gh, float* gscale, float* gshift, void* stream);
 int snb_row_minmax(const float* h, long long R, int L, float* vmax, float* vmin, int* imax, int* imin, void* stream);
 
+/* ---- Gridding / GriddingReverse (GRNet) --------------------------------------------------------------------
+ * replaces gridding.forward / backward / rev_forward / rev_backward (cuda/gridding/gridding_cuda.cpp:43-99,
+ * gridding.cu:179-335, gridding_reverse.cu:105-236).  ptcloud [B,n,3] already multiplied by scale/2; grid
+ * [B, len_x*len_y*len_z] with len = max - min + 1; grid_pt_weights [B,n,8,3], grid_pt_indexes [B,n,8] (-1 where a
+ * corner lies outside the grid: the reference writes out of bounds there).  Reverse: grid [B,S^3] -> ptcloud [B,S^3,3]. */
+int snb_gridding_fwd(const float* ptcloud, int B, int n, float min_x, float max_x, float min_y, float max_y,
+                     float min_z, float max_z, float* grid, float* grid_pt_weights, int* grid_pt_indexes, void* stream);
+int snb_gridding_bwd(const float* grid_pt_weights, const int* grid_pt_indexes, const float* grad_grid, int B, int n,
+                     long long n_grid_vertices, float* grad_ptcloud, void* stream);
+int snb_gridding_rev_fwd(const float* grid, int B, int scale, float* ptcloud, void* stream);
+int snb_gridding_rev_bwd(const float* ptcloud, const float* grid, const float* grad_ptcloud, int B, int scale,
+                         float* grad_grid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -220,3 +220,40 @@ def knn(x, k, return_dist=False):
     dist = torch.empty(B, N, k)
     lib().orc_knn(_p(x), B, C, N, int(k), _p(idx), _p(dist))
     return (idx, dist) if return_dist else idx
+
+
+# ------------------------------------------------------------------ gridding (GRNet)
+def gridding_fwd(pts, bounds):
+    """pts [B,n,3] already scaled; bounds = (minx, maxx, miny, maxy, minz, maxz) -> grid [B,V], weights [B,n,8,3], indexes [B,n,8]"""
+    pts = _f(pts)
+    B, n, _ = pts.shape
+    lens = [int(bounds[2 * i + 1] - bounds[2 * i] + 1) for i in range(3)]
+    V = lens[0] * lens[1] * lens[2]
+    grid, w, ix = torch.empty(B, V), torch.empty(B, n, 8, 3), torch.empty(B, n, 8, dtype=torch.int32)
+    lib().orc_gridding_fwd(_p(pts), B, n, *[ctypes.c_float(float(v)) for v in bounds], _p(grid), _p(w), _p(ix))
+    return grid, w, ix
+
+
+def gridding_bwd(weights, indexes, ggrid):
+    weights, indexes, ggrid = _f(weights), _i(indexes), _f(ggrid)
+    B, n = indexes.shape[:2]
+    g = torch.empty(B, n, 3)
+    lib().orc_gridding_bwd(_p(weights), _p(indexes), _p(ggrid), B, n, ctypes.c_size_t(ggrid.shape[1]), _p(g))
+    return g
+
+
+def gridding_rev_fwd(grid, scale):
+    grid = _f(grid).reshape(grid.shape[0], -1)
+    B = grid.shape[0]
+    pts = torch.empty(B, scale ** 3, 3)
+    lib().orc_gridding_rev_fwd(_p(grid), B, int(scale), _p(pts))
+    return pts
+
+
+def gridding_rev_bwd(pts, grid, gpts, scale):
+    pts, gpts = _f(pts), _f(gpts)
+    grid = _f(grid).reshape(grid.shape[0], -1)
+    B = grid.shape[0]
+    g = torch.empty(B, scale ** 3)
+    lib().orc_gridding_rev_bwd(_p(pts), _p(grid), _p(gpts), B, int(scale), _p(g))
+    return g

@@ -585,10 +585,11 @@ ORC_API void orc_knn(const float *x, int B, int C, int N, int k, int *idx, float
 }
 
 /* ------------------------------------------------------------------------------------------
- * Gridding (cuda/gridding/gridding.cu:29-177,213-312; gridding_reverse.cu:30-103,124-214)
- * Operates on one already-scaled cloud [n,3]; grid bounds [min,max] per axis as in
- * cuda/gridding/__init__.py:16-18.  Rows whose 3 coordinates are all zero are skipped
- * (gridding.cu:47-52).
+ * Gridding (cuda/gridding/gridding.cu:29-177,213-312) and GriddingReverse (gridding_reverse.cu:30-103,124-214)
+ * pts are already scaled ([B,n,3]); grid bounds [min,max] per axis as in cuda/gridding/__init__.py:16-18.
+ * Corner t = (x: t>>2, y: (t>>1)&1, z: t&1), 0 = lower (floor), 1 = upper (ceil, +1 when equal to floor);
+ * stored per-axis weight = 1 - |p - corner| (gridding.cu:27); grid += wx*wy*wz.  The reference does not bound-check
+ * (coordinates must lie in [min, max)); corners outside the grid are skipped here instead of written out of bounds.
  * ---------------------------------------------------------------------------------------- */
 static inline int grid_index(int len_y, int len_z, int ox, int oy, int oz) { return ox * len_y * len_z + oy * len_z + oz; }
 
@@ -602,25 +603,24 @@ ORC_API void orc_gridding_fwd(const float *pts, int B, int n, float minx, float 
       const float *p = pts + ((size_t)b * n + j) * 3;
       float *w = weights + ((size_t)b * n + j) * 24;
       int *ix = indexes + ((size_t)b * n + j) * 8;
-      for (int t = 0; t < 24; t++) w[t] = 0.f;
-      for (int t = 0; t < 8; t++) ix[t] = -1;
-      if (p[0] == 0.f && p[1] == 0.f && p[2] == 0.f) continue;
-      float lo[3], hi[3];
+      int lo[3], hi[3];
       for (int c = 0; c < 3; c++) {
-        lo[c] = floorf(p[c]); hi[c] = ceilf(p[c]);
-        if (lo[c] == hi[c]) hi[c] += 1.f;
+        lo[c] = (int)floorf(p[c]); hi[c] = (int)ceilf(p[c]);
+        if (lo[c] == hi[c]) hi[c] += 1;
       }
-      const int ox0 = (int)(lo[0] - minx), oy0 = (int)(lo[1] - miny), oz0 = (int)(lo[2] - minz);
-      const int ox1 = (int)(hi[0] - minx), oy1 = (int)(hi[1] - miny), oz1 = (int)(hi[2] - minz);
-      const float wl[3] = {hi[0] - p[0], hi[1] - p[1], hi[2] - p[2]}; /* weight of the lower corner */
-      const float wu[3] = {p[0] - lo[0], p[1] - lo[1], p[2] - lo[2]}; /* weight of the upper corner */
-      /* corner order LLL, LLU, LUL, LUU, ULL, ULU, UUL, UUU (gridding.cu:74-176) */
+      const float mn[3] = {minx, miny, minz};
+      const int len[3] = {lx, ly, lz};
       for (int t = 0; t < 8; t++) {
-        const int ux = (t >> 2) & 1, uy = (t >> 1) & 1, uz = t & 1;
-        const float wx = ux ? wu[0] : wl[0], wy = uy ? wu[1] : wl[1], wz = uz ? wu[2] : wl[2];
-        w[t * 3] = wx; w[t * 3 + 1] = wy; w[t * 3 + 2] = wz;
-        ix[t] = grid_index(ly, lz, ux ? ox1 : ox0, uy ? oy1 : oy0, uz ? oz1 : oz0);
-        grid[(size_t)b * nv + ix[t]] += wx * wy * wz;
+        const int u[3] = {(t >> 2) & 1, (t >> 1) & 1, t & 1};
+        int off[3], inside = 1;
+        for (int c = 0; c < 3; c++) {
+          const int corner = u[c] ? hi[c] : lo[c];
+          w[t * 3 + c] = 1.f - fabsf(p[c] - (float)corner);
+          off[c] = (int)((float)corner - mn[c]);
+          if (off[c] < 0 || off[c] >= len[c]) inside = 0;
+        }
+        ix[t] = inside ? grid_index(ly, lz, off[0], off[1], off[2]) : -1;
+        if (inside) grid[(size_t)b * nv + ix[t]] += w[t * 3] * w[t * 3 + 1] * w[t * 3 + 2];
       }
     }
 }
@@ -631,14 +631,67 @@ ORC_API void orc_gridding_bwd(const float *weights, const int *indexes, const fl
       const float *w = weights + ((size_t)b * n + j) * 24;
       const int *ix = indexes + ((size_t)b * n + j) * 8;
       float g[3] = {0.f, 0.f, 0.f};
-      for (int t = 0; t < 8; t++) {
+      for (int t = 0; t < 8; t++) { /* gridding.cu:231-309: - for a lower corner, + for an upper one */
         if (ix[t] < 0) continue;
         const float gv = ggrid[(size_t)b * nv + ix[t]];
         const int ux = (t >> 2) & 1, uy = (t >> 1) & 1, uz = t & 1;
-        g[0] += (ux ? 1.f : -1.f) * gv * w[t * 3 + 1] * w[t * 3 + 2];
-        g[1] += (uy ? 1.f : -1.f) * gv * w[t * 3] * w[t * 3 + 2];
-        g[2] += (uz ? 1.f : -1.f) * gv * w[t * 3] * w[t * 3 + 1];
+        g[0] += (ux ? gv : -gv) * w[t * 3 + 1] * w[t * 3 + 2];
+        g[1] += (uy ? gv : -gv) * w[t * 3] * w[t * 3 + 2];
+        g[2] += (uz ? gv : -gv) * w[t * 3] * w[t * 3 + 1];
       }
       for (int c = 0; c < 3; c++) gpts[((size_t)b * n + j) * 3 + c] = g[c];
+    }
+}
+
+/* GriddingReverse: every vertex with all offsets >= 1 emits the grid-value-weighted centroid of its 8-corner cell
+ * (the cell below/left/front of it), skipped when the weights sum below 1e-6 (gridding_reverse.cu:16 EPS). */
+ORC_API void orc_gridding_rev_fwd(const float *grid, int B, int S, float *pts) {
+  const size_t nv = (size_t)S * S * S;
+  memset(pts, 0, sizeof(float) * B * nv * 3);
+  for (int b = 0; b < B; b++)
+    for (size_t j = 0; j < nv; j++) {
+      const int x = (int)(j / ((size_t)S * S)), y = (int)(j % ((size_t)S * S) / S), z = (int)(j % S);
+      if (x == 0 || y == 0 || z == 0) continue;
+      const float *g = grid + (size_t)b * nv;
+      float w[8], sum = 0.f;
+      for (int t = 0; t < 8; t++) {
+        w[t] = g[((size_t)(x - 1 + ((t >> 2) & 1)) * S + (y - 1 + ((t >> 1) & 1))) * S + (z - 1 + (t & 1))];
+        sum += w[t];
+      }
+      if (sum < 1e-6f) continue;
+      const float cx = (float)(x - S / 2), cy = (float)(y - S / 2), cz = (float)(z - S / 2);
+      float px = 0.f, py = 0.f, pz = 0.f;
+      for (int t = 0; t < 8; t++) {
+        const float wn = w[t] / sum;
+        px += wn * (((t >> 2) & 1) ? cx : cx - 1.f);
+        py += wn * (((t >> 1) & 1) ? cy : cy - 1.f);
+        pz += wn * ((t & 1) ? cz : cz - 1.f);
+      }
+      float *o = pts + ((size_t)b * nv + j) * 3;
+      o[0] = px; o[1] = py; o[2] = pz;
+    }
+}
+
+ORC_API void orc_gridding_rev_bwd(const float *pts, const float *grid, const float *gpts, int B, int S, float *ggrid) {
+  const size_t nv = (size_t)S * S * S;
+  memset(ggrid, 0, sizeof(float) * B * nv);
+  for (int b = 0; b < B; b++)
+    for (size_t j = 0; j < nv; j++) {
+      const int x = (int)(j / ((size_t)S * S)), y = (int)(j % ((size_t)S * S) / S), z = (int)(j % S);
+      if (x == 0 || y == 0 || z == 0) continue;
+      const float *g = grid + (size_t)b * nv;
+      size_t ix[8];
+      float sum = 0.f;
+      for (int t = 0; t < 8; t++) {
+        ix[t] = ((size_t)(x - 1 + ((t >> 2) & 1)) * S + (y - 1 + ((t >> 1) & 1))) * S + (z - 1 + (t & 1));
+        sum += g[ix[t]];
+      }
+      if (sum < 1e-6f) continue;
+      const float cx = (float)(x - S / 2), cy = (float)(y - S / 2), cz = (float)(z - S / 2);
+      const float *p = pts + ((size_t)b * nv + j) * 3, *gp = gpts + ((size_t)b * nv + j) * 3;
+      for (int t = 0; t < 8; t++) {
+        const float vx = ((t >> 2) & 1) ? cx : cx - 1.f, vy = ((t >> 1) & 1) ? cy : cy - 1.f, vz = (t & 1) ? cz : cz - 1.f;
+        ggrid[(size_t)b * nv + ix[t]] += gp[0] * (vx - p[0]) / sum + gp[1] * (vy - p[1]) / sum + gp[2] * (vz - p[2]) / sum;
+      }
     }
 }

@@ -1,0 +1,48 @@
+"""Data-parallel plumbing for the hot path: one process per GPU, batches sharded by sample, ONE collective per optimizer
+step -- the gradient all-reduce (the reference wraps everything in nn.DataParallel,
+runners/base_runner.py:100-104).  Every op on the path is independent per sample, and the two cross-sample couplings
+(train-mode BatchNorm statistics, ComputeDepthMaps' depth min/max) are per-replica in the reference too, so rank-local
+statistics with local B=32 reproduce its single-GPU numerics on every rank.
+
+torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is the transport; there is no compute here.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(global_batch: int, rank: int, world: int):
+    """Contiguous sample shard [lo, hi) of rank `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_gradients(params, world: int = None, bucket_bytes: int = 256 << 20):
+    """Average .grad over ranks in flat buckets (few large NCCL calls: 330 MB of generator gradients per step).
+    Parameters whose .grad is None on this rank are skipped consistently (same set on every rank by construction)."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    n_calls, bucket, size = 0, [], 0
+    for g in grads + [None]:
+        if g is not None and (size + g.numel() * g.element_size() <= bucket_bytes or not bucket):
+            bucket.append(g)
+            size += g.numel() * g.element_size()
+            continue
+        flat = torch._utils._flatten_dense_tensors(bucket)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        for dst, src in zip(bucket, torch._utils._unflatten_dense_tensors(flat, bucket)):
+            dst.copy_(src)
+        n_calls += 1
+        bucket, size = ([g], g.numel() * g.element_size()) if g is not None else ([], 0)
+    return n_calls
+
+
+def max_over_ranks(value: float, device) -> float:
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

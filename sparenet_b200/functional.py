@@ -256,3 +256,46 @@ def knn_indices(x, k):
     with torch.cuda.device(x.device), _op("knn", 2):
         check(lib.snb_knn(ptr(x), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn")
     return idx
+
+
+# ----------------------------------------------------------------------------- gridding (GRNet)
+def gridding_forward(ptcloud, bounds):
+    """ptcloud [B,n,3] already scaled, bounds (min_x, max_x, min_y, max_y, min_z, max_z) -> grid [B,V], weights [B,n,8,3], idx [B,n,8]."""
+    ptcloud = _cuda_f32(ptcloud, "ptcloud")
+    B, n, _ = ptcloud.shape
+    lens = [int(bounds[2 * i + 1] - bounds[2 * i] + 1) for i in range(3)]
+    V = lens[0] * lens[1] * lens[2]
+    dev = ptcloud.device
+    grid = torch.empty(B, V, device=dev)
+    w = torch.empty(B, n, 8, 3, device=dev)
+    ix = torch.empty(B, n, 8, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _op("gridding_fwd", 1):
+        check(_lib.load().snb_gridding_fwd(ptr(ptcloud), B, n, *[float(v) for v in bounds], ptr(grid), ptr(w), ptr(ix), stream_ptr()), "gridding_fwd")
+    return grid, w, ix
+
+
+def gridding_backward(weights, indexes, grad_grid):
+    weights, grad_grid, indexes = _cuda_f32(weights, "grid_pt_weights"), _cuda_f32(grad_grid, "grad_grid"), _cuda_i32(indexes, "grid_pt_indexes")
+    B, n = indexes.shape[:2]
+    g = torch.empty(B, n, 3, device=weights.device)
+    with torch.cuda.device(weights.device), _op("gridding_bwd", 1):
+        check(_lib.load().snb_gridding_bwd(ptr(weights), ptr(indexes), ptr(grad_grid), B, n, grad_grid.shape[1], ptr(g), stream_ptr()), "gridding_bwd")
+    return g
+
+
+def gridding_reverse_forward(grid, scale):
+    grid = _cuda_f32(grid, "grid")
+    B = grid.shape[0]
+    pts = torch.empty(B, int(scale) ** 3, 3, device=grid.device)
+    with torch.cuda.device(grid.device), _op("gridding_rev_fwd", 1):
+        check(_lib.load().snb_gridding_rev_fwd(ptr(grid), B, int(scale), ptr(pts), stream_ptr()), "gridding_rev_fwd")
+    return pts
+
+
+def gridding_reverse_backward(ptcloud, grid, grad_ptcloud, scale):
+    ptcloud, grid, grad_ptcloud = _cuda_f32(ptcloud, "ptcloud"), _cuda_f32(grid, "grid"), _cuda_f32(grad_ptcloud, "grad_ptcloud")
+    B = grid.shape[0]
+    g = torch.empty(B, int(scale) ** 3, device=grid.device)
+    with torch.cuda.device(grid.device), _op("gridding_rev_bwd", 1):
+        check(_lib.load().snb_gridding_rev_bwd(ptr(ptcloud), ptr(grid), ptr(grad_ptcloud), B, int(scale), ptr(g), stream_ptr()), "gridding_rev_bwd")
+    return g

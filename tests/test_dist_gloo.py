@@ -1,0 +1,60 @@
+"""The N>1 path on CPU: world_size-2 gloo processes exercise the sharding and the bucketed gradient all-reduce that
+bench.py uses under torchrun (NCCL there, gloo here).  No GPU, no kernels."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparenet_b200.dist import allreduce_gradients, max_over_ranks, shard_batch
+    torch.manual_seed(0)                       # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3), torch.nn.Linear(3, 1, bias=False))
+    net[3].weight.requires_grad_(True)
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10.0       # the global batch, same on every rank
+    lo, hi = shard_batch(8, rank, world)
+    loss = net(x[lo:hi]).pow(2).sum() / 8.0    # per-rank share of the global mean loss
+    loss.backward()
+    calls = allreduce_gradients(list(net.parameters()), world, bucket_bytes=256)   # tiny buckets -> several collectives
+    for p in net.parameters():
+        p.grad.mul_(world)                     # undo the average: sum over shards == full-batch gradient
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3), torch.nn.Linear(3, 1, bias=False))
+    ref.load_state_dict(net.state_dict())
+    (ref(x).pow(2).sum() / 8.0).backward()
+    ok = all(torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-6) for a, b in zip(net.parameters(), ref.parameters()))
+    mx = max_over_ranks(float(rank + 1), torch.device("cpu"))
+    out[rank] = (ok, calls, mx, (lo, hi))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_full_batch():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        ok, calls, mx, shard = out[rank]
+        assert ok and calls >= 2 and mx == 2.0
+    assert out[0][3] == (0, 4) and out[1][3] == (4, 8)
+
+
+def test_shard_batch_covers_everything():
+    from sparenet_b200.dist import shard_batch
+    for gb in (32, 33, 255, 256):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_batch(gb, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == gb
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
