@@ -191,6 +191,49 @@ def build_gpu(args, dev, rank):
     return step, h_partial, h_gt
 
 
+def aux_ops_ms(dev, B=LOCAL_B):
+    """The second half of BASELINE.json's metric: CD + EMD + p2i ms/batch at B=32, N=16384 (forward + backward each),
+    CUDA events, 2 warm-up + median of 3.  EMD: eps 0.005, 50 iterations (runners/sparenet_runner.py:90-92) on iid U[0,1)^3
+    clouds; p2i: the 8-view 256x256 ComputeDepthMaps render at radius 5 (configs/sparenet.yaml:27-31)."""
+    from sparenet_b200.dropin.cuda.chamfer_distance import ChamferDistanceMean
+    from sparenet_b200.dropin.cuda.emd.emd_module import emdModule
+    from sparenet_b200.dropin.utils.p2i_utils import ComputeDepthMaps
+
+    def timed(fn):
+        ts = []
+        for i in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        return sorted(ts)[1]
+
+    g = torch.Generator(device=dev).manual_seed(4)
+    x = torch.rand(B, N_OUT, 3, device=dev, generator=g).requires_grad_()
+    y = torch.rand(B, N_OUT, 3, device=dev, generator=g)
+    cd, emd, render = ChamferDistanceMean(), emdModule(), ComputeDepthMaps("orthorgonal", 1.0, 256).to(dev)
+
+    def f_cd():
+        x.grad = None
+        cd(x, y + 0.0).backward()          # '+ 0.0': a fresh tensor each call, so the one-entry Chamfer memo never hits here
+
+    def f_emd():
+        x.grad = None
+        d, _ = emd(x, y, 0.005, 50)
+        torch.sqrt(d).mean(1).mean().backward()
+
+    xc = (x.detach() - 0.5).requires_grad_()
+
+    def f_p2i():
+        xc.grad = None
+        torch.cat([render(xc, view_id=v, radius_list=[5.0]) for v in range(8)], 1).mean().backward()
+
+    return {"cd_fwd_bwd_ms": timed(f_cd), "emd_fwd_bwd_ms": timed(f_emd), "p2i_8view_fwd_bwd_ms": timed(f_p2i), "B": B, "N": N_OUT}
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -297,6 +340,11 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(h_partial.numel() + h_gt.numel()) * 4, "d2h_bytes_per_step": 4, "last_loss": last},
             "roofline": roof}
+    if world == 1:
+        try:
+            line["ops_ms_per_batch"] = aux_ops_ms(dev, args.batch)
+        except Exception as e:  # the headline step stands on its own
+            line["ops_ms_per_batch"] = {"error": repr(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         torch.set_num_threads(cores)

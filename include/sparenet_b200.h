@@ -40,8 +40,10 @@ const char* snb_strerror(int code);
  * chamfer_distance.cu:139-155,189-209).
  * dist1[b,i] = min_j |xyz1[b,i]-xyz2[b,j]|^2, idx1 = smallest argmin; dist2/idx2 the other direction.
  * Outputs are fully written (no pre-zeroing needed).  Gradient buffers are fully written too. */
+size_t snb_chamfer_workspace_bytes(int B, int N, int M);  /* 0 when the shape is served by the brute-force kernel only */
 int snb_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int N, int M,
-                    float* dist1, float* dist2, int* idx1, int* idx2, void* stream);
+                    float* dist1, float* dist2, int* idx1, int* idx2,
+                    void* workspace, size_t workspace_bytes, void* stream);  /* workspace may be NULL: brute force */
 int snb_chamfer_bwd(const float* xyz1, const float* xyz2, int B, int N, int M,
                     const int* idx1, const int* idx2, const float* grad_dist1, const float* grad_dist2,
                     float* grad_xyz1, float* grad_xyz2, void* stream);

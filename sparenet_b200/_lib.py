@@ -16,7 +16,8 @@ P = c_void_p
 SIGNATURES = {
     "snb_version": (c_int, []),
     "snb_strerror": (ctypes.c_char_p, [c_int]),
-    "snb_chamfer_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P]),
+    "snb_chamfer_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "snb_chamfer_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     "snb_chamfer_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "snb_emd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "snb_emd_fwd": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P, P, c_size_t, P]),

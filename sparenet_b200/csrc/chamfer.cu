@@ -167,18 +167,32 @@ __global__ void __launch_bounds__(256) chamfer_grad_scatter_kernel(const float* 
   atomicAdd(&gc[j2 * 3 + 2], -(g * (a[j * 3 + 2] - c[j2 * 3 + 2])));
 }
 
+// chamfer_bvh.cu: exact search with spatial pruning (same bits, O(N log N) work); 0 bytes = shape not served
+size_t chamfer_bvh_workspace_bytes(int B, int N, int M);
+int chamfer_bvh_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2, int* idx1, int* idx2, void* workspace,
+                       cudaStream_t s);
+
 }  // namespace snb
 
 using namespace snb;
 
-// include/sparenet_b200.h: snb_chamfer_fwd
+SNB_API size_t snb_chamfer_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  return chamfer_bvh_workspace_bytes(B, N, M);
+}
+
+// include/sparenet_b200.h: snb_chamfer_fwd.  With a workspace of snb_chamfer_workspace_bytes() (> 0 for 256 <= N, M <= 16384) the
+// pruned search runs; without one (or for other shapes) the brute-force TMA-tiled kernel does.  Both return identical bits.
 SNB_API int snb_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2, int* idx1, int* idx2,
-                            void* stream) {
+                            void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 0 || N < 0 || M < 0) return SNB_EINVAL;
   if (B == 0 || (N == 0 && M == 0)) return SNB_OK;
   if (N == 0 || M == 0) return SNB_EINVAL;  // a nearest neighbour in an empty set is undefined
   if (B > 65535) return SNB_ELIMIT;
   cudaStream_t s = (cudaStream_t)stream;
+  const size_t need = chamfer_bvh_workspace_bytes(B, N, M);
+  if (need > 0 && workspace != nullptr && workspace_bytes >= need && (((uintptr_t)workspace & 15) == 0))
+    return chamfer_bvh_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, workspace, s);
   constexpr int Q = 4;
   const int qpb = CH_THREADS * Q;
   const int nmax = N > M ? N : M;

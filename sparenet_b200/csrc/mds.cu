@@ -19,6 +19,8 @@
 // No global/shared traffic for `temp`, no block barrier, no barrier.cluster and no global load inside the loop
 // (the reference does 11 block barriers and a global read-modify-write of `temp` per round).
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace snb {
@@ -269,7 +271,28 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   int rc;
   const int bm = bs - 1;
 #define MDS_GO(T, P) rc = mds_launch<T, P>(xyz, B, n, m, mean_mst_length, idx, cs, bm, lg, s)
-  if (per <= 256 * 2) MDS_GO(256, 2);
+  // Experiment hook (development): SNB_MDS_LAYOUT="<cluster size>,<threads>" picks another co-residency layout, e.g. "8,128":
+  // 8 thin CTAs per sample, two samples' CTAs sharing an SM so one sample's exchange latency hides behind the other's math.
+  int force_threads = 0;
+  if (const char* e = getenv("SNB_MDS_LAYOUT")) {
+    int a = 0, t = 0;
+    if (sscanf(e, "%d,%d", &a, &t) == 2 && (a == 1 || a == 2 || a == 4 || a == 8) && (t == 128 || t == 256 || t == 512)) {
+      cs = a;
+      force_threads = t;
+      per = (n + cs - 1) / cs;
+    }
+  }
+  if (force_threads == 128) {
+    if (per <= 128 * 9) MDS_GO(128, 9);
+    else if (per <= 128 * 18) MDS_GO(128, 18);
+    else if (per <= 128 * 36) MDS_GO(128, 36);
+    else return SNB_ELIMIT;
+  } else if (force_threads == 512) {
+    if (per <= 512 * 5) MDS_GO(512, 5);
+    else if (per <= 512 * 9) MDS_GO(512, 9);
+    else if (per <= 512 * 12) MDS_GO(512, 12);
+    else return SNB_ELIMIT;
+  } else if (per <= 256 * 2) MDS_GO(256, 2);
   else if (per <= 256 * 4) MDS_GO(256, 4);
   else if (per <= 256 * 6) MDS_GO(256, 6);
   else if (per <= 256 * 9) MDS_GO(256, 9);

@@ -59,6 +59,7 @@ def _ws(nbytes, device):
 
 # ----------------------------------------------------------------------------- Chamfer
 _CHAMFER_MEMO = {}
+CHAMFER_PRUNED = True   # False forces the brute-force kernel (tests compare the two bit for bit)
 
 
 def chamfer_forward(xyz1, xyz2):
@@ -80,8 +81,11 @@ def chamfer_forward(xyz1, xyz2):
     d2 = torch.empty(B, M, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
     i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev), _op("chamfer_fwd", 1):
-        check(_lib.load().snb_chamfer_fwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), stream_ptr()), "chamfer_fwd")
+    lib = _lib.load()
+    nbytes = lib.snb_chamfer_workspace_bytes(B, N, M) if CHAMFER_PRUNED else 0
+    ws = _ws(nbytes, dev) if nbytes else None
+    with torch.cuda.device(dev), _op("chamfer_fwd", 2 if nbytes else 1):
+        check(lib.snb_chamfer_fwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), ptr(ws), nbytes, stream_ptr()), "chamfer_fwd")
     c.clear()
     c.update(key=key, keep=(xyz1, xyz2), out=(d1, d2, i1, i2))
     return d1, d2, i1, i2

@@ -89,6 +89,39 @@ def test_chamfer_full_size_properties(cuda):
     assert torch.equal(e1, d1) and torch.equal(k1, i1) and torch.equal(e2, d2) and torch.equal(k2, i2)
 
 
+@pytest.mark.parametrize("kind", ["uniform", "blob_vs_uniform", "duplicates", "two_clusters", "ragged", "line"])
+def test_chamfer_pruned_search_equals_brute_force_bit_for_bit(cuda, kind):
+    """The spatially pruned search (Morton-sorted clusters + box lower bounds) must return the very same bits as the
+    brute-force kernel on any distribution, including exact ties (lowest index wins) and degenerate boxes."""
+    from sparenet_b200 import functional as F_
+    torch.manual_seed(hash(kind) % 1000)
+    B, N, M = 3, 4096, 4096
+    x, y = torch.rand(B, N, 3, device=cuda), torch.rand(B, M, 3, device=cuda)
+    if kind == "blob_vs_uniform":                 # the bench's situation: predictions in a tiny blob, targets spread out
+        x = 0.5 + 0.01 * torch.randn(B, N, 3, device=cuda)
+    elif kind == "duplicates":
+        y[:, M // 2:] = y[:, :M // 2]
+        x[:, -500:] = 0
+        y[:, -100:] = 0
+    elif kind == "two_clusters":
+        x[:, : N // 2] = 0.02 * torch.rand(B, N // 2, 3, device=cuda)
+        y[:, M // 3:] = 0.97 + 0.03 * torch.rand(B, M - M // 3, 3, device=cuda)
+    elif kind == "ragged":
+        x, y = torch.rand(B, 1000, 3, device=cuda), torch.rand(B, 5003, 3, device=cuda)
+    elif kind == "line":                          # degenerate extent on two axes
+        x[..., 1:] = 0.25
+        y[..., 1:] = 0.25
+    outs = []
+    for pruned in (True, False):
+        F_.CHAMFER_PRUNED = pruned
+        F_._CHAMFER_MEMO.clear()
+        outs.append(F_.chamfer_forward(x, y))
+    F_.CHAMFER_PRUNED = True
+    F_._CHAMFER_MEMO.clear()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_chamfer_dropin_modules_autograd(cuda):
     _dropin()
     from cuda.chamfer_dist import ChamferDistance as CDa, ChamferFunction
