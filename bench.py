@@ -41,7 +41,14 @@ def parse():
     ap.add_argument("--batch", type=int, default=LOCAL_B, help="local batch per GPU (default: BASELINE config)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed for the bounded CPU step inside the default run")
     return ap.parse_args()
+
+
+def cpu_threads():
+    """Host threads the CPU arm uses: every core up to 32.  Beyond that the B=2 sample has too little parallel work per
+    fork/join (measured on the 128-core B200 host: 128 threads ran the step 6x SLOWER than 8, almost all in kernel time)."""
+    return max(1, min(os.cpu_count() or 1, 32))
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -92,8 +99,9 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
-    cores = os.cpu_count()
+    cores = cpu_threads()
     torch.set_num_threads(cores)
+    oracle.set_threads(cores)
     step = cpu_step_factory(args.cpu_batch)
     for _ in range(min(args.warmup, 1)):
         step()
@@ -346,14 +354,18 @@ def run_ours(args):
         except Exception as e:  # the headline step stands on its own
             line["ops_ms_per_batch"] = {"error": repr(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count()
-        torch.set_num_threads(cores)
-        cstep = cpu_step_factory(args.cpu_batch)
-        t0 = time.perf_counter()
-        cstep()
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": args.cpu_batch / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"one step at B={args.cpu_batch} (same point counts and losses), oracle C kernels + plain PyTorch generator"}
+        # the CPU step runs in its own process (clean thread pools, hard time bound) through the --impl reference arm
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-batch", str(args.cpu_batch)]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=args.cpu_timeout).stdout
+            ref = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except subprocess.TimeoutExpired:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                                    "sample": f"one step at B={args.cpu_batch} did not finish within {args.cpu_timeout} s",
+                                    "upper_bound": args.cpu_batch / args.cpu_timeout}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "error": repr(e)[:200]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -51,6 +51,10 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
 def _f(t):
     assert t.dtype == torch.float32 and t.device.type == "cpu"
     return t.contiguous()

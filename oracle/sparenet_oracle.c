@@ -33,6 +33,14 @@ ORC_API int orc_num_threads(void) {
 #endif
 }
 
+ORC_API void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* squared distance exactly as the GPU kernels round it: fma(dz,dz, fma(dx,dx, dy*dy))
  * (chamfer.cu:41-45, emd_cuda.cu:141-146, MDS_cuda.cu:128). */
 static inline float sqdist(float dx, float dy, float dz) {
@@ -363,7 +371,9 @@ ORC_API void orc_mds(const float *xyz, int B, int n, int m, const float *mml, in
 #ifdef _OPENMP
   nth = omp_get_max_threads();
 #endif
-  const int inner = (B < nth && n >= 4096); /* few samples: spread every round's point loop over the host threads */
+  /* Few samples and a very large cloud: spread every round's point loop over the host threads.  For SpareNet-sized clouds
+   * (n ~ 18k) a round is ~0.3 ms of work, less than forking 100+ threads costs, so samples stay the only parallel axis. */
+  const int inner = (B < nth && n >= 131072);
 #pragma omp parallel for schedule(dynamic) if (!inner)
   for (int b = 0; b < B; b++) {
     const float *p = xyz + (size_t)b * n * 3;
