@@ -44,139 +44,197 @@ __device__ __forceinline__ void st_async_v4f32(uint32_t remote_addr, float a, fl
 
 constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_MAX_WARPS;  // up to 128 candidate slots per parity
 
-// The round loop is issue bound (4 warps per scheduler, every instruction counts), so it is written to the bone:
+// The round loop is issue bound (2 warps per scheduler, every instruction counts), so it is written to the bone:
 //   * -d/t with the loop-invariant divisor t becomes Markstein's 3-instruction correctly-rounded division
 //     (q = RN(d*r), rem = fma(-q,t,d) exact, q' = fma(rem,r,q) with r = RN(1/t)); the IEEE result is identical to
 //     div.rn whenever t's significand is not all ones and the quotient is a normal number -- outside the normal
 //     range expf(q') is exactly 1 or 0 either way; an all-ones significand falls back to div.rn (FAST_DIV=false).
 //   * the x2 weight of points k >= 8192 is a per-slot register factor folded into one FMA (2w is exact),
 //   * tie keys are per-slot registers, candidates are compared as packed u64 (density bits, key),
-//   * candidate coordinates come from a shared-memory copy of the CTA's own points, and only the warp that owns
-//     the winner runs the register-select chain that parks it.
-//   * few, fat warps: the per-round tail (two shuffle reductions, the exchange, parking) costs ~200 instructions per
-//     WARP, so 256 threads x 18 points beat 512 x 9 (2 warps per scheduler instead of 4, same points per SM).
+//   * candidate coordinates come from a shared-memory copy of the CTA's own points,
+//   * few, fat warps: 256 threads x 18 points beat 512 x 9 (the per-round tail is paid per WARP),
+//   * LIVE-POINT COMPACTION: a chosen point is parked at 1e9 for good and m/n of the points end up chosen (89 % in
+//     SpareNet's refiner), so the register layout is re-packed through shared memory whenever the CTA's live points
+//     fit a narrower unrolled loop (PT 18 -> 14 -> 10 -> 7 -> 4 -> 2): on average ~56 % of the points are still
+//     updated per round.  Every live point sees exactly the same sequence of fp32 additions as before, so the sampled
+//     indices are unchanged; dropped points could never be chosen again (the reference adds w to their 1e9 for nothing).
+struct MdsStage {          // staging area in dynamic shared memory, capacity = THREADS * PT0 entries
+  float* t;                // running density of the entry's point (2e9 = padding)
+  unsigned* k;             // tie key << 21 | point index (~0 = padding); coordinates and the x2 factor follow from the index
+  unsigned short* loc;     // point (k - kbeg) -> its entry in the current layout
+  int* count;
+};
+
+__host__ __device__ constexpr int mds_next_pt(int pt) { return pt > 12 ? pt - 4 : (pt > 6 ? pt - 3 : (pt > 2 ? pt - 2 : 0)); }
+
 template <int MDS_THREADS, int PT, bool FAST_DIV>
-__device__ __forceinline__ void mds_rounds(const float* __restrict__ dataset, int m, int* __restrict__ idxs, float t, int kbeg, int kend,
-                                           int bs_mask, int bs_log2, uint32_t cs, uint32_t rank, unsigned long long (*packs)[MDS_SLOTS],
-                                           float4 (*coords)[MDS_SLOTS], uint64_t* bars, const float* sxyz) {
-  constexpr int MDS_WARPS = MDS_THREADS / 32;
-  constexpr int NQ = (MDS_MAX_CLUSTER * MDS_WARPS + 31) / 32;  // candidate entries per lane in the final reduce
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float x[PT], y[PT], z[PT], temp[PT], fac[PT];
-  unsigned key[PT];
+struct MdsLevel {
+  // runs rounds j.. while the CTA still holds more live points than the next narrower layout can take; returns the next j
+  static __device__ __forceinline__ int run(int j, const float* __restrict__ dataset, int m, int* __restrict__ idxs, float t, float r, int kbeg,
+                                            int kend, uint32_t cs, uint32_t rank, unsigned long long (*packs)[MDS_SLOTS],
+                                            float4 (*coords)[MDS_SLOTS], uint64_t* bars, const float* sxyz, const MdsStage& st, int& live,
+                                            float& x1, float& y1, float& z1) {
+    constexpr int MDS_WARPS = MDS_THREADS / 32;
+    constexpr int NQ = (MDS_MAX_CLUSTER * MDS_WARPS + 31) / 32;  // candidate entries per lane in the final reduce
+    constexpr int NEXT = mds_next_pt(PT);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float x[PT], y[PT], z[PT], temp[PT], fac[PT];
+    unsigned key[PT];
 #pragma unroll
-  for (int i = 0; i < PT; i++) {
-    const int k = kbeg + tid + i * MDS_THREADS;
-    const bool ok = k < kend;
-    x[i] = ok ? sxyz[(k - kbeg) * 3 + 0] : 0.f;
-    y[i] = ok ? sxyz[(k - kbeg) * 3 + 1] : 0.f;
-    z[i] = ok ? sxyz[(k - kbeg) * 3 + 2] : 0.f;
-    temp[i] = ok ? (k == 0 ? 1e9f : 0.f) : 2e9f;  // out-of-range slots sit above every real density: they can never win
-    fac[i] = k < 8192 ? 1.0f : 2.0f;
-    const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
-    key[i] = (rev << 21) | (unsigned)k;
-  }
-  const float r = __frcp_rn(t);
-  float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];
+    for (int i = 0; i < PT; i++) {  // entry e = tid + i*THREADS of the staged layout
+      const int e = tid + i * MDS_THREADS;
+      temp[i] = st.t[e];
+      key[i] = st.k[e];
+      const int k = (int)(key[i] & 0x1fffffu);
+      const int kk = key[i] != 0xffffffffu ? k - kbeg : 0;
+      x[i] = sxyz[kk * 3 + 0];
+      y[i] = sxyz[kk * 3 + 1];
+      z[i] = sxyz[kk * 3 + 2];
+      fac[i] = k < 8192 ? 1.0f : 2.0f;  // MDS_cuda.cu:111-112 (k > 8191 counts double)
+    }
+    const uint32_t my_slot = rank * MDS_WARPS + warp;
+    uint32_t r_pack[2], r_coord[2], r_bar[2];
+#pragma unroll
+    for (int par = 0; par < 2; par++) {
+      const uint32_t dst = lane < (int)cs ? (uint32_t)lane : 0u;
+      r_pack[par] = mapa_shared(smem_u32(&packs[par][my_slot]), dst);
+      r_coord[par] = mapa_shared(smem_u32(&coords[par][my_slot]), dst);
+      r_bar[par] = mapa_shared(smem_u32(&bars[par]), dst);
+    }
+    const uint32_t round_bytes = cs * MDS_WARPS * 24u;
+    const int total = cs * MDS_WARPS;
 
-  // per-lane remote addresses (lane q < cs talks to CTA q): this warp's slot in both parities + the two barriers
-  const uint32_t my_slot = rank * MDS_WARPS + warp;
-  uint32_t r_pack[2], r_coord[2], r_bar[2];
+    for (; j < m && (NEXT == 0 || live > NEXT * MDS_THREADS); j++) {  // the last level also emits the "nothing left -> 0" rounds
+      const int par = j & 1;
+      if (tid == 0) mbar_expect_tx(&bars[par], round_bytes);  // arm this round's phase (the single expected arrival)
+      unsigned long long best = MDS_NONE;
 #pragma unroll
-  for (int par = 0; par < 2; par++) {
-    const uint32_t dst = lane < (int)cs ? (uint32_t)lane : 0u;
-    r_pack[par] = mapa_shared(smem_u32(&packs[par][my_slot]), dst);
-    r_coord[par] = mapa_shared(smem_u32(&coords[par][my_slot]), dst);
-    r_bar[par] = mapa_shared(smem_u32(&bars[par]), dst);
+      for (int i = 0; i < PT; i++) {
+        const float d = sqdist3(__fsub_rn(x[i], x1), __fsub_rn(y[i], y1), __fsub_rn(z[i], z1));
+        float q;
+        if (FAST_DIV) {
+          const float q0 = __fmul_rn(d, r);
+          q = __fmaf_rn(__fmaf_rn(-q0, t, d), r, q0);  // == div.rn(d, t) (see above)
+        } else {
+          q = __fdiv_rn(d, t);
+        }
+        const float v = __fmaf_rn(expf(-q), fac[i], temp[i]);  // temp + w or temp + 2w (2w exact): one rounding, as the reference
+        temp[i] = v;
+        const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key[i];
+        best = p < best ? p : best;  // densities are >= 0: u64 order == (density, tie key); parked / padding entries hold >= 1e9
+      }
+      unsigned long long wbest = best;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
+        wbest = other < wbest ? other : wbest;
+      }
+      if (lane < (int)cs) {
+        const int kc = (int)((unsigned)wbest & 0x1fffffu) - kbeg;  // the warp's candidate is one of this CTA's points
+        const int kk = (kc >= 0 && kc < kend - kbeg) ? kc : 0;
+        st_async_b64(r_pack[par], wbest, r_bar[par]);
+        st_async_v4f32(r_coord[par], sxyz[kk * 3 + 0], sxyz[kk * 3 + 1], sxyz[kk * 3 + 2], 0.f, r_bar[par]);
+      }
+      mbar_wait_cluster(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);  // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
+      // every warp reduces the cs*MDS_WARPS candidates redundantly
+      unsigned long long c[NQ], g = MDS_NONE;
+#pragma unroll
+      for (int qd = 0; qd < NQ; qd++) {
+        const int e = lane + 32 * qd;
+        c[qd] = e < total ? packs[par][e] : MDS_NONE;
+        g = c[qd] < g ? c[qd] : g;
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, g, o);
+        g = other < g ? other : g;
+      }
+      int we = -1;
+#pragma unroll
+      for (int qd = NQ - 1; qd >= 0; qd--)
+        if (c[qd] == g) we = lane + 32 * qd;
+      const int src = __ffs(__ballot_sync(0xffffffffu, we >= 0)) - 1;
+      we = __shfl_sync(0xffffffffu, we, src);
+      const float4 wc = coords[par][we];  // broadcast read
+      x1 = wc.x;
+      y1 = wc.y;
+      z1 = wc.z;
+      int old = (int)((unsigned)g & 0x1fffffu);
+      const bool none = (unsigned)(g >> 32) >= 0x4e6e6b28u;  // >= 1e9f: nothing left -> the reference returns index 0 (MDS_cuda.cu:121-133)
+      if (none) {
+        old = 0;
+        x1 = __ldg(&dataset[0]);
+        y1 = __ldg(&dataset[1]);
+        z1 = __ldg(&dataset[2]);
+      }
+      if (rank == 0 && tid == 0) idxs[j] = old;
+      if (!none && old >= kbeg && old < kend) {  // park it: every warp keeps the live count, only the owner touches its registers
+        live--;
+        const int e = st.loc[old - kbeg];
+        if ((e % MDS_THREADS) == tid) {
+          const int slot = e / MDS_THREADS;
+#pragma unroll
+          for (int i = 0; i < PT; i++)
+            if (i == slot) temp[i] = 1e9f;
+        }
+      }
+    }
+    if (NEXT > 0 && j < m) {  // re-pack the live points for the narrower layout (all warps take this branch in the same round)
+      __syncthreads();
+      if (tid == 0) *st.count = 0;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < PT; i++) {
+        if (temp[i] < 1e9f) {
+          const int e = atomicAdd(st.count, 1);
+          st.t[e] = temp[i];
+          st.k[e] = key[i];
+          st.loc[(int)(key[i] & 0x1fffffu) - kbeg] = (unsigned short)e;
+        }
+      }
+      __syncthreads();
+      for (int e = *st.count + tid; e < NEXT * MDS_THREADS; e += MDS_THREADS) {  // padding entries can never win
+        st.t[e] = 2e9f;
+        st.k[e] = 0xffffffffu;
+      }
+      __syncthreads();
+    }
+    return j;
   }
-  const uint32_t round_bytes = cs * MDS_WARPS * 24u;
-  const int total = cs * MDS_WARPS;
-  const int wbeg = kbeg + warp * 32;  // this warp owns points k with ((k - kbeg) % 512) / 32 == warp
+};
 
-  for (int j = 1; j < m; j++) {
-    const int par = j & 1;
-    if (tid == 0) mbar_expect_tx(&bars[par], round_bytes);  // arm this round's phase (the single expected arrival)
-    unsigned long long best = MDS_NONE;
-#pragma unroll
-    for (int i = 0; i < PT; i++) {
-      const float d = sqdist3(__fsub_rn(x[i], x1), __fsub_rn(y[i], y1), __fsub_rn(z[i], z1));
-      float q;
-      if (FAST_DIV) {
-        const float q0 = __fmul_rn(d, r);
-        q = __fmaf_rn(__fmaf_rn(-q0, t, d), r, q0);  // == div.rn(d, t) (see above)
-      } else {
-        q = __fdiv_rn(d, t);
-      }
-      const float v = __fmaf_rn(expf(-q), fac[i], temp[i]);  // temp + w or temp + 2w (2w exact): one rounding, as the reference
-      temp[i] = v;
-      const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key[i];
-      best = p < best ? p : best;  // densities are >= 0: u64 order == (density, tie key); parked points hold 1e9
-    }
-    unsigned long long wbest = best;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
-      wbest = other < wbest ? other : wbest;
-    }
-    if (lane < (int)cs) {
-      const int kc = (int)((unsigned)wbest & 0x1fffffu) - kbeg;  // the warp's candidate is one of this CTA's points
-      const int kk = (kc >= 0 && kc < kend - kbeg) ? kc : 0;
-      st_async_b64(r_pack[par], wbest, r_bar[par]);
-      st_async_v4f32(r_coord[par], sxyz[kk * 3 + 0], sxyz[kk * 3 + 1], sxyz[kk * 3 + 2], 0.f, r_bar[par]);
-    }
-    mbar_wait_cluster(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);  // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
-    // every warp reduces the cs*16 candidates redundantly (<= 128: up to 4 per lane)
-    unsigned long long c[NQ], g = MDS_NONE;
-#pragma unroll
-    for (int qd = 0; qd < NQ; qd++) {
-      const int e = lane + 32 * qd;
-      c[qd] = e < total ? packs[par][e] : MDS_NONE;
-      g = c[qd] < g ? c[qd] : g;
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, g, o);
-      g = other < g ? other : g;
-    }
-    int we = -1;
-#pragma unroll
-    for (int qd = NQ - 1; qd >= 0; qd--)
-      if (c[qd] == g) we = lane + 32 * qd;
-    const int src = __ffs(__ballot_sync(0xffffffffu, we >= 0)) - 1;
-    we = __shfl_sync(0xffffffffu, we, src);
-    const float4 wc = coords[par][we];  // broadcast read
-    x1 = wc.x;
-    y1 = wc.y;
-    z1 = wc.z;
-    int old = (int)((unsigned)g & 0x1fffffu);
-    if ((unsigned)(g >> 32) >= 0x4e6e6b28u) {  // >= 1e9f: every point is parked -> the reference returns index 0 (MDS_cuda.cu:121-133)
-      old = 0;
-      x1 = __ldg(&dataset[0]);
-      y1 = __ldg(&dataset[1]);
-      z1 = __ldg(&dataset[2]);
-    }
-    if (rank == 0 && tid == 0) idxs[j] = old;
-    // park the chosen point: only the warp that owns it runs the select chain
-    const int rel = old - wbeg;
-    if (old >= kbeg && old < kend && rel >= 0 && ((rel % MDS_THREADS) < 32)) {
-      if ((rel % MDS_THREADS) == lane) {
-        const int slot = rel / MDS_THREADS;
-#pragma unroll
-        for (int i = 0; i < PT; i++)
-          if (i == slot) temp[i] = 1e9f;
-      }
-    }
+template <int MDS_THREADS, int PT, bool FAST_DIV>
+struct MdsChain {
+  static __device__ __forceinline__ void run(int j, const float* __restrict__ dataset, int m, int* __restrict__ idxs, float t, float r, int kbeg,
+                                             int kend, uint32_t cs, uint32_t rank, unsigned long long (*packs)[MDS_SLOTS],
+                                             float4 (*coords)[MDS_SLOTS], uint64_t* bars, const float* sxyz, const MdsStage& st, int& live,
+                                             float& x1, float& y1, float& z1) {
+    j = MdsLevel<MDS_THREADS, PT, FAST_DIV>::run(j, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st, live, x1, y1, z1);
+    if (j < m) MdsChain<MDS_THREADS, mds_next_pt(PT), FAST_DIV>::run(j, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st,
+                                                                     live, x1, y1, z1);
   }
+};
+template <int MDS_THREADS, bool FAST_DIV>
+struct MdsChain<MDS_THREADS, 0, FAST_DIV> {
+  static __device__ __forceinline__ void run(int, const float*, int, int*, float, float, int, int, uint32_t, uint32_t, unsigned long long (*)[MDS_SLOTS],
+                                             float4 (*)[MDS_SLOTS], uint64_t*, const float*, const MdsStage&, int&, float&, float&, float&) {}
+};
+
+// dynamic shared memory: [stage t | stage k | count | loc | this CTA's points]; the points stay in global memory (L2) when
+// they do not fit next to the rest (only for > 9216 points per CTA, far beyond SpareNet's 2048)
+static inline size_t mds_smem_bytes(int per, int threads, int pt, bool stage_xyz) {
+  const size_t cap = (size_t)threads * pt;
+  return cap * 8 + 16 + (((size_t)per * 2 + 15) & ~(size_t)15) + (stage_xyz ? (size_t)per * 12 : 0);
 }
 
 template <int MDS_THREADS, int PT>
 __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
                                                                       const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
-                                                                      int bs_mask, int bs_log2) {
+                                                                      int bs_mask, int bs_log2, int stage_xyz) {
   __shared__ __align__(16) unsigned long long packs[2][MDS_SLOTS];
   __shared__ __align__(16) float4 coords[2][MDS_SLOTS];
   __shared__ __align__(8) uint64_t bars[2];
-  extern __shared__ __align__(16) float sxyz[];  // this CTA's points, AoS
+  extern __shared__ __align__(16) unsigned char dyn[];
   const uint32_t cs = cluster_nctarank();
   const uint32_t rank = cluster_ctarank();
   const int b = blockIdx.x / cs;
@@ -186,7 +244,30 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
   const int chunk = (n + cs - 1) / cs;
   const int kbeg = rank * chunk;
   const int kend = (kbeg + chunk) < n ? (kbeg + chunk) : n;
-  for (int i = tid; i < (kend - kbeg) * 3; i += MDS_THREADS) sxyz[i] = dataset[(size_t)kbeg * 3 + i];
+  const int per = kend - kbeg;
+  // carve the dynamic shared memory: this CTA's points (AoS), the staging SoA, the point -> entry map
+  constexpr int CAP = MDS_THREADS * PT;
+  MdsStage st;
+  st.t = reinterpret_cast<float*>(dyn);
+  st.k = reinterpret_cast<unsigned*>(st.t + CAP);
+  st.count = reinterpret_cast<int*>(st.k + CAP);
+  st.loc = reinterpret_cast<unsigned short*>(st.count + 4);
+  const float* sxyz = dataset + (size_t)kbeg * 3;
+  if (stage_xyz) {
+    float* sx = reinterpret_cast<float*>(dyn + (size_t)CAP * 8 + 16 + (((size_t)chunk * 2 + 15) & ~(size_t)15));
+    for (int i = tid; i < per * 3; i += MDS_THREADS) sx[i] = sxyz[i];
+    sxyz = sx;
+  }
+  // initial layout: every point of the CTA except the pre-chosen point 0 (MDS.cpp:119-121), then padding
+  for (int e = tid; e < CAP; e += MDS_THREADS) {
+    const int k = kbeg + e + ((kbeg == 0) ? 1 : 0);  // rank 0 skips k = 0
+    const bool ok = k < kend;
+    st.t[e] = ok ? 0.f : 2e9f;
+    const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
+    st.k[e] = ok ? ((rev << 21) | (unsigned)k) : 0xffffffffu;
+    if (ok) st.loc[k - kbeg] = (unsigned short)e;
+  }
+  int live = per - ((kbeg == 0) ? 1 : 0);
   const float mml = mean_mst_length[b];
   const float t = (float)(5.0 * (double)mml * (double)mml);
   if (tid == 0) {
@@ -197,10 +278,12 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
   if (rank == 0 && tid == 0) idxs[0] = 0;
   __syncthreads();
   cluster_sync_all();  // peers must see initialised barriers before the first remote complete_tx
+  float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];
   const unsigned tb = __float_as_uint(t);
   const bool fast = ((tb & 0x7fffffu) != 0x7fffffu) && ((tb >> 23) & 0xffu) > 1u && ((tb >> 23) & 0xffu) < 254u && !(tb >> 31);
-  if (fast) mds_rounds<MDS_THREADS, PT, true>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
-  else mds_rounds<MDS_THREADS, PT, false>(dataset, m, idxs, t, kbeg, kend, bs_mask, bs_log2, cs, rank, packs, coords, bars, sxyz);
+  const float r = __frcp_rn(t);
+  if (fast) MdsChain<MDS_THREADS, PT, true>::run(1, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st, live, x1, y1, z1);
+  else MdsChain<MDS_THREADS, PT, false>::run(1, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st, live, x1, y1, z1);
   cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
 }
 
@@ -226,7 +309,9 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cs));
   cfg.blockDim = dim3(MDS_THREADS);
-  const size_t smem = (size_t)((n + cs - 1) / cs) * 3 * sizeof(float);
+  const int per = (n + cs - 1) / cs;
+  int stage_xyz = mds_smem_bytes(per, MDS_THREADS, PT, true) <= (size_t)200 * 1024 ? 1 : 0;
+  const size_t smem = mds_smem_bytes(per, MDS_THREADS, PT, stage_xyz != 0);
   cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<MDS_THREADS, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea != cudaSuccess) return (int)ea;
   cfg.dynamicSmemBytes = smem;
@@ -238,7 +323,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<MDS_THREADS, PT>, xyz, n, m, mml, idx, bs_mask, bs_log2);
+  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<MDS_THREADS, PT>, xyz, n, m, mml, idx, bs_mask, bs_log2, stage_xyz);
 }
 
 }  // namespace snb
