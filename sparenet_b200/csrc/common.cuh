@@ -121,6 +121,29 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Wait for data delivered by st.async / complete_tx into THIS CTA's shared memory.  The default .acquire.cta semantics are what
+// the transaction-barrier pattern needs (the async-proxy writes are ordered before the phase flip); the .cluster form above
+// additionally invalidates L1 (CCTL.IVALL) on every successful wait.
+__device__ __forceinline__ void mbar_wait_tx(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONET_%=;\n\t"
+      "bra WAITT_%=;\n\t"
+      "DONET_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// warp-wide minimum of packed (hi, lo) u64 keys with two REDUX.MIN.U32 instead of five 64-bit shuffle levels
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
 // ---- order-preserving float <-> uint key (for atomicMax/Min on floats of either sign) ------------
 __device__ __forceinline__ uint32_t float_key(float f) {
   const uint32_t u = __float_as_uint(f);

@@ -93,14 +93,11 @@ struct MdsLevel {
       fac[i] = k < 8192 ? 1.0f : 2.0f;  // MDS_cuda.cu:111-112 (k > 8191 counts double)
     }
     const uint32_t my_slot = rank * MDS_WARPS + warp;
-    uint32_t r_pack[2], r_coord[2], r_bar[2];
-#pragma unroll
-    for (int par = 0; par < 2; par++) {
-      const uint32_t dst = lane < (int)cs ? (uint32_t)lane : 0u;
-      r_pack[par] = mapa_shared(smem_u32(&packs[par][my_slot]), dst);
-      r_coord[par] = mapa_shared(smem_u32(&coords[par][my_slot]), dst);
-      r_bar[par] = mapa_shared(smem_u32(&bars[par]), dst);
-    }
+    // peer addresses for parity 0; parity 1 is a constant offset further (a CTA's shared::cluster window is contiguous)
+    const uint32_t dst = lane < (int)cs ? (uint32_t)lane : 0u;
+    const uint32_t r_pack0 = mapa_shared(smem_u32(&packs[0][my_slot]), dst);
+    const uint32_t r_coord0 = mapa_shared(smem_u32(&coords[0][my_slot]), dst);
+    const uint32_t r_bar0 = mapa_shared(smem_u32(&bars[0]), dst);
     const uint32_t round_bytes = cs * MDS_WARPS * 24u;
     const int total = cs * MDS_WARPS;
 
@@ -123,19 +120,15 @@ struct MdsLevel {
         const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key[i];
         best = p < best ? p : best;  // densities are >= 0: u64 order == (density, tie key); parked / padding entries hold >= 1e9
       }
-      unsigned long long wbest = best;
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
-        wbest = other < wbest ? other : wbest;
-      }
+      const unsigned long long wbest = warp_min_u64(best);
       if (lane < (int)cs) {
         const int kc = (int)((unsigned)wbest & 0x1fffffu) - kbeg;  // the warp's candidate is one of this CTA's points
         const int kk = (kc >= 0 && kc < kend - kbeg) ? kc : 0;
-        st_async_b64(r_pack[par], wbest, r_bar[par]);
-        st_async_v4f32(r_coord[par], sxyz[kk * 3 + 0], sxyz[kk * 3 + 1], sxyz[kk * 3 + 2], 0.f, r_bar[par]);
+        const uint32_t r_bar = r_bar0 + par * (uint32_t)sizeof(uint64_t);
+        st_async_b64(r_pack0 + par * (uint32_t)(MDS_SLOTS * sizeof(unsigned long long)), wbest, r_bar);
+        st_async_v4f32(r_coord0 + par * (uint32_t)(MDS_SLOTS * sizeof(float4)), sxyz[kk * 3 + 0], sxyz[kk * 3 + 1], sxyz[kk * 3 + 2], 0.f, r_bar);
       }
-      mbar_wait_cluster(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);  // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
+      mbar_wait_tx(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);       // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
       // every warp reduces the cs*MDS_WARPS candidates redundantly
       unsigned long long c[NQ], g = MDS_NONE;
 #pragma unroll
@@ -144,17 +137,13 @@ struct MdsLevel {
         c[qd] = e < total ? packs[par][e] : MDS_NONE;
         g = c[qd] < g ? c[qd] : g;
       }
+      g = warp_min_u64(g);
+      int we = 0;  // the winning candidate's slot (keys carry the point index, so exactly one live entry matches; all-parked ties are harmless)
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, g, o);
-        g = other < g ? other : g;
+      for (int qd = NQ - 1; qd >= 0; qd--) {
+        const unsigned hit = __ballot_sync(0xffffffffu, c[qd] == g);
+        if (hit) we = 32 * qd + __ffs(hit) - 1;
       }
-      int we = -1;
-#pragma unroll
-      for (int qd = NQ - 1; qd >= 0; qd--)
-        if (c[qd] == g) we = lane + 32 * qd;
-      const int src = __ffs(__ballot_sync(0xffffffffu, we >= 0)) - 1;
-      we = __shfl_sync(0xffffffffu, we, src);
       const float4 wc = coords[par][we];  // broadcast read
       x1 = wc.x;
       y1 = wc.y;
