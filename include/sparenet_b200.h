@@ -130,6 +130,16 @@ int snb_row_affine_act_fwd(const float* h, const float* scale, const float* shif
 int snb_row_affine_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, long long R, int L,
                            int in_div, float slope, float* gh, float* gscale, float* gshift, void* stream);
 int snb_row_minmax(const float* h, long long R, int L, float* vmax, float* vmin, int* imax, int* imin, void* stream);
+/* row_stats + row_minmax in one pass (PointNetRes conv3 -> bn3 -> max over points, models/sparenet_generator.py:626-629). */
+int snb_row_stats_minmax(const float* h, long long R, int L, float* mean, float* var, float* vmax, float* vmin,
+                         int* imax, int* imin, void* stream);
+/* Two-phase backward of y = leaky_relu(scale*h + shift) when (scale, shift) depend on h's row statistics (BN o SE o ReLU):
+ * _reduce returns gscale[r] = sum_l d*h, gshift[r] = sum_l d with d = gy * act'(scale*h + shift); after the caller has
+ * pulled (gscale, gshift) back to (gmean, gvar), row_norm_act_bwd writes gh = d*scale + gmean/L + 2 gvar (h - mean)/L. */
+int snb_row_act_bwd_reduce(const float* gy, const float* h, const float* scale, const float* shift, long long R, int L,
+                           float slope, float* gscale, float* gshift, void* stream);
+int snb_row_norm_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, const float* mean,
+                         const float* gmean, const float* gvar, long long R, int L, float slope, float* gh, void* stream);
 
 /* ---- Gridding / GriddingReverse (GRNet) --------------------------------------------------------------------
  * replaces gridding.forward / backward / rev_forward / rev_backward (cuda/gridding/gridding_cuda.cpp:43-99,

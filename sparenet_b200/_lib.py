@@ -43,6 +43,9 @@ SIGNATURES = {
     "snb_row_affine_act_fwd": (c_int, [P, P, P, ctypes.c_longlong, c_int, c_int, c_float, P, P]),
     "snb_row_affine_act_bwd": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, c_int, c_float, P, P, P, P]),
     "snb_row_minmax": (c_int, [P, ctypes.c_longlong, c_int, P, P, P, P, P]),
+    "snb_row_stats_minmax": (c_int, [P, ctypes.c_longlong, c_int, P, P, P, P, P, P, P]),
+    "snb_row_act_bwd_reduce": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P]),
+    "snb_row_norm_act_bwd": (c_int, [P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P]),
     "snb_gridding_fwd": (c_int, [P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P, P]),
     "snb_gridding_bwd": (c_int, [P, P, P, c_int, c_int, ctypes.c_longlong, P, P]),
     "snb_gridding_rev_fwd": (c_int, [P, c_int, c_int, P, P]),

@@ -222,6 +222,137 @@ __global__ void __launch_bounds__(ROW_THREADS) row_minmax_kernel(const float* __
   }
 }
 
+// row_stats + row_minmax in ONE pass over h (the refiner's 1024-channel global feature needs all six per row)
+__global__ void __launch_bounds__(ROW_THREADS) row_stats_minmax_kernel(const float* __restrict__ h, long long R, int L, float* __restrict__ mean,
+                                                                        float* __restrict__ var, float* __restrict__ vmax,
+                                                                        float* __restrict__ vmin, int* __restrict__ imax, int* __restrict__ imin) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* __restrict__ p = h + r * L;
+  const float x0 = p[0];
+  float s = 0.f, q = 0.f, mx = -3.4e38f, mn = 3.4e38f;
+  int ax = 0, an = 0;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i];
+      const float a = v.x - x0, b = v.y - x0, c = v.z - x0, d = v.w - x0;
+      s += (a + b) + (c + d);
+      q = __fmaf_rn(a, a, __fmaf_rn(b, b, __fmaf_rn(c, c, __fmaf_rn(d, d, q))));
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {  // strict comparisons keep the first position within the lane's increasing sequence
+        if (e[u] > mx) { mx = e[u]; ax = 4 * i + u; }
+        if (e[u] < mn) { mn = e[u]; an = 4 * i + u; }
+      }
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) {
+      const float v = p[i], a = v - x0;
+      s += a;
+      q = __fmaf_rn(a, a, q);
+      if (v > mx) { mx = v; ax = i; }
+      if (v < mn) { mn = v; an = i; }
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o), omn = __shfl_xor_sync(0xffffffffu, mn, o);
+    const int oax = __shfl_xor_sync(0xffffffffu, ax, o), oan = __shfl_xor_sync(0xffffffffu, an, o);
+    if (omx > mx || (omx == mx && oax < ax)) { mx = omx; ax = oax; }
+    if (omn < mn || (omn == mn && oan < an)) { mn = omn; an = oan; }
+  }
+  if (lane == 0) {
+    const float m = s / (float)L;
+    mean[r] = x0 + m;
+    var[r] = fmaxf(q / (float)L - m * m, 0.f);
+    vmax[r] = mx; vmin[r] = mn; imax[r] = ax; imin[r] = an;
+  }
+}
+
+// Two-phase backward of  y = act(scale*h + shift)  when (scale, shift) are themselves functions of the row statistics of h
+// (BatchNorm o SE o ReLU): phase A reduces  gscale[r] = sum_l d*h, gshift[r] = sum_l d  (d = gy * act'(z)) without writing
+// anything per element; the host differentiates the small closed-form (mean, var) -> (scale, shift); phase B writes
+//     gh = d*scale + gmean/L + 2 gvar (h - mean)/L
+// in one pass.  5 tensor passes instead of the 8 of {affine_act_bwd, row_stats_bwd, add}.
+__global__ void __launch_bounds__(ROW_THREADS) row_act_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ h,
+                                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                          long long R, int L, float slope, float* __restrict__ gscale,
+                                                                          float* __restrict__ gshift) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float sc = scale[r], sh = shift[r];
+  const float* __restrict__ p = h + r * L;
+  const float* __restrict__ q = gy + r * L;
+  float as = 0.f, ab = 0.f;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    const float4* __restrict__ q4 = reinterpret_cast<const float4*>(q);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i], w = q4[i];
+      const float d0 = __fmaf_rn(v.x, sc, sh) > 0.f ? w.x : w.x * slope;
+      const float d1 = __fmaf_rn(v.y, sc, sh) > 0.f ? w.y : w.y * slope;
+      const float d2 = __fmaf_rn(v.z, sc, sh) > 0.f ? w.z : w.z * slope;
+      const float d3 = __fmaf_rn(v.w, sc, sh) > 0.f ? w.w : w.w * slope;
+      as = __fmaf_rn(d0, v.x, __fmaf_rn(d1, v.y, __fmaf_rn(d2, v.z, __fmaf_rn(d3, v.w, as))));
+      ab += (d0 + d1) + (d2 + d3);
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) {
+      const float v = p[i], w = q[i];
+      const float d = __fmaf_rn(v, sc, sh) > 0.f ? w : w * slope;
+      as = __fmaf_rn(d, v, as);
+      ab += d;
+    }
+  }
+  as = warp_sum(as);
+  ab = warp_sum(ab);
+  if (lane == 0) {
+    gscale[r] = as;
+    gshift[r] = ab;
+  }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) row_norm_act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ h,
+                                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                        const float* __restrict__ mean, const float* __restrict__ gmean,
+                                                                        const float* __restrict__ gvar, long long R, int L, float slope,
+                                                                        float* __restrict__ gh) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float sc = scale[r], sh = shift[r];
+  const float invL = 1.f / (float)L;
+  const float a = gmean[r] * invL, b = 2.f * gvar[r] * invL, m = mean[r];
+  const float s1 = sc, s0 = sc * slope;
+  const float* __restrict__ p = h + r * L;
+  const float* __restrict__ q = gy + r * L;
+  float* __restrict__ g = gh + r * L;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    const float4* __restrict__ q4 = reinterpret_cast<const float4*>(q);
+    float4* __restrict__ g4 = reinterpret_cast<float4*>(g);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i], w = q4[i];
+      float4 o;
+      o.x = __fmaf_rn(w.x, __fmaf_rn(v.x, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v.x - m, a));
+      o.y = __fmaf_rn(w.y, __fmaf_rn(v.y, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v.y - m, a));
+      o.z = __fmaf_rn(w.z, __fmaf_rn(v.z, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v.z - m, a));
+      o.w = __fmaf_rn(w.w, __fmaf_rn(v.w, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v.w - m, a));
+      g4[i] = o;
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) {
+      const float v = p[i];
+      g[i] = __fmaf_rn(q[i], __fmaf_rn(v, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v - m, a));
+    }
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -273,6 +404,36 @@ SNB_API int snb_row_minmax(const float* h, long long R, int L, float* vmax, floa
   if (R == 0) return SNB_OK;
   if (R > 0x3fffffffLL) return SNB_ELIMIT;
   row_minmax_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, R, L, vmax, vmin, imax, imin);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_stats_minmax(const float* h, long long R, int L, float* mean, float* var, float* vmax, float* vmin, int* imax, int* imin,
+                                 void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_stats_minmax_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, R, L, mean, var, vmax, vmin, imax, imin);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_act_bwd_reduce(const float* gy, const float* h, const float* scale, const float* shift, long long R, int L, float slope,
+                                   float* gscale, float* gshift, void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_act_bwd_reduce_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, R, L, slope, gscale, gshift);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_norm_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, const float* mean,
+                                 const float* gmean, const float* gvar, long long R, int L, float slope, float* gh, void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_norm_act_bwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, mean, gmean, gvar, R, L, slope, gh);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

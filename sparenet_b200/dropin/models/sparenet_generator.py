@@ -77,20 +77,17 @@ def _bn_stats(bn, x, dims):
     return bn.running_mean, bn.running_var
 
 
-def _channel_stats(bn, h, row_bias=None):
-    """BatchNorm1d statistics of (h + row_bias) for h [B,C,N] from one fused row pass: per-(b,c) mean/var -> per-channel
-    mean / biased var.  row_bias ([C] or [B,C]) is constant along N, so it only shifts the row means.
-    Returns (mean [C], var [C], row_mean [B,C]); running statistics are advanced in train mode."""
-    m_bc, v_bc = fused.row_stats(h)
-    if row_bias is not None:
-        m_bc = m_bc + row_bias
+def _bn_from_rows(bn, m_bc, v_bc, L):
+    """BatchNorm1d statistics of a [B,C,L] tensor from its per-(b,c) row mean / biased variance (one fused row pass):
+    returns (mean [C], var [C]); running statistics are advanced in train mode.  A bias that is constant along L only
+    shifts the row means, so callers add it to m_bc instead of to the activations."""
     if bn.training:
         mean = m_bc.mean(0)
         dm = m_bc - mean
         var = v_bc.mean(0) + (dm * dm).mean(0)              # within-row + between-row variance: no cancellation
-        _bn_apply_stats(bn, mean, var, h.size(0) * h.size(2))
-        return mean, var, m_bc
-    return bn.running_mean, bn.running_var, m_bc
+        _bn_apply_stats(bn, mean, var, m_bc.size(0) * L)
+        return mean, var
+    return bn.running_mean, bn.running_var
 
 
 def _pconv(x, W):
@@ -174,9 +171,13 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         x3 = self._edge_block(x2, self.conv3, self.bn3, self.se3, self.resconv2)
         x4 = self._edge_block(x3, self.conv4, self.bn4, self.se4, self.resconv3)
         h = self.conv5(torch.cat((x1, x2, x3, x4), dim=1))
-        mean, var, _ = _channel_stats(self.bn5, h)
-        scale = self.bn5.weight * torch.rsqrt(var + self.bn5.eps)
-        h = fused.row_affine_act(h, scale.expand(B, -1), (self.bn5.bias - scale * mean).expand(B, -1), slope=0.2)
+        bn, L = self.bn5, h.size(2)
+
+        def tail(m_bc, v_bc, g, beta):                                # BN5 as one per-channel scale/shift
+            mean, var = _bn_from_rows(bn, m_bc, v_bc, L)
+            scale = g * torch.rsqrt(var + bn.eps)
+            return scale.expand(B, -1), (beta - scale * mean).expand(B, -1)
+        h = fused.row_norm_act(h, tail, (bn.weight, bn.bias), slope=0.2)
         return torch.cat((h.amax(2), h.mean(2)), 1).view(B, self.output_size)
 
 
@@ -267,15 +268,22 @@ class SpareNetDecode(nn.Module):  # reference :289-391
     def _stack(self, getter):
         return torch.stack([getter(d.dec) for d in self.decoder])
 
-    def _bn_se(self, layer, wsty, bsty, v):
-        """Closed-form BN statistics + SE gate after AdaIN.  wsty/bsty [B,C] style scale/shift (shared by all
-        primitives), v [P,C,B] or [P,C,1] = variance of the instance-normalised activations (= s2/(s2+eps)).
-        Returns A, D [P,C,B] with AdaIN.BN.SE(x_hat) = A * x_hat + D."""
-        P = self.n_primitives
+    def _bn_se_params(self, layer):
+        """The 32 primitives' BN / SE parameters of one decoder layer, stacked: gam, bet [P,C,1], w1 [P,C/16,C], w2 [P,C,C/16]."""
         bns = [getattr(d.dec, f"bn{layer}") for d in self.decoder]
         ses = [getattr(d.dec, f"se{layer}") for d in self.decoder]
-        gam = torch.stack([b.weight for b in bns]).unsqueeze(-1)              # [P,C,1]
+        gam = torch.stack([b.weight for b in bns]).unsqueeze(-1)
         bet = torch.stack([b.bias for b in bns]).unsqueeze(-1)
+        w1 = torch.stack([s.fc[0].weight for s in ses])
+        w2 = torch.stack([s.fc[2].weight for s in ses])
+        return bns, (gam, bet, w1, w2)
+
+    def _bn_se(self, bns, wsty, bsty, v, gam, bet, w1, w2):
+        """Closed-form BN statistics + SE gate after AdaIN.  wsty/bsty [B,C] style scale/shift (shared by all
+        primitives), v [P,C,B] or [P,C,1] = variance of the instance-normalised activations (= s2/(s2+eps)); the stacked
+        parameters come from _bn_se_params (a pure function of its tensor arguments apart from the running statistics).
+        Returns A, D [P,C,B] with AdaIN.BN.SE(x_hat) = A * x_hat + D."""
+        P = self.n_primitives
         wt, bt = wsty.t().unsqueeze(0), bsty.t().unsqueeze(0)                 # [1,C,B]
         if self.training:
             mu = bt.mean(-1, keepdim=True).expand(P, -1, -1)                  # x_hat has zero mean over the points
@@ -293,8 +301,6 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             var = torch.stack([b.running_var for b in bns]).unsqueeze(-1)
         inv = torch.rsqrt(var + EPS)
         squeeze = gam * (bt - mu) * inv + bet                                 # [P,C,B]: mean over points of BN(AdaIN(.))
-        w1 = torch.stack([s.fc[0].weight for s in ses])                       # [P,C/16,C]
-        w2 = torch.stack([s.fc[2].weight for s in ses])                       # [P,C,C/16]
         gate = torch.sigmoid(torch.bmm(w2, torch.relu(torch.bmm(w1, squeeze))))   # [P,C,B]
         A = gate * gam * inv * wt
         D = gate * (gam * inv * (bt - mu) + bet)
@@ -323,7 +329,8 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         h = torch.matmul(W1, self._grid_t)                                    # [P,1026,pts], batch independent
         var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
         xhat = (h - mean) * torch.rsqrt(var + EPS)
-        A, D = self._bn_se(1, sty[0][0], sty[0][1], var / (var + EPS))
+        bns, prm = self._bn_se_params(1)
+        A, D = self._bn_se(bns, sty[0][0], sty[0][1], var / (var + EPS), *prm)
         cp = pad8(C1)
         x = fused.row_affine_act(padc(xhat, cp), padc(A, cp), padc(D, cp), in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D)
         cin = C1
@@ -333,11 +340,15 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             cop = pad8(cout)
             Wp = F.pad(W, (0, cp - cin, 0, cop - cout))                       # zero rows / columns for the padded channels
             h = torch.bmm(Wp, x.view(P, cp, B * npts)).view(P, cop, B, npts)
-            mean, var = fused.row_stats(h)                                    # per (primitive, channel, sample)
-            rstd = torch.rsqrt(var + EPS)
-            A, D = self._bn_se(layer, sty[layer - 1][0], sty[layer - 1][1], (var / (var + EPS))[:, :cout])
-            sc = padc(A, cop) * rstd
-            x = fused.row_affine_act(h, sc, padc(D, cop) - sc * mean)
+            bns, prm = self._bn_se_params(layer)
+
+            def tail(mean, var, wsty, bsty, gam, bet, w1, w2, bns=bns, cout=cout, cop=cop):
+                """instance norm (row statistics per primitive, channel, sample) + the closed-form AdaIN.BN.SE -> one scale/shift"""
+                rstd = torch.rsqrt(var + EPS)
+                A, D = self._bn_se(bns, wsty, bsty, (var / (var + EPS))[:, :cout], gam, bet, w1, w2)
+                sc = padc(A, cop) * rstd
+                return sc, padc(D, cop) - sc * mean
+            x = fused.row_norm_act(h, tail, (sty[layer - 1][0], sty[layer - 1][1]) + prm)
             cin, cp = cout, cop
         W4 = F.pad(self._stack(lambda d: d.conv4.weight.squeeze(-1)), (0, cp - cin))   # [P,3,256]
         b4 = self._stack(lambda d: d.conv4.bias).view(P, 3, 1)
@@ -372,23 +383,29 @@ class PointNetRes(nn.Module):  # reference :582-646
     def _bn_se_relu(h, bn, se, row_bias):
         """relu(SE(BN(h + row_bias))) as ONE per-(sample,channel) scale/shift over h [B,C,N]; row_bias ([C] conv bias or
         [B,C]) is never added to the activations: it only shifts the statistics and folds into the shift."""
-        mean, var, m_bc = _channel_stats(bn, h, row_bias)
-        inv = torch.rsqrt(var + bn.eps)
-        scale, shift = bn.weight * inv, bn.bias - bn.weight * inv * mean      # [C]
-        gate = se.gate(m_bc * scale + shift)                                   # [B,C]: SE squeeze = mean over points of BN(.)
-        gs = gate * scale
-        return fused.row_affine_act(h, gs, gate * shift + row_bias * gs)
+        L = h.size(2)
+
+        def tail(m_bc, v_bc, rb, g, beta, w1, w2):
+            m = m_bc + rb
+            mean, var = _bn_from_rows(bn, m, v_bc, L)
+            inv = torch.rsqrt(var + bn.eps)
+            scale, shift = g * inv, beta - g * inv * mean                      # [C]
+            gate = torch.sigmoid(F.linear(torch.relu(F.linear(m * scale + shift, w1)), w2))   # [B,C]: SE squeeze = mean over points of BN(.)
+            gs = gate * scale
+            return gs, gate * shift + rb * gs
+        return fused.row_norm_act(h, tail, (row_bias, bn.weight, bn.bias, se.fc[0].weight, se.fc[2].weight))
 
     def forward(self, x):
         B = x.size(0)
         x = self._bn_se_relu(_pconv(x, self.conv1.weight), self.bn1, self.se1, self.conv1.bias)
         pointfeat = x
         x = self._bn_se_relu(F.conv1d(x, self.conv2.weight), self.bn2, self.se2, self.conv2.bias)
-        h3 = F.conv1d(x, self.conv3.weight)                                    # [B,1024,N]; the bias is folded below
-        mean, var, _ = _channel_stats(self.bn3, h3, self.conv3.bias)
+        # conv3 -> bn3 -> max over points: only row statistics and extrema of h3 = W3 x are needed, so the [B,1024,N] tensor is
+        # reduced in one pass and never kept; its gradient goes through 128x128 Gram matrices (fused.conv_row_reduce)
+        m_bc, v_bc, hmax, hmin = fused.conv_row_reduce(x, self.conv3.weight)
+        mean, var = _bn_from_rows(self.bn3, m_bc + self.conv3.bias, v_bc, x.size(2))
         inv = torch.rsqrt(var + self.bn3.eps)
         g3 = self.bn3.weight
-        hmax, hmin = fused.row_minmax(h3)
         hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin) + self.conv3.bias   # max_N BN(h3) only needs max/min of h3
         glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
         W4 = self.conv4.weight

@@ -133,8 +133,132 @@ class RowMinMax(torch.autograd.Function):
         return gh
 
 
+class RowNormAct(torch.autograd.Function):
+    """y = leaky_relu(scale * h + shift, slope) with (scale, shift) = fn(row_mean(h), row_var(h), *tensors): the whole
+    BatchNorm o SE o ReLU tail of a dense layer as ONE autograd node.  Forward: row_stats kernel, the small closed form `fn`
+    (plain torch on [rows]-sized tensors, recorded on detached leaves), affine+act kernel.  Backward: phase A reduces
+    (gscale, gshift) without touching gh, autograd pulls them through the recorded small graph to (gmean, gvar) and the
+    gradients of `tensors`, phase B writes gh once -- the two gradient paths into h are summed inside the kernel instead of
+    by a third full-size pass (see snb_row_act_bwd_reduce / snb_row_norm_act_bwd)."""
+    @staticmethod
+    def forward(ctx, h, fn, slope, *tensors):
+        h = h.contiguous()
+        L = h.shape[-1]
+        R = h.numel() // L
+        lib = _lib.load()
+        mean = torch.empty(h.shape[:-1], device=h.device, dtype=torch.float32)
+        var = torch.empty_like(mean)
+        with torch.cuda.device(h.device), _op("row_stats", 1):
+            check(lib.snb_row_stats(ptr(h), R, L, ptr(mean), ptr(var), stream_ptr()), "row_stats")
+        with torch.enable_grad():
+            m_, v_ = mean.requires_grad_(True), var.requires_grad_(True)
+            ts = [t.detach().requires_grad_(t.requires_grad) for t in tensors]
+            scale, shift = fn(m_, v_, *ts)
+        assert scale.shape == mean.shape and shift.shape == mean.shape, "fn must return per-row scale/shift"
+        sc, sh = scale.detach().contiguous().float(), shift.detach().contiguous().float()
+        y = torch.empty_like(h)
+        with torch.cuda.device(h.device), _op("row_affine_act_fwd", 1):
+            check(lib.snb_row_affine_act_fwd(ptr(h), ptr(sc), ptr(sh), R, L, 1, float(slope), ptr(y), stream_ptr()), "row_affine_act_fwd")
+        ctx.save_for_backward(h, sc, sh)
+        ctx.graph = (m_, v_, ts, scale, shift)
+        ctx.slope = float(slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        h, sc, sh = ctx.saved_tensors
+        m_, v_, ts, scale, shift = ctx.graph
+        L = h.shape[-1]
+        R = h.numel() // L
+        lib = _lib.load()
+        gy = gy.contiguous()
+        gsc, gsh = torch.empty_like(sc), torch.empty_like(sh)
+        with torch.cuda.device(h.device), _op("row_act_bwd_reduce", 1):
+            check(lib.snb_row_act_bwd_reduce(ptr(gy), ptr(h), ptr(sc), ptr(sh), R, L, ctx.slope, ptr(gsc), ptr(gsh), stream_ptr()),
+                  "row_act_bwd_reduce")
+        wanted = [m_, v_] + [t for t in ts if t.requires_grad]
+        grads = torch.autograd.grad((scale, shift), wanted, (gsc.view_as(scale), gsh.view_as(shift)), allow_unused=True, retain_graph=True)
+        gm = (grads[0] if grads[0] is not None else torch.zeros_like(sc)).contiguous().float()
+        gv = (grads[1] if grads[1] is not None else torch.zeros_like(sc)).contiguous().float()
+        gh = torch.empty_like(h)
+        with torch.cuda.device(h.device), _op("row_norm_act_bwd", 1):
+            check(lib.snb_row_norm_act_bwd(ptr(gy), ptr(h), ptr(sc), ptr(sh), ptr(m_.detach()), ptr(gm), ptr(gv), R, L, ctx.slope, ptr(gh),
+                                           stream_ptr()), "row_norm_act_bwd")
+        it = iter(grads[2:])
+        gts = [next(it) if t.requires_grad else None for t in ts]
+        return (gh, None, None, *gts)
+
+
+def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, need_x=True, need_w=True):
+    """Adjoint of (x [B,Ci,N], W [Co,Ci]) -> per-row mean / biased var / max / min of h = W x WITHOUT h.
+    The statistics' gradient is dense in h but affine in it, gh = a*h + b per row (a = 2 gvar/N, b = gmean/N - a*mean), so with
+    h = W x:   gx = (W^T diag(a) W) x + W^T b 1^T,   gW = sum_b diag(a_b) W (x_b x_b^T) + b_b (sum_n x_b)^T
+    -- Ci x Ci Gram matrices instead of two GEMMs over the [B,Co,N] tensor; the max/min gradients touch one column each.
+    Device-agnostic torch (the small matrices in float64); verified against autograd in tests/."""
+    B, Ci, N = x.shape
+    dt = x.dtype
+    z = torch.zeros_like(mean)
+    gmean = z if gmean is None else gmean
+    gvar = z if gvar is None else gvar
+    a = gvar.double() * (2.0 / N)                                  # [B,Co]
+    b = gmean.double() / N - a * mean.double()
+    Wd = W.double()
+    WA = a.unsqueeze(-1) * Wd                                     # [B,Co,Ci]
+    gx = gW = None
+    if need_x:
+        M = torch.matmul(Wd.t(), WA).to(dt)                       # [B,Ci,Ci] = W^T diag(a_b) W
+        gx = torch.bmm(M, x)
+        gx += torch.matmul(b, Wd).to(dt).unsqueeze(-1)
+    if need_w:
+        G = torch.bmm(x, x.transpose(1, 2)).double()              # [B,Ci,Ci]
+        gW = torch.bmm(WA, G).sum(0) + torch.matmul(b.t(), x.sum(2).double())
+    for g, idx in ((gmax, imax), (gmin, imin)):
+        if g is None:
+            continue
+        col = idx.long().unsqueeze(1).expand(B, Ci, -1)           # column of x each (sample, out-channel) extremum sits in
+        if need_x:
+            gx.scatter_add_(2, col, (g.unsqueeze(-1) * W).transpose(1, 2))
+        if need_w:
+            gW += torch.einsum("bc,bic->ci", g.double(), x.gather(2, col).double())
+    return gx, (gW.to(dt) if gW is not None else None)
+
+
+class ConvRowReduce(torch.autograd.Function):
+    """x [B,Ci,N], W [Co,Ci] -> (mean, biased var, max, min) over N of h = W x, each [B,Co].  h is produced by the library
+    1x1 convolution, reduced by ONE pass of snb_row_stats_minmax and dropped; the backward is conv_row_reduce_backward."""
+    @staticmethod
+    def forward(ctx, x, W):
+        x = x.contiguous()
+        W2 = W.reshape(W.size(0), -1)
+        h = torch.nn.functional.conv1d(x, W2.unsqueeze(-1))
+        B, Co, N = h.shape
+        dev = h.device
+        mean, var, vmax, vmin = (torch.empty(B, Co, device=dev, dtype=torch.float32) for _ in range(4))
+        imax, imin = (torch.empty(B, Co, device=dev, dtype=torch.int32) for _ in range(2))
+        with torch.cuda.device(dev), _op("row_stats_minmax", 1):
+            check(_lib.load().snb_row_stats_minmax(ptr(h), B * Co, N, ptr(mean), ptr(var), ptr(vmax), ptr(vmin), ptr(imax), ptr(imin), stream_ptr()),
+                  "row_stats_minmax")
+        ctx.save_for_backward(x, W2, mean, imax, imin)
+        ctx.wshape = W.shape
+        return mean, var, vmax, vmin
+
+    @staticmethod
+    def backward(ctx, gmean, gvar, gmax, gmin):
+        x, W2, mean, imax, imin = ctx.saved_tensors
+        gx, gW = conv_row_reduce_backward(x, W2, mean, imax, imin, gmean, gvar, gmax, gmin, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return gx, (gW.view(ctx.wshape) if gW is not None else None)
+
+
 def edge_reduce(a, c, idx):
     return EdgeReduce.apply(a, c, idx)
+
+
+def row_norm_act(h, fn, tensors, slope=0.0):
+    return RowNormAct.apply(h, fn, slope, *tensors)
+
+
+def conv_row_reduce(x, W):
+    return ConvRowReduce.apply(x, W)
 
 
 def row_stats(h):

@@ -31,7 +31,19 @@ def row_minmax(h):
     return h.amax(-1), h.amin(-1)
 
 
+def row_norm_act(h, fn, tensors, slope=0.0):
+    mean, var = row_stats(h)
+    scale, shift = fn(mean, var, *tensors)
+    return F.leaky_relu(h * scale.unsqueeze(-1) + shift.unsqueeze(-1), slope)
+
+
+def conv_row_reduce(x, W):
+    h = torch.matmul(W.reshape(W.size(0), -1), x)
+    mean, var = row_stats(h)
+    return mean, var, h.amax(-1), h.amin(-1)
+
+
 def patch(monkeypatch):
     from sparenet_b200 import fused
-    for name in ("edge_reduce", "row_stats", "row_affine_act", "row_minmax"):
+    for name in ("edge_reduce", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce"):
         monkeypatch.setattr(fused, name, globals()[name])

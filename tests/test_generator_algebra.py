@@ -150,6 +150,26 @@ def test_full_generator_vs_restatement_on_cpu(cpu_point_ops):
     assert all(torch.isfinite(p.grad).all() for p in mine.parameters() if p.grad is not None)
 
 
+def test_conv_row_reduce_gram_backward_is_exact_in_float64():
+    """fused.conv_row_reduce_backward (Gram-matrix adjoint of the row statistics/extrema of h = W x, h never formed) against
+    autograd through the explicit h -- the identity behind the refiner's conv3 -> bn3 -> max path."""
+    from sparenet_b200 import fused
+    from tests import fused_ref
+    torch.manual_seed(5)
+    B, Ci, Co, N = 3, 7, 19, 200
+    x = torch.randn(B, Ci, N, dtype=torch.float64, requires_grad=True)
+    W = torch.randn(Co, Ci, dtype=torch.float64, requires_grad=True)
+    outs = fused_ref.conv_row_reduce(x, W)
+    gs = [torch.randn_like(o) for o in outs]
+    gx_ref, gW_ref = torch.autograd.grad(outs, (x, W), gs, retain_graph=True)
+    h = torch.matmul(W, x).detach()
+    gx, gW = fused.conv_row_reduce_backward(x.detach(), W.detach(), outs[0].detach(), h.argmax(-1).int(), h.argmin(-1).int(), *gs)
+    assert torch.allclose(gx, gx_ref, rtol=1e-10, atol=1e-12) and torch.allclose(gW, gW_ref, rtol=1e-10, atol=1e-12)
+    gx, gW = fused.conv_row_reduce_backward(x.detach(), W.detach(), outs[0].detach(), h.argmax(-1).int(), h.argmin(-1).int(), gs[0], None, None, gs[3])
+    gx_ref, gW_ref = torch.autograd.grad((outs[0], outs[3]), (x, W), (gs[0], gs[3]))
+    assert torch.allclose(gx, gx_ref, rtol=1e-10, atol=1e-12) and torch.allclose(gW, gW_ref, rtol=1e-10, atol=1e-12)
+
+
 def test_unsupported_configurations_raise():
     from sparenet_b200.dropin.models import sparenet_generator as M
     with pytest.raises(NotImplementedError):

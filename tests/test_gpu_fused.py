@@ -84,3 +84,61 @@ def test_row_minmax(cuda):
     (vmax.sum() + 2 * vmin.sum()).backward()
     assert h1.grad[0, 0, 10] == 1 and h1.grad[0, 0, 500] == 0
     assert h1.grad.sum().item() == pytest.approx(3 * 5 * 33)
+
+
+@pytest.mark.parametrize("B,C,L,slope", [(4, 16, 512, 0.0), (3, 8, 2048, 0.2), (2, 5, 333, 0.0)])
+def test_row_norm_act_forward_backward(cuda, B, C, L, slope):
+    """BN o SE o (leaky)ReLU as one node: two-phase backward (snb_row_act_bwd_reduce / snb_row_norm_act_bwd) vs autograd in fp64."""
+    from sparenet_b200 import fused
+    torch.manual_seed(B * 100 + L)
+    h = torch.randn(B, C, L, device=cuda) * 0.7 + 0.3
+    g, beta, rb = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1, torch.randn(B, C, device=cuda) * 0.2
+    w1, w2 = torch.randn(max(C // 4, 1), C, device=cuda) * 0.5, torch.randn(C, max(C // 4, 1), device=cuda) * 0.5
+
+    def tail(m_bc, v_bc, rb, g, beta, w1, w2):                  # the refiner's closed form (PointNetRes._bn_se_relu)
+        m = m_bc + rb
+        mean = m.mean(0)
+        var = v_bc.mean(0) + ((m - mean) ** 2).mean(0)
+        inv = torch.rsqrt(var + 1e-5)
+        scale, shift = g * inv, beta - g * inv * mean
+        gate = torch.sigmoid(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(m * scale + shift, w1)), w2))
+        return gate * scale, gate * shift + rb * gate * scale
+
+    leaves32 = [t.clone().requires_grad_() for t in (h, rb, g, beta, w1, w2)]
+    leaves64 = [t.double().requires_grad_() for t in (h, rb, g, beta, w1, w2)]
+    y1 = fused.row_norm_act(leaves32[0], tail, tuple(leaves32[1:]), slope)
+    y2 = R.row_norm_act(leaves64[0], tail, tuple(leaves64[1:]), slope)
+    assert _close(y1, y2, 1e-5, 1e-6)
+    w = torch.randn_like(y1)
+    (y1 * w).sum().backward()
+    (y2 * w.double()).sum().backward()
+    for name, a, b in zip(("h", "row_bias", "gamma", "beta", "w1", "w2"), leaves32, leaves64):
+        err = (a.grad.double() - b.grad).abs().max().item() / (b.grad.abs().max().item() + 1e-30)
+        print(f"[row_norm_act] B={B} C={C} L={L} grad {name}: err/scale {err:.2e}")
+        assert err < 2e-5, name
+
+
+@pytest.mark.parametrize("B,Ci,Co,N", [(3, 16, 40, 700), (2, 128, 1024, 4096)])
+def test_conv_row_reduce_forward_backward(cuda, B, Ci, Co, N):
+    """h = W x reduced to row mean/var/max/min in one pass; Gram-matrix backward vs autograd through the explicit h (fp64)."""
+    from sparenet_b200 import fused
+    torch.manual_seed(Co + N)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # fp32 GEMMs: test the algebra, not TF32
+    try:
+        x, W = torch.randn(B, Ci, N, device=cuda), torch.randn(Co, Ci, 1, device=cuda) / Ci ** 0.5
+        x1, W1 = x.clone().requires_grad_(), W.clone().requires_grad_()
+        x2, W2 = x.double().requires_grad_(), W.double().requires_grad_()
+        o1 = fused.conv_row_reduce(x1, W1)
+        o2 = R.conv_row_reduce(x2, W2)
+        for a, b, tol in zip(o1, o2, (1e-5, 1e-5, 1e-5, 1e-5)):
+            assert _close(a, b, tol, 1e-6)
+        ws = [torch.randn_like(t) for t in o1]
+        sum((a * w).sum() for a, w in zip(o1, ws)).backward()
+        sum((a * w.double()).sum() for a, w in zip(o2, ws)).backward()
+        ex = (x1.grad.double() - x2.grad).abs().max().item() / x2.grad.abs().max().item()
+        ew = (W1.grad.double() - W2.grad).abs().max().item() / W2.grad.abs().max().item()
+        print(f"[conv_row_reduce] B={B} {Ci}->{Co} N={N}: grad err/scale x={ex:.2e} W={ew:.2e}")
+        assert ex < 2e-5 and ew < 2e-5
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
