@@ -131,8 +131,8 @@ def test_conv_row_reduce_forward_backward(cuda, B, Ci, Co, N):
         x2, W2 = x.double().requires_grad_(), W.double().requires_grad_()
         o1 = fused.conv_row_reduce(x1, W1)
         o2 = R.conv_row_reduce(x2, W2)
-        for a, b, tol in zip(o1, o2, (1e-5, 1e-5, 1e-5, 1e-5)):
-            assert _close(a, b, tol, 1e-6)
+        for a, b in zip(o1, o2):                                  # h has unit scale: the row means nearly cancel, so the floor is absolute
+            assert torch.allclose(a.double(), b, rtol=1e-5, atol=2e-6)
         ws = [torch.randn_like(t) for t in o1]
         sum((a * w).sum() for a, w in zip(o1, ws)).backward()
         sum((a * w.double()).sum() for a, w in zip(o2, ws)).backward()
