@@ -34,8 +34,8 @@ PROFILE = None  # set to a dict {op: [(start_event, end_event), ...]} by bench.p
 
 class _op:
     """Counts the kernels a C-ABI call launches and, when PROFILE is set, brackets it with CUDA events."""
-    def __init__(self, name, launches):
-        self.name, self.launches = name, launches
+    def __init__(self, name, launches, nbytes=None):
+        self.name, self.launches, self.nbytes = name, launches, nbytes   # nbytes: algorithmic HBM bytes of the call (roofline)
 
     def __enter__(self):
         LAUNCHES["count"] += self.launches
@@ -48,7 +48,7 @@ class _op:
         if PROFILE is not None:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
-            PROFILE.setdefault(self.name, []).append((self.a, b))
+            PROFILE.setdefault(self.name, []).append((self.a, b, self.nbytes))
         return False
 
 

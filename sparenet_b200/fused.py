@@ -53,7 +53,7 @@ class RowStats(torch.autograd.Function):
         R = h.numel() // L
         mean = torch.empty(h.shape[:-1], device=h.device, dtype=torch.float32)
         var = torch.empty_like(mean)
-        with torch.cuda.device(h.device), _op("row_stats", 1):
+        with torch.cuda.device(h.device), _op("row_stats", 1, 4 * h.numel()):
             check(_lib.load().snb_row_stats(ptr(h), R, L, ptr(mean), ptr(var), stream_ptr()), "row_stats")
         ctx.save_for_backward(h, mean)
         return mean, var
@@ -66,7 +66,7 @@ class RowStats(torch.autograd.Function):
         gmean = (gmean if gmean is not None else torch.zeros_like(mean)).contiguous()
         gvar = (gvar if gvar is not None else torch.zeros_like(mean)).contiguous()
         gh = torch.empty_like(h)
-        with torch.cuda.device(h.device), _op("row_stats_bwd", 1):
+        with torch.cuda.device(h.device), _op("row_stats_bwd", 1, 8 * h.numel()):
             check(_lib.load().snb_row_stats_bwd(ptr(h), ptr(mean), ptr(gmean), ptr(gvar), R, L, ptr(gh), stream_ptr()), "row_stats_bwd")
         return gh
 
@@ -148,7 +148,7 @@ class RowNormAct(torch.autograd.Function):
         lib = _lib.load()
         mean = torch.empty(h.shape[:-1], device=h.device, dtype=torch.float32)
         var = torch.empty_like(mean)
-        with torch.cuda.device(h.device), _op("row_stats", 1):
+        with torch.cuda.device(h.device), _op("row_stats", 1, 4 * h.numel()):
             check(lib.snb_row_stats(ptr(h), R, L, ptr(mean), ptr(var), stream_ptr()), "row_stats")
         with torch.enable_grad():
             m_, v_ = mean.requires_grad_(True), var.requires_grad_(True)
@@ -157,7 +157,7 @@ class RowNormAct(torch.autograd.Function):
         assert scale.shape == mean.shape and shift.shape == mean.shape, "fn must return per-row scale/shift"
         sc, sh = scale.detach().contiguous().float(), shift.detach().contiguous().float()
         y = torch.empty_like(h)
-        with torch.cuda.device(h.device), _op("row_affine_act_fwd", 1):
+        with torch.cuda.device(h.device), _op("row_affine_act_fwd", 1, 8 * h.numel()):
             check(lib.snb_row_affine_act_fwd(ptr(h), ptr(sc), ptr(sh), R, L, 1, float(slope), ptr(y), stream_ptr()), "row_affine_act_fwd")
         ctx.save_for_backward(h, sc, sh)
         ctx.graph = (m_, v_, ts, scale, shift)
@@ -173,7 +173,7 @@ class RowNormAct(torch.autograd.Function):
         lib = _lib.load()
         gy = gy.contiguous()
         gsc, gsh = torch.empty_like(sc), torch.empty_like(sh)
-        with torch.cuda.device(h.device), _op("row_act_bwd_reduce", 1):
+        with torch.cuda.device(h.device), _op("row_act_bwd_reduce", 1, 8 * h.numel()):
             check(lib.snb_row_act_bwd_reduce(ptr(gy), ptr(h), ptr(sc), ptr(sh), R, L, ctx.slope, ptr(gsc), ptr(gsh), stream_ptr()),
                   "row_act_bwd_reduce")
         wanted = [m_, v_] + [t for t in ts if t.requires_grad]
@@ -181,7 +181,7 @@ class RowNormAct(torch.autograd.Function):
         gm = (grads[0] if grads[0] is not None else torch.zeros_like(sc)).contiguous().float()
         gv = (grads[1] if grads[1] is not None else torch.zeros_like(sc)).contiguous().float()
         gh = torch.empty_like(h)
-        with torch.cuda.device(h.device), _op("row_norm_act_bwd", 1):
+        with torch.cuda.device(h.device), _op("row_norm_act_bwd", 1, 12 * h.numel()):
             check(lib.snb_row_norm_act_bwd(ptr(gy), ptr(h), ptr(sc), ptr(sh), ptr(m_.detach()), ptr(gm), ptr(gv), R, L, ctx.slope, ptr(gh),
                                            stream_ptr()), "row_norm_act_bwd")
         it = iter(grads[2:])
@@ -235,7 +235,7 @@ class ConvRowReduce(torch.autograd.Function):
         dev = h.device
         mean, var, vmax, vmin = (torch.empty(B, Co, device=dev, dtype=torch.float32) for _ in range(4))
         imax, imin = (torch.empty(B, Co, device=dev, dtype=torch.int32) for _ in range(2))
-        with torch.cuda.device(dev), _op("row_stats_minmax", 1):
+        with torch.cuda.device(dev), _op("row_stats_minmax", 1, 4 * h.numel()):
             check(_lib.load().snb_row_stats_minmax(ptr(h), B * Co, N, ptr(mean), ptr(var), ptr(vmax), ptr(vmin), ptr(imax), ptr(imin), stream_ptr()),
                   "row_stats_minmax")
         ctx.save_for_backward(x, W2, mean, imax, imin)

@@ -1,0 +1,44 @@
+"""CUDA-graph capture of one training step's forward + backward (host plumbing; no arithmetic here).
+
+The generator step issues ~2000 launches, most of them microsecond-sized closed-form normalisation math between the big
+kernels; replaying them as one graph removes the per-launch gaps.  The optimizer step (and, under data parallelism, the
+gradient all-reduce) stays outside the graph so the same capture serves 1 and N GPUs.
+
+    step = GraphedForwardBackward(loss_fn, params, example_inputs)   # warms up on a side stream, then captures
+    loss = step(partial, gt)        # copies into the static inputs (host or device sources), replays, returns the static loss
+    optimizer.step()                # gradients live in static .grad tensors: never call zero_grad(set_to_none=True) afterwards
+
+Everything the sm_100a kernels need during capture is capture-safe: they launch on the current stream, take their scratch
+from the caching allocator (graph-private pool) and never synchronise.
+"""
+import torch
+
+
+class GraphedForwardBackward:
+    def __init__(self, loss_fn, params, example_inputs, warmup=3):
+        self.params = [p for p in params if p.requires_grad]
+        self.static_inputs = [torch.empty_like(t, device=self.params[0].device) for t in example_inputs]
+        for s, t in zip(self.static_inputs, example_inputs):
+            s.copy_(t)
+        dev = self.params[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                for p in self.params:
+                    p.grad = None
+                loss_fn(*self.static_inputs).backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = loss_fn(*self.static_inputs)
+            self.static_loss.backward()
+
+    def __call__(self, *inputs):
+        for s, t in zip(self.static_inputs, inputs):
+            if t is not s:
+                s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
