@@ -87,9 +87,10 @@ def chamfer_forward(xyz1, xyz2):
     with torch.cuda.device(dev), _op("chamfer_fwd", 2 if nbytes else 1):
         check(lib.snb_chamfer_fwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), ptr(ws), nbytes, stream_ptr()), "chamfer_fwd")
     c.clear()
-    # detached aliases share storage and version counter but not the autograd graph: holding the inputs themselves would keep the
+    # detached aliases share storage and version counter but not the autograd graph: the inputs carry their history, and the
+    # outputs get the calling autograd.Function's grad_fn attached in place once it returns -- holding either would keep the
     # previous step's whole graph (and its AccumulateGrad nodes) alive
-    c.update(key=key, keep=(xyz1.detach(), xyz2.detach()), out=(d1, d2, i1, i2))
+    c.update(key=key, keep=(xyz1.detach(), xyz2.detach()), out=(d1.detach(), d2.detach(), i1, i2))
     return d1, d2, i1, i2
 
 

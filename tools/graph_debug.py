@@ -21,6 +21,17 @@ p, g = hp.to(dev), hg.to(dev)
 for _ in range(2):
     step(p, g)
 torch.cuda.synchronize()
+import gc  # noqa: E402
+
+live = [o for o in gc.get_objects() if isinstance(o, torch.Tensor) and o.grad_fn is not None]
+print("tensors still holding a graph after the eager steps:", len(live))
+for o in live[:20]:
+    print("   ", tuple(o.shape), type(o.grad_fn).__name__, "referrers:", [type(r).__name__ for r in gc.get_referrers(o)][:6])
+del live
+gc.collect()
+live = [o for o in gc.get_objects() if isinstance(o, torch.Tensor) and o.grad_fn is not None]
+print("after gc.collect():", len(live))
+del live
 mode = os.environ.get("MODE", "fwd")
 for prm in step.params:
     prm.grad = None
