@@ -165,7 +165,7 @@ def build_gpu(args, dev, rank):
     sys.path.insert(0, sparenet_b200.dropin_path())
     from sparenet_b200.dropin.cuda.chamfer_distance import ChamferDistance, ChamferDistanceMean
     from sparenet_b200.dropin.models.sparenet_generator import SpareNetGenerator
-    from oracle.generator_ref import init_weights  # initialisation recipe only (utils/model_init.py:137-159), no compute
+    from sparenet_b200.dropin.utils.model_init import init_weights  # utils/model_init.py:137-159
 
     torch.backends.cuda.matmul.allow_tf32 = True       # the reference's cuDNN convs run TF32 by default on this class of GPU
     torch.backends.cudnn.allow_tf32 = True

@@ -190,7 +190,7 @@ def test_emd_vs_reference_extension(cuda):
     ours = (ass == ra1).float().mean().item()
     e_ref1, e_ref2, e_ours = rd1.sqrt().mean().item(), rd2.sqrt().mean().item(), dist.sqrt().mean().item()
     print(f"[emd] ref-vs-ref identical={ref_self:.6f} ours-vs-ref identical={ours:.6f} emd ref={e_ref1:.7f}/{e_ref2:.7f} ours={e_ours:.7f}")
-    # tools/diag2.py (crafted duplicate bidders) shows the reference's GetMax winner is scheduling dependent: lower lane
+    # tests/perf/diag2.py (crafted duplicate bidders) shows the reference's GetMax winner is scheduling dependent: lower lane
     # inside a warp, otherwise whichever warp/block stores last -- no index rule reproduces it.  Our rule (largest index)
     # therefore departs from it on a few bids per round; the loss value agrees to ~1e-5 and >99% of matches coincide.
     band = max(abs(e_ref1 - e_ref2), 1e-5 * e_ref1)
