@@ -73,8 +73,9 @@ SELayer1D = SELayer
 def get_graph_feature(x, k, knn_fn):  # :880-906
     B, C, N = x.shape
     idx = knn_fn(x, k).long()                                   # [B, N, k]
-    xt = x.transpose(2, 1)                                      # [B, N, C]
-    nb = torch.gather(xt.unsqueeze(1).expand(-1, N, -1, -1), 2, idx.unsqueeze(-1).expand(-1, -1, -1, C))  # [B,N,k,C]
+    xt = x.transpose(2, 1).contiguous()                         # [B, N, C]
+    flat = (idx + torch.arange(B, device=x.device).view(B, 1, 1) * N).view(-1)    # :893-899: batch offset, flat row gather
+    nb = xt.view(B * N, C)[flat].view(B, N, k, C)
     ctr = xt.unsqueeze(2).expand(-1, -1, k, -1)
     return torch.cat((nb - ctr, ctr), dim=3).permute(0, 3, 1, 2).contiguous()  # [B, 2C, N, k]
 

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_graphed_forward_backward_matches_eager(cuda):
-    from oracle.generator_ref import init_weights          # initialisation recipe only
+    from sparenet_b200.dropin.utils.model_init import init_weights
     from sparenet_b200.dropin.cuda.chamfer_distance import ChamferDistanceMean
     from sparenet_b200.dropin.models.sparenet_generator import SpareNetGenerator
     from sparenet_b200.graph import GraphedForwardBackward
@@ -41,12 +41,20 @@ def test_graphed_forward_backward_matches_eager(cuda):
     net.load_state_dict(state)
     loss_g = g(partial, gt).item()
     assert abs(loss_g - loss_e) <= 1e-6 * abs(loss_e)
-    worst = 0.0
+    # Parameters whose gradient is identically zero in exact arithmetic (conv biases in front of a normalisation) carry
+    # only rounding noise, which float atomics reorder between runs: each deviation is measured against the parameter's
+    # own gradient scale plus a floor of 1e-4 of the largest gradient in the model.
+    gmax = max(v.abs().max().item() for v in grads_e.values())
+    rows = []
     for n, p in net.named_parameters():
         if n in grads_e:
-            scale = grads_e[n].abs().max().item() + 1e-12
-            worst = max(worst, (p.grad - grads_e[n]).abs().max().item() / scale)
-    print(f"[graph] loss eager {loss_e:.8f} graph {loss_g:.8f}; worst grad deviation / scale {worst:.2e}")
-    assert worst < 1e-4                                      # atomics in the scatter kernels may reorder float additions
+            scale = grads_e[n].abs().max().item() + 1e-4 * gmax
+            rows.append(((p.grad - grads_e[n]).abs().max().item() / scale, n, grads_e[n].abs().max().item()))
+    rows.sort(reverse=True)
+    worst = rows[0][0]
+    print(f"[graph] loss eager {loss_e:.8f} graph {loss_g:.8f}; largest gradient {gmax:.3e}; worst deviations / scale:")
+    for r in rows[:5]:
+        print(f"    {r[0]:.2e}  {r[1]}  (|grad|max {r[2]:.3e})")
+    assert worst < 1e-4, rows[:5]                             # atomics in the scatter kernels may reorder float additions
     loss_g2 = g(partial, gt).item()                          # replay is repeatable
     assert abs(loss_g2 - loss_g) <= 1e-6 * abs(loss_g)

@@ -17,6 +17,13 @@ dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 step, hp, hg = bench.build_gpu(A, dev, 0)
 p, g = hp.to(dev), hg.to(dev)
-for _ in range(int(os.environ.get("NSTEPS", "2"))):
+n = int(os.environ.get("NSTEPS", "2"))
+rng = os.environ.get("NCU_RANGE") == "1"   # with `ncu --profile-from-start off`: profile only the last step
+for i in range(n):
+    if rng and i == n - 1:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
     step(p, g)
 torch.cuda.synchronize()
+if rng:
+    torch.cuda.cudart().cudaProfilerStop()
