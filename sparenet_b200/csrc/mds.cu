@@ -11,13 +11,22 @@
 //   The reference accumulates as (float)((double)temp + (double)w): for one addition of two floats, double
 //   rounding through fp64 is innocuous (53 >= 2*24+2), so a plain fp32 add is bit-identical.
 //
-// Design: the m-1 rounds are a latency chain, so the only lever is the time of ONE round.  A thread-block
-// CLUSTER (up to 8 CTAs = 8 SMs) owns one sample; every point (xyz + density) lives in registers for the
-// whole kernel; a round is: register update -> packed (density,key) u64 warp arg-min by shuffles -> each warp
-// pushes its candidate (+ coordinates) into every CTA of the cluster with st.async, which also completes tx-bytes
-// on the peer's mbarrier -> every warp waits on its own CTA's mbarrier and reduces the <= 128 candidates.
-// No global/shared traffic for `temp`, no block barrier, no barrier.cluster and no global load inside the loop
-// (the reference does 11 block barriers and a global read-modify-write of `temp` per round).
+// Design.  The m-1 picks are a dependent chain, but only locally: a pick changes the densities of its neighbourhood
+// (for 90 % of the live points the added weight is below half an ulp of their density) and the NEXT pick is almost always
+// somewhere else.  So the chain is cut into GENERATIONS that are exact, not speculative:
+//   1. every warp publishes its MDS_M lowest (density, tie key) candidates -- with coordinates -- and its (MDS_M+1)-th lowest
+//      pair as a bound; all candidates of the cluster form the POOL (<= 128 warps x 4), theta = min over warps of the bounds.
+//      Every point outside the pool is >= theta, and densities only ever grow;
+//   2. ONE warp per CTA replays the sequential algorithm on the pool alone, in registers, with the very same arithmetic:
+//      update the pool with the last pick's weights, take the arg-min, accept it while (density, key) < theta -- an accepted
+//      pick is the global arg-min of the sequential algorithm (nothing outside the pool can have dropped below theta).  The
+//      first candidate is always accepted, typically ~18 are (measured on the bench clouds: 932 generations for 16383 picks);
+//   3. all warps apply the accepted picks, in order, to their own points (the same sequence of fp32 additions as the
+//      reference's rounds), park the picked points, and select again.
+// One cluster exchange (st.async + mbarrier complete_tx, no barrier.cluster) per generation instead of one per pick; the
+// per-pick chain shrinks to ~130 instructions of one warp.  A thread-block CLUSTER (up to 8 CTAs) owns one sample; every point
+// (xyz + density) lives in registers for the whole kernel; the reference does 11 block barriers and a global read-modify-write
+// of `temp` per pick.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,11 +34,13 @@
 
 namespace snb {
 
-constexpr int MDS_MAX_WARPS = 16;  // warps per CTA: 8 (256 threads, the default) or 16
+constexpr int MDS_MAX_WARPS = 16;  // warps per CTA: 4 (128 threads, the default), 8 or 16
 constexpr int MDS_MAX_CLUSTER = 8;
+constexpr int MDS_M = 4;           // candidates each warp contributes to a generation's pool
+constexpr int MDS_MAXK = 256;      // picks per generation (capacity of the pick list)
 constexpr unsigned long long MDS_NONE = 0xffffffffffffffffull;
+constexpr unsigned MDS_PARKED = 0x4e6e6b28u;  // bits of 1e9f: parked / padding entries compare >= this
 
-// DSMEM message of one warp for one round: packed (density bits, tie key) + the candidate's coordinates.
 // st.async writes the payload into the peer CTA's shared memory AND completes the same number of tx-bytes on the
 // peer's mbarrier, so data and "it arrived" are one instruction; nobody executes barrier.cluster inside the loop.
 __device__ __forceinline__ void st_async_b64(uint32_t remote_addr, unsigned long long v, uint32_t remote_bar) {
@@ -42,22 +53,36 @@ __device__ __forceinline__ void st_async_v4f32(uint32_t remote_addr, float a, fl
                : "memory");
 }
 
-constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_MAX_WARPS;  // up to 128 candidate slots per parity
+constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_MAX_WARPS;  // up to 128 warps per sample
 
-// The round loop is issue bound (2 warps per scheduler, every instruction counts), so it is written to the bone:
+// The update is issue bound, so it is written to the bone:
 //   * -d/t with the loop-invariant divisor t becomes Markstein's 3-instruction correctly-rounded division
 //     (q = RN(d*r), rem = fma(-q,t,d) exact, q' = fma(rem,r,q) with r = RN(1/t)); the IEEE result is identical to
 //     div.rn whenever t's significand is not all ones and the quotient is a normal number -- outside the normal
 //     range expf(q') is exactly 1 or 0 either way; an all-ones significand falls back to div.rn (FAST_DIV=false).
 //   * the x2 weight of points k >= 8192 is a per-slot register factor folded into one FMA (2w is exact),
 //   * tie keys are per-slot registers, candidates are compared as packed u64 (density bits, key),
-//   * candidate coordinates come from a shared-memory copy of the CTA's own points,
-//   * few, fat warps: 256 threads x 18 points beat 512 x 9 (the per-round tail is paid per WARP),
 //   * LIVE-POINT COMPACTION: a chosen point is parked at 1e9 for good and m/n of the points end up chosen (89 % in
 //     SpareNet's refiner), so the register layout is re-packed through shared memory whenever the CTA's live points
 //     fit a narrower unrolled loop (PT 18 -> 14 -> 10 -> 7 -> 4 -> 2): on average ~56 % of the points are still
-//     updated per round.  Every live point sees exactly the same sequence of fp32 additions as before, so the sampled
+//     updated per pick.  Every live point sees exactly the same sequence of fp32 additions as before, so the sampled
 //     indices are unchanged; dropped points could never be chosen again (the reference adds w to their 1e9 for nothing).
+template <bool FAST_DIV>
+__device__ __forceinline__ float mds_add(float temp, float fac, float x, float y, float z, float x1, float y1, float z1, float t, float r) {
+  const float d = sqdist3(__fsub_rn(x, x1), __fsub_rn(y, y1), __fsub_rn(z, z1));
+  float q;
+  if (FAST_DIV) {
+    const float q0 = __fmul_rn(d, r);
+    q = __fmaf_rn(__fmaf_rn(-q0, t, d), r, q0);  // == div.rn(d, t) (see above)
+  } else {
+    q = __fdiv_rn(d, t);
+  }
+  return __fmaf_rn(expf(-q), fac, temp);  // temp + w or temp + 2w (2w exact): one rounding, as the reference
+}
+__device__ __forceinline__ unsigned long long mds_pack(float v, unsigned key) {
+  return ((unsigned long long)__float_as_uint(v) << 32) | key;  // densities are >= 0: u64 order == (density, tie key)
+}
+
 struct MdsStage {          // staging area in dynamic shared memory, capacity = THREADS * PT0 entries
   float* t;                // running density of the entry's point (2e9 = padding)
   unsigned* k;             // tie key << 21 | point index (~0 = padding); coordinates and the x2 factor follow from the index
@@ -65,148 +90,234 @@ struct MdsStage {          // staging area in dynamic shared memory, capacity = 
   int* count;
 };
 
+struct MdsShared {         // static shared memory of one CTA
+  unsigned long long pack[2][MDS_SLOTS * MDS_M];   // pool candidates (density bits, key), double buffered by generation parity
+  float4 xyz[2][MDS_SLOTS * MDS_M];                // ... their coordinates
+  unsigned long long theta[2][MDS_SLOTS];          // per-warp bounds: the warp's (MDS_M+1)-th lowest pair
+  float4 picks[MDS_MAXK];                          // accepted picks of the last generation: x, y, z, bits(index)
+  uint64_t bars[2];
+  int npicks;
+};
+
+struct MdsCtx {
+  const float* dataset;
+  int* idxs;
+  const float* sxyz;   // this CTA's points (shared memory copy when it fits)
+  MdsShared* sh;
+  MdsStage st;
+  int m, kbeg, kend;
+  uint32_t cs, rank;
+  float t, r;
+};
+
 __host__ __device__ constexpr int mds_next_pt(int pt) { return pt > 12 ? pt - 4 : (pt > 6 ? pt - 3 : (pt > 2 ? pt - 2 : 0)); }
 
 template <int MDS_THREADS, int PT, bool FAST_DIV>
 struct MdsLevel {
-  // runs rounds j.. while the CTA still holds more live points than the next narrower layout can take; returns the next j
-  static __device__ __forceinline__ int run(int j, const float* __restrict__ dataset, int m, int* __restrict__ idxs, float t, float r, int kbeg,
-                                            int kend, uint32_t cs, uint32_t rank, unsigned long long (*packs)[MDS_SLOTS],
-                                            float4 (*coords)[MDS_SLOTS], uint64_t* bars, const float* sxyz, const MdsStage& st, int& live,
-                                            float& x1, float& y1, float& z1) {
+  // runs generations while the CTA still holds more live points than the next narrower layout can take; returns the next j
+  static __device__ __forceinline__ int run(int j, const MdsCtx& c, int& live, int& gen) {
     constexpr int MDS_WARPS = MDS_THREADS / 32;
-    constexpr int NQ = (MDS_MAX_CLUSTER * MDS_WARPS + 31) / 32;  // candidate entries per lane in the final reduce
+    constexpr int NQ = (MDS_MAX_CLUSTER * MDS_WARPS * MDS_M + 31) / 32;  // pool entries per lane of the replaying warp
     constexpr int NEXT = mds_next_pt(PT);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    MdsShared& sh = *c.sh;
+    const float t = c.t, r = c.r;
     float x[PT], y[PT], z[PT], temp[PT], fac[PT];
     unsigned key[PT];
 #pragma unroll
     for (int i = 0; i < PT; i++) {  // entry e = tid + i*THREADS of the staged layout
       const int e = tid + i * MDS_THREADS;
-      temp[i] = st.t[e];
-      key[i] = st.k[e];
+      temp[i] = c.st.t[e];
+      key[i] = c.st.k[e];
       const int k = (int)(key[i] & 0x1fffffu);
-      const int kk = key[i] != 0xffffffffu ? k - kbeg : 0;
-      x[i] = sxyz[kk * 3 + 0];
-      y[i] = sxyz[kk * 3 + 1];
-      z[i] = sxyz[kk * 3 + 2];
+      const int kk = key[i] != 0xffffffffu ? k - c.kbeg : 0;
+      x[i] = c.sxyz[kk * 3 + 0];
+      y[i] = c.sxyz[kk * 3 + 1];
+      z[i] = c.sxyz[kk * 3 + 2];
       fac[i] = k < 8192 ? 1.0f : 2.0f;  // MDS_cuda.cu:111-112 (k > 8191 counts double)
     }
-    const uint32_t my_slot = rank * MDS_WARPS + warp;
+    const uint32_t cs = c.cs;
+    const uint32_t my_slot = c.rank * MDS_WARPS + warp;
+    const int total = cs * MDS_WARPS;
     // peer addresses for parity 0; parity 1 is a constant offset further (a CTA's shared::cluster window is contiguous)
     const uint32_t dst = lane < (int)cs ? (uint32_t)lane : 0u;
-    const uint32_t r_pack0 = mapa_shared(smem_u32(&packs[0][my_slot]), dst);
-    const uint32_t r_coord0 = mapa_shared(smem_u32(&coords[0][my_slot]), dst);
-    const uint32_t r_bar0 = mapa_shared(smem_u32(&bars[0]), dst);
-    const uint32_t round_bytes = cs * MDS_WARPS * 24u;
-    const int total = cs * MDS_WARPS;
+    const uint32_t r_pack0 = mapa_shared(smem_u32(&sh.pack[0][my_slot * MDS_M]), dst);
+    const uint32_t r_xyz0 = mapa_shared(smem_u32(&sh.xyz[0][my_slot * MDS_M]), dst);
+    const uint32_t r_theta0 = mapa_shared(smem_u32(&sh.theta[0][my_slot]), dst);
+    const uint32_t r_bar0 = mapa_shared(smem_u32(&sh.bars[0]), dst);
+    const uint32_t gen_bytes = (uint32_t)total * (MDS_M * 24u + 8u);
 
-    for (; j < m && (NEXT == 0 || live > NEXT * MDS_THREADS); j++) {  // the last level also emits the "nothing left -> 0" rounds
-      const int par = j & 1;
-      if (tid == 0) mbar_expect_tx(&bars[par], round_bytes);  // arm this round's phase (the single expected arrival)
-      unsigned long long best = MDS_NONE;
+    for (;;) {
+      // ---- apply the picks of the previous generation, in order, to this thread's points ----------------------------
+      const int np = sh.npicks;
+#pragma unroll 1
+      for (int p = 0; p < np; p++) {
+        const float4 pk = sh.picks[p];  // broadcast read
+        const int pidx = __float_as_int(pk.w);
+        if (pidx >= c.kbeg && pidx < c.kend) {  // park it: every warp keeps the live count, only the owner touches its registers
+          live--;
+          const int e = c.st.loc[pidx - c.kbeg];
+          if ((e % MDS_THREADS) == tid) {
+            const int slot = e / MDS_THREADS;
+#pragma unroll
+            for (int i = 0; i < PT; i++)
+              if (i == slot) temp[i] = 1e9f;   // 1e9f + w == 1e9f for every later w <= 2
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < PT; i++) temp[i] = mds_add<FAST_DIV>(temp[i], fac[i], x[i], y[i], z[i], pk.x, pk.y, pk.z, t, r);
+      }
+      if (NEXT > 0 && live <= NEXT * MDS_THREADS) break;  // re-pack into the narrower layout (uniform over the CTA)
+
+      // ---- this warp's MDS_M lowest (density, key) pairs and the next one as its bound -------------------------------
+      unsigned long long mine = MDS_NONE;
 #pragma unroll
       for (int i = 0; i < PT; i++) {
-        const float d = sqdist3(__fsub_rn(x[i], x1), __fsub_rn(y[i], y1), __fsub_rn(z[i], z1));
-        float q;
-        if (FAST_DIV) {
-          const float q0 = __fmul_rn(d, r);
-          q = __fmaf_rn(__fmaf_rn(-q0, t, d), r, q0);  // == div.rn(d, t) (see above)
-        } else {
-          q = __fdiv_rn(d, t);
-        }
-        const float v = __fmaf_rn(expf(-q), fac[i], temp[i]);  // temp + w or temp + 2w (2w exact): one rounding, as the reference
-        temp[i] = v;
-        const unsigned long long p = ((unsigned long long)__float_as_uint(v) << 32) | key[i];
-        best = p < best ? p : best;  // densities are >= 0: u64 order == (density, tie key); parked / padding entries hold >= 1e9
+        const unsigned long long p = mds_pack(temp[i], key[i]);
+        mine = p < mine ? p : mine;
       }
-      const unsigned long long wbest = warp_min_u64(best);
+      unsigned long long sel[MDS_M + 1];
+#pragma unroll
+      for (int s = 0; s <= MDS_M; s++) {
+        unsigned long long w = warp_min_u64(mine);
+        if ((unsigned)(w >> 32) >= MDS_PARKED) w = MDS_NONE;  // parked / padding: this warp has run out of live points
+        sel[s] = w;
+        if (s < MDS_M && mine == w && w != MDS_NONE) {         // the owning lane (keys are unique) moves on to its next entry
+          unsigned long long nx = MDS_NONE;
+#pragma unroll
+          for (int i = 0; i < PT; i++) {
+            const unsigned long long p = mds_pack(temp[i], key[i]);
+            nx = (p > w && p < nx) ? p : nx;
+          }
+          mine = nx;
+        }
+      }
+      // ---- publish them to every CTA of the cluster ------------------------------------------------------------------
+      const int par = gen & 1;
+      if (tid == 0) mbar_expect_tx(&sh.bars[par], gen_bytes);  // arm this generation's phase (the single expected arrival)
       if (lane < (int)cs) {
-        const int kc = (int)((unsigned)wbest & 0x1fffffu) - kbeg;  // the warp's candidate is one of this CTA's points
-        const int kk = (kc >= 0 && kc < kend - kbeg) ? kc : 0;
         const uint32_t r_bar = r_bar0 + par * (uint32_t)sizeof(uint64_t);
-        st_async_b64(r_pack0 + par * (uint32_t)(MDS_SLOTS * sizeof(unsigned long long)), wbest, r_bar);
-        st_async_v4f32(r_coord0 + par * (uint32_t)(MDS_SLOTS * sizeof(float4)), sxyz[kk * 3 + 0], sxyz[kk * 3 + 1], sxyz[kk * 3 + 2], 0.f, r_bar);
-      }
-      mbar_wait_tx(&bars[par], (uint32_t)((j - 1) >> 1) & 1u);       // k-th use of bars[par] (rounds par, par+2, ...) has parity k & 1
-      // every warp reduces the cs*MDS_WARPS candidates redundantly
-      unsigned long long c[NQ], g = MDS_NONE;
+        const uint32_t r_pack = r_pack0 + par * (uint32_t)sizeof(sh.pack[0]);
+        const uint32_t r_xyz = r_xyz0 + par * (uint32_t)sizeof(sh.xyz[0]);
 #pragma unroll
-      for (int qd = 0; qd < NQ; qd++) {
-        const int e = lane + 32 * qd;
-        c[qd] = e < total ? packs[par][e] : MDS_NONE;
-        g = c[qd] < g ? c[qd] : g;
-      }
-      g = warp_min_u64(g);
-      int we = 0;  // the winning candidate's slot (keys carry the point index, so exactly one live entry matches; all-parked ties are harmless)
-#pragma unroll
-      for (int qd = NQ - 1; qd >= 0; qd--) {
-        const unsigned hit = __ballot_sync(0xffffffffu, c[qd] == g);
-        if (hit) we = 32 * qd + __ffs(hit) - 1;
-      }
-      const float4 wc = coords[par][we];  // broadcast read
-      x1 = wc.x;
-      y1 = wc.y;
-      z1 = wc.z;
-      int old = (int)((unsigned)g & 0x1fffffu);
-      const bool none = (unsigned)(g >> 32) >= 0x4e6e6b28u;  // >= 1e9f: nothing left -> the reference returns index 0 (MDS_cuda.cu:121-133)
-      if (none) {
-        old = 0;
-        x1 = __ldg(&dataset[0]);
-        y1 = __ldg(&dataset[1]);
-        z1 = __ldg(&dataset[2]);
-      }
-      if (rank == 0 && tid == 0) idxs[j] = old;
-      if (!none && old >= kbeg && old < kend) {  // park it: every warp keeps the live count, only the owner touches its registers
-        live--;
-        const int e = st.loc[old - kbeg];
-        if ((e % MDS_THREADS) == tid) {
-          const int slot = e / MDS_THREADS;
-#pragma unroll
-          for (int i = 0; i < PT; i++)
-            if (i == slot) temp[i] = 1e9f;
+        for (int s = 0; s < MDS_M; s++) {
+          const int kc = (int)((unsigned)sel[s] & 0x1fffffu) - c.kbeg;  // a candidate of this warp is one of this CTA's points
+          const int kk = (sel[s] != MDS_NONE && kc >= 0 && kc < c.kend - c.kbeg) ? kc : 0;
+          st_async_b64(r_pack + s * 8u, sel[s], r_bar);
+          st_async_v4f32(r_xyz + s * 16u, c.sxyz[kk * 3 + 0], c.sxyz[kk * 3 + 1], c.sxyz[kk * 3 + 2], 0.f, r_bar);
         }
+        st_async_b64(r_theta0 + par * (uint32_t)sizeof(sh.theta[0]), sel[MDS_M], r_bar);
+      }
+      mbar_wait_tx(&sh.bars[par], (uint32_t)(gen >> 1) & 1u);  // k-th use of bars[par] (generations par, par+2, ...) has parity k & 1
+      gen++;
+
+      // ---- warp 0 replays the sequential algorithm on the pool --------------------------------------------------------
+      if (warp == 0) {
+        float px[NQ], py[NQ], pz[NQ], pt[NQ], pf[NQ];
+        unsigned pkey[NQ];
+        const int nent = total * MDS_M;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const int e = lane + 32 * q;
+          const unsigned long long p = e < nent ? sh.pack[par][e] : MDS_NONE;
+          const float4 cx = sh.xyz[par][e < nent ? e : 0];
+          const bool ok = (unsigned)(p >> 32) < MDS_PARKED;
+          pt[q] = ok ? __uint_as_float((unsigned)(p >> 32)) : 2e9f;
+          pkey[q] = ok ? (unsigned)p : 0xffffffffu;
+          px[q] = cx.x;
+          py[q] = cx.y;
+          pz[q] = cx.z;
+          pf[q] = (pkey[q] & 0x1fffffu) < 8192u ? 1.0f : 2.0f;
+        }
+        unsigned long long th = MDS_NONE;
+        for (int e = lane; e < total; e += 32) {
+          const unsigned long long v = sh.theta[par][e];
+          th = v < th ? v : th;
+        }
+        th = warp_min_u64(th);
+        const int kmax = (c.m - j) < MDS_MAXK ? (c.m - j) : MDS_MAXK;
+        int K = 0;
+        float lx = 0.f, ly = 0.f, lz = 0.f;
+        while (K < kmax) {
+          unsigned long long cand = MDS_NONE;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            if (K > 0) pt[q] = mds_add<FAST_DIV>(pt[q], pf[q], px[q], py[q], pz[q], lx, ly, lz, t, r);
+            const unsigned long long p = mds_pack(pt[q], pkey[q]);
+            cand = p < cand ? p : cand;
+          }
+          const unsigned long long g = warp_min_u64(cand);
+          if (!(g < th) || (unsigned)(g >> 32) >= MDS_PARKED) break;  // something outside the pool may be lower: next generation
+          const int ol = __ffs(__ballot_sync(0xffffffffu, cand == g)) - 1;  // keys are unique: exactly one lane holds it
+          float ox = 0.f, oy = 0.f, oz = 0.f;
+          if (lane == ol) {
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+              if (mds_pack(pt[q], pkey[q]) == g) {
+                ox = px[q];
+                oy = py[q];
+                oz = pz[q];
+                pt[q] = 1e9f;  // parked
+              }
+          }
+          lx = __shfl_sync(0xffffffffu, ox, ol);
+          ly = __shfl_sync(0xffffffffu, oy, ol);
+          lz = __shfl_sync(0xffffffffu, oz, ol);
+          const int old = (int)((unsigned)g & 0x1fffffu);
+          if (lane == 0) {
+            sh.picks[K] = make_float4(lx, ly, lz, __int_as_float(old));
+            if (c.rank == 0) c.idxs[j + K] = old;
+          }
+          K++;
+        }
+        if (lane == 0) sh.npicks = K;
+      }
+      __syncthreads();
+      const int K = sh.npicks;
+      if (K == 0) {  // nothing left anywhere: the reference keeps returning index 0 (MDS_cuda.cu:121-133)
+        if (c.rank == 0)
+          for (int q = j + tid; q < c.m; q += MDS_THREADS) c.idxs[q] = 0;
+        return c.m;
+      }
+      j += K;
+      if (j >= c.m) return j;
+    }
+    // re-pack the live points for the narrower layout (all warps take this branch in the same generation)
+    __syncthreads();
+    if (tid == 0) {
+      *c.st.count = 0;
+      sh.npicks = 0;  // the pending picks have been applied
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PT; i++) {
+      if (temp[i] < 1e9f) {
+        const int e = atomicAdd(c.st.count, 1);
+        c.st.t[e] = temp[i];
+        c.st.k[e] = key[i];
+        c.st.loc[(int)(key[i] & 0x1fffffu) - c.kbeg] = (unsigned short)e;
       }
     }
-    if (NEXT > 0 && j < m) {  // re-pack the live points for the narrower layout (all warps take this branch in the same round)
-      __syncthreads();
-      if (tid == 0) *st.count = 0;
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < PT; i++) {
-        if (temp[i] < 1e9f) {
-          const int e = atomicAdd(st.count, 1);
-          st.t[e] = temp[i];
-          st.k[e] = key[i];
-          st.loc[(int)(key[i] & 0x1fffffu) - kbeg] = (unsigned short)e;
-        }
-      }
-      __syncthreads();
-      for (int e = *st.count + tid; e < NEXT * MDS_THREADS; e += MDS_THREADS) {  // padding entries can never win
-        st.t[e] = 2e9f;
-        st.k[e] = 0xffffffffu;
-      }
-      __syncthreads();
+    __syncthreads();
+    for (int e = *c.st.count + tid; e < NEXT * MDS_THREADS; e += MDS_THREADS) {  // padding entries can never win
+      c.st.t[e] = 2e9f;
+      c.st.k[e] = 0xffffffffu;
     }
+    __syncthreads();
     return j;
   }
 };
 
 template <int MDS_THREADS, int PT, bool FAST_DIV>
 struct MdsChain {
-  static __device__ __forceinline__ void run(int j, const float* __restrict__ dataset, int m, int* __restrict__ idxs, float t, float r, int kbeg,
-                                             int kend, uint32_t cs, uint32_t rank, unsigned long long (*packs)[MDS_SLOTS],
-                                             float4 (*coords)[MDS_SLOTS], uint64_t* bars, const float* sxyz, const MdsStage& st, int& live,
-                                             float& x1, float& y1, float& z1) {
-    j = MdsLevel<MDS_THREADS, PT, FAST_DIV>::run(j, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st, live, x1, y1, z1);
-    if (j < m) MdsChain<MDS_THREADS, mds_next_pt(PT), FAST_DIV>::run(j, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st,
-                                                                     live, x1, y1, z1);
+  static __device__ __forceinline__ void run(int j, const MdsCtx& c, int& live, int& gen) {
+    j = MdsLevel<MDS_THREADS, PT, FAST_DIV>::run(j, c, live, gen);
+    if (j < c.m) MdsChain<MDS_THREADS, mds_next_pt(PT), FAST_DIV>::run(j, c, live, gen);
   }
 };
 template <int MDS_THREADS, bool FAST_DIV>
 struct MdsChain<MDS_THREADS, 0, FAST_DIV> {
-  static __device__ __forceinline__ void run(int, const float*, int, int*, float, float, int, int, uint32_t, uint32_t, unsigned long long (*)[MDS_SLOTS],
-                                             float4 (*)[MDS_SLOTS], uint64_t*, const float*, const MdsStage&, int&, float&, float&, float&) {}
+  static __device__ __forceinline__ void run(int, const MdsCtx&, int&, int&) {}
 };
 
 // dynamic shared memory: [stage t | stage k | count | loc | this CTA's points]; the points stay in global memory (L2) when
@@ -220,9 +331,7 @@ template <int MDS_THREADS, int PT>
 __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
                                                                       const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
                                                                       int bs_mask, int bs_log2, int stage_xyz) {
-  __shared__ __align__(16) unsigned long long packs[2][MDS_SLOTS];
-  __shared__ __align__(16) float4 coords[2][MDS_SLOTS];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(16) MdsShared sh;
   extern __shared__ __align__(16) unsigned char dyn[];
   const uint32_t cs = cluster_nctarank();
   const uint32_t rank = cluster_ctarank();
@@ -233,14 +342,14 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
   const int chunk = (n + cs - 1) / cs;
   const int kbeg = rank * chunk;
   const int kend = (kbeg + chunk) < n ? (kbeg + chunk) : n;
-  const int per = kend - kbeg;
+  const int per = kend > kbeg ? kend - kbeg : 0;
   // carve the dynamic shared memory: this CTA's points (AoS), the staging SoA, the point -> entry map
   constexpr int CAP = MDS_THREADS * PT;
-  MdsStage st;
-  st.t = reinterpret_cast<float*>(dyn);
-  st.k = reinterpret_cast<unsigned*>(st.t + CAP);
-  st.count = reinterpret_cast<int*>(st.k + CAP);
-  st.loc = reinterpret_cast<unsigned short*>(st.count + 4);
+  MdsCtx c;
+  c.st.t = reinterpret_cast<float*>(dyn);
+  c.st.k = reinterpret_cast<unsigned*>(c.st.t + CAP);
+  c.st.count = reinterpret_cast<int*>(c.st.k + CAP);
+  c.st.loc = reinterpret_cast<unsigned short*>(c.st.count + 4);
   const float* sxyz = dataset + (size_t)kbeg * 3;
   if (stage_xyz) {
     float* sx = reinterpret_cast<float*>(dyn + (size_t)CAP * 8 + 16 + (((size_t)chunk * 2 + 15) & ~(size_t)15));
@@ -251,28 +360,43 @@ __global__ void __launch_bounds__(MDS_THREADS, 1) mds_cluster_kernel(const float
   for (int e = tid; e < CAP; e += MDS_THREADS) {
     const int k = kbeg + e + ((kbeg == 0) ? 1 : 0);  // rank 0 skips k = 0
     const bool ok = k < kend;
-    st.t[e] = ok ? 0.f : 2e9f;
+    c.st.t[e] = ok ? 0.f : 2e9f;
     const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
-    st.k[e] = ok ? ((rev << 21) | (unsigned)k) : 0xffffffffu;
-    if (ok) st.loc[k - kbeg] = (unsigned short)e;
+    c.st.k[e] = ok ? ((rev << 21) | (unsigned)k) : 0xffffffffu;
+    if (ok) c.st.loc[k - kbeg] = (unsigned short)e;
   }
-  int live = per - ((kbeg == 0) ? 1 : 0);
+  int live = per - ((kbeg == 0 && per > 0) ? 1 : 0);
   const float mml = mean_mst_length[b];
   const float t = (float)(5.0 * (double)mml * (double)mml);
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(&sh.bars[0], 1);
+    mbar_init(&sh.bars[1], 1);
     fence_mbar_init();
+    // generation 0 applies the pre-chosen point 0; index -1: it was never part of the layout, nothing to park
+    sh.picks[0] = make_float4(dataset[0], dataset[1], dataset[2], __int_as_float(-1));
+    sh.npicks = 1;
   }
   if (rank == 0 && tid == 0) idxs[0] = 0;
   __syncthreads();
   cluster_sync_all();  // peers must see initialised barriers before the first remote complete_tx
-  float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];
+  c.dataset = dataset;
+  c.idxs = idxs;
+  c.sxyz = sxyz;
+  c.sh = &sh;
+  c.m = m;
+  c.kbeg = kbeg;
+  c.kend = kend;
+  c.cs = cs;
+  c.rank = rank;
+  c.t = t;
+  c.r = __frcp_rn(t);
   const unsigned tb = __float_as_uint(t);
   const bool fast = ((tb & 0x7fffffu) != 0x7fffffu) && ((tb >> 23) & 0xffu) > 1u && ((tb >> 23) & 0xffu) < 254u && !(tb >> 31);
-  const float r = __frcp_rn(t);
-  if (fast) MdsChain<MDS_THREADS, PT, true>::run(1, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st, live, x1, y1, z1);
-  else MdsChain<MDS_THREADS, PT, false>::run(1, dataset, m, idxs, t, r, kbeg, kend, cs, rank, packs, coords, bars, sxyz, st, live, x1, y1, z1);
+  int gen = 0;
+  if (m > 1) {
+    if (fast) MdsChain<MDS_THREADS, PT, true>::run(1, c, live, gen);
+    else MdsChain<MDS_THREADS, PT, false>::run(1, c, live, gen);
+  }
   cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
 }
 
@@ -299,7 +423,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   cfg.gridDim = dim3((unsigned)(B * cs));
   cfg.blockDim = dim3(MDS_THREADS);
   const int per = (n + cs - 1) / cs;
-  int stage_xyz = mds_smem_bytes(per, MDS_THREADS, PT, true) <= (size_t)200 * 1024 ? 1 : 0;
+  int stage_xyz = mds_smem_bytes(per, MDS_THREADS, PT, true) + sizeof(MdsShared) <= (size_t)220 * 1024 ? 1 : 0;
   const size_t smem = mds_smem_bytes(per, MDS_THREADS, PT, stage_xyz != 0);
   cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<MDS_THREADS, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea != cudaSuccess) return (int)ea;
