@@ -39,7 +39,6 @@ constexpr int MDS_MAX_WARPS = 16;  // worker warps per CTA: 4, 8 or 16 (plus the
 constexpr int MDS_MAX_CLUSTER = 8;
 constexpr int MDS_MAXM = 8;        // candidates a worker warp contributes to a generation's pool (fewer when > 32 warps)
 constexpr int MDS_POOL = 256;      // pool capacity = total worker warps x M
-constexpr int MDS_NQ = MDS_POOL / 32;
 constexpr int MDS_MAXK = MDS_POOL; // picks per generation (capacity of the pick list)
 constexpr unsigned long long MDS_NONE = 0xffffffffffffffffull;
 constexpr unsigned MDS_PARKED = 0x4e6e6b28u;  // bits of 1e9f: parked / padding entries compare >= this
@@ -83,6 +82,7 @@ __device__ unsigned long long g_mds_stats[16];
 #else
 #define MDS_STAT_ADD(i, v) do { } while (0)
 #define MDS_CLOCK() 0ll
+#pragma nv_diag_suppress 177
 #endif
 
 // The update is issue bound, so it is written to the bone:
