@@ -455,6 +455,11 @@ class SpareNetGenerator(nn.Module):  # reference :12-82
         style = self.encoder(partial)
         outs = self.decoder(style, partial)                                   # [B,3,N]
         coarse = outs.transpose(1, 2).contiguous()
+        hook = getattr(self, "stage_hook", None)   # optional callable(name, cloud): lets the caller start work on an intermediate
+        if hook is not None:                        # output (e.g. its Chamfer loss on a side stream) while the refiner's sampler runs
+            hook("coarse", coarse)
         middle, loss_mst = self.refine(outs, partial, coarse)
+        if hook is not None:
+            hook("middle", middle)
         refine, _ = self.refine(middle.transpose(1, 2).contiguous(), partial, middle)
         return coarse, middle, refine, loss_mst
