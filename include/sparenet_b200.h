@@ -117,6 +117,13 @@ int snb_edge_reduce_bwd(const float* a, const float* c, const int* idx, const un
                         const unsigned char* slot_min, const float* g_umax, const float* g_umin,
                         const double* gS1, const double* gS2, int B, int C, int N, int k,
                         float* ga, float* gc, void* stream);
+/* The same with the extremum chosen per channel (sel_max[ch] != 0: max, else min -- the sign of the channel's BatchNorm
+ * weight, models/sparenet_generator.py:213-216): ustar [B,C,N] and ONE slot tensor instead of two of each. */
+int snb_edge_reduce_sel_fwd(const float* a, const float* c, const int* idx, const unsigned char* sel_max, int B, int C,
+                            int N, int k, float* ustar, unsigned char* slot, double* S1, double* S2, void* stream);
+int snb_edge_reduce_sel_bwd(const float* a, const float* c, const int* idx, const unsigned char* slot,
+                            const float* g_ustar, const double* gS1, const double* gS2, int B, int C, int N, int k,
+                            float* ga, float* gc, void* stream);
 
 /* ---- row-wise tails of the folded normalisation stacks (models/sparenet_generator.py:618-646,1053-1061) ----
  * h [R,L] contiguous rows.  row_stats: mean / biased variance per row.  row_affine_act:

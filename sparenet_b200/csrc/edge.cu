@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_fwd_kernel(const flo
                                                                         const int* __restrict__ idx, int C, int N, int k,
                                                                         float* __restrict__ umax, float* __restrict__ umin,
                                                                         unsigned char* __restrict__ smax, unsigned char* __restrict__ smin,
-                                                                        double* __restrict__ S1, double* __restrict__ S2) {
+                                                                        double* __restrict__ S1, double* __restrict__ S2,
+                                                                        const unsigned char* __restrict__ sel) {
   extern __shared__ float arow[];
   __shared__ double red[EDGE_THREADS / 32];
   const int ch = blockIdx.x, b = blockIdx.y;
@@ -57,10 +58,16 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_fwd_kernel(const flo
       if (v > mx) { mx = v; ax = m; }   // first maximum / minimum wins, like torch.max over dim=-1 on CUDA is free to
       if (v < mn) { mn = v; an = m; }
     }
-    umax[row + i] = mx + ci;
-    umin[row + i] = mn + ci;
-    smax[row + i] = (unsigned char)ax;
-    smin[row + i] = (unsigned char)an;
+    if (sel) {  // only the extremum the sign of the channel's BatchNorm weight asks for (written to umax / smax)
+      const bool up = sel[ch] != 0;
+      umax[row + i] = (up ? mx : mn) + ci;
+      smax[row + i] = (unsigned char)(up ? ax : an);
+    } else {
+      umax[row + i] = mx + ci;
+      umin[row + i] = mn + ci;
+      smax[row + i] = (unsigned char)ax;
+      smin[row + i] = (unsigned char)an;
+    }
     // sum_m (a_j + c)   and   sum_m (a_j + c)^2 = sum a_j^2 + 2 c sum a_j + k c^2
     s1 += (double)sa + (double)k * (double)ci;
     s2 += (double)sq + 2.0 * (double)ci * (double)sa + (double)k * (double)ci * (double)ci;
@@ -96,8 +103,8 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_bwd_kernel(const flo
   const int* __restrict__ ib = idx + (size_t)b * N * k;
   for (int i = threadIdx.x; i < N; i += EDGE_THREADS) {
     const float ci = c[row + i];
-    const float gx = gmax[row + i], gn = gmin[row + i];
-    const int ax = smax[row + i], an = smin[row + i];
+    const float gx = gmax[row + i], gn = gmin ? gmin[row + i] : 0.f;   // gmin == nullptr: the selected-extremum form
+    const int ax = smax[row + i], an = gmin ? (int)smin[row + i] : -1;
     float sa = 0.f;
     for (int m = 0; m < k; m++) {
       const int j = ib[(size_t)i * k + m];
@@ -131,7 +138,34 @@ SNB_API int snb_edge_reduce_fwd(const float* a, const float* c, const int* idx, 
   if (B == 0 || C == 0 || N == 0) return SNB_OK;
   const size_t smem = (size_t)N * sizeof(float);
   if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_reduce_fwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, C, N, k, umax, umin, slot_max, slot_min, S1, S2);
+  edge_reduce_fwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, C, N, k, umax, umin, slot_max, slot_min, S1, S2,
+                                                                                  nullptr);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_edge_reduce_sel_fwd(const float* a, const float* c, const int* idx, const unsigned char* sel_max, int B, int C, int N, int k,
+                                    float* ustar, unsigned char* slot, double* S1, double* S2, void* stream) {
+  int rc = edge_check(B, C, N, k);
+  if (rc) return rc;
+  if (!sel_max) return SNB_EINVAL;
+  if (B == 0 || C == 0 || N == 0) return SNB_OK;
+  const size_t smem = (size_t)N * sizeof(float);
+  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_reduce_fwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, C, N, k, ustar, nullptr, slot, nullptr, S1, S2, sel_max);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_edge_reduce_sel_bwd(const float* a, const float* c, const int* idx, const unsigned char* slot, const float* g_ustar,
+                                    const double* gS1, const double* gS2, int B, int C, int N, int k, float* ga, float* gc, void* stream) {
+  int rc = edge_check(B, C, N, k);
+  if (rc) return rc;
+  if (B == 0 || C == 0 || N == 0) return SNB_OK;
+  const size_t smem = (size_t)N * 2 * sizeof(float);
+  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_reduce_bwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, slot, nullptr, g_ustar, nullptr, gS1, gS2, C, N, k, ga,
+                                                                                  gc);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -145,7 +145,9 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         a = _pconv(x, Wa)                                          # per-POINT 1x1 convs (k x fewer flops than per edge)
         c = _pconv(x, Wb - Wa)
         # u[b,c,i,m] = a[b,c,idx[b,i,m]] + c[b,c,i] is never formed: the fused kernel returns its max/min over m and its moments
-        umax, umin, S1, S2 = fused.edge_reduce(a, c, idx)
+        g = bn.weight
+        # max_k commutes with the monotone BN.SE.LeakyReLU tail: the sign of gamma picks max or min, inside the kernel
+        ustar, S1, S2 = fused.edge_reduce_sel(a, c, idx, (g > 0).detach())
         n = B * N * k
         if bn.training:
             mean64 = S1.sum(0) / n
@@ -154,11 +156,10 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
             _bn_apply_stats(bn, mean, var, n)
         else:
             mean, var = bn.running_mean, bn.running_var
-        g, beta = bn.weight, bn.bias
+        beta = bn.bias
         scale = g * torch.rsqrt(var + bn.eps)                      # [Co]
         shift = beta - scale * mean
         gate = se.gate((S1 / (N * k)).to(x.dtype) * scale + shift)  # [B,Co] in (0,1): SE squeeze = mean_{N,k} BN(u)
-        ustar = torch.where((g > 0).view(1, Co, 1), umax, umin)    # max_k commutes with the monotone BN.SE.LeakyReLU tail
         out = fused.row_affine_act(ustar, gate * scale, gate * shift, slope=0.2)
         if res is not None:
             out = out + res(x)
@@ -237,6 +238,27 @@ class StyleBasedAdaIn(nn.Module):  # reference :394-422 (parameter holder)
         self.dec = GridDecoder(input_dim, bottleneck_size, use_SElayer=use_SElayer)
 
 
+class _StackParams(torch.autograd.Function):
+    """torch.stack over the 32 primitives' copies of one parameter (the reference keeps them as 32 modules, :306-318, and the
+    state_dict keys stay per primitive).  Backward hands every parameter ITS SLICE of the stacked gradient as .grad -- a view,
+    no kernel -- instead of 32 AccumulateGrad copies per stacked tensor (~550 microsecond-sized launches per step)."""
+    @staticmethod
+    def forward(ctx, *params):
+        ctx.params = params
+        return torch.stack([p.detach() for p in params])
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        for i, p in enumerate(ctx.params):
+            if p.requires_grad:
+                if p.grad is None:
+                    p.grad = g[i]
+                else:
+                    p.grad.add_(g[i])
+        return (None,) * len(ctx.params)
+
+
 def grid_generation(num_points, nb_primitives):
     """Reference :793-812: the same 2^floor x 2^ceil lattice on [0,1]^2 for every primitive (list of lists)."""
     per = num_points / nb_primitives
@@ -266,16 +288,16 @@ class SpareNetDecode(nn.Module):  # reference :289-391
 
     # ---- stacked views of the 32 primitives' parameters -----------------------------------------------------
     def _stack(self, getter):
-        return torch.stack([getter(d.dec) for d in self.decoder])
+        return _StackParams.apply(*[getter(d.dec) for d in self.decoder])
 
     def _bn_se_params(self, layer):
         """The 32 primitives' BN / SE parameters of one decoder layer, stacked: gam, bet [P,C,1], w1 [P,C/16,C], w2 [P,C,C/16]."""
         bns = [getattr(d.dec, f"bn{layer}") for d in self.decoder]
         ses = [getattr(d.dec, f"se{layer}") for d in self.decoder]
-        gam = torch.stack([b.weight for b in bns]).unsqueeze(-1)
-        bet = torch.stack([b.bias for b in bns]).unsqueeze(-1)
-        w1 = torch.stack([s.fc[0].weight for s in ses])
-        w2 = torch.stack([s.fc[2].weight for s in ses])
+        gam = _StackParams.apply(*[b.weight for b in bns]).unsqueeze(-1)
+        bet = _StackParams.apply(*[b.bias for b in bns]).unsqueeze(-1)
+        w1 = _StackParams.apply(*[s.fc[0].weight for s in ses])
+        w2 = _StackParams.apply(*[s.fc[2].weight for s in ses])
         return bns, (gam, bet, w1, w2)
 
     def _bn_se(self, bns, wsty, bsty, v, gam, bet, w1, w2):
@@ -325,7 +347,7 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             return t if t.size(1) == cp else F.pad(t, (0, 0) * (t.dim() - 2) + (0, cp - t.size(1)))
 
         C1 = sizes[0]
-        W1 = self._stack(lambda d: d.conv1.weight.squeeze(-1))                # [P,1026,2] (bias cancels under instance norm)
+        W1 = self._stack(lambda d: d.conv1.weight).squeeze(-1)                # [P,1026,2] (bias cancels under instance norm)
         h = torch.matmul(W1, self._grid_t)                                    # [P,1026,pts], batch independent
         var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
         xhat = (h - mean) * torch.rsqrt(var + EPS)
@@ -335,7 +357,7 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         x = fused.row_affine_act(padc(xhat, cp), padc(A, cp), padc(D, cp), in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D)
         cin = C1
         for layer, name in ((2, "conv2"), (3, "conv3")):
-            W = self._stack(lambda d: getattr(d, name).weight.squeeze(-1))    # [P,Cout,Cin]
+            W = self._stack(lambda d: getattr(d, name).weight).squeeze(-1)    # [P,Cout,Cin]
             cout = W.size(1)
             cop = pad8(cout)
             Wp = F.pad(W, (0, cp - cin, 0, cop - cout))                       # zero rows / columns for the padded channels
@@ -350,7 +372,7 @@ class SpareNetDecode(nn.Module):  # reference :289-391
                 return sc, padc(D, cop) - sc * mean
             x = fused.row_norm_act(h, tail, (sty[layer - 1][0], sty[layer - 1][1]) + prm)
             cin, cp = cout, cop
-        W4 = F.pad(self._stack(lambda d: d.conv4.weight.squeeze(-1)), (0, cp - cin))   # [P,3,256]
+        W4 = F.pad(self._stack(lambda d: d.conv4.weight).squeeze(-1), (0, cp - cin))   # [P,3,256]
         b4 = self._stack(lambda d: d.conv4.bias).view(P, 3, 1)
         out = torch.tanh(torch.bmm(W4, x.view(P, cp, B * npts)) + b4).view(P, 3, B, npts)
         return out.permute(2, 1, 0, 3).reshape(B, 3, P * npts).contiguous()   # primitive i owns points [512 i, 512 (i+1))

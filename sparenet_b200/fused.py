@@ -44,6 +44,41 @@ class EdgeReduce(torch.autograd.Function):
         return ga, gc, None
 
 
+class EdgeReduceSel(torch.autograd.Function):
+    """(a, c [B,C,N], idx [B,N,k] int32, sel_max [C] bool) -> ustar [B,C,N] = max_m u where sel_max else min_m u, and
+    S1, S2 [B,C] (float64) of u = a[idx] + c: one extremum tensor and one slot tensor instead of two (no torch.where)."""
+    @staticmethod
+    def forward(ctx, a, c, idx, sel_max):
+        a, c, idx = a.contiguous(), c.contiguous(), idx.contiguous()
+        sel = sel_max.to(torch.uint8).contiguous()
+        B, C, N = a.shape
+        k = idx.shape[2]
+        dev = a.device
+        ustar = torch.empty_like(a)
+        slot = torch.empty(B, C, N, dtype=torch.uint8, device=dev)
+        S1 = torch.empty(B, C, dtype=torch.float64, device=dev)
+        S2 = torch.empty(B, C, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev), _op("edge_reduce_fwd", 1):
+            check(_lib.load().snb_edge_reduce_sel_fwd(ptr(a), ptr(c), ptr(idx), ptr(sel), B, C, N, k, ptr(ustar), ptr(slot), ptr(S1), ptr(S2),
+                                                      stream_ptr()), "edge_reduce_sel_fwd")
+        ctx.save_for_backward(a, c, idx, slot)
+        return ustar, S1, S2
+
+    @staticmethod
+    def backward(ctx, gu, gS1, gS2):
+        a, c, idx, slot = ctx.saved_tensors
+        B, C, N = a.shape
+        k = idx.shape[2]
+        ga, gc = torch.empty_like(a), torch.empty_like(c)
+        gu = (gu if gu is not None else torch.zeros_like(a)).contiguous()
+        gS1 = (gS1 if gS1 is not None else torch.zeros(B, C, dtype=torch.float64, device=a.device)).contiguous()
+        gS2 = (gS2 if gS2 is not None else torch.zeros(B, C, dtype=torch.float64, device=a.device)).contiguous()
+        with torch.cuda.device(a.device), _op("edge_reduce_bwd", 1):
+            check(_lib.load().snb_edge_reduce_sel_bwd(ptr(a), ptr(c), ptr(idx), ptr(slot), ptr(gu), ptr(gS1), ptr(gS2), B, C, N, k, ptr(ga), ptr(gc),
+                                                      stream_ptr()), "edge_reduce_sel_bwd")
+        return ga, gc, None, None
+
+
 class RowStats(torch.autograd.Function):
     """h [..., L] -> (mean, biased var) over the last dim, shape h.shape[:-1]."""
     @staticmethod
@@ -251,6 +286,10 @@ class ConvRowReduce(torch.autograd.Function):
 
 def edge_reduce(a, c, idx):
     return EdgeReduce.apply(a, c, idx)
+
+
+def edge_reduce_sel(a, c, idx, sel_max):
+    return EdgeReduceSel.apply(a, c, idx, sel_max)
 
 
 def row_norm_act(h, fn, tensors, slope=0.0):

@@ -13,6 +13,11 @@ def edge_reduce(a, c, idx):
     return u.amax(-1), u.amin(-1), ud.sum((2, 3)), (ud * ud).sum((2, 3))
 
 
+def edge_reduce_sel(a, c, idx, sel_max):
+    umax, umin, S1, S2 = edge_reduce(a, c, idx)
+    return torch.where(sel_max.view(1, -1, 1), umax, umin), S1, S2
+
+
 def row_stats(h):
     var, mean = torch.var_mean(h, dim=-1, unbiased=False)
     return mean, var
@@ -45,5 +50,5 @@ def conv_row_reduce(x, W):
 
 def patch(monkeypatch):
     from sparenet_b200 import fused
-    for name in ("edge_reduce", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce"):
+    for name in ("edge_reduce", "edge_reduce_sel", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce"):
         monkeypatch.setattr(fused, name, globals()[name])

@@ -36,6 +36,29 @@ def test_edge_reduce_forward_backward(cuda, B, C, N, k):
     assert ea < 1e-5 and ec < 1e-5      # fp32 accumulation of ~k terms per point against float64
 
 
+@pytest.mark.parametrize("B,C,N,k", [(2, 5, 300, 8), (3, 64, 2048, 8), (1, 16, 97, 3)])
+def test_edge_reduce_sel_forward_backward(cuda, B, C, N, k):
+    """the per-channel selected extremum (no torch.where, one slot tensor) against the two-output reference"""
+    from sparenet_b200 import fused
+    torch.manual_seed(B * 1000 + N + 1)
+    a = (torch.randperm(B * C * N, device=cuda).float() / (B * C * N) * 6 - 3).view(B, C, N)
+    c = torch.randn(B, C, N, device=cuda)
+    idx = torch.stack([torch.stack([torch.randperm(N, device=cuda)[:k] for _ in range(N)]) for _ in range(B)]).int()
+    sel = torch.rand(C, device=cuda) > 0.4
+    a1, c1 = a.clone().requires_grad_(), c.clone().requires_grad_()
+    a2, c2 = a.double().requires_grad_(), c.double().requires_grad_()
+    o1 = fused.edge_reduce_sel(a1, c1, idx, sel)
+    o2 = R.edge_reduce_sel(a2, c2, idx, sel)
+    assert torch.equal(o1[0], o2[0].float())
+    assert _close(o1[1], o2[1], 1e-6) and _close(o1[2], o2[2], 1e-6)
+    w = [torch.randn_like(t) for t in o1]
+    sum((x * y).sum() for x, y in zip(o1, w)).backward()
+    sum((x * y.double()).sum() for x, y in zip(o2, w)).backward()
+    ea = (a1.grad.double() - a2.grad).abs().max().item() / a2.grad.abs().max().item()
+    ec = (c1.grad.double() - c2.grad).abs().max().item() / c2.grad.abs().max().item()
+    assert ea < 1e-5 and ec < 1e-5
+
+
 @pytest.mark.parametrize("shape", [(4, 7, 512), (3, 5, 2048), (2, 3, 333), (1, 2, 16384), (6, 1)])
 def test_row_stats_forward_backward(cuda, shape):
     from sparenet_b200 import fused
