@@ -19,7 +19,7 @@ constexpr int KNN_BT = 128;  // block tile (rows = cols)
 constexpr int KNN_KT = 16;   // channels per smem stage
 constexpr int KNN_MAXK = 32;
 
-__global__ void __launch_bounds__(256) knn_dist_kernel(const float* __restrict__ x, int C, int N, float* __restrict__ D) {
+__global__ void __launch_bounds__(256, 2) knn_dist_kernel(const float* __restrict__ x, int C, int N, float* __restrict__ D) {
   __shared__ __align__(16) float sa[KNN_KT][KNN_BT];
   __shared__ __align__(16) float sb[KNN_KT][KNN_BT];
   const int b = blockIdx.z;
@@ -33,16 +33,30 @@ __global__ void __launch_bounds__(256) knn_dist_kernel(const float* __restrict__
 #pragma unroll
     for (int c = 0; c < 8; c++) acc[r][c] = 0.f;
 
-  for (int c0 = 0; c0 < C; c0 += KNN_KT) {
-    // stage KNN_KT channels x 128 points for rows and columns (coalesced along N)
-    for (int e = threadIdx.x; e < KNN_KT * KNN_BT; e += 256) {
+  // software pipeline: the next stage's global loads are in flight (registers) while the current stage is computed from smem
+  constexpr int PER = KNN_KT * KNN_BT / 256;  // elements of each operand a thread stages
+  float ra[PER], rb[PER];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int e = threadIdx.x + u * 256;
       const int cc = e / KNN_BT, p = e % KNN_BT;
       const int c = c0 + cc;
       const int ia = i0 + p, jb = j0 + p;
-      sa[cc][p] = (c < C && ia < N) ? xb[(size_t)c * N + ia] : 0.f;
-      sb[cc][p] = (c < C && jb < N) ? xb[(size_t)c * N + jb] : 0.f;
+      ra[u] = (c < C && ia < N) ? xb[(size_t)c * N + ia] : 0.f;
+      rb[u] = (c < C && jb < N) ? xb[(size_t)c * N + jb] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int c0 = 0; c0 < C; c0 += KNN_KT) {
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int e = threadIdx.x + u * 256;
+      sa[e / KNN_BT][e % KNN_BT] = ra[u];
+      sb[e / KNN_BT][e % KNN_BT] = rb[u];
     }
     __syncthreads();
+    if (c0 + KNN_KT < C) fetch(c0 + KNN_KT);
 #pragma unroll
     for (int cc = 0; cc < KNN_KT; cc++) {
       const float4 a0 = *reinterpret_cast<const float4*>(&sa[cc][ty * 8]);
@@ -108,9 +122,7 @@ __global__ void __launch_bounds__(256) knn_topk_kernel(const float* __restrict__
     bd[t] = __int_as_float(0x7f800000);
     bi[t] = 0x7fffffff;
   }
-  for (int j = lane; j < N; j += 32) {
-    float v = d[j];
-    int vi = j;
+  auto offer = [&](float v, int vi) {
     if (v < bd[K - 1]) {  // within a lane j ascends, so strict '<' keeps the smaller index on ties
       bool ins = false;
 #pragma unroll
@@ -126,6 +138,27 @@ __global__ void __launch_bounds__(256) knn_topk_kernel(const float* __restrict__
         }
       }
     }
+  };
+  if ((N & 3) == 0) {  // 128-bit loads, two in flight per lane; j still ascends within a lane
+    const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
+    const int n4 = N >> 2;
+    for (int q = lane; q < n4; q += 64) {
+      const float4 v0 = d4[q];
+      const bool two = q + 32 < n4;
+      const float4 v1 = two ? d4[q + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+      offer(v0.x, 4 * q);
+      offer(v0.y, 4 * q + 1);
+      offer(v0.z, 4 * q + 2);
+      offer(v0.w, 4 * q + 3);
+      if (two) {
+        offer(v1.x, 4 * (q + 32));
+        offer(v1.y, 4 * (q + 32) + 1);
+        offer(v1.z, 4 * (q + 32) + 2);
+        offer(v1.w, 4 * (q + 32) + 3);
+      }
+    }
+  } else {
+    for (int j = lane; j < N; j += 32) offer(d[j], j);
   }
   int* out = idx + row * k;
   for (int t = 0; t < k; t++) {
