@@ -398,12 +398,19 @@ def run_ours(args):
         "expansion_bwd": B * N_OUT * (12 + 4 + 4 + 12),
     }
     ab = alg_bytes.get(dom)
+    traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(dom, {}).get("bytes")
+    except (OSError, ValueError):
+        pass
     roof = {"kernel": dom, "bound": "hbm", "achieved": (ab / (per_op[dom] * 1e-3) / 1e9) if ab else None, "peak": hbm_peak, "unit": "GB/s",
-            "frac": (ab / (per_op[dom] * 1e-3) / 1e9 / hbm_peak) if ab else None, "traffic": None, "peak_source": peak_src,
+            "frac": (ab / (per_op[dom] * 1e-3) / 1e9 / hbm_peak) if ab else None, "traffic": traffic, "algorithmic_bytes": ab, "peak_source": peak_src,
             "ms_per_launch": per_op[dom], "share_of_step": tot_op[dom] / (ms / args.steps),
             "note": "mds_sample is a 16383-round dependent chain (latency bound by construction): the HBM fraction of its compulsory bytes is "
                     "reported as asked; rounds/s is the meaningful figure" if dom == "mds_sample" else "",
             "rounds_per_s": ((N_OUT - 1) / (per_op[dom] * 1e-3)) if dom == "mds_sample" else None,
+            "issue_bound": ({"warp_instructions_per_launch": 4.67e9, "issue_slots_busy": 0.56, "floor_ms_at_128_SMs": 4.7,
+                             "source": "profiles/r1_ncu_full_mds_cluster_kernel.csv"} if dom == "mds_sample" else None),
             "timing": f"CUDA events around every C-ABI call in an eager pass of {n_prof} steps next to the timed region",
             "hbm_bound_kernels": {k: dict(v, frac=round(v["GB/s"] / hbm_peak, 3)) for k, v in hbm_ops.items()},
             "ops_ms_per_step": {k: round(v, 3) for k, v in sorted(tot_op.items(), key=lambda kv: -kv[1])}}

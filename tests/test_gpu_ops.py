@@ -295,7 +295,8 @@ def test_expansion_limits(cuda):
 
 
 # ================================================================ MDS + gather
-@pytest.mark.parametrize("B,n,m,seed", [(2, 640, 320, 9), (3, 2304, 2048, 10), (1, 100, 60, 11), (2, 9216, 1024, 12), (33, 1100, 64, 13)])
+@pytest.mark.parametrize("B,n,m,seed", [(2, 640, 320, 9), (3, 2304, 2048, 10), (1, 100, 60, 11), (2, 9216, 1024, 12), (33, 1100, 64, 13),
+                                        (150, 700, 64, 17), (5, 4099, 1500, 18)])
 def test_mds_vs_oracle(cuda, B, n, m, seed):
     """Host expf is not bit-identical to CUDA's, so the sequence is replayed step by step: every choice must be an
     arg-min of the oracle's own densities within 1e-5 rel; in practice the sequences coincide."""
@@ -346,6 +347,23 @@ def test_mds_vs_reference_extension(cuda):
     assert torch.equal(F_.gather_forward(f, idx), ext.gather_points(f, ridx))
     g = torch.rand(4, 4, 4096, device=cuda)
     assert torch.equal(F_.gather_backward(g, idx, 9216), ext.gather_points_grad(g, ridx, 9216))
+
+
+@pytest.mark.parametrize("mml", [0.0227, 0.048])
+def test_mds_full_size_vs_reference_extension(cuda, mml):
+    """BASELINE size (B=32, n=18432 = 16384 generated + 2048 partial points, m=16384) in the two regimes the bench step meets:
+    a neighbourhood-sized kernel width and one where every pick moves every density.  Bit-exact sequence."""
+    ext = ref_ext("MDS")
+    if ext is None:
+        pytest.skip("oracle/_ref/MDS.so not present")
+    from sparenet_b200 import functional as F_
+    torch.manual_seed(19)
+    x = torch.rand(32, 18432, 3, device=cuda) * 1.2 - 0.6
+    mm = torch.full((32,), mml, device=cuda) * (0.9 + 0.2 * torch.rand(32, device=cuda))
+    idx = F_.mds_sample(x, 16384, mm)
+    ridx = refcalls.mds(ext, x, 16384, mm)
+    assert torch.equal(idx, ridx)
+    assert all(idx[b].unique().numel() == 16384 for b in (0, 31))
 
 
 def test_gather_vs_oracle_and_autograd(cuda):
