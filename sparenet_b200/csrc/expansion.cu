@@ -80,16 +80,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expansion_kernel(const float* _
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (od < bd || (od == bd && oi > bi)) {
-        bd = od;
-        bi = oi;
-      }
-    }
-    last = bi;
+    // arg-min as two warp reductions instead of a 5-level (distance, index) shuffle butterfly:
+    // distances are >= 0, so their bit patterns order like the values; ties go to the larger index
+    const unsigned mbits = __reduce_min_sync(0xffffffffu, __float_as_uint(bd));
+    last = __reduce_max_sync(0xffffffffu, __float_as_uint(bd) == mbits ? bi : -1);
     if ((last & 31) == lane) {  // owner lane records the tree edge
       const int slot = last >> 5;
       int u = 0;
