@@ -153,14 +153,35 @@ __device__ __forceinline__ void emd_bid_pass(const EmdWs& w, const float* __rest
     mbar_wait(&bars[buf], phase[buf]);
     phase[buf] ^= 1u;
     const float4* __restrict__ tp = tiles + (size_t)buf * EMD_TILE;
-#pragma unroll 4
-    for (int k = g; k < cnt; k += G) {
-      const float4 o = tp[k];
+    // The filter is evaluated for a GROUP of 8 (object, bidder) pairs first -- straight-line code, one flag word -- and the exact
+    // path (rare: ~2 ln n times per bidder plus near-ties) sits behind ONE branch per group instead of one per pair.  That keeps
+    // the hot loop small enough for the instruction cache (the per-pair inlined exact path made `no_instruction` the top stall)
+    // and gives the few-bidder rounds (Q = 1) eight independent shared-memory loads in flight.  A pair filtered with a threshold
+    // that is stale within its group is only ever over-flagged, and flagged pairs are evaluated in ascending k: results unchanged.
+    constexpr int KU = Q >= 8 ? 1 : 8 / Q;  // objects per group
+#pragma unroll 1
+    for (int k0 = g; k0 < cnt; k0 += G * KU) {
+      float4 o[KU];
+      float sv[KU][Q];
+      unsigned flags = 0u;
 #pragma unroll
-      for (int q = 0; q < Q; q++) {
-        const float s = sqdist3(__fsub_rn(o.x, bx[q]), __fsub_rn(o.y, by[q]), __fsub_rn(o.z, bz[q]));
-        const float qq = fmaxf(st[q].c - o.w, 0.f);
-        if (__fmaf_rn(qq, qq, -s) > 0.f) emd_exact_update(st[q], s, o.w, base + k, n, tpu);
+      for (int u = 0; u < KU; u++) {
+        const int k = k0 + u * G;
+        const bool valid = k < cnt;
+        o[u] = tp[valid ? k : k0];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          sv[u][q] = sqdist3(__fsub_rn(o[u].x, bx[q]), __fsub_rn(o[u].y, by[q]), __fsub_rn(o[u].z, bz[q]));
+          const float qq = fmaxf(st[q].c - o[u].w, 0.f);
+          flags |= (valid && __fmaf_rn(qq, qq, -sv[u][q]) > 0.f) ? (1u << (u * Q + q)) : 0u;
+        }
+      }
+      if (flags) {
+#pragma unroll
+        for (int u = 0; u < KU; u++)
+#pragma unroll
+          for (int q = 0; q < Q; q++)
+            if ((flags >> (u * Q + q)) & 1u) emd_exact_update(st[q], sv[u][q], o[u].w, base + k0 + u * G, n, tpu);
       }
     }
     __syncthreads();
