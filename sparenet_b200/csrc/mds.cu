@@ -156,8 +156,10 @@ __host__ __device__ constexpr int mds_next_pt(int pt) { return pt > 12 ? pt - 4 
 // pick.  So in the default layout (WORKERS = 192, 8 warps) the replay warp is warp 0 and warp 4 -- the other warp of its
 // scheduler (warp id mod 4) -- only waits at the final barrier; warps 1-3 and 5-7 are the workers.  The other layouts put the
 // replay warp after the workers (WORKERS + 32 threads).
+// A third layout (WORKERS = 224) keeps warp 4 as a worker: the replay warp then shares its scheduler with ONE worker instead of two.
 __host__ __device__ constexpr bool mds_iso(int workers) { return workers == 192; }
-__host__ __device__ constexpr int mds_threads(int workers) { return mds_iso(workers) ? 256 : workers + 32; }
+__host__ __device__ constexpr bool mds_first(int workers) { return workers == 192 || workers == 224; }  // replay warp = warp 0
+__host__ __device__ constexpr int mds_threads(int workers) { return mds_first(workers) ? 256 : workers + 32; }
 
 // ---- worker warps ------------------------------------------------------------------------------------------------------
 template <int WORKERS, int PT, bool FAST_DIV>
@@ -168,7 +170,8 @@ struct MdsLevel {
     constexpr int WARPS = WORKERS / 32;
     constexpr int NEXT = mds_next_pt(PT);
     const int lane = threadIdx.x & 31;
-    const int warp = mds_iso(WORKERS) ? (int)(threadIdx.x >> 5) - 1 - (int)(threadIdx.x >= 160) : (int)(threadIdx.x >> 5);  // worker warp
+    const int warp = mds_iso(WORKERS) ? (int)(threadIdx.x >> 5) - 1 - (int)(threadIdx.x >= 160)
+                                      : (mds_first(WORKERS) ? (int)(threadIdx.x >> 5) - 1 : (int)(threadIdx.x >> 5));  // worker warp
     const int tid = warp * 32 + lane;                                                                                      // worker thread
     MdsShared& sh = *c.sh;
     const float t = c.t, r = c.r;
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(mds_threads(WORKERS), OCC) mds_cluster_kernel(
   c.t = t;
   c.r = rcp;
   if (m > 1) {
-    const bool replayer = mds_iso(WORKERS) ? tid < 32 : tid >= WORKERS;
+    const bool replayer = mds_first(WORKERS) ? tid < 32 : tid >= WORKERS;
     const bool idle = mds_iso(WORKERS) && (tid >> 5) == 4;
     if (replayer) {
       if (fast) mds_replay<true>(c, (int)cs * (WORKERS / 32));
@@ -725,7 +728,7 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   int force_threads = 0;
   if (const char* e = getenv("SNB_MDS_LAYOUT")) {
     int a = 0, t = 0;
-    if (sscanf(e, "%d,%d", &a, &t) == 2 && (a == 1 || a == 2 || a == 4 || a == 8) && (t == 128 || t == 192 || t == 256 || t == 512)) {
+    if (sscanf(e, "%d,%d", &a, &t) == 2 && (a == 1 || a == 2 || a == 4 || a == 8) && (t == 128 || t == 192 || t == 224 || t == 256 || t == 512)) {
       cs = a;
       force_threads = t;
       per = (n + cs - 1) / cs;
@@ -739,6 +742,10 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
     if (per <= 512 * 5) MDS_GO(512, 5, 1);
     else if (per <= 512 * 9) MDS_GO(512, 9, 1);
     else if (per <= 512 * 12) MDS_GO(512, 12, 1);
+    else return SNB_ELIMIT;
+  } else if (force_threads == 224) {
+    if (per <= 224 * 9) MDS_GO(224, 9, 1);
+    else if (per <= 224 * 21) MDS_GO(224, 21, 1);
     else return SNB_ELIMIT;
   } else if (force_threads == 192) {
     if (per > 192 * 24) return SNB_ELIMIT;
@@ -755,6 +762,7 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   else if (per <= 256 * 6) MDS_GO(256, 6, 1);
   else if (per <= 256 * 9) MDS_GO(256, 9, 1);
   else if (per <= 256 * 12) MDS_GO(256, 12, 1);
+  else if (per <= 224 * 21) MDS_GO(224, 21, 1);  // SpareNet's refiner (4608 points per CTA): replay warp beside ONE worker warp
   else if (per <= 256 * 18) MDS_GO(256, 18, 1);
   else if (per <= 512 * 12) MDS_GO(512, 12, 1);
   else if (per <= 512 * 18) MDS_GO(512, 18, 1);

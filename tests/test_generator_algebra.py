@@ -177,3 +177,42 @@ def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
         M.SpareNetGenerator(use_SElayer=True, use_AdaIn="share", encode="Pointfeat")
     assert np.allclose(np.array(M.grid_generation(16384, 32)[0], dtype=np.float32), GOLD["grid"])
+
+
+def test_stacked_parameter_gradients_are_views_of_one_buffer():
+    """_StackParams: the forward equals torch.stack; the backward hands each parameter its slice of the stacked gradient as .grad
+    (accumulating when a gradient already exists), exactly what torch.stack + AccumulateGrad would leave behind."""
+    from sparenet_b200.dropin.models.sparenet_generator import _StackParams
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(3, 4)) for _ in range(5)]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    w = torch.randn(5, 3, 4)
+    for rep in range(2):                                   # second pass: accumulation into existing .grad
+        (_StackParams.apply(*ps) * w).sum().backward()
+        (torch.stack(qs) * w).sum().backward()
+    for p, q in zip(ps, qs):
+        assert torch.equal(p.grad, q.grad)
+    base = ps[0].grad.untyped_storage().data_ptr()
+    assert all(p.grad.untyped_storage().data_ptr() == base for p in ps)      # one buffer, five views
+    frozen = [torch.nn.Parameter(torch.randn(2), requires_grad=False), torch.nn.Parameter(torch.randn(2))]
+    _StackParams.apply(*frozen).sum().backward()
+    assert frozen[0].grad is None and torch.equal(frozen[1].grad, torch.ones(2))
+
+
+def test_stage_hook_sees_coarse_and_middle(cpu_point_ops):
+    """SpareNetGenerator.stage_hook (used by bench.py to start the intermediate Chamfer losses on a side stream) is called with the
+    very tensors the forward returns, in order, and leaves the outputs untouched."""
+    from sparenet_b200.dropin.models import sparenet_generator as M
+    torch.manual_seed(1)
+    net = M.SpareNetGenerator(n_primitives=2, hide_size=64, bottleneck_size=64, num_points=2 * 512, use_SElayer=True, use_AdaIn="share",
+                              encode="Residualnet").train()
+    G.deterministic_fill(net)
+    x = torch.rand(2, 128, 3) - 0.5
+    seen = []
+    net.stage_hook = lambda name, cloud: seen.append((name, cloud))
+    coarse, middle, refine, loss_mst = net({"partial_cloud": x})
+    assert [n for n, _ in seen] == ["coarse", "middle"] and seen[0][1] is coarse and seen[1][1] is middle
+    net.stage_hook = None
+    G.deterministic_fill(net)
+    c2, m2, r2, l2 = net({"partial_cloud": x})
+    assert torch.equal(c2, coarse)
