@@ -21,11 +21,11 @@
 //      registers, with the very same arithmetic: update with the last pick's weights, take the arg-min, accept it while
 //      (density, key) < theta -- an accepted pick is the global arg-min of the sequential algorithm (nothing outside the pool
 //      can have dropped below theta).  The first candidate is always accepted;
-//   3. every accepted pick is STREAMED to the worker warps through shared memory (release/acquire counter) the moment it is
-//      known: they apply it to their own points (the same sequence of fp32 additions as the reference's rounds) while the
+//   3. every accepted pick is STREAMED to the worker warps through shared memory (one self-validating 16-byte entry) the moment
+//      it is known: they apply it to their own points (the same sequence of fp32 additions as the reference's rounds) while the
 //      replay warp is already working on the next one, park the picked points, and select again when the generation is done.
-// One cluster exchange (st.async + mbarrier complete_tx, no barrier.cluster) per generation instead of one per pick; the
-// per-pick chain is ~130 instructions of one warp, overlapped with the workers' arithmetic.  A thread-block CLUSTER (up to 8
+// One cluster exchange (a bulk copy per warp and peer CTA + mbarrier complete_tx, no barrier.cluster) per generation instead of
+// one per pick; the per-pick chain is ~130 instructions of one warp, overlapped with the workers' arithmetic.  A thread-block CLUSTER (up to 8
 // CTAs) owns one sample; every point (xyz + density) lives in registers for the whole kernel; the reference does 11 block
 // barriers and a global read-modify-write of `temp` per pick.
 #include <math.h>
@@ -69,10 +69,12 @@ __device__ __forceinline__ void ld_volatile_v4(const float4* p, float& a, float&
   b = __uint_as_float(ub);
   c = __uint_as_float(uc);
 }
+__device__ __forceinline__ void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned mds_tag(int gen) { return ((unsigned)(gen % 2047) + 1u) << 21; }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-constexpr int MDS_SLOTS = MDS_MAX_CLUSTER * MDS_MAX_WARPS;  // up to 128 worker warps per sample
 
 // Development statistics (SNB_MDS_STATS builds only): cycle accounting of block 0's replay warp and worker warp 0.
 #ifdef SNB_MDS_STATS
@@ -152,11 +154,12 @@ struct MdsCtx {
 __host__ __device__ constexpr int mds_next_pt(int pt) { return pt > 12 ? pt - 4 : (pt > 6 ? pt - 3 : (pt > 2 ? pt - 2 : 0)); }  // 24 20 16 12 9 6 4 2
 
 // Thread layout of a CTA.  The replay warp's per-pick chain is the critical path of the whole kernel and it is latency bound,
-// while the workers' updates are always ready to issue: sharing a warp scheduler with two worker warps tripled its time per
-// pick.  So in the default layout (WORKERS = 192, 8 warps) the replay warp is warp 0 and warp 4 -- the other warp of its
-// scheduler (warp id mod 4) -- only waits at the final barrier; warps 1-3 and 5-7 are the workers.  The other layouts put the
-// replay warp after the workers (WORKERS + 32 threads).
-// A third layout (WORKERS = 224) keeps warp 4 as a worker: the replay warp then shares its scheduler with ONE worker instead of two.
+// while the workers' updates are always ready to issue, so the warp schedulers (warp id mod 4) matter:
+//   WORKERS = 224 (the layout SpareNet's refiner size gets): 8 warps, the replay warp is warp 0 and shares its scheduler with ONE
+//                 worker warp (warp 4); measured best on the bench clouds (8.3 / 10.1 ms per call);
+//   WORKERS = 192 (experiment, SNB_MDS_LAYOUT="4,192"): warp 4 only waits at the final barrier, the replay warp has its scheduler to
+//                 itself -- 450 instead of 740 cycles per pick, but the workers lose a quarter of their issue slots (9.2 ms);
+//   otherwise     WORKERS + 32 threads, the replay warp comes after the workers and shares its scheduler with two of them.
 __host__ __device__ constexpr bool mds_iso(int workers) { return workers == 192; }
 __host__ __device__ constexpr bool mds_first(int workers) { return workers == 192 || workers == 224; }  // replay warp = warp 0
 __host__ __device__ constexpr int mds_threads(int workers) { return mds_first(workers) ? 256 : workers + 32; }
@@ -230,24 +233,34 @@ struct MdsLevel {
       const int par = gen & 1;
       {
         const int mb = mds_msg_bytes(msel);
-        unsigned char* msg = &sh.stage[par][warp * mb];
+        unsigned char* msg = &sh.stage[par][warp * mb];       // source of the bulk copies to the peers
+        unsigned char* own = &sh.pool[par][my_slot * mb];     // this CTA's copy is written directly (no copy onto itself)
         if (lane < msel) {
           const int kk = mysel != MDS_NONE ? (int)((unsigned)mysel & 0x1fffffu) >> c.csh : 0;  // one of this CTA's points
-          reinterpret_cast<float4*>(msg + 16)[lane] = make_float4(c.sxyz[kk * c.xs + 0], c.sxyz[kk * c.xs + 1], c.sxyz[kk * c.xs + 2], 0.f);
+          const float4 cx = make_float4(c.sxyz[kk * c.xs + 0], c.sxyz[kk * c.xs + 1], c.sxyz[kk * c.xs + 2], 0.f);
+          reinterpret_cast<float4*>(msg + 16)[lane] = cx;
           reinterpret_cast<unsigned long long*>(msg + 16 + 16 * msel)[lane] = mysel;
+          reinterpret_cast<float4*>(own + 16)[lane] = cx;
+          reinterpret_cast<unsigned long long*>(own + 16 + 16 * msel)[lane] = mysel;
         } else if (lane == msel) {
           *reinterpret_cast<unsigned long long*>(msg) = mysel;
+          *reinterpret_cast<unsigned long long*>(own) = mysel;
 #ifdef SNB_MDS_STATS
           unsigned long long gt;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
           *reinterpret_cast<unsigned long long*>(msg + 8) = gt;
+          *reinterpret_cast<unsigned long long*>(own + 8) = gt;
 #endif
         }
         fence_proxy_async();  // the generic-proxy writes above, before the async-proxy reads of the bulk copies
         __syncwarp();
-        if (lane < cs)
+        if (lane < cs && lane != (int)c.rank)
           bulk_copy_to_peer(mapa_shared(smem_u32(&sh.pool[par][my_slot * mb]), (uint32_t)lane), smem_u32(msg), (uint32_t)mb,
                             mapa_shared(smem_u32(&sh.bars[par]), (uint32_t)lane));
+        if (lane == (int)c.rank) {  // the local message: its bytes are complete (ordered by the __syncwarp and this fence)
+          __threadfence_block();
+          mbar_complete_tx(&sh.bars[par], (uint32_t)mb);
+        }
       }
       gen++;
       const long long w1 = MDS_CLOCK();
@@ -728,42 +741,29 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   int force_threads = 0;
   if (const char* e = getenv("SNB_MDS_LAYOUT")) {
     int a = 0, t = 0;
-    if (sscanf(e, "%d,%d", &a, &t) == 2 && (a == 1 || a == 2 || a == 4 || a == 8) && (t == 128 || t == 192 || t == 224 || t == 256 || t == 512)) {
+    if (sscanf(e, "%d,%d", &a, &t) == 2 && (a == 1 || a == 2 || a == 4 || a == 8) && (t == 128 || t == 192 || t == 224 || t == 256)) {
       cs = a;
       force_threads = t;
       per = (n + cs - 1) / cs;
     }
   }
-  if (force_threads == 128) {
-    if (per <= 128 * 9) MDS_GO(128, 9, 2);
-    else if (per <= 128 * 18) MDS_GO(128, 18, 2);
-    else return SNB_ELIMIT;
-  } else if (force_threads == 512) {
-    if (per <= 512 * 5) MDS_GO(512, 5, 1);
-    else if (per <= 512 * 9) MDS_GO(512, 9, 1);
-    else if (per <= 512 * 12) MDS_GO(512, 12, 1);
+  if (force_threads == 128) {  // two samples' CTAs per SM
+    if (per <= 128 * 18) MDS_GO(128, 18, 2);
     else return SNB_ELIMIT;
   } else if (force_threads == 224) {
     if (per <= 224 * 9) MDS_GO(224, 9, 1);
     else if (per <= 224 * 21) MDS_GO(224, 21, 1);
     else return SNB_ELIMIT;
   } else if (force_threads == 192) {
-    if (per > 192 * 24) return SNB_ELIMIT;
-    if (per <= 192 * 2) MDS_GO(192, 2, 1);
-    else if (per <= 192 * 4) MDS_GO(192, 4, 1);
-    else if (per <= 192 * 6) MDS_GO(192, 6, 1);
-    else if (per <= 192 * 9) MDS_GO(192, 9, 1);
-    else if (per <= 192 * 12) MDS_GO(192, 12, 1);
-    else if (per <= 192 * 16) MDS_GO(192, 16, 1);
-    else if (per <= 192 * 20) MDS_GO(192, 20, 1);
-    else MDS_GO(192, 24, 1);
-  } else if (per <= 256 * 2) MDS_GO(256, 2, 1);
+    if (per <= 192 * 24) MDS_GO(192, 24, 1);
+    else return SNB_ELIMIT;
+  } else if (force_threads == 256 && per > 256 * 12 && per <= 256 * 18) MDS_GO(256, 18, 1);
+  else if (per <= 256 * 2) MDS_GO(256, 2, 1);
   else if (per <= 256 * 4) MDS_GO(256, 4, 1);
   else if (per <= 256 * 6) MDS_GO(256, 6, 1);
   else if (per <= 256 * 9) MDS_GO(256, 9, 1);
   else if (per <= 256 * 12) MDS_GO(256, 12, 1);
   else if (per <= 224 * 21) MDS_GO(224, 21, 1);  // SpareNet's refiner (4608 points per CTA): replay warp beside ONE worker warp
-  else if (per <= 256 * 18) MDS_GO(256, 18, 1);
   else if (per <= 512 * 12) MDS_GO(512, 12, 1);
   else if (per <= 512 * 18) MDS_GO(512, 18, 1);
   else return SNB_ELIMIT;  // n > 8*512*18 = 73728 points per sample
