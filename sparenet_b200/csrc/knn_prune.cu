@@ -1,0 +1,269 @@
+// knn_prune.cu -- kNN for wide features (C >= 64) with a tensor-core Gram matrix as a PRUNING filter, sm_100a.
+//
+// STATUS: written at the end of round 1 after the GPU budget was spent; compiled, NOT yet run on a GPU.  It is therefore off by
+// default (sparenet_b200.functional.knn_indices uses it only with SNB_KNN_PRUNE=1) and its parity test is skipped unless
+// SNB_TEST_KNN_PRUNE=1.  The rule it implements was validated on the CPU on the encoder's real features
+// (tests/perf/knn_prune_study.py: ~9 candidates per row survive for k = 8).
+//
+// Same contract and the SAME BITS as snb_knn (knn.cu): for every point the k points with the smallest
+//     d(i,j) = sum_c (x[c,j] - x[c,i])^2,  accumulated with FMAs in ascending c, fp32,
+// ordered by (d, j).  SURVEY.md 8(d): the |a|^2 + |b|^2 - 2ab GEMM form may not DEFINE the result (cancellation), but it may
+// PRUNE: with G~ = X^T X from a TF32 library GEMM (operands truncated to 10 mantissa bits, fp32 accumulation)
+//     d~(i,j) = n_i + n_j - 2 G~(i,j),   |d~ - d| <= eps_i = 2^-7.5 |a_i| max_j |a_j| + 2^-13 (n_i + max_j n_j)
+// (2 * 2^-10 relative per product from the truncation, Cauchy-Schwarz, the factor 2 of the formula; the second term covers the
+// fp32 rounding of the norms and of the accumulations for C <= 1024).  Every j among the exact k nearest of i then satisfies
+//     d~(i,j) <= kth_smallest_j d~(i,j) * (1 + 2^-10) + 2 eps_i,
+// so the exact distances are evaluated only for those candidates (a handful per row) and the exact (d, j) order picks the k.
+// Rows whose candidate list overflows fall back to evaluating every j exactly.
+//
+// Inputs: xT [B,N,C] point-major copy of the features (candidate rows are contiguous), gram [B,N,N] from the library GEMM.
+#include "common.cuh"
+
+namespace snb {
+
+constexpr int KP_MAXK = 32;
+constexpr int KP_CAND = 96;  // candidate capacity per row (3 per lane)
+
+// squared norms of the points (fp32) and their per-sample maximum (bit pattern; norms are >= 0)
+__global__ void __launch_bounds__(256) knn_norm_kernel(const float* __restrict__ xT, int C, int N, size_t rows, float* __restrict__ nrm,
+                                                        unsigned* __restrict__ nmax_bits) {
+  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* __restrict__ p = xT + row * C;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = __fmaf_rn(p[c], p[c], acc);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    nrm[row] = acc;
+    atomicMax(&nmax_bits[row / N], __float_as_uint(acc));
+  }
+}
+
+// exact distance of candidate j to query i, the arithmetic of knn_dist_kernel: d = x_j[c] - x_i[c]; acc = fma(d, d, acc), ascending c
+__device__ __forceinline__ float knn_exact_dist(const float* __restrict__ xi, const float* __restrict__ xj, int C) {
+  float acc = 0.f;
+  int c = 0;
+  if ((C & 3) == 0) {
+    for (; c < C; c += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(xi + c);
+      const float4 b = *reinterpret_cast<const float4*>(xj + c);
+      float d = __fsub_rn(b.x, a.x);
+      acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(b.y, a.y);
+      acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(b.z, a.z);
+      acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(b.w, a.w);
+      acc = __fmaf_rn(d, d, acc);
+    }
+  } else {
+    for (; c < C; c++) {
+      const float d = __fsub_rn(xj[c], xi[c]);
+      acc = __fmaf_rn(d, d, acc);
+    }
+  }
+  return acc;
+}
+
+// warp per query row
+template <int K>
+__global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict__ xT, const float* __restrict__ gram, const float* __restrict__ nrm,
+                                                         const unsigned* __restrict__ nmax_bits, int C, int N, size_t rows, int k,
+                                                         int* __restrict__ idx) {
+  __shared__ int cand[8][KP_CAND];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t row = (size_t)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const size_t b = row / N;
+  const int i = (int)(row - b * N);
+  const float* __restrict__ g = gram + row * N;
+  const float* __restrict__ nb = nrm + b * N;
+  const float ni = nb[i];
+  // ---- pass 1: the k-th smallest approximate distance of the row (per-lane sorted lists, then k pops of the warp minimum) ----
+  float bd[K];
+#pragma unroll
+  for (int t = 0; t < K; t++) bd[t] = __int_as_float(0x7f800000);
+  for (int j = lane; j < N; j += 32) {
+    float v = __fmaf_rn(-2.f, g[j], ni + nb[j]);
+    if (v < bd[K - 1]) {
+      bool ins = false;
+#pragma unroll
+      for (int t = 0; t < K; t++) {
+        if (ins || v < bd[t]) {
+          ins = true;
+          const float tv = bd[t];
+          bd[t] = v;
+          v = tv;
+        }
+      }
+    }
+  }
+  float kth = 0.f;
+  for (int t = 0; t < k; t++) {
+    float mv = bd[0];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mv = fminf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+    kth = mv;
+    const unsigned owners = __ballot_sync(0xffffffffu, bd[0] == mv);
+    if (lane == __ffs(owners) - 1) {  // ONE lane pops (equal approximate values in several lanes count separately)
+#pragma unroll
+      for (int u = 0; u + 1 < K; u++) bd[u] = bd[u + 1];
+      bd[K - 1] = __int_as_float(0x7f800000);
+    }
+  }
+  const float nmx = __uint_as_float(nmax_bits[b]);
+  // 2^-7.5 |a_i| max|a_j| for the truncated products, 2^-13 (n_i + max n_j) for the fp32 rounding of the norms and the accumulations
+  // (also what keeps the rule valid for an all-zero query point, whose first term vanishes)
+  const float eps = __fmaf_rn(0.0055242717f * sqrtf(ni), sqrtf(nmx), 0.00012207031f * (ni + nmx));
+  const float thr = __fmaf_rn(fabsf(kth), 0.0009765625f, kth) + 2.f * eps;
+  // ---- pass 2: candidates ----
+  int ncand = 0;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    const int j = j0 + lane;
+    const bool ok = j < N && __fmaf_rn(-2.f, g[j], ni + nb[j]) <= thr;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int pos = ncand + __popc(m & ((1u << lane) - 1u));
+      if (pos < KP_CAND) cand[warp][pos] = j;
+    }
+    ncand += __popc(m);
+  }
+  __syncwarp();
+  // ---- exact distances of the candidates, then the k smallest by (d, j) ----
+  const float* __restrict__ xb = xT + b * (size_t)N * C;
+  const float* __restrict__ xi = xb + (size_t)i * C;
+  float cd[3];
+  int cj[3];
+#pragma unroll
+  for (int u = 0; u < 3; u++) {
+    cd[u] = __int_as_float(0x7f800000);
+    cj[u] = 0x7fffffff;
+  }
+  int* out = idx + row * k;
+  if (ncand <= KP_CAND) {
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      const int e = lane + 32 * u;
+      if (e < ncand) {
+        cj[u] = cand[warp][e];
+        cd[u] = knn_exact_dist(xi, xb + (size_t)cj[u] * C, C);
+      }
+    }
+    for (int t = 0; t < k; t++) {
+      // this lane's best remaining candidate
+      float hv = cd[0];
+      int hj = cj[0];
+#pragma unroll
+      for (int u = 1; u < 3; u++)
+        if (cd[u] < hv || (cd[u] == hv && cj[u] < hj)) {
+          hv = cd[u];
+          hj = cj[u];
+        }
+      float mv = hv;
+      int mj = hj;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
+        if (ov < mv || (ov == mv && oj < mj)) {
+          mv = ov;
+          mj = oj;
+        }
+      }
+      if (lane == 0) out[t] = mj;
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+        if (cj[u] == mj) {  // indices are unique: exactly one slot of one lane
+          cd[u] = __int_as_float(0x7f800000);
+          cj[u] = 0x7fffffff;
+        }
+    }
+  } else {
+    // overflow (degenerate rows, e.g. many identical points): every j evaluated exactly, per-lane sorted lists as in knn_topk_kernel
+    float ed[K];
+    int ei[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) {
+      ed[t] = __int_as_float(0x7f800000);
+      ei[t] = 0x7fffffff;
+    }
+    for (int j = lane; j < N; j += 32) {
+      float v = knn_exact_dist(xi, xb + (size_t)j * C, C);
+      int vi = j;
+      if (v < ed[K - 1]) {
+        bool ins = false;
+#pragma unroll
+        for (int t = 0; t < K; t++) {
+          if (ins || v < ed[t]) {
+            ins = true;
+            const float tv = ed[t];
+            const int ti = ei[t];
+            ed[t] = v;
+            ei[t] = vi;
+            v = tv;
+            vi = ti;
+          }
+        }
+      }
+    }
+    for (int t = 0; t < k; t++) {
+      const float hv = ed[0];
+      const int hi = ei[0];
+      float mv = hv;
+      int mi = hi;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov < mv || (ov == mv && oi < mi)) {
+          mv = ov;
+          mi = oi;
+        }
+      }
+      if (lane == 0) out[t] = mi;
+      if (hi == mi && hv == mv) {
+#pragma unroll
+        for (int u = 0; u + 1 < K; u++) {
+          ed[u] = ed[u + 1];
+          ei[u] = ei[u + 1];
+        }
+        ed[K - 1] = __int_as_float(0x7f800000);
+        ei[K - 1] = 0x7fffffff;
+      }
+    }
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+// workspace: norms [B,N] floats + per-sample maxima [B] (16-byte aligned pieces)
+SNB_API size_t snb_knn_pruned_workspace_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return (((size_t)B * N * sizeof(float) + 15) & ~(size_t)15) + (((size_t)B * sizeof(unsigned) + 15) & ~(size_t)15);
+}
+
+SNB_API int snb_knn_pruned(const float* xT, const float* gram, int B, int C, int N, int k, int* idx, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (B < 0 || C <= 0 || N < 0 || k <= 0) return SNB_EINVAL;
+  if (k > KP_MAXK || k > N) return SNB_ELIMIT;
+  if (B == 0 || N == 0) return SNB_OK;
+  if (!workspace || workspace_bytes < snb_knn_pruned_workspace_bytes(B, N)) return SNB_EWORKSPACE;
+  if (((uintptr_t)workspace & 15) != 0 || ((uintptr_t)xT & 15) != 0) return SNB_EALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* nrm = (float*)workspace;
+  unsigned* nmax = (unsigned*)((char*)workspace + (((size_t)B * N * sizeof(float) + 15) & ~(size_t)15));
+  SNB_CUDA(cudaMemsetAsync(nmax, 0, sizeof(unsigned) * (size_t)B, s));
+  const size_t rows = (size_t)B * N;
+  knn_norm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(xT, C, N, rows, nrm, nmax);
+  SNB_LAUNCH_CHECK();
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (k <= 8) knn_prune_kernel<8><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+  else if (k <= 16) knn_prune_kernel<16><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+  else knn_prune_kernel<32><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

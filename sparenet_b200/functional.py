@@ -3,6 +3,8 @@
 PyTorch is plumbing here: it owns device memory (outputs and scratch come from its caching allocator) and
 the current stream.  All arithmetic happens in libsparenet_b200.so; there is no fallback path.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -252,10 +254,28 @@ def p2i_sum_backward(grad_out, points, feat, batch_inds, kernel_kind, radius):
 
 
 # ----------------------------------------------------------------------------- kNN
+def knn_indices_pruned(x, k):
+    """Same result as knn_indices for wide features: a TF32 library GEMM (X^T X) prunes, snb_knn_pruned re-evaluates the surviving
+    candidates exactly (csrc/knn_prune.cu).  Experimental: not GPU-validated in round 1, used only with SNB_KNN_PRUNE=1."""
+    x = _cuda_f32(x, "x")
+    B, C, N = x.shape
+    xT = x.transpose(1, 2).contiguous()
+    gram = torch.bmm(xT, x)
+    idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    nbytes = lib.snb_knn_pruned_workspace_bytes(B, N)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device), _op("knn", 2):
+        check(lib.snb_knn_pruned(ptr(xT), ptr(gram), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn_pruned")
+    return idx
+
+
 def knn_indices(x, k):
     """x: [B, C, N] float32 (channel-major, as the encoder holds it) -> idx [B, N, k] int32."""
     x = _cuda_f32(x, "x")
     B, C, N = x.shape
+    if C >= 64 and (C & 3) == 0 and os.environ.get("SNB_KNN_PRUNE") == "1":
+        return knn_indices_pruned(x, k)
     idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
     lib = _lib.load()
     nbytes = lib.snb_knn_workspace_bytes(B, N)

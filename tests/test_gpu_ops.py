@@ -5,6 +5,8 @@ BASELINE.json's full sizes.  Bar: bit-exact for indices, and for values wherever
 replicated; tolerances are written next to each comparison otherwise."""
 import sys
 
+import os
+
 import pytest
 import torch
 
@@ -486,6 +488,28 @@ def test_knn_vs_oracle_sets(cuda, B, C, N, k, seed):
             do = (xt[b, oidx[b, i].long()] - xt[b, i]).pow(2).sum(-1).max()
             assert abs(dm - do) <= 1e-5 * do
     assert same.float().mean().item() > 0.999
+
+
+@pytest.mark.skipif(os.environ.get("SNB_TEST_KNN_PRUNE") != "1", reason="pruned kNN was written after round 1's GPU budget was spent: "
+                    "validate with SNB_TEST_KNN_PRUNE=1 before enabling SNB_KNN_PRUNE")
+@pytest.mark.parametrize("B,C,N,k,offset", [(2, 64, 500, 8, 0.0), (3, 256, 2048, 8, 3.0), (2, 512, 1024, 16, 1.0), (1, 128, 300, 8, 0.0)])
+def test_knn_pruned_identical_to_brute_force(cuda, B, C, N, k, offset):
+    """tensor-core Gram matrix as a pruning filter + exact re-evaluation == the brute-force kernel, index for index; `offset` adds
+    a common mean to the features (large norms, small distances: the cancellation case the bound has to survive); the last case
+    has duplicated and all-zero points."""
+    from sparenet_b200 import functional as F_
+    torch.manual_seed(B * 100 + C)
+    x = torch.randn(B, C, N, device=cuda) + offset
+    if C == 128:
+        x[:, :, 200:260] = x[:, :, 100:160]
+        x[:, :, 280:] = 0
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = F_.knn_indices_pruned(x, k)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert torch.equal(a, F_.knn_indices(x, k))
 
 
 def test_knn_cuda_shim(cuda):
