@@ -106,7 +106,7 @@ size_t snb_knn_workspace_bytes(int B, int N);
 int snb_knn(const float* x, int B, int C, int N, int k, int* idx, void* workspace, size_t workspace_bytes, void* stream);
 /* The same result (bit-identical indices) for wide features, with a caller-supplied Gram matrix gram [B,N,N] = X^T X from a
  * TF32 library GEMM used as a PRUNING filter and exact fp32 re-evaluation of the surviving candidates (csrc/knn_prune.cu).
- * xT [B,N,C] is the point-major copy of the features.  Experimental in round 1 (not yet GPU-validated, off by default). */
+ * xT [B,N,C] is the point-major copy of the features.  Parity-tested on B200; timing pending (round 2). */
 size_t snb_knn_pruned_workspace_bytes(int B, int N);
 int snb_knn_pruned(const float* xT, const float* gram, int B, int C, int N, int k, int* idx, void* workspace,
                    size_t workspace_bytes, void* stream);

@@ -1,9 +1,10 @@
 // knn_prune.cu -- kNN for wide features (C >= 64) with a tensor-core Gram matrix as a PRUNING filter, sm_100a.
 //
-// STATUS: written at the end of round 1 after the GPU budget was spent; compiled, NOT yet run on a GPU.  It is therefore off by
-// default (sparenet_b200.functional.knn_indices uses it only with SNB_KNN_PRUNE=1) and its parity test is skipped unless
-// SNB_TEST_KNN_PRUNE=1.  The rule it implements was validated on the CPU on the encoder's real features
-// (tests/perf/knn_prune_study.py: ~9 candidates per row survive for k = 8).
+// STATUS (end of round 1): parity-tested on a B200 (tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force: identical
+// indices incl. the large-norm cancellation case and duplicated / all-zero points); NOT yet timed -- the round's GPU budget ended
+// with that test.  sparenet_b200.functional.knn_indices therefore uses it by default only for C >= 512 with TF32 matmul allowed
+// (SNB_KNN_PRUNE=1 / 0 forces it on / off).  The rule was also checked on the CPU on the encoder's real features
+// (tests/perf/knn_prune_study.py: ~11 candidates per row survive for k = 8).
 //
 // Same contract and the SAME BITS as snb_knn (knn.cu): for every point the k points with the smallest
 //     d(i,j) = sum_c (x[c,j] - x[c,i])^2,  accumulated with FMAs in ascending c, fp32,

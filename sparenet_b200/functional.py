@@ -256,16 +256,16 @@ def p2i_sum_backward(grad_out, points, feat, batch_inds, kernel_kind, radius):
 # ----------------------------------------------------------------------------- kNN
 def knn_indices_pruned(x, k):
     """Same result as knn_indices for wide features: a TF32 library GEMM (X^T X) prunes, snb_knn_pruned re-evaluates the surviving
-    candidates exactly (csrc/knn_prune.cu).  Experimental: not GPU-validated in round 1, used only with SNB_KNN_PRUNE=1."""
+    candidates exactly (csrc/knn_prune.cu).  Indices identical to knn_indices (tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force)."""
     x = _cuda_f32(x, "x")
     B, C, N = x.shape
-    xT = x.transpose(1, 2).contiguous()
-    gram = torch.bmm(xT, x)
     idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
     lib = _lib.load()
     nbytes = lib.snb_knn_pruned_workspace_bytes(B, N)
     ws = _ws(nbytes, x.device)
-    with torch.cuda.device(x.device), _op("knn", 2):
+    with torch.cuda.device(x.device), _op("knn", 2):     # the op's time includes the transpose and the library GEMM
+        xT = x.transpose(1, 2).contiguous()
+        gram = torch.bmm(xT, x)
         check(lib.snb_knn_pruned(ptr(xT), ptr(gram), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn_pruned")
     return idx
 
@@ -274,7 +274,11 @@ def knn_indices(x, k):
     """x: [B, C, N] float32 (channel-major, as the encoder holds it) -> idx [B, N, k] int32."""
     x = _cuda_f32(x, "x")
     B, C, N = x.shape
-    if C >= 64 and (C & 3) == 0 and os.environ.get("SNB_KNN_PRUNE") == "1":
+    # Wide features: the TF32 Gram matrix prunes, exact fp32 re-evaluation decides (identical indices; parity-tested on B200).  On by
+    # default only where the arithmetic margin over the brute-force kernel is 2x or more (C >= 512) and the GEMM really runs on the
+    # tensor cores (TF32 matmul allowed); SNB_KNN_PRUNE=1 / 0 forces it on (for C >= 64) / off.
+    force = os.environ.get("SNB_KNN_PRUNE")
+    if (C & 3) == 0 and force != "0" and ((force == "1" and C >= 64) or (C >= 512 and torch.backends.cuda.matmul.allow_tf32)):
         return knn_indices_pruned(x, k)
     idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
     lib = _lib.load()

@@ -490,8 +490,6 @@ def test_knn_vs_oracle_sets(cuda, B, C, N, k, seed):
     assert same.float().mean().item() > 0.999
 
 
-@pytest.mark.skipif(os.environ.get("SNB_TEST_KNN_PRUNE") != "1", reason="pruned kNN was written after round 1's GPU budget was spent: "
-                    "validate with SNB_TEST_KNN_PRUNE=1 before enabling SNB_KNN_PRUNE")
 @pytest.mark.parametrize("B,C,N,k,offset", [(2, 64, 500, 8, 0.0), (3, 256, 2048, 8, 3.0), (2, 512, 1024, 16, 1.0), (1, 128, 300, 8, 0.0)])
 def test_knn_pruned_identical_to_brute_force(cuda, B, C, N, k, offset):
     """tensor-core Gram matrix as a pruning filter + exact re-evaluation == the brute-force kernel, index for index; `offset` adds
