@@ -491,7 +491,7 @@ def test_knn_vs_oracle_sets(cuda, B, C, N, k, seed):
 
 
 @pytest.mark.parametrize("B,C,N,k,offset", [(2, 64, 500, 8, 0.0), (3, 256, 2048, 8, 3.0), (2, 512, 1024, 16, 1.0), (1, 128, 300, 8, 0.0)])
-def test_knn_pruned_identical_to_brute_force(cuda, B, C, N, k, offset):
+def test_knn_pruned_identical_to_brute_force(cuda, monkeypatch, B, C, N, k, offset):
     """tensor-core Gram matrix as a pruning filter + exact re-evaluation == the brute-force kernel, index for index; `offset` adds
     a common mean to the features (large norms, small distances: the cancellation case the bound has to survive); the last case
     has duplicated and all-zero points."""
@@ -507,6 +507,7 @@ def test_knn_pruned_identical_to_brute_force(cuda, B, C, N, k, offset):
         a = F_.knn_indices_pruned(x, k)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
+    monkeypatch.setenv("SNB_KNN_PRUNE", "0")             # the reference side is always the brute-force kernels
     assert torch.equal(a, F_.knn_indices(x, k))
 
 
