@@ -257,7 +257,7 @@ def p2i_sum_backward(grad_out, points, feat, batch_inds, kernel_kind, radius):
 def knn_indices_pruned(x, k):
     """Same result as knn_indices for wide features: a TF32 library GEMM (X^T X) prunes, snb_knn_pruned re-evaluates the surviving
     candidates exactly (csrc/knn_prune.cu).  Indices identical to knn_indices (tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force)."""
-    x = _cuda_f32(x, "x")
+    x = _cuda_f32(x, "x").detach()                       # indices carry no gradient: keep the GEMM out of the autograd graph
     B, C, N = x.shape
     idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
     lib = _lib.load()
