@@ -88,6 +88,9 @@ for j in range(1, npick + 1):
         has = np.isfinite(tmin)
         skip = wmax < tmin * np.float32(2.0 ** -25)                         # < ulp/2 for every density >= tmin
         stats[name].append(skip[has].mean())
+        chg = np.zeros(ng, dtype=bool)
+        np.logical_or.at(chg, g[live], changed[live])
+        assert not (skip & chg).any(), "the box criterion skipped a group with a point whose density changes"   # exactness
     temp = new
     cand = np.where(live, temp, np.float32(np.inf))
     last = int(np.lexsort((key, cand))[0])
