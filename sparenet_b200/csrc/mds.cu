@@ -165,7 +165,7 @@ __host__ __device__ constexpr bool mds_first(int workers) { return workers == 19
 __host__ __device__ constexpr int mds_threads(int workers) { return mds_first(workers) ? 256 : workers + 32; }
 
 // ---- worker warps ------------------------------------------------------------------------------------------------------
-template <int WORKERS, int PT, bool FAST_DIV>
+template <int WORKERS, int PT, bool FAST_DIV, bool CULL>
 struct MdsLevel {
   // runs generations while the CTA still holds more live points than the next narrower layout can take;
   // returns true when the kernel is finished
@@ -192,6 +192,32 @@ struct MdsLevel {
       z[i] = c.sxyz[kk * c.xs + 2];
       fac[i] = k < 8192 ? 1.0f : 2.0f;  // MDS_cuda.cu:111-112 (k > 8191 counts double)
     }
+    // CULL (experimental, SNB_MDS_CULL=1; see tools/mds_cull_study.py): lane s keeps the bounding box of the live points in register
+    // slot s of this warp and, per generation, a lower bound of their densities.  For a pick, slot s can be skipped when the
+    // largest weight anywhere in the box is below half an ulp of that bound: fl(temp + w) == temp for every point of the slot.
+    float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f, btmin = 0.f;
+    if (CULL) {
+      static_assert(!CULL || PT <= 32, "one lane per register slot");
+#pragma unroll
+      for (int i = 0; i < PT; i++) {
+        const bool lv = temp[i] < 1e9f;
+        float lx = lv ? x[i] : 3e38f, ly = lv ? y[i] : 3e38f, lz = lv ? z[i] : 3e38f;
+        float hx = lv ? x[i] : -3e38f, hy = lv ? y[i] : -3e38f, hz = lv ? z[i] : -3e38f;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
+          ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+          lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+          hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+          hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+          hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+        }
+        if (lane == i) {
+          blx = lx; bly = ly; blz = lz;
+          bhx = hx; bhy = hy; bhz = hz;
+        }
+      }
+    }
     const int cs = (int)c.cs, msel = c.msel;
     const uint32_t my_slot = c.rank * WARPS + warp;
     const int total = cs * WARPS;
@@ -207,6 +233,13 @@ struct MdsLevel {
         const unsigned long long hi2 = p < mine ? mine : p;
         mine = p < mine ? p : mine;
         second = hi2 < second ? hi2 : second;
+      }
+      if (CULL) {  // densities only grow, so the minimum taken here bounds the whole generation from below
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+          const unsigned mbits = __reduce_min_sync(0xffffffffu, temp[i] < 1e9f ? __float_as_uint(temp[i]) : 0x7f800000u);
+          if (lane == i) btmin = __uint_as_float(mbits);
+        }
       }
       unsigned long long mysel = MDS_NONE;
       int taken = 0;
@@ -306,8 +339,23 @@ struct MdsLevel {
           }
         }
 #ifndef SNB_MDS_NOAPPLY  // (timing experiment: the replay warp's chain with idle workers; results are wrong)
+        if (CULL) {
+          // lane s: squared distance from the pick to the box of slot s (shrunk by 1e-4 relative: far more than the fp32 rounding
+          // of the per-point distances), upper bound 2.02 exp(-d/t) of the weight of any of its points (x2 factor, 1 % for the
+          // fast exponential), against half an ulp (>= density * 2^-25) of the slot's smallest live density
+          const float ddx = fmaxf(fmaxf(blx - pk.x, pk.x - bhx), 0.f);
+          const float ddy = fmaxf(fmaxf(bly - pk.y, pk.y - bhy), 0.f);
+          const float ddz = fmaxf(fmaxf(blz - pk.z, pk.z - bhz), 0.f);
+          const float dmin = (ddx * ddx + ddy * ddy + ddz * ddz) * 0.9999f;
+          const bool skip = lane >= PT || 2.02f * __expf(-dmin * r) < btmin * 2.9802322e-8f;
+          const unsigned act = ~__ballot_sync(0xffffffffu, skip);
 #pragma unroll
-        for (int i = 0; i < PT; i++) temp[i] = mds_add<FAST_DIV>(temp[i], fac[i], x[i], y[i], z[i], pk.x, pk.y, pk.z, t, r);
+          for (int i = 0; i < PT; i++)
+            if ((act >> i) & 1u) temp[i] = mds_add<FAST_DIV>(temp[i], fac[i], x[i], y[i], z[i], pk.x, pk.y, pk.z, t, r);
+        } else {
+#pragma unroll
+          for (int i = 0; i < PT; i++) temp[i] = mds_add<FAST_DIV>(temp[i], fac[i], x[i], y[i], z[i], pk.x, pk.y, pk.z, t, r);
+        }
 #endif
         applied++;
 #ifdef SNB_MDS_STATS
@@ -350,14 +398,14 @@ struct MdsLevel {
   }
 };
 
-template <int WORKERS, int PT, bool FAST_DIV>
+template <int WORKERS, int PT, bool FAST_DIV, bool CULL>
 struct MdsChain {
   static __device__ __forceinline__ void run(const MdsCtx& c, int& live, int& gen) {
-    if (!MdsLevel<WORKERS, PT, FAST_DIV>::run(c, live, gen)) MdsChain<WORKERS, mds_next_pt(PT), FAST_DIV>::run(c, live, gen);
+    if (!MdsLevel<WORKERS, PT, FAST_DIV, CULL>::run(c, live, gen)) MdsChain<WORKERS, mds_next_pt(PT), FAST_DIV, CULL>::run(c, live, gen);
   }
 };
-template <int WORKERS, bool FAST_DIV>
-struct MdsChain<WORKERS, 0, FAST_DIV> {
+template <int WORKERS, bool FAST_DIV, bool CULL>
+struct MdsChain<WORKERS, 0, FAST_DIV, CULL> {
   static __device__ __forceinline__ void run(const MdsCtx&, int&, int&) {}
 };
 
@@ -552,7 +600,7 @@ static inline size_t mds_smem_bytes(int per, int threads, int pt, bool stage_xyz
   return cap * 8 + 16 + (((size_t)per * 2 + 15) & ~(size_t)15) + (stage_xyz ? (size_t)per * 12 : 0);
 }
 
-template <int WORKERS, int PT, int OCC>
+template <int WORKERS, int PT, int OCC, bool CULL = false>
 __global__ void __launch_bounds__(mds_threads(WORKERS), OCC) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
                                                                         const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
                                                                         int bs_mask, int bs_log2, int stage_xyz, int msel) {
@@ -640,8 +688,8 @@ __global__ void __launch_bounds__(mds_threads(WORKERS), OCC) mds_cluster_kernel(
       else mds_replay<false>(c, (int)cs * (WORKERS / 32));
     } else if (!idle) {
       int gen = 0;
-      if (fast) MdsChain<WORKERS, PT, true>::run(c, live, gen);
-      else MdsChain<WORKERS, PT, false>::run(c, live, gen);
+      if (fast) MdsChain<WORKERS, PT, true, CULL>::run(c, live, gen);
+      else MdsChain<WORKERS, PT, false, CULL>::run(c, live, gen);
     }
   }
   __syncthreads();
@@ -665,7 +713,7 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float* __restrict
   atomicAdd(&gf[((size_t)b * C + c) * n + idx[(size_t)b * m + j]], g[((size_t)b * C + c) * m + j]);
 }
 
-template <int WORKERS, int PT, int OCC>
+template <int WORKERS, int PT, int OCC, bool CULL = false>
 static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, int* idx, int cs, int bs_mask, int bs_log2, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cs));
@@ -681,7 +729,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
     if (v >= 1 && v <= msel) msel = v;
   }
   while (msel & (msel - 1)) msel &= msel - 1;  // a power of two: 1, 2, 4 or 8
-  cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<WORKERS, PT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<WORKERS, PT, OCC, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea != cudaSuccess) return (int)ea;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -692,7 +740,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<WORKERS, PT, OCC>, xyz, n, m, mml, idx, bs_mask, bs_log2, stage_xyz, msel);
+  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<WORKERS, PT, OCC, CULL>, xyz, n, m, mml, idx, bs_mask, bs_log2, stage_xyz, msel);
 }
 
 }  // namespace snb
@@ -763,6 +811,8 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   else if (per <= 256 * 6) MDS_GO(256, 6, 1);
   else if (per <= 256 * 9) MDS_GO(256, 9, 1);
   else if (per <= 256 * 12) MDS_GO(256, 12, 1);
+  else if (per <= 224 * 21 && getenv("SNB_MDS_CULL") && getenv("SNB_MDS_CULL")[0] == '1')  // experimental, not GPU-validated yet
+    rc = mds_launch<224, 21, 1, true>(xyz, B, n, m, mean_mst_length, idx, cs, bm, lg, s);
   else if (per <= 224 * 21) MDS_GO(224, 21, 1);  // SpareNet's refiner (4608 points per CTA): replay warp beside ONE worker warp
   else if (per <= 512 * 12) MDS_GO(512, 12, 1);
   else if (per <= 512 * 18) MDS_GO(512, 18, 1);

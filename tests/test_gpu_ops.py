@@ -368,6 +368,20 @@ def test_mds_full_size_vs_reference_extension(cuda, mml):
     assert all(idx[b].unique().numel() == 16384 for b in (0, 31))
 
 
+@pytest.mark.skipif(os.environ.get("SNB_TEST_MDS_CULL") != "1", reason="the culling variant of the MDS worker (SNB_MDS_CULL=1) was written "
+                    "after round 1's GPU budget was spent: validate with SNB_TEST_MDS_CULL=1 before enabling it")
+@pytest.mark.parametrize("mml", [0.0227, 0.048])
+def test_mds_culling_variant_is_bit_identical(cuda, monkeypatch, mml):
+    """Skipping register slots whose bounding box proves every update a no-op must not change a single pick."""
+    from sparenet_b200 import functional as F_
+    torch.manual_seed(21)
+    x = torch.rand(32, 18432, 3, device=cuda) * 1.2 - 0.6
+    mm = torch.full((32,), mml, device=cuda)
+    ref = F_.mds_sample(x, 16384, mm)
+    monkeypatch.setenv("SNB_MDS_CULL", "1")
+    assert torch.equal(F_.mds_sample(x, 16384, mm), ref)
+
+
 def test_gather_vs_oracle_and_autograd(cuda):
     _dropin()
     from cuda.MDS.MDS_module import gather_operation, minimum_density_sample
