@@ -643,6 +643,106 @@ __global__ void __launch_bounds__(mds_threads(WORKERS), OCC) mds_cluster_kernel(
   // initial layout: every point of the CTA except the pre-chosen point 0 (MDS.cpp:119-121), then padding; the densities
   // start at the weights of round 1 (the pick is point 0: 0 + w is exact)
   const float x0 = dataset[0], y0 = dataset[1], z0 = dataset[2];
+  if (CULL) {
+    // CULL variant: the CTA's points enter the register layout in Z-order of a 16^3 grid over their bounding box (counting sort in
+    // shared memory), so the 32 points of a warp's register slot are neighbours and the slot's box is small.  Any order of the
+    // layout yields the same picks (tie keys travel with the points); only the skipping rate depends on it.
+    static_assert(!CULL || mds_threads(WORKERS) == 256, "the scan below assumes 256 threads");
+    const int first = (rank == 0) ? 1 : 0;
+    const int nsorted = per > first ? per - first : 0;
+    const size_t off = ((size_t)CAP * 8 + 16 + (((size_t)chunk * 2 + 15) & ~(size_t)15) + (stage_xyz ? (size_t)chunk * 12 : 0) + 15) & ~(size_t)15;
+    int* hist = reinterpret_cast<int*>(dyn + off);
+    unsigned short* order = reinterpret_cast<unsigned short*>(hist + 4096);
+    unsigned* bb = reinterpret_cast<unsigned*>(order + ((chunk + 7) & ~7));
+    int* wsum = reinterpret_cast<int*>(bb + 8);
+    for (int i = tid; i < 4096; i += THREADS) hist[i] = 0;
+    if (tid < 3) bb[tid] = 0xffffffffu;
+    else if (tid < 6) bb[tid] = 0u;
+    __syncthreads();
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int li = tid + first; li < per; li += THREADS) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const float v = sxyz[(size_t)li * xs + a];
+        lo[a] = fminf(lo[a], v);
+        hi[a] = fmaxf(hi[a], v);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+      }
+      if ((tid & 31) == 0) {
+        atomicMin(&bb[a], float_key(lo[a]));
+        atomicMax(&bb[3 + a], float_key(hi[a]));
+      }
+    }
+    __syncthreads();
+    float bl[3], sc[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      bl[a] = key_float(bb[a]);
+      sc[a] = 16.f / (key_float(bb[3 + a]) - bl[a] + 1e-20f);
+    }
+    auto cell = [&](int li) {
+      unsigned code = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        int q = (int)((sxyz[(size_t)li * xs + a] - bl[a]) * sc[a]);
+        q = q < 0 ? 0 : (q > 15 ? 15 : q);
+        const unsigned v = (unsigned)q;
+        code |= ((v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6)) << a;
+      }
+      return (int)code;
+    };
+    for (int li = tid + first; li < per; li += THREADS) atomicAdd(&hist[cell(li)], 1);
+    __syncthreads();
+    {  // exclusive scan of the 4096 bins: 16 per thread, warp scans, warp totals
+      int v[16], sum = 0;
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        v[u] = hist[tid * 16 + u];
+        sum += v[u];
+      }
+      int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += up;
+      }
+      if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < (tid >> 5); w++) base += wsum[w];
+      int run = base + inc - sum;
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        hist[tid * 16 + u] = run;
+        run += v[u];
+      }
+    }
+    __syncthreads();
+    for (int li = tid + first; li < per; li += THREADS) order[atomicAdd(&hist[cell(li)], 1)] = (unsigned short)li;
+    __syncthreads();
+    for (int e = tid; e < CAP; e += THREADS) {
+      const bool ok = e < nsorted;
+      const int li = ok ? (int)order[e] : 0;
+      const int k = (li << csh) + (int)rank;
+      float w0 = 2e9f;
+      if (ok) {
+        const float* p = sxyz + (size_t)li * xs;
+        const float fac = k < 8192 ? 1.0f : 2.0f;
+        w0 = fast ? mds_add<true>(0.f, fac, p[0], p[1], p[2], x0, y0, z0, t, rcp) : mds_add<false>(0.f, fac, p[0], p[1], p[2], x0, y0, z0, t, rcp);
+      }
+      c.st.t[e] = w0;
+      const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
+      c.st.k[e] = ok ? ((rev << 21) | (unsigned)k) : 0xffffffffu;
+      if (ok) c.st.loc[li] = (unsigned short)e;
+    }
+  } else
   for (int e = tid; e < CAP; e += THREADS) {
     const int li = e + ((rank == 0) ? 1 : 0);  // local point index; rank 0 skips k = 0
     const int k = (li << csh) + (int)rank;
@@ -720,7 +820,8 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   cfg.blockDim = dim3(mds_threads(WORKERS));
   const int per = (n + cs - 1) / cs;
   int stage_xyz = mds_smem_bytes(per, WORKERS, PT, true) + sizeof(MdsShared) <= (size_t)(OCC > 1 ? 100 : 220) * 1024 ? 1 : 0;
-  const size_t smem = mds_smem_bytes(per, WORKERS, PT, stage_xyz != 0);
+  size_t smem = mds_smem_bytes(per, WORKERS, PT, stage_xyz != 0);
+  if (CULL) smem = ((smem + 15) & ~(size_t)15) + 4096 * sizeof(int) + 2 * (size_t)((per + 7) & ~7) + 64;  // histogram, order, box keys, warp sums
   const int total_warps = cs * (WORKERS / 32);
   int msel = MDS_POOL / total_warps;
   if (msel > MDS_MAXM) msel = MDS_MAXM;
