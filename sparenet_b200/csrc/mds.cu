@@ -376,6 +376,62 @@ struct MdsLevel {
       if (NEXT > 0 && live <= NEXT * WORKERS) break;  // re-pack into the narrower layout (uniform over the CTA's workers)
     }
     // re-pack the live points for the narrower layout (all worker warps take this branch in the same generation)
+    if (CULL) {
+      // order-preserving compaction (entry order = Z-order): per (slot row, warp) counts -> exclusive offsets -> ballot ranks.
+      // The offsets live behind the new layout (entries NEXT*WORKERS .. CAP of the density staging array are free here).
+      int* rowoff = reinterpret_cast<int*>(c.st.t + NEXT * WORKERS);
+      static_assert(!CULL || NEXT == 0 || (PT - NEXT) * WORKERS >= PT * WARPS + 1, "scratch for the row offsets");
+      bar_sync_named(1, WORKERS);
+#pragma unroll
+      for (int i = 0; i < PT; i++) {
+        const unsigned mk = __ballot_sync(0xffffffffu, temp[i] < 1e9f);
+        if (lane == 0) rowoff[i * WARPS + warp] = __popc(mk);
+      }
+      bar_sync_named(1, WORKERS);
+      if (warp == 0) {  // exclusive prefix over the PT*WARPS counts in (row, warp) order
+        constexpr int TOT = PT * WARPS, PERL = (TOT + 31) / 32;
+        int v[PERL], sum = 0;
+#pragma unroll
+        for (int u = 0; u < PERL; u++) {
+          const int q = lane * PERL + u;
+          v[u] = q < TOT ? rowoff[q] : 0;
+          sum += v[u];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += up;
+        }
+        int run = inc - sum;
+#pragma unroll
+        for (int u = 0; u < PERL; u++) {
+          const int q = lane * PERL + u;
+          if (q < TOT) rowoff[q] = run;
+          run += v[u];
+        }
+        if (lane == 31) *c.st.count = inc;
+      }
+      bar_sync_named(1, WORKERS);
+#pragma unroll
+      for (int i = 0; i < PT; i++) {
+        const bool lv = temp[i] < 1e9f;
+        const unsigned mk = __ballot_sync(0xffffffffu, lv);
+        if (lv) {
+          const int e = rowoff[i * WARPS + warp] + __popc(mk & ((1u << lane) - 1u));
+          c.st.t[e] = temp[i];
+          c.st.k[e] = key[i];
+          c.st.loc[(int)(key[i] & 0x1fffffu) >> c.csh] = (unsigned short)e;
+        }
+      }
+      bar_sync_named(1, WORKERS);
+      for (int e = *c.st.count + tid; e < NEXT * WORKERS; e += WORKERS) {  // padding entries can never win
+        c.st.t[e] = 2e9f;
+        c.st.k[e] = 0xffffffffu;
+      }
+      bar_sync_named(1, WORKERS);
+      return false;
+    }
     bar_sync_named(1, WORKERS);
     if (tid == 0) *c.st.count = 0;
     bar_sync_named(1, WORKERS);
