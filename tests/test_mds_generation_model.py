@@ -134,3 +134,49 @@ def test_oversampling_returns_index_zero():
     ref = sequential(xyz, 50, t)
     got, _ = generations(xyz, 50, t, 4, 2)
     assert got == ref and got[40:] == [0] * 10
+
+
+@pytest.mark.parametrize("mml,seed", [(0.02, 0), (0.08, 1)])
+def test_box_culling_criterion_never_skips_a_changing_point(mml, seed):
+    """The slot test of the culling variant (csrc/mds.cu, CULL): a group of points may be skipped for a pick when
+    2.02 * exp(-0.9999 * dist2(pick, box) / t) < min live density * 2^-25.  Then fl(density + w) == density must hold for every live
+    point of the group -- checked here in float32 over a replay of the sampler, for groups of 32 in Z-order."""
+    rng = np.random.default_rng(seed)
+    n = 1536
+    xyz = rng.random((n, 3), dtype=np.float32)
+    t = np.float32(5.0 * mml * mml)
+    fac = np.where(np.arange(n) < 700, np.float32(1), np.float32(2))     # both weights occur
+    q = (xyz * 15.999).astype(np.int64)
+    code = np.zeros(n, dtype=np.int64)
+    for b in range(4):
+        for a in range(3):
+            code |= ((q[:, a] >> b) & 1) << (3 * b + a)
+    group = np.empty(n, dtype=np.int64)
+    group[np.argsort(code, kind="stable")] = np.arange(n) // 32
+    ng = n // 32
+    lo = np.full((ng, 3), np.inf, dtype=np.float32)
+    hi = np.full((ng, 3), -np.inf, dtype=np.float32)
+    np.minimum.at(lo, group, xyz)
+    np.maximum.at(hi, group, xyz)
+    temp = np.zeros(n, dtype=np.float32)
+    live = np.ones(n, dtype=bool)
+    live[0] = False
+    last, skipped = 0, 0
+    for _ in range(400):
+        w = (_weights(xyz, last, t) * fac).astype(np.float32)
+        new = (temp + w).astype(np.float32)
+        dd = np.maximum(np.maximum(lo - xyz[last], xyz[last] - hi), 0).astype(np.float32)
+        dmin = ((dd * dd).sum(1) * np.float32(0.9999)).astype(np.float32)
+        wmax = np.float32(2.02) * np.exp(-(dmin / t))
+        tmin = np.full(ng, np.inf, dtype=np.float32)
+        np.minimum.at(tmin, group[live], temp[live])
+        skip = wmax < tmin * np.float32(2.0 ** -25)
+        changed = (new != temp) & live
+        assert not skip[group[changed]].any()
+        skipped += int(skip[np.isfinite(tmin)].sum())
+        temp = new
+        cand = np.where(live, temp, np.float32(np.inf))
+        last = int(np.lexsort((np.arange(n), cand))[0])
+        live[last] = False
+    if mml < 0.05:
+        assert skipped > 0      # the criterion is not vacuous in the regime it is meant for
