@@ -270,6 +270,20 @@ def knn_indices_pruned(x, k):
     return idx
 
 
+_KNN_PRUNE_CHECKED = {}   # (C, N, k) -> bool: the pruned path reproduced the brute-force indices on its first use in this process
+
+
+def _knn_brute(x, k):
+    B, C, N = x.shape
+    idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    nbytes = lib.snb_knn_workspace_bytes(B, N)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device), _op("knn", 2):
+        check(lib.snb_knn(ptr(x), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn")
+    return idx
+
+
 def knn_indices(x, k):
     """x: [B, C, N] float32 (channel-major, as the encoder holds it) -> idx [B, N, k] int32."""
     x = _cuda_f32(x, "x")
@@ -279,14 +293,23 @@ def knn_indices(x, k):
     # tensor cores (TF32 matmul allowed); SNB_KNN_PRUNE=1 / 0 forces it on (for C >= 64) / off.
     force = os.environ.get("SNB_KNN_PRUNE")
     if (C & 3) == 0 and force != "0" and ((force == "1" and C >= 64) or (C >= 512 and torch.backends.cuda.matmul.allow_tf32)):
-        return knn_indices_pruned(x, k)
-    idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
-    lib = _lib.load()
-    nbytes = lib.snb_knn_workspace_bytes(B, N)
-    ws = _ws(nbytes, x.device)
-    with torch.cuda.device(x.device), _op("knn", 2):
-        check(lib.snb_knn(ptr(x), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn")
-    return idx
+        key = (C, N, int(k))
+        ok = _KNN_PRUNE_CHECKED.get(key)
+        if ok is None and not torch.cuda.is_current_stream_capturing():
+            # First use of a shape in this process: both paths once, compared on the device.  The pruning bound assumes a GEMM at
+            # least as accurate as TF32 with fp32 accumulation; a process that lowered the fp32 matmul precision further (e.g.
+            # torch.set_float32_matmul_precision("medium")) would break it, and then the brute-force kernels keep serving -- loudly.
+            a, b = knn_indices_pruned(x, k), _knn_brute(x, k)
+            ok = bool(torch.equal(a, b))
+            _KNN_PRUNE_CHECKED[key] = ok
+            if not ok:
+                import warnings
+                warnings.warn(f"sparenet_b200: Gram-pruned kNN disagreed with the brute-force kernels for C={C}, N={N}, k={k}; "
+                              "using the brute-force kernels for this shape", RuntimeWarning)
+            return b
+        if ok is not False:
+            return knn_indices_pruned(x, k)
+    return _knn_brute(x, k)
 
 
 # ----------------------------------------------------------------------------- gridding (GRNet)
