@@ -12,6 +12,9 @@ N > 1   : one process per GPU (torchrun), batch sharded by sample (local B=32 pe
           all-reduce over NVLink -- the only collective the path has.
 --impl reference : the CPU restatement of the same step (oracle/: C kernels + plain PyTorch generator) on the box's
           host cores, on a bounded sample (B=2) of the same workload.
+--impl reference-gpu : the reference's OWN CUDA extensions rebuilt for sm_100a (oracle/_ref/*.so) under the plain-PyTorch
+          restatement of its generator, same GPU, same inputs, same step (oracle/ref_gpu.py).  The default N=1 run also
+          executes it in a subprocess and reports it as "reference_gpu" with the ratio north_star targets (>= 10x).
 
 Prints ONE JSON line (rank 0).
 """
@@ -37,7 +40,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-extension step on the same GPU")
+    ap.add_argument("--ref-gpu-timeout", type=int, default=420)
     ap.add_argument("--batch", type=int, default=LOCAL_B, help="local batch per GPU (default: BASELINE config)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -124,6 +129,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_gpu(args):
+    """The reference's own extensions + generator on the same GPU (oracle/ref_gpu.py): rank 0 only, one JSON line."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import ref_gpu
+    k = max(1, min(args.steps, 5))
+    res = ref_gpu.run(B=args.batch, warm=max(2, min(args.warmup, 3)), reps=k, ops=True)
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": 1, "steps": k, "warmup": res["warmup"],
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tf32 cuDNN convolutions)", "data": "synthetic", "impl": "reference-gpu",
+            "config": {"workload": "configs[1]: SpareNet generator + CD loss, synthetic ShapeNet B=32 2048->16384 pts", "local_batch": args.batch,
+                       "n_out": N_OUT, "n_partial": N_PARTIAL, "n_primitives": N_PRIM, "what": res["what"]},
+            "reference_gpu": res}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
@@ -175,6 +196,8 @@ def build_gpu(args, dev, rank):
                             use_AdaIn="share", encode="Residualnet")
     net.apply(init_weights)
     net = net.to(dev).train()
+    net.decoder.fast_param_grads = True   # stacked-parameter gradients as .grad views: valid here because the step uses
+    #                                        sparenet_b200.dist.allreduce_gradients instead of DDP hooks
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9), fused=True)
     cd_mean, cd = ChamferDistanceMean(), ChamferDistance()
     B = args.batch
@@ -431,6 +454,25 @@ def run_ours(args):
             line["ops_ms_per_batch"] = aux_ops_ms(dev, args.batch)
         except Exception as e:  # the headline step stands on its own
             line["ops_ms_per_batch"] = {"error": repr(e)[:200]}
+    if world == 1 and not args.no_reference_gpu:
+        # north_star: "next to the reference's own cuda/ extensions on the same GPU" -- its step and loss ops in a subprocess
+        # (own CUDA context and allocator; this process is idle meanwhile), target >= 10x on the end-to-end step
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--steps", "3", "--warmup", "2", "--batch", str(args.batch)]
+        try:
+            torch.cuda.empty_cache()
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=args.ref_gpu_timeout)
+            ref = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])["reference_gpu"]
+            ref["speedup_device_resident"] = value / ref["value"]
+            ref["speedup_e2e"] = e2e_val / ref["value"]
+            ref["target"] = ">= 10x the reference extensions' end-to-end step throughput (BASELINE.json north_star)"
+            ours_ops, ref_ops = line.get("ops_ms_per_batch", {}), ref.get("ops_ms_per_batch", {})
+            ref["ops_speedup"] = {k: round(ref_ops[k] / ours_ops[k], 2) for k in ("cd_fwd_bwd_ms", "emd_fwd_bwd_ms", "p2i_8view_fwd_bwd_ms")
+                                  if isinstance(ref_ops.get(k), float) and isinstance(ours_ops.get(k), float)}
+            line["reference_gpu"] = ref
+        except subprocess.TimeoutExpired:
+            line["reference_gpu"] = {"error": f"did not finish within {args.ref_gpu_timeout} s"}
+        except Exception as e:
+            line["reference_gpu"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         # the CPU step runs in its own process (clean thread pools, hard time bound) through the --impl reference arm
         cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-batch", str(args.cpu_batch)]
@@ -453,5 +495,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-gpu":
+        run_reference_gpu(a)
     else:
         run_ours(a)

@@ -154,6 +154,39 @@ int snb_row_act_bwd_reduce(const float* gy, const float* h, const float* scale, 
 int snb_row_norm_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, const float* mean,
                          const float* gmean, const float* gvar, long long R, int L, float slope, float* gh, void* stream);
 
+/* ---- TF32 tensor-core GEMM of the 1x1-conv / AdaIN-folding stacks (csrc/gemm_tc.cu: tcgen05.mma + TMEM + TMA) ----------
+ * replaces the cuDNN/cuBLAS calls behind nn.Conv1d / nn.Conv2d(kernel_size=1) in models/sparenet_generator.py:146-186,
+ * 188-242 (EdgeConv), :593-646 (PointNetRes), :984-991,1044-1062 (GridDecoder) on channel-major activations
+ * [G, C, Npos] (positions contiguous), TF32 operands with fp32 accumulation like the reference's cuDNN default.
+ *   mode 0 FWD    D[g] (M x N) = A (M x K) . T(B[g]) (K x N)      A = weight [M=Cout, K=Cin] (lda), B = X[g] [K rows, N]
+ *   mode 1 DGRAD  D[g] (M x N) = A^T . B[g]                        A = weight stored [K=Cout rows, M=Cin] (lda), B = gY[g]
+ *   mode 2 WGRAD  D[g] (M x N) = sum_{bi<BI} A[g*BI+bi] . T(B[g*BI+bi])^T   A = gY [M=Cout rows, K positions],
+ *                                                                    B = X [N=Cin rows, K positions]
+ * T(x) = leaky_relu(scale*x + shift, slope) per (batch, input channel, segment) when scale != NULL (FWD, WGRAD): the
+ * folded AdaIN.BN.SE.ReLU tail of the previous layer applied while the operand sits in shared memory;
+ * scale/shift are [batches, Cin, Npos/seg], seg a multiple of block_n (FWD) / 32 (WGRAD).
+ * Epilogue (from TMEM): store (1) / TMA reduce-add into a caller-initialised D (2) / nothing (0), and optionally
+ * per-tile row statistics pmean/pm2 [G, M, N/block_n] (mean and CENTRED second moment of each tile row) and
+ * pmax/pmin/pimax/pimin [G, M, N/block_n] (extrema and their column in the full row).  Limits: leading dimensions and
+ * batch strides multiples of 4 elements, pointers 16-byte aligned, N % 32 == 0 (FWD/DGRAD), M % 32 == 0 (DGRAD),
+ * block_n in {32,64,...,256} (0 = auto), statistics need N % block_n == 0. */
+typedef struct snb_gemm_desc {
+  int mode;
+  int G, BI;
+  int M, N, K;
+  const float* A; long long lda; long long a_batch_stride;   /* a_batch_stride == 0: one A for all batches */
+  const float* B; long long ldb; long long b_batch_stride;
+  float* D; long long ldd; long long d_batch_stride;
+  int block_n;
+  int store;
+  int split;                                                  /* WGRAD split-K (0 = auto, needs store == 2 when > 1) */
+  const float* scale; const float* shift; float slope; int seg;
+  float* pmean; float* pm2;
+  float* pmax; float* pmin; int* pimax; int* pimin;
+} snb_gemm_desc;
+int snb_gemm_tf32(const snb_gemm_desc* desc, void* stream);
+int snb_gemm_tf32_tiles(int N, int block_n);                  /* number of column tiles (last dim of the statistics) */
+
 /* ---- Gridding / GriddingReverse (GRNet) --------------------------------------------------------------------
  * replaces gridding.forward / backward / rev_forward / rev_backward (cuda/gridding/gridding_cuda.cpp:43-99,
  * gridding.cu:179-335, gridding_reverse.cu:105-236).  ptcloud [B,n,3] already multiplied by scale/2; grid

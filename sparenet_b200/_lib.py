@@ -12,6 +12,19 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsparenet_b200.so")
 c_int, c_float, c_double, c_size_t, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p
 P = c_void_p
 
+
+
+class GemmDesc(ctypes.Structure):
+    """snb_gemm_desc of include/sparenet_b200.h (field order and types must match)."""
+    _fields_ = [("mode", c_int), ("G", c_int), ("BI", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
+                ("A", c_void_p), ("lda", ctypes.c_longlong), ("a_batch_stride", ctypes.c_longlong),
+                ("B", c_void_p), ("ldb", ctypes.c_longlong), ("b_batch_stride", ctypes.c_longlong),
+                ("D", c_void_p), ("ldd", ctypes.c_longlong), ("d_batch_stride", ctypes.c_longlong),
+                ("block_n", c_int), ("store", c_int), ("split", c_int),
+                ("scale", c_void_p), ("shift", c_void_p), ("slope", c_float), ("seg", c_int),
+                ("pmean", c_void_p), ("pm2", c_void_p), ("pmax", c_void_p), ("pmin", c_void_p), ("pimax", c_void_p), ("pimin", c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/sparenet_b200.h (tests/test_abi.py checks)
 SIGNATURES = {
     "snb_version": (c_int, []),
@@ -50,6 +63,8 @@ SIGNATURES = {
     "snb_row_stats_minmax": (c_int, [P, ctypes.c_longlong, c_int, P, P, P, P, P, P, P]),
     "snb_row_act_bwd_reduce": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P]),
     "snb_row_norm_act_bwd": (c_int, [P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P]),
+    "snb_gemm_tf32": (c_int, [ctypes.POINTER(GemmDesc), P]),
+    "snb_gemm_tf32_tiles": (c_int, [c_int, c_int]),
     "snb_gridding_fwd": (c_int, [P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P, P]),
     "snb_gridding_bwd": (c_int, [P, P, P, c_int, c_int, ctypes.c_longlong, P, P]),
     "snb_gridding_rev_fwd": (c_int, [P, c_int, c_int, P, P]),

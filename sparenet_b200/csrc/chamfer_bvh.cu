@@ -266,11 +266,8 @@ int chamfer_bvh_launch(const float* xyz1, const float* xyz2, int B, int N, int M
   int npad = 1;
   while (npad < nmax) npad <<= 1;
   const size_t smem = (size_t)npad * sizeof(unsigned long long);
-  static bool attr_done = false;
-  if (!attr_done) {
-    SNB_CUDA(cudaFuncSetAttribute(chamfer_bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BVH_MAXN * sizeof(unsigned long long))));
-    attr_done = true;
-  }
+  // per device/context and cheap: set before every launch (a process-wide flag would leave the other GPUs of one process without it)
+  SNB_CUDA(cudaFuncSetAttribute(chamfer_bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BVH_MAXN * sizeof(unsigned long long))));
   chamfer_bvh_build_kernel<<<dim3(2, B), BVH_BUILD_THREADS, smem, s>>>(xyz1, xyz2, N, M, (float4*)workspace, per);
   SNB_LAUNCH_CHECK();
   chamfer_bvh_query_kernel<<<dim3((nmax + 127) / 128, B, 2), 128, 0, s>>>(N, M, (float4*)workspace, per, dist1, dist2, idx1, idx2);

@@ -354,11 +354,8 @@ SNB_API int snb_emd_fwd(const float* xyz1, const float* xyz2, int B, int N, floa
   if (!workspace || workspace_bytes < snb_emd_workspace_bytes(B, N)) return SNB_EWORKSPACE;
   if (((uintptr_t)workspace & 15) != 0) return SNB_EALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  static bool attr_done = false;  // idempotent attribute; benign if two threads race here
-  if (!attr_done) {
-    SNB_CUDA(cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMD_SMEM));
-    attr_done = true;
-  }
+  // per device/context and cheap: set before every launch (a process-wide flag would leave the other GPUs of one process without it)
+  SNB_CUDA(cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMD_SMEM));
   int cs = 1;
   while (cs * 2 <= EMD_MAX_CLUSTER && B * cs * 2 <= kNumSMs) cs *= 2;
   cudaLaunchConfig_t cfg = {};

@@ -239,9 +239,12 @@ class StyleBasedAdaIn(nn.Module):  # reference :394-422 (parameter holder)
 
 
 class _StackParams(torch.autograd.Function):
-    """torch.stack over the 32 primitives' copies of one parameter (the reference keeps them as 32 modules, :306-318, and the
-    state_dict keys stay per primitive).  Backward hands every parameter ITS SLICE of the stacked gradient as .grad -- a view,
-    no kernel -- instead of 32 AccumulateGrad copies per stacked tensor (~550 microsecond-sized launches per step)."""
+    """OPT-IN fast path of torch.stack over the 32 primitives' copies of one parameter (the reference keeps them as 32 modules,
+    :306-318, and the state_dict keys stay per primitive).  Backward hands every parameter ITS SLICE of the stacked gradient as
+    .grad -- a view, no kernel -- instead of 32 AccumulateGrad copies per stacked tensor (~550 microsecond-sized launches per
+    step).  Because it bypasses AccumulateGrad, DDP/FSDP reducer hooks, Tensor.register_hook, post-accumulate-grad hooks and
+    torch.autograd.grad(..., params) do not see these parameters: use it only with sparenet_b200.dist.allreduce_gradients (as
+    bench.py does) by setting SpareNetDecode.fast_param_grads = True.  The default is plain torch.stack."""
     @staticmethod
     def forward(ctx, *params):
         ctx.params = params
@@ -287,17 +290,22 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         self.register_buffer("_grid_t", g.t().contiguous(), persistent=False)  # [2, pts]
 
     # ---- stacked views of the 32 primitives' parameters -----------------------------------------------------
+    fast_param_grads = False   # True: _StackParams (direct .grad views; see its docstring for what that is incompatible with)
+
+    def _stack_list(self, params):
+        return _StackParams.apply(*params) if self.fast_param_grads else torch.stack(list(params))
+
     def _stack(self, getter):
-        return _StackParams.apply(*[getter(d.dec) for d in self.decoder])
+        return self._stack_list([getter(d.dec) for d in self.decoder])
 
     def _bn_se_params(self, layer):
         """The 32 primitives' BN / SE parameters of one decoder layer, stacked: gam, bet [P,C,1], w1 [P,C/16,C], w2 [P,C,C/16]."""
         bns = [getattr(d.dec, f"bn{layer}") for d in self.decoder]
         ses = [getattr(d.dec, f"se{layer}") for d in self.decoder]
-        gam = _StackParams.apply(*[b.weight for b in bns]).unsqueeze(-1)
-        bet = _StackParams.apply(*[b.bias for b in bns]).unsqueeze(-1)
-        w1 = _StackParams.apply(*[s.fc[0].weight for s in ses])
-        w2 = _StackParams.apply(*[s.fc[2].weight for s in ses])
+        gam = self._stack_list([b.weight for b in bns]).unsqueeze(-1)
+        bet = self._stack_list([b.bias for b in bns]).unsqueeze(-1)
+        w1 = self._stack_list([s.fc[0].weight for s in ses])
+        w2 = self._stack_list([s.fc[2].weight for s in ses])
         return bns, (gam, bet, w1, w2)
 
     def _bn_se(self, bns, wsty, bsty, v, gam, bet, w1, w2):

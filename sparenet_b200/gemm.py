@@ -1,0 +1,173 @@
+"""Host plumbing of the tcgen05 TF32 GEMM (csrc/gemm_tc.cu, C ABI snb_gemm_tf32): 1x1 convolutions on channel-major activations.
+
+Everything here is shape bookkeeping: torch CUDA tensors in, one C-ABI call, torch CUDA tensors out.  No fallback: a shape the kernel
+does not serve raises (thin layers -- fewer than 32 channels on the contracted / transposed side -- are routed to a batched library
+GEMM by the CALLER, explicitly, in dropin/models/sparenet_generator.py).
+
+Activations are [G, C, *pos] with the positions contiguous (any trailing shape, e.g. [P, C, B, 512] for the folding decoders);
+weights are [Cout, Cin] (shared) or [G, Cout, Cin] (one per batch entry), last dimension contiguous, row stride a multiple of 4.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, stream_ptr
+from .functional import SnbValueError, _op
+
+FWD, DGRAD, WGRAD = 0, 1, 2
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _act3(x, name):
+    """[G, C, *pos] -> (G, C, Npos, row stride, batch stride) of a tensor whose positions are contiguous."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise SnbValueError(f"{name} must be a CUDA float32 tensor (sparenet_b200 has no CPU path)")
+    if x.dim() < 3:
+        raise SnbValueError(f"{name} must be [G, C, *positions]")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    G, C = x.shape[0], x.shape[1]
+    n = x.numel() // (G * C) if G * C else 0
+    return x, G, C, n
+
+
+def _weight(W, G, name):
+    if not W.is_cuda or W.dtype != torch.float32:
+        raise SnbValueError(f"{name} must be a CUDA float32 tensor")
+    if W.dim() == 3 and W.shape[0] != G:
+        raise SnbValueError(f"{name}: batched weight needs {G} entries, got {W.shape[0]}")
+    if W.dim() not in (2, 3):
+        raise SnbValueError(f"{name} must be [Cout, Cin] or [G, Cout, Cin]")
+    if W.stride(-1) != 1 or W.stride(-2) % 4 != 0 or (W.dim() == 3 and W.stride(0) % 4 != 0) or W.data_ptr() % 16 != 0:
+        W = W.contiguous()
+        if W.stride(-2) % 4 != 0:
+            raise SnbValueError(f"{name}: the contiguous dimension must be a multiple of 4 (got {tuple(W.shape)})")
+    return W
+
+
+def stat_tiles(N, block_n=0):
+    """(number of statistics tiles along N, their width) of a forward call."""
+    t = _lib.load().snb_gemm_tf32_tiles(int(N), int(block_n))
+    bn = block_n if block_n > 0 else (256 if N >= 256 else (N + 63) // 64 * 64)
+    return t, bn // 2
+
+
+def _run(desc, dev, what, nbytes=None):
+    with torch.cuda.device(dev), _op(what, 1, nbytes):
+        check(_lib.load().snb_gemm_tf32(ctypes.byref(desc), stream_ptr()), what)
+
+
+def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, minmax=False, store=True):
+    """y[g] = W . T(x[g]),  T(x) = leaky_relu(scale*x + shift, slope) per (g, channel, segment of `seg` positions) when scale is given.
+    Returns (y or None, stats) with stats = {} or {"mean","var": [G, Cout, Npos/stats_seg]} (biased variance of every segment of
+    `stats_seg` positions of the OUTPUT rows) and, with minmax, {"max","min","imax","imin": [G, Cout]} over all positions."""
+    x, G, Cin, N = _act3(x, "x")
+    W = _weight(W, G, "W")
+    Cout = W.shape[-2]
+    if W.shape[-1] != Cin:
+        raise SnbValueError(f"weight {tuple(W.shape)} does not match {Cin} input channels")
+    if N % 32 != 0 or Cin % 4 != 0:
+        raise SnbValueError(f"conv_fwd needs positions % 32 == 0 and Cin % 4 == 0 (got {N}, {Cin})")
+    dev = x.device
+    d = GemmDesc()
+    d.mode, d.G, d.BI, d.M, d.N, d.K = FWD, G, 1, Cout, N, Cin
+    d.A, d.lda, d.a_batch_stride = _p(W), W.stride(-2), (W.stride(0) if W.dim() == 3 else 0)
+    d.B, d.ldb, d.b_batch_stride = _p(x), N, Cin * N
+    y = None
+    if store:
+        y = torch.empty((G, Cout) + tuple(x.shape[2:]), device=dev, dtype=torch.float32)
+        d.D, d.ldd, d.d_batch_stride = _p(y), N, Cout * N
+    d.store = 1 if store else 0
+    keep = [x, W, y]
+    if scale is not None:
+        seg = N if seg is None else int(seg)
+        scale, shift = scale.contiguous().float(), shift.contiguous().float()
+        if scale.numel() != G * Cin * (N // seg) or shift.numel() != scale.numel() or N % seg != 0:
+            raise SnbValueError(f"scale/shift must hold G*Cin*(N/seg) = {G * Cin * (N // seg)} entries")
+        d.scale, d.shift, d.slope, d.seg = _p(scale), _p(shift), float(slope), seg
+        keep += [scale, shift]
+    T, w = stat_tiles(N)
+    pm = p2 = px = pn = ix = in_ = None
+    if stats_seg is not None:
+        if N % (2 * w) != 0 or stats_seg % w != 0 or N % stats_seg != 0:
+            raise SnbValueError(f"statistics need positions % {2 * w} == 0 and segment % {w} == 0 (got {N}, {stats_seg})")
+        pm, p2 = (torch.empty(G, Cout, T, device=dev, dtype=torch.float32) for _ in range(2))
+        d.pmean, d.pm2 = _p(pm), _p(p2)
+    if minmax:
+        if N % (2 * w) != 0:
+            raise SnbValueError(f"extrema need positions % {2 * w} == 0 (got {N})")
+        px, pn = (torch.empty(G, Cout, T, device=dev, dtype=torch.float32) for _ in range(2))
+        ix, in_ = (torch.empty(G, Cout, T, device=dev, dtype=torch.int32) for _ in range(2))
+        d.pmax, d.pmin, d.pimax, d.pimin = _p(px), _p(pn), _p(ix), _p(in_)
+    _run(d, dev, "gemm_fwd", 4 * (x.numel() + (y.numel() if store else 0)))
+    stats = {}
+    if stats_seg is not None:
+        tps = stats_seg // w                                  # tiles per segment
+        m_t = pm.view(G, Cout, N // stats_seg, tps)
+        mean = m_t.mean(-1)
+        dm = m_t - mean.unsqueeze(-1)
+        m2 = p2.view(G, Cout, N // stats_seg, tps).sum(-1) + float(w) * (dm * dm).sum(-1)   # Chan: within-tile + between-tile
+        stats["mean"], stats["var"] = mean, m2 / float(stats_seg)
+    if minmax:
+        vmax, jx = px.max(-1)
+        vmin, jn = pn.min(-1)
+        stats["max"], stats["min"] = vmax, vmin
+        stats["imax"] = ix.gather(-1, jx.unsqueeze(-1)).squeeze(-1)
+        stats["imin"] = in_.gather(-1, jn.unsqueeze(-1)).squeeze(-1)
+    return y, stats
+
+
+def conv_dgrad(gy, W):
+    """gx[g] = W^T . gy[g]: gy [G, Cout, *pos] -> gx [G, Cin, *pos].  Cin % 32 == 0."""
+    gy, G, Cout, N = _act3(gy, "gy")
+    W = _weight(W, G, "W")
+    Cin = W.shape[-1]
+    if W.shape[-2] != Cout:
+        raise SnbValueError(f"weight {tuple(W.shape)} does not match {Cout} output channels")
+    if N % 32 != 0 or Cin % 32 != 0:
+        raise SnbValueError(f"conv_dgrad needs positions % 32 == 0 and Cin % 32 == 0 (got {N}, {Cin})")
+    gx = torch.empty((G, Cin) + tuple(gy.shape[2:]), device=gy.device, dtype=torch.float32)
+    d = GemmDesc()
+    d.mode, d.G, d.BI, d.M, d.N, d.K = DGRAD, G, 1, Cin, N, Cout
+    d.A, d.lda, d.a_batch_stride = _p(W), W.stride(-2), (W.stride(0) if W.dim() == 3 else 0)
+    d.B, d.ldb, d.b_batch_stride = _p(gy), N, Cout * N
+    d.D, d.ldd, d.d_batch_stride = _p(gx), N, Cin * N
+    d.store = 1
+    _run(d, gy.device, "gemm_dgrad", 4 * (gy.numel() + gx.numel()))
+    return gx
+
+
+def conv_wgrad(gy, x, batched, scale=None, shift=None, slope=0.0, seg=None):
+    """gW = sum over (batch,) positions of gy . T(x)^T: gy [G, Cout, *pos], x [G, Cin, *pos] -> [Cout, Cin] (batched=False: the
+    batch is reduced) or [G, Cout, Cin] (batched=True: one weight per batch entry).  T as in conv_fwd (the forward's prologue)."""
+    gy, G, Cout, N = _act3(gy, "gy")
+    x, G2, Cin, N2 = _act3(x, "x")
+    if G2 != G or N2 != N:
+        raise SnbValueError("gy and x must agree in batch and positions")
+    if N % 4 != 0:
+        raise SnbValueError("conv_wgrad needs positions % 4 == 0")
+    dev = x.device
+    GO, BI = (G, 1) if batched else (1, G)
+    gW = torch.zeros((GO, Cout, Cin) if batched else (Cout, Cin), device=dev, dtype=torch.float32)
+    d = GemmDesc()
+    d.mode, d.G, d.BI, d.M, d.N, d.K = WGRAD, GO, BI, Cout, Cin, N
+    d.A, d.lda, d.a_batch_stride = _p(gy), N, Cout * N
+    d.B, d.ldb, d.b_batch_stride = _p(x), N, Cin * N
+    d.D, d.ldd, d.d_batch_stride = _p(gW), Cin, Cout * Cin
+    d.store, d.split = 2, 0                                   # TMA reduce-add into the zeroed gradient; split-K chosen by the library
+    keep = [gy, x, gW]
+    if scale is not None:
+        seg = N if seg is None else int(seg)
+        scale, shift = scale.contiguous().float(), shift.contiguous().float()
+        if scale.numel() != G * Cin * (N // seg) or N % seg != 0 or seg % 32 != 0:
+            raise SnbValueError("scale/shift must hold G*Cin*(N/seg) entries, seg % 32 == 0")
+        d.scale, d.shift, d.slope, d.seg = _p(scale), _p(shift), float(slope), seg
+        keep += [scale, shift]
+    if Cin % 4 != 0:
+        raise SnbValueError("conv_wgrad needs Cin % 4 == 0")
+    _run(d, dev, "gemm_wgrad", 4 * (gy.numel() + x.numel()))
+    return gW
