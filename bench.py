@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-extension step on the same GPU")
     ap.add_argument("--ref-gpu-timeout", type=int, default=420)
+    ap.add_argument("--config", default="generator", choices=["generator", "gan"],
+                    help="generator: configs[1] (the metric's config); gan: configs[4]/[2] -- the full sparenet_gan_runner training step "
+                         "(EMD rec loss, 24 depth-map renders, ProjectionD, D step + G step)")
+    ap.add_argument("--library-gemm", action="store_true", help="measurement switch: dense 1x1 convs through cuDNN/cuBLAS (round-1 arrangement)")
     ap.add_argument("--batch", type=int, default=LOCAL_B, help="local batch per GPU (default: BASELINE config)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,7 +193,12 @@ def build_gpu(args, dev, rank):
     from sparenet_b200.dropin.models.sparenet_generator import SpareNetGenerator
     from sparenet_b200.dropin.utils.model_init import init_weights  # utils/model_init.py:137-159
 
-    torch.backends.cuda.matmul.allow_tf32 = True       # the reference's cuDNN convs run TF32 by default on this class of GPU
+    # Dense 1x1 convolutions run on the repository's own tcgen05 TF32 GEMM (the reference: cuDNN with TF32 allowed, torch's default);
+    # nn.Linear layers stay fp32 like the reference's (torch default: matmul TF32 off).  --library-gemm restores round 1's cuDNN/cuBLAS
+    # arrangement (TF32 library GEMMs everywhere) for A/B timing.
+    from sparenet_b200.dropin.models import sparenet_generator as _gen
+    _gen.LIBRARY_GEMM = bool(getattr(args, "library_gemm", False))
+    torch.backends.cuda.matmul.allow_tf32 = _gen.LIBRARY_GEMM
     torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(0)
     net = SpareNetGenerator(n_primitives=N_PRIM, hide_size=4096, bottleneck_size=4096, num_points=N_OUT, use_SElayer=True,
@@ -296,6 +305,132 @@ def aux_ops_ms(dev, B=LOCAL_B):
         torch.cat([render(xc, view_id=v, radius_list=[5.0]) for v in range(8)], 1).mean().backward()
 
     return {"cd_fwd_bwd_ms": timed(f_cd), "emd_fwd_bwd_ms": timed(f_emd), "p2i_8view_fwd_bwd_ms": timed(f_p2i), "B": B, "N": N_OUT}
+
+
+def run_gan(args):
+    """configs[4] (and the renderer + discriminator of configs[2]): the full GAN training step of runners/sparenet_gan_runner.py:69-118
+    with configs/sparenet_gan.yaml's settings (metric "emd", consistency CD, cGAN ProjectionD, feature + image matching, weights
+    200 / 0.1 / 1 / 1), local B=32 per GPU, synthetic clouds and class labels.  Eager execution (two optimizers, dropout RNG)."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sparenet_b200 has no CPU path")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import sparenet_b200
+    from sparenet_b200 import functional as F_
+    from sparenet_b200.dist import allreduce_gradients
+    from sparenet_b200.dropin.models.sparenet_discriminator import ProjectionD
+    from sparenet_b200.dropin.models.sparenet_generator import SpareNetGenerator
+    from sparenet_b200.dropin.runners.sparenet_gan_runner import sparenetGANStep
+    from sparenet_b200.dropin.utils.model_init import init_weights, init_weights_D
+    from sparenet_b200.dropin.utils.p2i_utils import ComputeDepthMaps
+
+    torch.backends.cudnn.allow_tf32 = True          # the discriminator's cuDNN convolutions, like the reference's default
+    torch.manual_seed(0)
+    net = SpareNetGenerator(n_primitives=N_PRIM, hide_size=4096, bottleneck_size=4096, num_points=N_OUT, use_SElayer=True,
+                            use_AdaIn="share", encode="Residualnet")
+    net.apply(init_weights)
+    net = net.to(dev).train()
+    net.decoder.fast_param_grads = True
+    net_D = ProjectionD(num_classes=8, img_shape=(16, 256, 256))
+    net_D.apply(init_weights_D)
+    net_D = net_D.to(dev).train()
+    renderer = ComputeDepthMaps("orthorgonal", 1.0, 256).to(dev)
+    opt_G = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9), fused=True)
+    opt_D = torch.optim.Adam([p for p in net_D.parameters() if p.requires_grad], lr=1e-4, betas=(0.0, 0.9), fused=True)
+    pG, pD = list(net.parameters()), [p for p in net_D.parameters() if p.requires_grad]
+    gan = sparenetGANStep(net, net_D, renderer, opt_G, opt_D,
+                          allreduce_G=(lambda: allreduce_gradients(pG, world)) if world > 1 else None,
+                          allreduce_D=(lambda: allreduce_gradients(pD, world)) if world > 1 else None)
+    B = args.batch
+    h_partial = (torch.rand(B, N_PARTIAL, 3, generator=torch.Generator().manual_seed(1 + 100 * rank)) - 0.5).pin_memory()
+    h_gt = (torch.rand(B, N_OUT, 3, generator=torch.Generator().manual_seed(2 + 100 * rank)) - 0.5).pin_memory()
+    h_labels = torch.randint(0, 8, (B,), generator=torch.Generator().manual_seed(3 + 100 * rank)).pin_memory()
+    partial, gt, labels = h_partial.to(dev), h_gt.to(dev), h_labels.to(dev)
+    random_radius = __import__("random").Random(0)
+
+    def step(p, g, y):
+        return gan.train_step({"partial_cloud": p, "gtcloud": g}, y, radius=random_radius.choice(gan.radius_list))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step(partial, gt, labels)
+    barrier()
+    F_.LAUNCHES["count"] = 0
+    F_.PROFILE = {}
+    step(partial, gt, labels)
+    barrier()
+    prof, F_.PROFILE = F_.PROFILE, None
+    launches = F_.LAUNCHES["count"]
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(partial, gt, labels)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    last = None
+    for _ in range(args.steps):
+        out = step(h_partial.to(dev, non_blocking=True), h_gt.to(dev, non_blocking=True), h_labels.to(dev, non_blocking=True))
+        last = {k: float(v) for k, v in out.items()}          # device -> host read of the step's seven losses
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        Bg = B * world
+        tot_op = {k: sum(a.elapsed_time(b) for a, b, _ in v) for k, v in prof.items()}
+        dom = max(tot_op, key=tot_op.get)
+        n_dom = len(prof[dom])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg = {"emd_fwd": B * N_OUT * (24 + 8), "mds_sample": B * (12 * (N_OUT + N_PARTIAL) + 4 * N_OUT),
+               "depthmaps_fwd": B * N_OUT * 12 + B * 256 * 256 * 8}.get(dom)
+        per = tot_op[dom] / n_dom
+        line = {"metric": METRIC, "value": Bg * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (tf32 tensor-core GEMMs)", "data": "synthetic",
+                "config": {"workload": "configs[4]: full sparenet_gan_runner training step (EMD x3 + consistency CD + expansion, 24 renders 256x256, "
+                                       "ProjectionD, D step + G step), local B=32", "local_batch": B, "global_batch": Bg, "n_out": N_OUT,
+                           "n_partial": N_PARTIAL, "n_primitives": N_PRIM, "parallelism": f"dp{world}", "execution": "eager",
+                           "l2": "working set per step exceeds the 126 MB L2; no explicit flush"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": Bg * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(h_partial.numel() + h_gt.numel()) * 4 + h_labels.numel() * 8, "d2h_bytes_per_step": 28,
+                        "last_losses": last},
+                "roofline": {"kernel": dom, "bound": "hbm", "achieved": (alg / (per * 1e-3) / 1e9) if alg else None, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (alg / (per * 1e-3) / 1e9 / hbm_peak) if alg else None, "traffic": None, "algorithmic_bytes": alg,
+                             "ms_per_launch": per, "share_of_step": tot_op[dom] / (ms / args.steps),
+                             "note": "the auction is FP32-issue / barrier-latency bound (DESIGN.md 4): the HBM fraction of its compulsory bytes is "
+                                     "reported as asked" if dom == "emd_fwd" else "",
+                             "ops_ms_per_step": {k: round(v, 3) for k, v in sorted(tot_op.items(), key=lambda kv: -kv[1])}}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def run_ours(args):
@@ -497,5 +632,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.impl == "reference-gpu":
         run_reference_gpu(a)
+    elif a.config == "gan":
+        run_gan(a)
     else:
         run_ours(a)

@@ -99,6 +99,20 @@ int snb_p2i_sum_bwd(const void* grad_out, const void* points, const void* featur
                     int npoints, int B, int C, int H, int W, int kernel_kind, double radius, int is_double,
                     void* grad_points, void* grad_features, void* stream);
 
+/* ---- fused depth-map renderer (csrc/depthmaps.cu) -----------------------------------------------------
+ * replaces ComputeDepthMaps.forward (utils/p2i_utils.py:211-252) + p2i(reduce="max") (cuda/p2i_op/__init__.py:99-131) for ONE
+ * view and ONE radius: q = M [p;1], pos = q.xyz/q.w, (row, col) = ((-pos.y, pos.x) + 1)/2 * (H-1, W-1),
+ * feature = 1 - (pos.z - zmin)/(zmax - zmin) with zmin/zmax over all B*N points of the call, out = max(0, max feature * w(r)).
+ * data [B,N,3]; view_matrix: 16 floats on the HOST (row-major projection . look_at, utils/p2i_utils.py:200-209);
+ * out [B,1,H,W], ids [B,1,H,W] (winner point index in [0, B*N) or -1).  The workspace must be kept by the caller from _fwd to
+ * _bwd (it holds the per-point pixel coordinates and the depth range).  _bwd writes grad_data [B,N,3] completely, including the
+ * gradient that reaches the two extreme points through zmin / zmax. */
+size_t snb_depthmaps_workspace_bytes(int B, int N, int H, int W);
+int snb_depthmaps_fwd(const float* data, int B, int N, const float* view_matrix, int H, int W, double radius,
+                      float* out, int* ids, void* workspace, size_t workspace_bytes, void* stream);
+int snb_depthmaps_bwd(const float* grad_out, const int* ids, const float* data, int B, int N, const float* view_matrix,
+                      int H, int W, double radius, void* workspace, size_t workspace_bytes, float* grad_data, void* stream);
+
 /* ---- kNN (replaces the un-vendored knn_cuda.KNN used by models/sparenet_generator.py:852-877) -------
  * x [B,C,N] channel-major features; idx [B,N,k] int32 = the k nearest points (self included) by exact fp32
  * squared distance, ascending; ties by smaller index.  k <= 32. */

@@ -47,6 +47,9 @@ SIGNATURES = {
     "snb_p2i_max_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P, P, P]),
     "snb_p2i_sum_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P]),
     "snb_p2i_sum_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, P, P, P]),
+    "snb_depthmaps_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "snb_depthmaps_fwd": (c_int, [P, c_int, c_int, P, c_int, c_int, c_double, P, P, P, c_size_t, P]),
+    "snb_depthmaps_bwd": (c_int, [P, P, P, c_int, c_int, P, c_int, c_int, c_double, P, c_size_t, P, P]),
     "snb_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "snb_knn": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
     "snb_knn_pruned_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -216,7 +216,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     prefetch_map(&map_d);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&ready[s], XF_WARPS);
+      mbar_init(&ready[s], XF_WARPS / 2);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -397,61 +397,63 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) bulk_wait_all();
   } else if (XFORM) {
     // ================================================================ prologue: activation operand transformed in shared memory
-    // 256 threads; thread tw owns the 16-byte column tw % 8 of the 128-byte rows (tw / 8) + 32 i of the stage.
-    const int tw = threadIdx.x - (2 + EPI_WARPS) * 32;       // 0..255
-    const int iters = p.block_n >> 5;                        // rows of this thread per stage (<= 8)
-    const int r0 = tw >> 3;
+    // Two groups of four warps take alternate k-blocks, so the load -> fma/max -> store -> proxy fence -> arrive chain of one stage
+    // overlaps the next stage's.  Thread tw of a group owns the 128-byte rows tw and tw + 128 of the stage (8 + 8 vectors, visited
+    // in a lane-rotated order so that a quarter-warp touches 8 different 16-byte columns: no bank conflicts).
+    const int xw = threadIdx.x - (2 + EPI_WARPS) * 32;       // 0..255
+    const int grp = xw >> 7, tw = xw & 127;
+    const int nrow = (tw < p.block_n ? 1 : 0) + (tw + 128 < p.block_n ? 1 : 0);   // rows of this thread that exist in the stage
     int s = 0;
-    uint32_t ph = 0;
-    float pa[8], pb[8];                                      // K-major stage: the parameters of this thread's rows, cached per segment
+    uint32_t ph = 0, cnt = 0;
+    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
     long long key = -1;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(p, t);
-      for (int kb = c.kb0; kb < c.kb1; ++kb) {
-        uint8_t* sb = smem + s * STAGE_BYTES + A_BYTES + tw * 16;
-        if (b_mn) {
-          // MN-major stage [chunk][32 k-rows][32 positions]: row r0 + 32 i is k-row r0 of chunk i -> ONE channel per thread and stage
-          const int chn = kb * BK + r0;
-          const bool valid = chn < p.xf_rows;                // k-rows past Cin stay zero (TMA fill): A's columns there are zero too
-          const size_t o = ((size_t)c.g * p.xf_rows + (valid ? chn : 0)) * p.xf_S + c.n0 / p.seg;
-          const float a = __ldg(p.scale + o), b = __ldg(p.shift + o);
-          mbar_wait_wd(&full[s], ph);
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < iters) {
-                float4* ptr = reinterpret_cast<float4*>(sb + i * 4096);
-                *ptr = xf4(*ptr, a, b, p.slope);
-              }
-            }
-          }
-        } else {
-          // K-major stage [channel rows][32 positions]: rows r0 + 32 i are channels n0 + r0 + 32 i, constant over the k-blocks of a segment
-          const int bi = kb / p.kb_per_batch, batch = c.g * p.BI + bi, segi = ((kb - bi * p.kb_per_batch) * BK) / p.seg;
-          const long long k2 = ((long long)batch * p.xf_S + segi) * p.nt + (c.n0 / p.block_n);
-          if (k2 != key) {
-            key = k2;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int chn = c.n0 + r0 + 32 * i;
-              const bool valid = i < iters && chn < p.xf_rows;
-              const size_t o = ((size_t)batch * p.xf_rows + (valid ? chn : 0)) * p.xf_S + segi;
-              pa[i] = valid ? __ldg(p.scale + o) : 0.f;      // rows past Cin: 0*x + 0 keeps the TMA zero fill
-              pb[i] = valid ? __ldg(p.shift + o) : 0.f;
+      for (int kb = c.kb0; kb < c.kb1; ++kb, ++cnt) {
+        if ((cnt & 1u) == (uint32_t)grp) {
+          bool v0, v1;
+          if (b_mn) {
+            // MN-major stage [chunk][32 k-rows][32 positions]: rows tw and tw + 128 are both k-row tw % 32 -> ONE channel per thread
+            const int chn = kb * BK + (tw & 31);
+            v0 = v1 = chn < p.xf_rows;                       // k-rows past Cin stay zero (TMA fill): A's columns there are zero too
+            const size_t o = ((size_t)c.g * p.xf_rows + (v0 ? chn : 0)) * p.xf_S + c.n0 / p.seg;
+            a0 = a1 = __ldg(p.scale + o);
+            b0 = b1 = __ldg(p.shift + o);
+          } else {
+            // K-major stage [channel rows][32 positions]: row r is channel n0 + r, constant over the k-blocks of a segment
+            const int bi = kb / p.kb_per_batch, batch = c.g * p.BI + bi, segi = ((kb - bi * p.kb_per_batch) * BK) / p.seg;
+            const long long k2 = ((long long)batch * p.xf_S + segi) * p.nt + (c.n0 / p.block_n);
+            const int c0 = c.n0 + tw, c1 = c0 + 128;
+            v0 = c0 < p.xf_rows;                             // rows past Cin keep the TMA zero fill
+            v1 = c1 < p.xf_rows;
+            if (k2 != key) {
+              key = k2;
+              const size_t o0 = ((size_t)batch * p.xf_rows + (v0 ? c0 : 0)) * p.xf_S + segi;
+              const size_t o1 = ((size_t)batch * p.xf_rows + (v1 ? c1 : 0)) * p.xf_S + segi;
+              a0 = __ldg(p.scale + o0); b0 = __ldg(p.shift + o0);
+              a1 = __ldg(p.scale + o1); b1 = __ldg(p.shift + o1);
             }
           }
           mbar_wait_wd(&full[s], ph);
+          uint8_t* base = smem + s * STAGE_BYTES + A_BYTES + tw * 128;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < iters) {
-              float4* ptr = reinterpret_cast<float4*>(sb + i * 4096);
-              *ptr = xf4(*ptr, pa[i], pb[i], p.slope);
+          for (int h = 0; h < 2; ++h) {
+            if (h < nrow && (h == 0 ? v0 : v1)) {
+              uint8_t* rp = base + h * (128 * 128);
+              const float a = h == 0 ? a0 : a1, b = h == 0 ? b0 : b1;
+              float4 x[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4*>(rp + (((j + tw) & 7) << 4));
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = xf4(x[j], a, b, p.slope);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(rp + (((j + tw) & 7) << 4)) = x[j];
             }
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ready[s]);
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }

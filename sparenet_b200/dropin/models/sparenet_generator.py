@@ -90,13 +90,19 @@ def _bn_from_rows(bn, m_bc, v_bc, L):
     return bn.running_mean, bn.running_var
 
 
+LIBRARY_GEMM = False   # measurement switch only (bench.py --library-gemm): route the dense 1x1 convs through cuDNN/cuBLAS like round 1
+
+
 def _pconv(x, W):
-    """1x1 convolution y[b] = W x[b] for x [B,Cin,N], W [Cout,Cin(,1)].  Thin layers (<= 8 channels on either side) go through
-    a batched GEMM: cuDNN's weight-gradient kernel for them is a slow direct kernel; everything else is a cuDNN 1x1 conv."""
+    """1x1 convolution y[b] = W x[b] for x [B,Cin,N], W [Cout,Cin(,1)] on the tcgen05 TF32 GEMM (sparenet_b200/csrc/gemm_tc.cu).
+    Thin layers (<= 8 channels on either side: the xyz / id inputs and the 3-channel outputs, < 0.5 % of the flops) have rows
+    shorter than a TMA box and go through a batched library GEMM."""
     W2 = W.reshape(W.size(0), -1)
     if min(W2.shape) <= 8:
         return torch.bmm(W2.unsqueeze(0).expand(x.size(0), -1, -1), x)
-    return F.conv1d(x, W2.unsqueeze(-1))
+    if LIBRARY_GEMM:
+        return F.conv1d(x, W2.unsqueeze(-1))
+    return fused.conv1x1(x, W2)
 
 
 def knn(x, k: int):
@@ -162,7 +168,7 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         gate = se.gate((S1 / (N * k)).to(x.dtype) * scale + shift)  # [B,Co] in (0,1): SE squeeze = mean_{N,k} BN(u)
         out = fused.row_affine_act(ustar, gate * scale, gate * shift, slope=0.2)
         if res is not None:
-            out = out + res(x)
+            out = out + _pconv(x, res.weight)
         return out
 
     def forward(self, x):
@@ -171,14 +177,19 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         x2 = self._edge_block(x1, self.conv2, self.bn2, self.se2, self.resconv1)
         x3 = self._edge_block(x2, self.conv3, self.bn3, self.se3, self.resconv2)
         x4 = self._edge_block(x3, self.conv4, self.bn4, self.se4, self.resconv3)
-        h = self.conv5(torch.cat((x1, x2, x3, x4), dim=1))
+        xcat = torch.cat((x1, x2, x3, x4), dim=1)
+        if LIBRARY_GEMM:
+            h, st5 = self.conv5(xcat), None
+        else:                                                        # row statistics of h come out of the GEMM epilogue
+            h, m5, v5 = fused.conv1x1(xcat, self.conv5.weight.squeeze(-1), stats_seg=xcat.size(2))
+            st5 = (m5, v5)
         bn, L = self.bn5, h.size(2)
 
         def tail(m_bc, v_bc, g, beta):                                # BN5 as one per-channel scale/shift
             mean, var = _bn_from_rows(bn, m_bc, v_bc, L)
             scale = g * torch.rsqrt(var + bn.eps)
             return scale.expand(B, -1), (beta - scale * mean).expand(B, -1)
-        h = fused.row_norm_act(h, tail, (bn.weight, bn.bias), slope=0.2)
+        h = fused.row_norm_act(h, tail, (bn.weight, bn.bias), slope=0.2, stats=st5)
         return torch.cat((h.amax(2), h.mean(2)), 1).view(B, self.output_size)
 
 
@@ -346,10 +357,10 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             sty.append((params[:, off + nf:off + 2 * nf], params[:, off:off + nf]))
             off += 2 * nf
         # layer 1: the input lattice is constant, so the instance-normalised activations are batch independent
-        # Channel counts are padded to multiples of 8 (1026 -> 1032, 513 -> 520) with all-zero channels so every GEMM
-        # operand row is 16-byte aligned for the tensor-core kernels; padded channels stay exactly zero end to end.
+        # Channel counts are padded to multiples of 32 (1026 -> 1056, 513 -> 544) with all-zero channels: a TMA box of the
+        # tensor-core GEMM is 32 fp32 wide in every operand arrangement; padded channels stay exactly zero end to end.
         def pad8(n):
-            return (n + 7) // 8 * 8
+            return (n + 31) // 32 * 32
 
         def padc(t, cp):                                                      # zero-pad dim 1 of a small tensor
             return t if t.size(1) == cp else F.pad(t, (0, 0) * (t.dim() - 2) + (0, cp - t.size(1)))
@@ -364,12 +375,12 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         cp = pad8(C1)
         x = fused.row_affine_act(padc(xhat, cp), padc(A, cp), padc(D, cp), in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D)
         cin = C1
+        pro = None                                                            # folded tail of the previous layer, applied inside the next GEMM
         for layer, name in ((2, "conv2"), (3, "conv3")):
             W = self._stack(lambda d: getattr(d, name).weight).squeeze(-1)    # [P,Cout,Cin]
             cout = W.size(1)
             cop = pad8(cout)
             Wp = F.pad(W, (0, cp - cin, 0, cop - cout))                       # zero rows / columns for the padded channels
-            h = torch.bmm(Wp, x.view(P, cp, B * npts)).view(P, cop, B, npts)
             bns, prm = self._bn_se_params(layer)
 
             def tail(mean, var, wsty, bsty, gam, bet, w1, w2, bns=bns, cout=cout, cop=cop):
@@ -378,7 +389,21 @@ class SpareNetDecode(nn.Module):  # reference :289-391
                 A, D = self._bn_se(bns, wsty, bsty, (var / (var + EPS))[:, :cout], gam, bet, w1, w2)
                 sc = padc(A, cop) * rstd
                 return sc, padc(D, cop) - sc * mean
-            x = fused.row_norm_act(h, tail, (sty[layer - 1][0], sty[layer - 1][1]) + prm)
+            tensors = (sty[layer - 1][0], sty[layer - 1][1]) + prm
+            if LIBRARY_GEMM:
+                h = torch.bmm(Wp, x.view(P, cp, B * npts)).view(P, cop, B, npts)
+                x = fused.row_norm_act(h, tail, tensors)
+            else:
+                # tcgen05 GEMM per primitive; its epilogue returns the instance statistics, the NEXT GEMM's prologue applies the
+                # resulting scale/shift + ReLU to its operand in shared memory: the activated [P,C,B,512] tensor is never stored
+                if pro is None:
+                    h, m, v = fused.conv1x1(x, Wp, stats_seg=npts)
+                else:
+                    h, m, v = fused.act_conv(Wp, pro, stats_seg=npts, h=h)
+                if layer == 2:
+                    pro = fused.Prologue(h, m, v, tail, tensors)
+                else:
+                    x = fused.row_norm_act(h, tail, tensors, stats=(m, v))
             cin, cp = cout, cop
         W4 = F.pad(self._stack(lambda d: d.conv4.weight).squeeze(-1), (0, cp - cin))   # [P,3,256]
         b4 = self._stack(lambda d: d.conv4.bias).view(P, 3, 1)
@@ -410,11 +435,10 @@ class PointNetRes(nn.Module):  # reference :582-646
         self.th = nn.Tanh()
 
     @staticmethod
-    def _bn_se_relu(h, bn, se, row_bias):
-        """relu(SE(BN(h + row_bias))) as ONE per-(sample,channel) scale/shift over h [B,C,N]; row_bias ([C] conv bias or
-        [B,C]) is never added to the activations: it only shifts the statistics and folds into the shift."""
-        L = h.size(2)
-
+    def _bn_se_tail(bn, se, row_bias, L):
+        """relu(SE(BN(h + row_bias))) over h [B,C,L] as ONE per-(sample,channel) scale/shift: returns (fn, tensors) for
+        fused.row_norm_act / fused.Prologue.  row_bias ([C] conv bias or [B,C]) is never added to the activations: it only shifts
+        the statistics and folds into the shift."""
         def tail(m_bc, v_bc, rb, g, beta, w1, w2):
             m = m_bc + rb
             mean, var = _bn_from_rows(bn, m, v_bc, L)
@@ -423,27 +447,60 @@ class PointNetRes(nn.Module):  # reference :582-646
             gate = torch.sigmoid(F.linear(torch.relu(F.linear(m * scale + shift, w1)), w2))   # [B,C]: SE squeeze = mean over points of BN(.)
             gs = gate * scale
             return gs, gate * shift + rb * gs
-        return fused.row_norm_act(h, tail, (row_bias, bn.weight, bn.bias, se.fc[0].weight, se.fc[2].weight))
+        return tail, (row_bias, bn.weight, bn.bias, se.fc[0].weight, se.fc[2].weight)
 
-    def forward(self, x):
-        B = x.size(0)
+    @classmethod
+    def _bn_se_relu(cls, h, bn, se, row_bias, stats=None):
+        fn, tensors = cls._bn_se_tail(bn, se, row_bias, h.size(2))
+        return fused.row_norm_act(h, fn, tensors, stats=stats)
+
+    def _forward_library(self, x):
+        """Round-1 arrangement (measurement switch LIBRARY_GEMM): cuDNN convs + separate row passes."""
         x = self._bn_se_relu(_pconv(x, self.conv1.weight), self.bn1, self.se1, self.conv1.bias)
         pointfeat = x
         x = self._bn_se_relu(F.conv1d(x, self.conv2.weight), self.bn2, self.se2, self.conv2.bias)
-        # conv3 -> bn3 -> max over points: only row statistics and extrema of h3 = W3 x are needed, so the [B,1024,N] tensor is
-        # reduced in one pass and never kept; its gradient goes through 128x128 Gram matrices (fused.conv_row_reduce)
         m_bc, v_bc, hmax, hmin = fused.conv_row_reduce(x, self.conv3.weight)
         mean, var = _bn_from_rows(self.bn3, m_bc + self.conv3.bias, v_bc, x.size(2))
+        inv = torch.rsqrt(var + self.bn3.eps)
+        g3 = self.bn3.weight
+        hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin) + self.conv3.bias
+        glob = (hstar - mean) * (g3 * inv) + self.bn3.bias
+        W4 = self.conv4.weight
+        pb = F.linear(glob, W4[:, :1024, 0], self.conv4.bias)
+        x = self._bn_se_relu(F.conv1d(pointfeat, W4[:, 1024:].contiguous()), self.bn4, self.se4, pb)
+        x = self._bn_se_relu(F.conv1d(x, self.conv5.weight), self.bn5, self.se5, self.conv5.bias)
+        x = self._bn_se_relu(F.conv1d(x, self.conv6.weight), self.bn6, self.se6, self.conv6.bias)
+        return self.th(_pconv(x, self.conv7.weight) + self.conv7.bias.view(1, -1, 1))
+
+    def forward(self, x):
+        if LIBRARY_GEMM:
+            return self._forward_library(x)
+        N = x.size(2)
+        # Every hidden activation exists in HBM only as its PRE-normalisation tensor h_k: each tcgen05 GEMM applies the previous
+        # layer's folded BN.SE.ReLU (one scale/shift per (sample, channel)) to its operand in shared memory and returns the row
+        # statistics of its own output from the epilogue, which define the next layer's scale/shift.
+        h1 = _pconv(x, self.conv1.weight)                                     # thin (4 -> 64): batched library GEMM
+        m1, v1 = fused.row_stats_nograd(h1)
+        pro1 = fused.Prologue(h1, m1, v1, *self._bn_se_tail(self.bn1, self.se1, self.conv1.bias, N))   # pointfeat = relu(...) of h1
+        h2, m2, v2 = fused.act_conv(self.conv2.weight.squeeze(-1), pro1, stats_seg=N, h=h1)
+        pro2 = fused.Prologue(h2, m2, v2, *self._bn_se_tail(self.bn2, self.se2, self.conv2.bias, N))
+        # conv3 -> bn3 -> max over points: only row statistics and extrema of h3 = W3 x are needed; the [B,1024,N] product never
+        # leaves the tensor memory, its gradient goes through 128x128 Gram matrices (fused.conv_row_reduce_backward)
+        m_bc, v_bc, hmax, hmin = fused.act_conv_row_reduce(self.conv3.weight, pro2, h=h2)
+        mean, var = _bn_from_rows(self.bn3, m_bc + self.conv3.bias, v_bc, N)
         inv = torch.rsqrt(var + self.bn3.eps)
         g3 = self.bn3.weight
         hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin) + self.conv3.bias   # max_N BN(h3) only needs max/min of h3
         glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
         W4 = self.conv4.weight
         pb = F.linear(glob, W4[:, :1024, 0], self.conv4.bias)                 # [B,512]: the broadcast global half of conv4
-        x = self._bn_se_relu(F.conv1d(pointfeat, W4[:, 1024:].contiguous()), self.bn4, self.se4, pb)
-        x = self._bn_se_relu(F.conv1d(x, self.conv5.weight), self.bn5, self.se5, self.conv5.bias)
-        x = self._bn_se_relu(F.conv1d(x, self.conv6.weight), self.bn6, self.se6, self.conv6.bias)
-        return self.th(_pconv(x, self.conv7.weight) + self.conv7.bias.view(1, -1, 1))
+        h4, m4, v4 = fused.act_conv(W4[:, 1024:, 0], pro1, stats_seg=N, h=h1)  # the pointfeat half of conv4 (strided weight view)
+        pro4 = fused.Prologue(h4, m4, v4, *self._bn_se_tail(self.bn4, self.se4, pb, N))
+        h5, m5, v5 = fused.act_conv(self.conv5.weight.squeeze(-1), pro4, stats_seg=N, h=h4)
+        pro5 = fused.Prologue(h5, m5, v5, *self._bn_se_tail(self.bn5, self.se5, self.conv5.bias, N))
+        h6, m6, v6 = fused.act_conv(self.conv6.weight.squeeze(-1), pro5, stats_seg=N, h=h5)
+        x6 = self._bn_se_relu(h6, self.bn6, self.se6, self.conv6.bias, stats=(m6, v6))
+        return self.th(_pconv(x6, self.conv7.weight) + self.conv7.bias.view(1, -1, 1))
 
 
 class SpareNetRefine(nn.Module):  # reference :530-579

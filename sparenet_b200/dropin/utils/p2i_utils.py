@@ -6,16 +6,34 @@ views from the cube corners (:173-182), "orthorgonal" (scale 1.5, near 0.1, far 
 projection (:185-198), pixel row = -y, col = x (:225), feature = 1 - (z - zmin)/(zmax - zmin) with min/max over
 the WHOLE call (:226), one p2i(max) per radius (:230-251).
 
-Differences from the reference are host-side only: the 4x4 view-projection matrix is applied as one
-[B*N,3] x [3,4] product instead of expanding a CPU matrix to [B*N,4,4] and uploading 33 MB per call (:217), and the
-batch-index / background tensors are cached per shape.  The splat itself is the sm_100a kernel behind
-cuda.p2i_op.p2i (snb_p2i_max_*).
+float32 CUDA clouds take the FUSED renderer (snb_depthmaps_fwd/bwd, sparenet_b200/csrc/depthmaps.cu): view transform, depth
+normalisation (with the gradient through zmin/zmax) and the lock-free max-splat in one C-ABI call per (view, radius); the 4x4
+matrix travels as 16 kernel arguments instead of a [B*N,4,4] tensor expanded on the host and uploaded (33 MB per call, :217).
+float64 (the reference's gradcheck dtype) keeps the step-by-step route through cuda.p2i_op.p2i (snb_p2i_max_*).
 """
 import math
 
 import torch
 
+from sparenet_b200 import functional as F_
 from sparenet_b200.dropin.cuda.p2i_op import p2i
+
+
+class DepthMapFunction(torch.autograd.Function):
+    """data [B,N,3] -> depth map [B,1,S,S] for one view matrix and one radius (snb_depthmaps_fwd / _bwd)."""
+    @staticmethod
+    def forward(ctx, data, view_matrix, size, radius):
+        data = data.contiguous()
+        out, ids, ws = F_.depthmaps_forward(data, view_matrix, size, size, radius)
+        ctx.save_for_backward(data, ids, ws)
+        ctx.meta = (view_matrix, float(radius))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        data, ids, ws = ctx.saved_tensors
+        view_matrix, radius = ctx.meta
+        return F_.depthmaps_backward(grad_out.contiguous(), ids, data, view_matrix, radius, ws), None, None, None
 
 N_VIEWS_PREDEFINED = 8
 
@@ -88,6 +106,7 @@ class ComputeDepthMaps(torch.nn.Module):
         # the reference re-registers one buffer per view, so its state_dict holds the LAST view's matrix (:208)
         self.register_buffer("_pre_matrix", pre[-1:].clone())
         self.register_buffer("_all_pre", pre.clone(), persistent=False)
+        self._view_rows = [tuple(pre[i].reshape(-1).tolist()) for i in range(self.num_views)]   # 16 floats per view, host side
         self._cache = {}
 
     def _aux(self, B, N, dtype, device):
@@ -102,6 +121,9 @@ class ComputeDepthMaps(torch.nn.Module):
         if view_id >= self.num_views:
             return None
         B, N = data.size(0), data.size(1)
+        if data.dtype == torch.float32 and data.is_cuda:     # (CPU tensors fall through to p2i, which rejects them: no CPU path)
+            maps = [DepthMapFunction.apply(data, self._view_rows[view_id], self.image_size, float(r)) for r in radius_list]
+            return maps[0] if len(maps) == 1 else torch.cat(maps, dim=1)
         m = self._all_pre[view_id].to(device=data.device, dtype=data.dtype)
         batch_inds, background = self._aux(B, N, data.dtype, data.device)
         pos = transform(m, data.reshape(-1, 3))

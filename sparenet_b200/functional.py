@@ -201,6 +201,38 @@ def _p2i_dtype(points):
     return 1 if points.dtype == torch.float64 else 0
 
 
+def depthmaps_forward(data, view_matrix, H, W, radius):
+    """data [B,N,3] float32 CUDA, view_matrix: 16 python floats (row-major 4x4) -> (out [B,1,H,W], ids [B,1,H,W] int32, workspace).
+    The workspace must be handed back to depthmaps_backward (it keeps the per-point pixel coordinates and the depth range)."""
+    import ctypes
+    data = _cuda_f32(data, "data")
+    B, N = data.shape[0], data.shape[1]
+    dev = data.device
+    out = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+    ids = torch.empty(B, 1, H, W, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.snb_depthmaps_workspace_bytes(B, N, H, W)
+    ws = _ws(nbytes, dev)
+    vm = (ctypes.c_float * 16)(*[float(v) for v in view_matrix])
+    with torch.cuda.device(dev), _op("depthmaps_fwd", 4):
+        check(lib.snb_depthmaps_fwd(ptr(data), B, N, vm, H, W, float(radius), ptr(out), ptr(ids), ptr(ws), nbytes, stream_ptr()), "depthmaps_fwd")
+    return out, ids, ws
+
+
+def depthmaps_backward(grad_out, ids, data, view_matrix, radius, ws):
+    import ctypes
+    data = _cuda_f32(data, "data")
+    grad_out = _cuda_f32(grad_out, "grad_out")
+    B, N = data.shape[0], data.shape[1]
+    H, W = grad_out.shape[-2], grad_out.shape[-1]
+    gdata = torch.empty_like(data)
+    vm = (ctypes.c_float * 16)(*[float(v) for v in view_matrix])
+    with torch.cuda.device(data.device), _op("depthmaps_bwd", 3):
+        check(_lib.load().snb_depthmaps_bwd(ptr(grad_out), ptr(ids), ptr(data), B, N, vm, H, W, float(radius), ptr(ws), ws.numel(),
+                                            ptr(gdata), stream_ptr()), "depthmaps_bwd")
+    return gdata
+
+
 def p2i_max_forward(points, feat, batch_inds, background, kernel_kind, radius):
     dbl = _p2i_dtype(points)
     points, feat, background = points.contiguous(), feat.to(points.dtype).contiguous(), background.to(points.dtype).contiguous()

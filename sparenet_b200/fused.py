@@ -5,6 +5,7 @@ Used by sparenet_b200/dropin/models/sparenet_generator.py.  CUDA float32 only; n
 import torch
 
 from . import _lib
+from . import gemm
 from ._lib import check, ptr, stream_ptr
 from .functional import _op
 
@@ -176,15 +177,18 @@ class RowNormAct(torch.autograd.Function):
     gradients of `tensors`, phase B writes gh once -- the two gradient paths into h are summed inside the kernel instead of
     by a third full-size pass (see snb_row_act_bwd_reduce / snb_row_norm_act_bwd)."""
     @staticmethod
-    def forward(ctx, h, fn, slope, *tensors):
+    def forward(ctx, h, fn, slope, stats, *tensors):
         h = h.contiguous()
         L = h.shape[-1]
         R = h.numel() // L
         lib = _lib.load()
-        mean = torch.empty(h.shape[:-1], device=h.device, dtype=torch.float32)
-        var = torch.empty_like(mean)
-        with torch.cuda.device(h.device), _op("row_stats", 1, 4 * h.numel()):
-            check(lib.snb_row_stats(ptr(h), R, L, ptr(mean), ptr(var), stream_ptr()), "row_stats")
+        if stats is not None:                                   # row statistics already produced by the GEMM epilogue
+            mean, var = (t.detach().reshape(h.shape[:-1]).contiguous().float() for t in stats)
+        else:
+            mean = torch.empty(h.shape[:-1], device=h.device, dtype=torch.float32)
+            var = torch.empty_like(mean)
+            with torch.cuda.device(h.device), _op("row_stats", 1, 4 * h.numel()):
+                check(lib.snb_row_stats(ptr(h), R, L, ptr(mean), ptr(var), stream_ptr()), "row_stats")
         with torch.enable_grad():
             m_, v_ = mean.requires_grad_(True), var.requires_grad_(True)
             ts = [t.detach().requires_grad_(t.requires_grad) for t in tensors]
@@ -221,7 +225,7 @@ class RowNormAct(torch.autograd.Function):
                                            stream_ptr()), "row_norm_act_bwd")
         it = iter(grads[2:])
         gts = [next(it) if t.requires_grad else None for t in ts]
-        return (gh, None, None, *gts)
+        return (gh, None, None, None, *gts)
 
 
 def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, need_x=True, need_w=True):
@@ -292,8 +296,167 @@ def edge_reduce_sel(a, c, idx, sel_max):
     return EdgeReduceSel.apply(a, c, idx, sel_max)
 
 
-def row_norm_act(h, fn, tensors, slope=0.0):
-    return RowNormAct.apply(h, fn, slope, *tensors)
+def row_norm_act(h, fn, tensors, slope=0.0, stats=None):
+    return RowNormAct.apply(h, fn, slope, stats, *tensors)
+
+
+def row_stats_nograd(h):
+    """(mean, biased var) over the last dim WITHOUT an autograd edge: for consumers that own the statistics' gradient
+    (Prologue / RowNormAct fold it into their single backward pass over h)."""
+    h = h.detach().contiguous()
+    L = h.shape[-1]
+    mean = torch.empty(h.shape[:-1], device=h.device, dtype=torch.float32)
+    var = torch.empty_like(mean)
+    with torch.cuda.device(h.device), _op("row_stats", 1, 4 * h.numel()):
+        check(_lib.load().snb_row_stats(ptr(h), h.numel() // L, L, ptr(mean), ptr(var), stream_ptr()), "row_stats")
+    return mean, var
+
+
+# ---------------------------------------------------------------------------- tensor-core 1x1 convolutions (csrc/gemm_tc.cu)
+class Conv1x1(torch.autograd.Function):
+    """y = W x on [G, Cin, *pos] (W [Cout, Cin] or one per batch entry [G, Cout, Cin]) through snb_gemm_tf32: forward, data
+    gradient and weight gradient are the three operand arrangements of the same tcgen05 kernel.  With stats_seg the epilogue
+    also returns the mean / biased variance of every output row segment, as NON-differentiable tensors: their consumer
+    (Prologue or row_norm_act(stats=...)) owns that gradient."""
+    @staticmethod
+    def forward(ctx, x, W, stats_seg):
+        x = x.contiguous()
+        y, st = gemm.conv_fwd(x, W, stats_seg=stats_seg)
+        ctx.save_for_backward(x, W)
+        if stats_seg is None:
+            return y
+        mean, var = st["mean"].reshape(y.shape[:-1]), st["var"].reshape(y.shape[:-1])
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, *_):
+        x, W = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gemm.conv_dgrad(gy, W) if ctx.needs_input_grad[0] else None
+        gW = gemm.conv_wgrad(gy, x, batched=W.dim() == 3) if ctx.needs_input_grad[1] else None
+        return gx, gW, None
+
+
+class Prologue:
+    """The folded normalisation tail of a dense layer, y = leaky_relu(scale*h + shift, slope) with
+    (scale, shift) = fn(row_mean(h), row_var(h), *tensors), held as DATA instead of being applied: the next layer's GEMM applies it
+    to its operand in shared memory (ActConv), so y never exists in HBM.  fn runs once, here (it may advance BatchNorm running
+    statistics), on detached leaves; every consumer pulls its gradient through the recorded small graph in `backward`."""
+
+    def __init__(self, h, mean, var, fn, tensors, slope=0.0):
+        self.h = h.detach().contiguous()
+        self.tensors = tuple(tensors)
+        self.slope = float(slope)
+        rows = self.h.shape[:-1]
+        with torch.enable_grad():
+            m_ = mean.detach().reshape(rows).contiguous().float().requires_grad_(True)
+            v_ = var.detach().reshape(rows).contiguous().float().requires_grad_(True)
+            ts = [t.detach().requires_grad_(t.requires_grad) for t in self.tensors]
+            scale, shift = fn(m_, v_, *ts)
+        assert scale.shape == rows and shift.shape == rows, "fn must return per-row scale/shift"
+        self.sc, self.sh = scale.detach().contiguous().float(), shift.detach().contiguous().float()
+        self.graph = (m_, v_, ts, scale, shift)
+
+    def backward(self, gy):
+        """gy = gradient w.r.t. the activated tensor -> (gradient w.r.t. h, gradients of `tensors`): the two-phase row backward of
+        RowNormAct (reduce, small graph, one write of gh)."""
+        h, sc, sh = self.h, self.sc, self.sh
+        m_, v_, ts, scale, shift = self.graph
+        L = h.shape[-1]
+        R = h.numel() // L
+        lib = _lib.load()
+        gy = gy.contiguous()
+        gsc, gsh = torch.empty_like(sc), torch.empty_like(sh)
+        with torch.cuda.device(h.device), _op("row_act_bwd_reduce", 1, 8 * h.numel()):
+            check(lib.snb_row_act_bwd_reduce(ptr(gy), ptr(h), ptr(sc), ptr(sh), R, L, self.slope, ptr(gsc), ptr(gsh), stream_ptr()),
+                  "row_act_bwd_reduce")
+        wanted = [m_, v_] + [t for t in ts if t.requires_grad]
+        grads = torch.autograd.grad((scale, shift), wanted, (gsc.view_as(scale), gsh.view_as(shift)), allow_unused=True, retain_graph=True)
+        gm = (grads[0] if grads[0] is not None else torch.zeros_like(sc)).contiguous().float()
+        gv = (grads[1] if grads[1] is not None else torch.zeros_like(sc)).contiguous().float()
+        gh = torch.empty_like(h)
+        with torch.cuda.device(h.device), _op("row_norm_act_bwd", 1, 12 * h.numel()):
+            check(lib.snb_row_norm_act_bwd(ptr(gy), ptr(h), ptr(sc), ptr(sh), ptr(m_.detach()), ptr(gm), ptr(gv), R, L, self.slope, ptr(gh),
+                                           stream_ptr()), "row_norm_act_bwd")
+        it = iter(grads[2:])
+        return gh, [next(it) if t.requires_grad else None for t in ts]
+
+    def materialise(self):
+        """The activated tensor itself (backward of the layers that need it as a plain operand)."""
+        h = self.h
+        L = h.shape[-1]
+        y = torch.empty_like(h)
+        with torch.cuda.device(h.device), _op("row_affine_act_fwd", 1, 8 * h.numel()):
+            check(_lib.load().snb_row_affine_act_fwd(ptr(h), ptr(self.sc), ptr(self.sh), h.numel() // L, L, 1, self.slope, ptr(y), stream_ptr()),
+                  "row_affine_act_fwd")
+        return y
+
+
+class ActConv(torch.autograd.Function):
+    """y = W . leaky_relu(scale*h + shift) with the activation applied to the GEMM operand in shared memory (`pro` is the
+    Prologue of h).  Backward: data gradient (tcgen05 DGRAD), weight gradient with the activation re-applied on the fly (WGRAD
+    prologue: the activated tensor is never stored), then the Prologue's row backward.  `h` and `tensors` are passed so that
+    autograd routes their gradients; the statistics outputs are non-differentiable (see Conv1x1)."""
+    @staticmethod
+    def forward(ctx, h, W, pro, stats_seg, *tensors):
+        L = pro.h.shape[-1]
+        y, st = gemm.conv_fwd(pro.h, W, scale=pro.sc, shift=pro.sh, slope=pro.slope, seg=L, stats_seg=stats_seg)
+        ctx.pro = pro
+        ctx.save_for_backward(W)
+        if stats_seg is None:
+            return y
+        mean, var = st["mean"].reshape(y.shape[:-1]), st["var"].reshape(y.shape[:-1])
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, *_):
+        (W,) = ctx.saved_tensors
+        pro = ctx.pro
+        gy = gy.contiguous()
+        L = pro.h.shape[-1]
+        gW = gemm.conv_wgrad(gy, pro.h, batched=W.dim() == 3, scale=pro.sc, shift=pro.sh, slope=pro.slope, seg=L) if ctx.needs_input_grad[1] else None
+        gh, gts = pro.backward(gemm.conv_dgrad(gy, W))
+        return (gh, gW, None, None, *gts)
+
+
+class ActConvRowReduce(torch.autograd.Function):
+    """(mean, biased var, max, min) over the positions of W . leaky_relu(scale*h + shift), each [G, Cout], WITHOUT storing the
+    product: statistics and extrema come out of the GEMM epilogue (PointNetRes conv3 -> bn3 -> max over points,
+    models/sparenet_generator.py:626-629).  Backward: conv_row_reduce_backward (Gram matrices) on the re-materialised operand."""
+    @staticmethod
+    def forward(ctx, h, W, pro, *tensors):
+        W2 = W.reshape(W.size(0), -1)
+        N = pro.h.shape[-1]
+        _, st = gemm.conv_fwd(pro.h, W2, scale=pro.sc, shift=pro.sh, slope=pro.slope, seg=N, stats_seg=N, minmax=True, store=False)
+        mean, var = st["mean"].reshape(pro.h.shape[0], -1), st["var"].reshape(pro.h.shape[0], -1)
+        ctx.pro = pro
+        ctx.save_for_backward(W2, mean, st["imax"], st["imin"])
+        ctx.wshape = W.shape
+        return mean, var, st["max"], st["min"]
+
+    @staticmethod
+    def backward(ctx, gmean, gvar, gmax, gmin):
+        W2, mean, imax, imin = ctx.saved_tensors
+        pro = ctx.pro
+        x = pro.materialise()
+        gx, gW = conv_row_reduce_backward(x, W2, mean, imax, imin, gmean, gvar, gmax, gmin, True, ctx.needs_input_grad[1])
+        gh, gts = pro.backward(gx)
+        return (gh, gW.view(ctx.wshape) if gW is not None else None, None, *gts)
+
+
+def conv1x1(x, W, stats_seg=None):
+    return Conv1x1.apply(x, W, stats_seg)
+
+
+def act_conv(W, pro, stats_seg=None, h=None):
+    """h: the autograd-connected tensor the Prologue was built from (pro.h is its detached copy)."""
+    return ActConv.apply(h, W, pro, stats_seg, *pro.tensors)
+
+
+def act_conv_row_reduce(W, pro, h):
+    return ActConvRowReduce.apply(h, W, pro, *pro.tensors)
 
 
 def conv_row_reduce(x, W):

@@ -36,7 +36,7 @@ def row_minmax(h):
     return h.amax(-1), h.amin(-1)
 
 
-def row_norm_act(h, fn, tensors, slope=0.0):
+def row_norm_act(h, fn, tensors, slope=0.0, stats=None):   # stats (from a GEMM epilogue) are recomputed here: plain autograd
     mean, var = row_stats(h)
     scale, shift = fn(mean, var, *tensors)
     return F.leaky_relu(h * scale.unsqueeze(-1) + shift.unsqueeze(-1), slope)
@@ -48,7 +48,41 @@ def conv_row_reduce(x, W):
     return mean, var, h.amax(-1), h.amin(-1)
 
 
+def row_stats_nograd(h):
+    return row_stats(h.detach())
+
+
+def conv1x1(x, W, stats_seg=None):
+    """y = W x on [G, Cin, *pos], W [Cout, Cin] or [G, Cout, Cin]; with stats_seg also the row statistics of y's last dim."""
+    G, Cin = x.shape[0], x.shape[1]
+    y = torch.matmul(W, x.reshape(G, Cin, -1)).view((G, W.shape[-2]) + tuple(x.shape[2:]))
+    if stats_seg is None:
+        return y
+    assert stats_seg == y.shape[-1]
+    return (y,) + row_stats(y)
+
+
+class Prologue:
+    """Reference of fused.Prologue: the activated tensor is simply formed, with plain autograd through the row statistics (the
+    statistics handed in by a GEMM epilogue are ignored and recomputed from h)."""
+
+    def __init__(self, h, mean, var, fn, tensors, slope=0.0):
+        self.tensors = tuple(tensors)
+        m, v = row_stats(h)
+        scale, shift = fn(m, v, *tensors)
+        self.y = F.leaky_relu(h * scale.unsqueeze(-1) + shift.unsqueeze(-1), slope)
+
+
+def act_conv(W, pro, stats_seg=None, h=None):
+    return conv1x1(pro.y, W, stats_seg)
+
+
+def act_conv_row_reduce(W, pro, h):
+    return conv_row_reduce(pro.y, W)
+
+
 def patch(monkeypatch):
     from sparenet_b200 import fused
-    for name in ("edge_reduce", "edge_reduce_sel", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce"):
+    for name in ("edge_reduce", "edge_reduce_sel", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce",
+                 "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce"):
         monkeypatch.setattr(fused, name, globals()[name])

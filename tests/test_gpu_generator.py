@@ -1,5 +1,12 @@
-"""GPU parity of the drop-in generator (fused algebra + sm_100a point ops) against the plain restatement
-(oracle/generator_ref.py, itself pinned to the real reference classes) with the SAME state_dict."""
+"""GPU parity of the drop-in generator (fused algebra + sm_100a point ops + tcgen05 TF32 GEMMs) against the plain restatement
+(oracle/generator_ref.py, itself pinned to the real reference classes) with the SAME state_dict.
+
+Numerics contract.  The reference runs its 1x1 convolutions through cuDNN with TF32 allowed (torch's default for convolutions) and
+its nn.Linear layers in fp32; ours runs the same convolutions on its own TF32 tensor-core GEMM (same operand precision, different
+accumulation order and fused normalisation algebra) and the Linear layers in fp32.  The algebra itself is verified exactly
+(float64, CPU) in tests/test_generator_algebra.py.  Here the tolerance is CALIBRATED instead of guessed: the restatement is run twice,
+with cuDNN TF32 on (the reference as shipped) and off (fp32), and the distance between those two runs -- the reference's own TF32
+band -- bounds how far ours may be from the fp32 run (factor 3, floor 2e-3 of the coordinate scale)."""
 import pytest
 import torch
 
@@ -31,13 +38,27 @@ class GpuOps:
         return gather_operation(f.contiguous(), idx)
 
 
-@pytest.fixture(autouse=True)
-def _no_tf32():
-    a, b = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
-    yield
-    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = a, b
+class _tf32:
+    """cuDNN TF32 on/off for the restatement; matmul stays fp32 like the reference's nn.Linear layers."""
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = self.on
+
+    def __exit__(self, *a):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.old
+
+
+def _band(a_fp32, a_tf32, ours, what, factor=3.0, floor=2e-3):
+    scale = a_fp32.abs().max().item()
+    band = (a_tf32 - a_fp32).abs().max().item()
+    err = (ours - a_fp32).abs().max().item()
+    print(f"[{what}] scale {scale:.3g}: reference TF32-vs-fp32 band {band / scale:.2e}, ours-vs-fp32 {err / scale:.2e}")
+    assert err <= max(factor * band, floor * scale), what
+    return band / scale, err / scale
 
 
 def test_generator_matches_restatement(cuda):
@@ -49,19 +70,25 @@ def test_generator_matches_restatement(cuda):
     ref = ref.to(cuda).train()
     mine = M.SpareNetGenerator(use_SElayer=True, use_AdaIn="share", encode="Residualnet", **kw).to(cuda).train()
     assert sorted(mine.state_dict()) == sorted(ref.state_dict())
-    mine.load_state_dict(ref.state_dict())
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    mine.load_state_dict(sd0)
     torch.manual_seed(1)
     data = {"partial_cloud": (torch.rand(4, 1024, 3, device=cuda) - 0.5)}
-    c1, m1, r1, l1 = ref(data)
-    c2, m2, r2, l2 = mine(data)
-    # B=4 batch-norms amplify fp32 re-association noise (float64 CPU test: 1e-13); hold to 1% of the coordinate scale
-    assert torch.allclose(c1, c2, rtol=1e-2, atol=2e-3), (c1 - c2).abs().max()
-    assert abs(l1.item() - l2.item()) <= 1e-2 * abs(l1.item()) + 1e-8   # MST edges over/under the alpha threshold flip with 1e-3 noise
+    with _tf32(False):
+        c1, m1, r1, l1 = ref(data)
+    b1 = {k: v.clone() for k, v in ref.named_buffers()}
+    ref.load_state_dict(sd0)
+    with _tf32(True):
+        c1t, _, _, l1t = ref(data)
+    with _tf32(False):
+        c2, m2, r2, l2 = mine(data)
+    _band(c1, c1t, c2, "coarse cloud, n_primitives=8 hide=256 B=4")
+    assert abs(l1.item() - l2.item()) <= max(3 * abs(l1.item() - l1t.item()), 1e-2 * abs(l1.item())) + 1e-8   # MST edges flip across the alpha threshold
     # running statistics advanced identically (sample a few)
-    b1, b2 = dict(ref.named_buffers()), dict(mine.named_buffers())
+    b2 = dict(mine.named_buffers())
     for k in ("encoder.feat_extractor.bn3.running_var", "decoder.decoder.5.dec.bn2.running_mean", "refine.residual.bn4.running_var",
               "encoder.bn.running_mean", "decoder.decoder.0.dec.bn1.num_batches_tracked"):
-        assert torch.allclose(b1[k].float(), b2[k].float(), rtol=2e-2, atol=1e-4), k   # fp32 noise through B=4 batch norms
+        assert torch.allclose(b1[k].float(), b2[k].float(), rtol=3e-2, atol=3e-4), k   # TF32 noise through B=4 batch norms
     (r2.mean() + l2).backward()
     assert all(torch.isfinite(p.grad).all() for p in mine.parameters() if p.grad is not None)
 
@@ -72,21 +99,32 @@ def test_refiner_matches_restatement_given_same_inputs(cuda):
     torch.manual_seed(2)
     ref.apply(G.init_weights)
     mine = M.SpareNetRefine(n_primitives=4, num_points=2048, use_SElayer=True).to(cuda).train()
-    mine.load_state_dict(ref.state_dict())
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    mine.load_state_dict(sd0)
     coarse = (torch.rand(3, 2048, 3, device=cuda) - 0.5) * 0.8
     partial = (torch.rand(3, 3, 512, device=cuda) - 0.5)
-    c1, c2 = coarse.clone().requires_grad_(), coarse.clone().requires_grad_()
-    o1, l1 = ref(c1.transpose(1, 2).contiguous(), partial, c1)
+    c1, c1t, c2 = (coarse.clone().requires_grad_() for _ in range(3))
+    with _tf32(False):
+        o1, l1 = ref(c1.transpose(1, 2).contiguous(), partial, c1)
+    ref.load_state_dict(sd0)
+    with _tf32(True):
+        o1t, _ = ref(c1t.transpose(1, 2).contiguous(), partial, c1t)
     o2, l2 = mine(c2.transpose(1, 2).contiguous(), partial, c2)
     assert torch.equal(l1, l2)
-    assert torch.allclose(o1, o2, rtol=1e-3, atol=1e-4), (o1 - o2).abs().max()
+    _band(o1, o1t, o2, "refined cloud B=3 N=2048")
     w = torch.randn_like(o1)
-    ((o1 * w).sum() + l1).backward()
+    with _tf32(False):
+        ((o1 * w).sum() + l1).backward()
+    with _tf32(True):
+        (o1t * w).sum().backward()
     ((o2 * w).sum() + l2).backward()
-    # 7 BatchNorms over a batch of 3 clouds: fp32 re-association noise reaches ~1e-3 relative in the gradient; in addition a
-    # handful of the 3072 global max-pool winners are decided by ~1e-6 gaps and may route their gradient to a different point.
-    bad = ~torch.isclose(c1.grad, c2.grad, rtol=2e-2, atol=2e-3 * c1.grad.abs().max().item())
-    assert bad.float().mean().item() < 5e-3
+    # 7 BatchNorms over a batch of 3 clouds and ReLU / max-pool switches: a TF32-sized perturbation flips a few of them, so the
+    # gradient is compared as a relative L2 distance against the same distance between the reference's own TF32 and fp32 runs
+    def rel(a, b):
+        return ((a - b).norm() / b.norm()).item()
+    band, err = rel(c1t.grad, c1.grad), rel(c2.grad, c1.grad)
+    print(f"[refiner input gradient] reference TF32-vs-fp32 relative L2 {band:.2e}, ours-vs-fp32 {err:.2e}")
+    assert err <= max(3 * band, 2e-2)
 
 
 def test_training_step_runs_and_learns(cuda):
