@@ -247,20 +247,27 @@ def build_gpu(args, dev, rank):
         d1, _ = cd(refine, gt)
         return loss + torch.mean(d1).mean() * 0.5
 
+    arena = None
+    if world > 1:
+        from sparenet_b200.dist import GradArena
+        arena = GradArena(params)                   # gradients in one flat buffer: the all-reduce runs in place, no cat / copy-back
+
     def finish():
-        if world > 1:
-            from sparenet_b200.dist import allreduce_gradients
-            allreduce_gradients(params, world)      # the path's only collective: NCCL all-reduce of the gradients over NVLink
+        if arena is not None:
+            arena.allreduce(world)                  # the path's only collective: NCCL all-reduce of the gradients over NVLink
         opt.step()
 
     def step(partial, gt):                          # eager step (warm-up and the per-op event pass)
         loss = loss_fn(partial, gt)
-        opt.zero_grad(set_to_none=True)
+        if arena is not None:
+            arena.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         loss.backward()
         finish()
         return loss
 
-    step.loss_fn, step.finish, step.params, step.overlap = loss_fn, finish, params, overlap
+    step.loss_fn, step.finish, step.params, step.overlap, step.arena = loss_fn, finish, params, overlap, arena
     return step, h_partial, h_gt
 
 
@@ -477,7 +484,7 @@ def run_ours(args):
     if not args.no_graph:
         try:
             from sparenet_b200.graph import GraphedForwardBackward
-            gfb = GraphedForwardBackward(step.loss_fn, step.params, (partial, gt))
+            gfb = GraphedForwardBackward(step.loss_fn, step.params, (partial, gt), zero_fn=step.arena.zero if step.arena is not None else None)
 
             def run(p, g):
                 loss = gfb(p, g)

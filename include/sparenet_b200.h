@@ -197,9 +197,12 @@ typedef struct snb_gemm_desc {
   const float* scale; const float* shift; float slope; int seg;
   float* pmean; float* pm2;
   float* pmax; float* pmin; int* pimax; int* pimin;
+  int b_pos_mod;                                              /* > 0 (FWD, WGRAD): B holds only b_pos_mod positions per batch entry
+                                                                 and is tiled along the position axis (the scale/shift still vary) */
 } snb_gemm_desc;
 int snb_gemm_tf32(const snb_gemm_desc* desc, void* stream);
-int snb_gemm_tf32_tiles(int N, int block_n);                  /* number of column tiles (last dim of the statistics) */
+int snb_gemm_tf32_block_n(int N, int block_n);                /* the column-tile width the library uses (block_n = 0: its choice) */
+int snb_gemm_tf32_tiles(int N, int block_n);                  /* statistics tiles along N: 2 per column tile (width block_n/2) */
 
 /* ---- Gridding / GriddingReverse (GRNet) --------------------------------------------------------------------
  * replaces gridding.forward / backward / rev_forward / rev_backward (cuda/gridding/gridding_cuda.cpp:43-99,
@@ -213,6 +216,23 @@ int snb_gridding_bwd(const float* grid_pt_weights, const int* grid_pt_indexes, c
 int snb_gridding_rev_fwd(const float* grid, int B, int scale, float* ptcloud, void* stream);
 int snb_gridding_rev_bwd(const float* ptcloud, const float* grid, const float* grad_ptcloud, int B, int scale,
                          float* grad_grid, void* stream);
+
+
+/* ---- GRNet's gridding loss and cubic feature sampling -----------------------------------
+ * snb_gridding_dist_*: replaces gridding_distance.forward / backward (cuda/gridding_loss/gridding_distance_cuda.cpp,
+ * gridding_distance.cu:179-338): like snb_gridding_* but every vertex keeps EIGHT accumulators, one per corner role:
+ * grid [B, V, 8], grid_pt_indexes = vertex * 8 + corner (-1 outside the grid).
+ * snb_cubic_sampling_*: replaces cubic_feature_sampling.forward / backward (cubic_feature_sampling.cu:105-204): ptcloud
+ * [B,n,3] in grid units, cubic_features [B,C,S,S,S] -> point_features [B,n,(2 ns)^3,C] (zeros outside the grid) and
+ * grid_pt_indexes [B,n,(2 ns)^3]; the backward fully writes grad_cubic_features (the cloud receives no gradient). */
+int snb_gridding_dist_fwd(const float* ptcloud, int B, int n, float min_x, float max_x, float min_y, float max_y,
+                          float min_z, float max_z, float* grid, float* grid_pt_weights, int* grid_pt_indexes, void* stream);
+int snb_gridding_dist_bwd(const float* grid_pt_weights, const int* grid_pt_indexes, const float* grad_grid, int B, int n,
+                          long long n_grid_vertices, float* grad_ptcloud, void* stream);
+int snb_cubic_sampling_fwd(const float* ptcloud, const float* cubic_features, int B, int n, int C, int scale,
+                           int neighborhood_size, float* point_features, int* grid_pt_indexes, void* stream);
+int snb_cubic_sampling_bwd(const float* grad_point_features, const int* grid_pt_indexes, int B, int n, int C, int scale,
+                           int neighborhood_size, float* grad_cubic_features, void* stream);
 
 #ifdef __cplusplus
 }

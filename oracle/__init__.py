@@ -261,3 +261,37 @@ def gridding_rev_bwd(pts, grid, gpts, scale):
     g = torch.empty(B, scale ** 3)
     lib().orc_gridding_rev_bwd(_p(pts), _p(grid), _p(gpts), B, int(scale), _p(g))
     return g
+
+
+# ------------------------------------------------------------------ gridding loss grid / cubic feature sampling (GRNet)
+def gridding_dist_fwd(pts, bounds):
+    pts = _f(pts)
+    B, n, _ = pts.shape
+    lens = [int(bounds[2 * i + 1] - bounds[2 * i] + 1) for i in range(3)]
+    V = lens[0] * lens[1] * lens[2]
+    grid, w, ix = torch.empty(B, V, 8), torch.empty(B, n, 8, 3), torch.empty(B, n, 8, dtype=torch.int32)
+    lib().orc_gridding_dist_fwd(_p(pts), B, n, *[ctypes.c_float(float(v)) for v in bounds], _p(grid), _p(w), _p(ix))
+    return grid, w, ix
+
+
+def gridding_dist_bwd(weights, indexes, ggrid):
+    """Same routing as gridding_bwd; the gradient grid is [B, V, 8]."""
+    return gridding_bwd(weights, indexes, _f(ggrid).reshape(ggrid.shape[0], -1))
+
+
+def cubic_sampling_fwd(pts, feat, ns):
+    pts, feat = _f(pts), _f(feat)
+    B, n, _ = pts.shape
+    C, S = feat.shape[1], feat.shape[2]
+    V = (2 * ns) ** 3
+    out, ix = torch.empty(B, n, V, C), torch.empty(B, n, V, dtype=torch.int32)
+    lib().orc_cubic_sampling_fwd(_p(pts), _p(feat), B, n, C, S, int(ns), _p(out), _p(ix))
+    return out, ix
+
+
+def cubic_sampling_bwd(gout, indexes, S, ns):
+    gout, indexes = _f(gout), _i(indexes)
+    B, n, V, C = gout.shape
+    g = torch.empty(B, C, S, S, S)
+    lib().orc_cubic_sampling_bwd(_p(gout), _p(indexes), B, n, C, int(S), int(ns), _p(g))
+    return g

@@ -34,6 +34,8 @@ EXTS = {
     "MDS": ("MDS", ["MDS.cpp", "MDS_cuda.cu"], []),
     "ext": ("p2i_op", ["ext.cpp", "p2i_sum.cu", "p2i_max.cu"], ["--expt-extended-lambda", "-O3"]),
     "gridding": ("gridding", ["gridding_cuda.cpp", "gridding.cu", "gridding_reverse.cu"], []),
+    "gridding_distance": ("gridding_loss", ["gridding_distance_cuda.cpp", "gridding_distance.cu"], []),
+    "cubic_feature_sampling": ("cubic_feature_sampling", ["cubic_feature_sampling_cuda.cpp", "cubic_feature_sampling.cu"], []),
 }
 
 

@@ -705,3 +705,85 @@ ORC_API void orc_gridding_rev_bwd(const float *pts, const float *grid, const flo
       }
     }
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * GRNet's gridding LOSS grid (cuda/gridding_loss/gridding_distance.cu:29-177,213-338): the gridding above with EIGHT accumulators
+ * per vertex, one per corner role: index = vertex * 8 + corner (:74-129), grid [B, V, 8]; the backward routes exactly like
+ * orc_gridding_bwd through those indexes.  Corners outside the grid are skipped (the reference would write out of bounds).
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_gridding_dist_fwd(const float *pts, int B, int n, float minx, float maxx, float miny, float maxy, float minz,
+                                   float maxz, float *grid, float *weights, int *indexes) {
+  const int lx = (int)(maxx - minx + 1), ly = (int)(maxy - miny + 1), lz = (int)(maxz - minz + 1);
+  const size_t nv = (size_t)lx * ly * lz * 8;
+  memset(grid, 0, sizeof(float) * B * nv);
+  for (int b = 0; b < B; b++)
+    for (int j = 0; j < n; j++) {
+      const float *p = pts + ((size_t)b * n + j) * 3;
+      float *w = weights + ((size_t)b * n + j) * 24;
+      int *ix = indexes + ((size_t)b * n + j) * 8;
+      int lo[3], hi[3];
+      for (int c = 0; c < 3; c++) {
+        lo[c] = (int)floorf(p[c]); hi[c] = (int)ceilf(p[c]);
+        if (lo[c] == hi[c]) hi[c] += 1;
+      }
+      const float mn[3] = {minx, miny, minz};
+      const int len[3] = {lx, ly, lz};
+      for (int t = 0; t < 8; t++) {
+        const int u[3] = {(t >> 2) & 1, (t >> 1) & 1, t & 1};
+        int off[3], inside = 1;
+        for (int c = 0; c < 3; c++) {
+          const int corner = u[c] ? hi[c] : lo[c];
+          w[t * 3 + c] = 1.f - fabsf(p[c] - (float)corner);
+          off[c] = (int)((float)corner - mn[c]);
+          if (off[c] < 0 || off[c] >= len[c]) inside = 0;
+        }
+        ix[t] = inside ? grid_index(ly, lz, off[0], off[1], off[2]) * 8 + t : -1;
+        if (inside) grid[(size_t)b * nv + ix[t]] += w[t * 3] * w[t * 3 + 1] * w[t * 3 + 2];
+      }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cubic_feature_sampling (cuda/cubic_feature_sampling/cubic_feature_sampling.cu:29-103,139-180): per point the (2 ns)^3 vertices
+ * lower-(ns-1) .. upper+(ns-1) per axis (x outermost), index -1 outside [0,S)^3; point_features[b,i,v,k] = features[b,k,vertex]
+ * (zero outside); backward: grad_features[b,k,vertex] += grad_point_features[b,i,v,k], no gradient for the cloud (:165-170).
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_cubic_sampling_fwd(const float *pts, const float *feat, int B, int n, int C, int S, int ns, float *out, int *indexes) {
+  const int side = 2 * ns, V = side * side * side, e = ns - 1;
+  const size_t cub = (size_t)S * S * S;
+  memset(out, 0, sizeof(float) * (size_t)B * n * V * C);
+  for (int b = 0; b < B; b++)
+    for (int i = 0; i < n; i++) {
+      const float *p = pts + ((size_t)b * n + i) * 3;
+      int lo[3], hi[3];
+      for (int c = 0; c < 3; c++) {
+        lo[c] = (int)floorf(p[c]); hi[c] = (int)ceilf(p[c]);
+        if (lo[c] == hi[c]) hi[c] += 1;
+      }
+      int v = 0;
+      for (int j = lo[0] - e; j <= hi[0] + e; ++j)
+        for (int k = lo[1] - e; k <= hi[1] + e; ++k)
+          for (int m = lo[2] - e; m <= hi[2] + e; ++m) {
+            const int outside = j < 0 || j >= S || k < 0 || k >= S || m < 0 || m >= S;
+            const int ix = outside ? -1 : (j * S + k) * S + m;
+            indexes[((size_t)b * n + i) * V + v] = ix;
+            if (!outside)
+              for (int c = 0; c < C; c++) out[(((size_t)b * n + i) * V + v) * C + c] = feat[((size_t)b * C + c) * cub + ix];
+            v++;
+          }
+    }
+}
+
+ORC_API void orc_cubic_sampling_bwd(const float *gout, const int *indexes, int B, int n, int C, int S, int ns, float *gfeat) {
+  const int side = 2 * ns, V = side * side * side;
+  const size_t cub = (size_t)S * S * S;
+  memset(gfeat, 0, sizeof(float) * (size_t)B * C * cub);
+  for (int b = 0; b < B; b++)
+    for (int i = 0; i < n; i++)
+      for (int v = 0; v < V; v++) {
+        const int ix = indexes[((size_t)b * n + i) * V + v];
+        if (ix < 0) continue;
+        for (int c = 0; c < C; c++) gfeat[((size_t)b * C + c) * cub + ix] += gout[(((size_t)b * n + i) * V + v) * C + c];
+      }
+}

@@ -22,7 +22,8 @@ class GemmDesc(ctypes.Structure):
                 ("D", c_void_p), ("ldd", ctypes.c_longlong), ("d_batch_stride", ctypes.c_longlong),
                 ("block_n", c_int), ("store", c_int), ("split", c_int),
                 ("scale", c_void_p), ("shift", c_void_p), ("slope", c_float), ("seg", c_int),
-                ("pmean", c_void_p), ("pm2", c_void_p), ("pmax", c_void_p), ("pmin", c_void_p), ("pimax", c_void_p), ("pimin", c_void_p)]
+                ("pmean", c_void_p), ("pm2", c_void_p), ("pmax", c_void_p), ("pmin", c_void_p), ("pimax", c_void_p), ("pimin", c_void_p),
+                ("b_pos_mod", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/sparenet_b200.h (tests/test_abi.py checks)
@@ -68,10 +69,15 @@ SIGNATURES = {
     "snb_row_norm_act_bwd": (c_int, [P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P]),
     "snb_gemm_tf32": (c_int, [ctypes.POINTER(GemmDesc), P]),
     "snb_gemm_tf32_tiles": (c_int, [c_int, c_int]),
+    "snb_gemm_tf32_block_n": (c_int, [c_int, c_int]),
     "snb_gridding_fwd": (c_int, [P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P, P]),
     "snb_gridding_bwd": (c_int, [P, P, P, c_int, c_int, ctypes.c_longlong, P, P]),
     "snb_gridding_rev_fwd": (c_int, [P, c_int, c_int, P, P]),
     "snb_gridding_rev_bwd": (c_int, [P, P, P, c_int, c_int, P, P]),
+    "snb_gridding_dist_fwd": (c_int, [P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P, P]),
+    "snb_gridding_dist_bwd": (c_int, [P, P, P, c_int, c_int, ctypes.c_longlong, P, P]),
+    "snb_cubic_sampling_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "snb_cubic_sampling_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
 }
 
 _lib = None

@@ -50,6 +50,8 @@ struct KParams {
   int kb_total;         // k-blocks of one output batch = BI * ceil(K/BK)  (FWD/DGRAD: ceil(K/BK))
   int kb_per_batch;     // ceil(K/BK)
   int total_tiles;
+  int b_mod;            // > 0: the activation operand holds only b_mod positions and is tiled along the position axis (decoder layer 1:
+                        //      one lattice response per primitive, shared by all samples; only scale/shift differ per sample)
   // prologue
   const float* scale;
   const float* shift;
@@ -252,12 +254,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (p.mode == MODE_WGRAD) {
             const int bi = kb / p.kb_per_batch, kpos = (kb - bi * p.kb_per_batch) * BK, batch = c.g * p.BI + bi;
             tma_load_4d(sa, &map_a, bar, kpos, c.m0, batch, 0);
-            tma_load_4d(sb, &map_b, bar, kpos, c.n0, batch, 0);
+            tma_load_4d(sb, &map_b, bar, p.b_mod > 0 ? kpos % p.b_mod : kpos, c.n0, batch, 0);
           } else {
             const int ga = p.a_batched ? c.g : 0;
             if (a_mn) tma_load_4d(sa, &map_a, bar, 0, kb * BK, c.m0 >> 5, ga);
             else tma_load_4d(sa, &map_a, bar, kb * BK, c.m0, ga, 0);
-            tma_load_4d(sb, &map_b, bar, 0, kb * BK, c.n0 >> 5, c.g);
+            tma_load_4d(sb, &map_b, bar, 0, kb * BK, (p.b_mod > 0 ? c.n0 % p.b_mod : c.n0) >> 5, c.g);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -534,9 +536,17 @@ int encode_out(CUtensorMap* m, const float* base, int cols, int rows, int batch,
 
 // The C ABI takes a plain descriptor struct (include/sparenet_b200.h: snb_gemm_desc).
 static int pick_block_n(int N, int block_n) {
-  if (block_n <= 0) block_n = N >= 256 ? 256 : ((N + 63) / 64) * 64;
-  return block_n;
+  if (block_n > 0) return block_n;
+  if (N <= 256) return ((N + 63) / 64) * 64;
+  int best = 256, pad = ((N + 255) / 256) * 256;     // least padding among 256 / 192 / 128 columns per tile, larger tile on ties
+  for (int bn = 192; bn >= 128; bn -= 64) {
+    const int q = ((N + bn - 1) / bn) * bn;
+    if (q < pad) { pad = q; best = bn; }
+  }
+  return best;
 }
+
+SNB_API int snb_gemm_tf32_block_n(int N, int block_n) { return pick_block_n(N, block_n); }
 
 // number of statistics tiles along N: every column tile is reduced in two halves of block_n/2 columns
 SNB_API int snb_gemm_tf32_tiles(int N, int block_n) {
@@ -590,8 +600,12 @@ SNB_API int snb_gemm_tf32(const snb_gemm_desc* d, void* stream) {
     p.xf_S = xform ? (d->N + p.seg - 1) / p.seg : 1;
     if (xform && (p.seg % block_n) != 0) return SNB_EINVAL;
     if ((rc = encode_kmajor(&ma, d->A, d->K, d->M, p.a_batched ? d->G : 1, d->lda, d->a_batch_stride, BM)) != SNB_OK) return rc;
-    if ((rc = encode_mnmajor(&mb, d->B, d->N, d->K, d->G, d->ldb, d->b_batch_stride, block_n / 32)) != SNB_OK) return rc;
+    const int nb = d->b_pos_mod > 0 ? d->b_pos_mod : d->N;
+    if (d->b_pos_mod > 0 && ((d->N % nb) != 0 || (nb % block_n) != 0)) return SNB_EINVAL;
+    p.b_mod = d->b_pos_mod > 0 ? nb : 0;
+    if ((rc = encode_mnmajor(&mb, d->B, nb, d->K, d->G, d->ldb, d->b_batch_stride, block_n / 32)) != SNB_OK) return rc;
   } else if (d->mode == MODE_DGRAD) {
+    if (d->b_pos_mod > 0) return SNB_EINVAL;
     // A = W^T: W stored [Ga, K rows (Cout), M (Cin) contiguous] MN-major; B = gY [G, K rows, N] MN-major
     if ((rc = encode_mnmajor(&ma, d->A, d->M, d->K, p.a_batched ? d->G : 1, d->lda, d->a_batch_stride, BM / 32)) != SNB_OK) return rc;
     if ((rc = encode_mnmajor(&mb, d->B, d->N, d->K, d->G, d->ldb, d->b_batch_stride, block_n / 32)) != SNB_OK) return rc;
@@ -601,7 +615,10 @@ SNB_API int snb_gemm_tf32(const snb_gemm_desc* d, void* stream) {
     p.xf_S = xform ? (d->K + p.seg - 1) / p.seg : 1;
     if (xform && (p.seg % BK) != 0) return SNB_EINVAL;
     if ((rc = encode_kmajor(&ma, d->A, d->K, d->M, d->G * BI, d->lda, d->a_batch_stride, BM)) != SNB_OK) return rc;
-    if ((rc = encode_kmajor(&mb, d->B, d->K, d->N, d->G * BI, d->ldb, d->b_batch_stride, block_n)) != SNB_OK) return rc;
+    const int kb_ = d->b_pos_mod > 0 ? d->b_pos_mod : d->K;
+    if (d->b_pos_mod > 0 && (BI != 1 || (d->K % kb_) != 0 || (kb_ % BK) != 0)) return SNB_EINVAL;
+    p.b_mod = d->b_pos_mod > 0 ? kb_ : 0;
+    if ((rc = encode_kmajor(&mb, d->B, kb_, d->N, d->G * BI, d->ldb, d->b_batch_stride, block_n)) != SNB_OK) return rc;
   }
   if (d->store != 0) {
     if ((rc = encode_out(&md, d->D, d->N, d->M, d->G, d->ldd, d->d_batch_stride)) != SNB_OK) return rc;

@@ -8,14 +8,18 @@
 // grid-weighted centroid of the cell below it (skipped when the weights sum < 1e-6).
 // The reference runs ONE block per sample (<<<B, 512>>>); here every point / vertex is a thread of a full grid.
 // Unlike the reference, corners that fall outside the grid are skipped (index -1) instead of written out of bounds.
+//
+// The same two kernels serve GRNet's gridding LOSS (cuda/gridding_loss/gridding_distance.cu:29-177,213-338): there every vertex
+// keeps EIGHT accumulators, one per corner role (index = vertex * 8 + corner), so `slots` = 8 instead of 1.
+// cubic_feature_sampling (cuda/cubic_feature_sampling/cubic_feature_sampling.cu:29-204) is at the end of this file.
 #include <math.h>
 #include "common.cuh"
 
 namespace snb {
 
 __global__ void __launch_bounds__(256) gridding_fwd_kernel(const float* __restrict__ pts, size_t total, int n, float minx, float miny, float minz,
-                                                            int lx, int ly, int lz, float* __restrict__ grid, float* __restrict__ weights,
-                                                            int* __restrict__ indexes) {
+                                                            int lx, int ly, int lz, int slots, float* __restrict__ grid,
+                                                            float* __restrict__ weights, int* __restrict__ indexes) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t b = i / n;
@@ -29,7 +33,7 @@ __global__ void __launch_bounds__(256) gridding_fwd_kernel(const float* __restri
     hi[c] = (int)ceilf(p[c]);
     if (lo[c] == hi[c]) hi[c] += 1;
   }
-  float* __restrict__ g = grid + b * (size_t)lx * ly * lz;
+  float* __restrict__ g = grid + b * (size_t)lx * ly * lz * slots;
 #pragma unroll
   for (int t = 0; t < 8; t++) {
     const int u[3] = {(t >> 2) & 1, (t >> 1) & 1, t & 1};
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(256) gridding_fwd_kernel(const float* __restri
       inside = inside && off[c] >= 0 && off[c] < len[c];
       weights[i * 24 + t * 3 + c] = w[c];
     }
-    const int ix = inside ? (off[0] * ly + off[1]) * lz + off[2] : -1;
+    const int ix = inside ? ((off[0] * ly + off[1]) * lz + off[2]) * slots + (slots == 8 ? t : 0) : -1;
     indexes[i * 8 + t] = ix;
     if (inside) atomicAdd(&g[ix], __fmul_rn(__fmul_rn(w[0], w[1]), w[2]));
   }
@@ -132,9 +136,92 @@ __global__ void __launch_bounds__(256) gridding_rev_bwd_kernel(const float* __re
   }
 }
 
+// ---- cubic feature sampling (GRNet) ---------------------------------------------------------------------------------------------
+// per point the (2 ns)^3 grid vertices around it (lower - (ns-1) .. upper + (ns-1) per axis, x outermost), -1 outside the grid
+// (cubic_feature_sampling.cu:49-87); point_features[b, i, v, :] = cubic_features[b, :, vertex] (zeros where outside, :89-103).
+// One thread per (point, vertex, channel): the channel axis of the output is contiguous, the gather reads the L2-resident volume.
+__global__ void __launch_bounds__(256) cubic_sampling_index_kernel(const float* __restrict__ pts, size_t total, int S, int ns,
+                                                                    int* __restrict__ indexes) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // point
+  if (i >= total) return;
+  int lo[3], hi[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float p = pts[i * 3 + c];
+    lo[c] = (int)floorf(p);
+    hi[c] = (int)ceilf(p);
+    if (lo[c] == hi[c]) hi[c] += 1;
+  }
+  const int e = ns - 1, side = 2 * ns;
+  int v = 0;
+  for (int j = lo[0] - e; j <= hi[0] + e; ++j)
+    for (int k = lo[1] - e; k <= hi[1] + e; ++k)
+      for (int m = lo[2] - e; m <= hi[2] + e; ++m) {
+        const bool out = j < 0 || j >= S || k < 0 || k >= S || m < 0 || m >= S;
+        indexes[i * (size_t)(side * side * side) + v++] = out ? -1 : (j * S + k) * S + m;
+      }
+}
+
+__global__ void __launch_bounds__(256) cubic_sampling_gather_kernel(const float* __restrict__ feat, const int* __restrict__ indexes, size_t total,
+                                                                     size_t per_batch, int C, size_t cub, float* __restrict__ out) {
+  const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // ((b*n + i)*V + v)*C + k
+  if (o >= total) return;
+  const int k = (int)(o % C);
+  const size_t pv = o / C;                                           // (b*n + i)*V + v
+  const int ix = indexes[pv];
+  const size_t b = pv / per_batch;
+  out[o] = ix < 0 ? 0.f : feat[(b * C + k) * cub + ix];
+}
+
+__global__ void __launch_bounds__(256) cubic_sampling_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ indexes, size_t total,
+                                                                  size_t per_batch, int C, size_t cub, float* __restrict__ gfeat) {
+  const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  const int k = (int)(o % C);
+  const size_t pv = o / C;
+  const int ix = indexes[pv];
+  if (ix < 0) return;
+  atomicAdd(&gfeat[((pv / per_batch) * C + k) * cub + ix], gout[o]);
+}
+
 }  // namespace snb
 
 using namespace snb;
+
+// cubic_feature_sampling.forward (cubic_feature_sampling_cuda.cpp, .cu:105-137): ptcloud [B,n,3] in grid units, cubic_features
+// [B,C,S,S,S] -> point_features [B,n,(2 ns)^3,C], grid_pt_indexes [B,n,(2 ns)^3]
+SNB_API int snb_cubic_sampling_fwd(const float* ptcloud, const float* cubic_features, int B, int n, int C, int scale, int neighborhood_size,
+                                   float* point_features, int* grid_pt_indexes, void* stream) {
+  if (B < 0 || n < 0 || C < 0 || scale <= 0 || neighborhood_size <= 0) return SNB_EINVAL;
+  if (scale > 1024 || neighborhood_size > 4) return SNB_ELIMIT;
+  const size_t V = (size_t)8 * neighborhood_size * neighborhood_size * neighborhood_size, pts = (size_t)B * n;
+  if (pts == 0) return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  cubic_sampling_index_kernel<<<(unsigned)((pts + 255) / 256), 256, 0, s>>>(ptcloud, pts, scale, neighborhood_size, grid_pt_indexes);
+  const size_t total = pts * V * C;
+  if (total)
+    cubic_sampling_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(cubic_features, grid_pt_indexes, total, (size_t)n * V, C,
+                                                                                (size_t)scale * scale * scale, point_features);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+// cubic_feature_sampling.backward (.cu:139-204): grad_cubic_features [B,C,S,S,S] (fully written); the cloud receives no gradient
+// (floor / ceil have zero derivative, :165-170): the wrapper returns zeros for it like the reference
+SNB_API int snb_cubic_sampling_bwd(const float* grad_point_features, const int* grid_pt_indexes, int B, int n, int C, int scale,
+                                   int neighborhood_size, float* grad_cubic_features, void* stream) {
+  if (B < 0 || n < 0 || C < 0 || scale <= 0 || neighborhood_size <= 0) return SNB_EINVAL;
+  if (scale > 1024 || neighborhood_size > 4) return SNB_ELIMIT;
+  const size_t V = (size_t)8 * neighborhood_size * neighborhood_size * neighborhood_size, cub = (size_t)scale * scale * scale;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((size_t)B * C * cub) SNB_CUDA(cudaMemsetAsync(grad_cubic_features, 0, sizeof(float) * (size_t)B * C * cub, s));
+  const size_t total = (size_t)B * n * V * C;
+  if (total)
+    cubic_sampling_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(grad_point_features, grid_pt_indexes, total, (size_t)n * V, C, cub,
+                                                                             grad_cubic_features);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
 
 SNB_API int snb_gridding_fwd(const float* ptcloud, int B, int n, float min_x, float max_x, float min_y, float max_y, float min_z, float max_z,
                              float* grid, float* grid_pt_weights, int* grid_pt_indexes, void* stream) {
@@ -147,8 +234,38 @@ SNB_API int snb_gridding_fwd(const float* ptcloud, int B, int n, float min_x, fl
   SNB_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)B * lx * ly * lz, s));
   const size_t total = (size_t)B * n;
   if (total == 0) return SNB_OK;
-  gridding_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ptcloud, total, n, min_x, min_y, min_z, lx, ly, lz, grid, grid_pt_weights,
+  gridding_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ptcloud, total, n, min_x, min_y, min_z, lx, ly, lz, 1, grid, grid_pt_weights,
                                                                      grid_pt_indexes);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+// gridding_distance.forward (cuda/gridding_loss/gridding_distance_cuda.cpp, gridding_distance.cu:179-211): grid [B, V, 8]
+SNB_API int snb_gridding_dist_fwd(const float* ptcloud, int B, int n, float min_x, float max_x, float min_y, float max_y, float min_z, float max_z,
+                                  float* grid, float* grid_pt_weights, int* grid_pt_indexes, void* stream) {
+  if (B < 0 || n < 0) return SNB_EINVAL;
+  const int lx = (int)(max_x - min_x + 1), ly = (int)(max_y - min_y + 1), lz = (int)(max_z - min_z + 1);
+  if (lx <= 0 || ly <= 0 || lz <= 0) return SNB_EINVAL;
+  if ((long long)lx * ly * lz * 8 > 0x7fffffffLL) return SNB_ELIMIT;
+  if (B == 0) return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  SNB_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)B * lx * ly * lz * 8, s));
+  const size_t total = (size_t)B * n;
+  if (total == 0) return SNB_OK;
+  gridding_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ptcloud, total, n, min_x, min_y, min_z, lx, ly, lz, 8, grid, grid_pt_weights,
+                                                                     grid_pt_indexes);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+// gridding_distance.backward (gridding_distance.cu:213-338): identical routing, the gradient grid is [B, V, 8]
+SNB_API int snb_gridding_dist_bwd(const float* grid_pt_weights, const int* grid_pt_indexes, const float* grad_grid, int B, int n,
+                                  long long n_grid_vertices, float* grad_ptcloud, void* stream) {
+  if (B < 0 || n < 0 || n_grid_vertices < 0) return SNB_EINVAL;
+  const size_t total = (size_t)B * n;
+  if (total == 0) return SNB_OK;
+  gridding_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grid_pt_weights, grid_pt_indexes, grad_grid, total, n,
+                                                                                        (size_t)n_grid_vertices * 8, grad_ptcloud);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

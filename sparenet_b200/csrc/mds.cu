@@ -165,7 +165,7 @@ __host__ __device__ constexpr bool mds_first(int workers) { return workers == 19
 __host__ __device__ constexpr int mds_threads(int workers) { return mds_first(workers) ? 256 : workers + 32; }
 
 // ---- worker warps ------------------------------------------------------------------------------------------------------
-template <int WORKERS, int PT, bool FAST_DIV, bool CULL>
+template <int WORKERS, int PT, bool FAST_DIV>
 struct MdsLevel {
   // runs generations while the CTA still holds more live points than the next narrower layout can take;
   // returns true when the kernel is finished
@@ -192,32 +192,6 @@ struct MdsLevel {
       z[i] = c.sxyz[kk * c.xs + 2];
       fac[i] = k < 8192 ? 1.0f : 2.0f;  // MDS_cuda.cu:111-112 (k > 8191 counts double)
     }
-    // CULL (experimental, SNB_MDS_CULL=1; see tools/mds_cull_study.py): lane s keeps the bounding box of the live points in register
-    // slot s of this warp and, per generation, a lower bound of their densities.  For a pick, slot s can be skipped when the
-    // largest weight anywhere in the box is below half an ulp of that bound: fl(temp + w) == temp for every point of the slot.
-    float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f, btmin = 0.f;
-    if (CULL) {
-      static_assert(!CULL || PT <= 32, "one lane per register slot");
-#pragma unroll
-      for (int i = 0; i < PT; i++) {
-        const bool lv = temp[i] < 1e9f;
-        float lx = lv ? x[i] : 3e38f, ly = lv ? y[i] : 3e38f, lz = lv ? z[i] : 3e38f;
-        float hx = lv ? x[i] : -3e38f, hy = lv ? y[i] : -3e38f, hz = lv ? z[i] : -3e38f;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
-          ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
-          lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
-          hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
-          hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
-          hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
-        }
-        if (lane == i) {
-          blx = lx; bly = ly; blz = lz;
-          bhx = hx; bhy = hy; bhz = hz;
-        }
-      }
-    }
     const int cs = (int)c.cs, msel = c.msel;
     const uint32_t my_slot = c.rank * WARPS + warp;
     const int total = cs * WARPS;
@@ -233,13 +207,6 @@ struct MdsLevel {
         const unsigned long long hi2 = p < mine ? mine : p;
         mine = p < mine ? p : mine;
         second = hi2 < second ? hi2 : second;
-      }
-      if (CULL) {  // densities only grow, so the minimum taken here bounds the whole generation from below
-#pragma unroll
-        for (int i = 0; i < PT; i++) {
-          const unsigned mbits = __reduce_min_sync(0xffffffffu, temp[i] < 1e9f ? __float_as_uint(temp[i]) : 0x7f800000u);
-          if (lane == i) btmin = __uint_as_float(mbits);
-        }
       }
       unsigned long long mysel = MDS_NONE;
       int taken = 0;
@@ -339,20 +306,7 @@ struct MdsLevel {
           }
         }
 #ifndef SNB_MDS_NOAPPLY  // (timing experiment: the replay warp's chain with idle workers; results are wrong)
-        if (CULL) {
-          // lane s: squared distance from the pick to the box of slot s (shrunk by 1e-4 relative: far more than the fp32 rounding
-          // of the per-point distances), upper bound 2.02 exp(-d/t) of the weight of any of its points (x2 factor, 1 % for the
-          // fast exponential), against half an ulp (>= density * 2^-25) of the slot's smallest live density
-          const float ddx = fmaxf(fmaxf(blx - pk.x, pk.x - bhx), 0.f);
-          const float ddy = fmaxf(fmaxf(bly - pk.y, pk.y - bhy), 0.f);
-          const float ddz = fmaxf(fmaxf(blz - pk.z, pk.z - bhz), 0.f);
-          const float dmin = (ddx * ddx + ddy * ddy + ddz * ddz) * 0.9999f;
-          const bool skip = lane >= PT || 2.02f * __expf(-dmin * r) < btmin * 2.9802322e-8f;
-          const unsigned act = ~__ballot_sync(0xffffffffu, skip);
-#pragma unroll
-          for (int i = 0; i < PT; i++)
-            if ((act >> i) & 1u) temp[i] = mds_add<FAST_DIV>(temp[i], fac[i], x[i], y[i], z[i], pk.x, pk.y, pk.z, t, r);
-        } else {
+        {
 #pragma unroll
           for (int i = 0; i < PT; i++) temp[i] = mds_add<FAST_DIV>(temp[i], fac[i], x[i], y[i], z[i], pk.x, pk.y, pk.z, t, r);
         }
@@ -376,62 +330,6 @@ struct MdsLevel {
       if (NEXT > 0 && live <= NEXT * WORKERS) break;  // re-pack into the narrower layout (uniform over the CTA's workers)
     }
     // re-pack the live points for the narrower layout (all worker warps take this branch in the same generation)
-    if (CULL) {
-      // order-preserving compaction (entry order = Z-order): per (slot row, warp) counts -> exclusive offsets -> ballot ranks.
-      // The offsets live behind the new layout (entries NEXT*WORKERS .. CAP of the density staging array are free here).
-      int* rowoff = reinterpret_cast<int*>(c.st.t + NEXT * WORKERS);
-      static_assert(!CULL || NEXT == 0 || (PT - NEXT) * WORKERS >= PT * WARPS + 1, "scratch for the row offsets");
-      bar_sync_named(1, WORKERS);
-#pragma unroll
-      for (int i = 0; i < PT; i++) {
-        const unsigned mk = __ballot_sync(0xffffffffu, temp[i] < 1e9f);
-        if (lane == 0) rowoff[i * WARPS + warp] = __popc(mk);
-      }
-      bar_sync_named(1, WORKERS);
-      if (warp == 0) {  // exclusive prefix over the PT*WARPS counts in (row, warp) order
-        constexpr int TOT = PT * WARPS, PERL = (TOT + 31) / 32;
-        int v[PERL], sum = 0;
-#pragma unroll
-        for (int u = 0; u < PERL; u++) {
-          const int q = lane * PERL + u;
-          v[u] = q < TOT ? rowoff[q] : 0;
-          sum += v[u];
-        }
-        int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += up;
-        }
-        int run = inc - sum;
-#pragma unroll
-        for (int u = 0; u < PERL; u++) {
-          const int q = lane * PERL + u;
-          if (q < TOT) rowoff[q] = run;
-          run += v[u];
-        }
-        if (lane == 31) *c.st.count = inc;
-      }
-      bar_sync_named(1, WORKERS);
-#pragma unroll
-      for (int i = 0; i < PT; i++) {
-        const bool lv = temp[i] < 1e9f;
-        const unsigned mk = __ballot_sync(0xffffffffu, lv);
-        if (lv) {
-          const int e = rowoff[i * WARPS + warp] + __popc(mk & ((1u << lane) - 1u));
-          c.st.t[e] = temp[i];
-          c.st.k[e] = key[i];
-          c.st.loc[(int)(key[i] & 0x1fffffu) >> c.csh] = (unsigned short)e;
-        }
-      }
-      bar_sync_named(1, WORKERS);
-      for (int e = *c.st.count + tid; e < NEXT * WORKERS; e += WORKERS) {  // padding entries can never win
-        c.st.t[e] = 2e9f;
-        c.st.k[e] = 0xffffffffu;
-      }
-      bar_sync_named(1, WORKERS);
-      return false;
-    }
     bar_sync_named(1, WORKERS);
     if (tid == 0) *c.st.count = 0;
     bar_sync_named(1, WORKERS);
@@ -454,14 +352,14 @@ struct MdsLevel {
   }
 };
 
-template <int WORKERS, int PT, bool FAST_DIV, bool CULL>
+template <int WORKERS, int PT, bool FAST_DIV>
 struct MdsChain {
   static __device__ __forceinline__ void run(const MdsCtx& c, int& live, int& gen) {
-    if (!MdsLevel<WORKERS, PT, FAST_DIV, CULL>::run(c, live, gen)) MdsChain<WORKERS, mds_next_pt(PT), FAST_DIV, CULL>::run(c, live, gen);
+    if (!MdsLevel<WORKERS, PT, FAST_DIV>::run(c, live, gen)) MdsChain<WORKERS, mds_next_pt(PT), FAST_DIV>::run(c, live, gen);
   }
 };
-template <int WORKERS, bool FAST_DIV, bool CULL>
-struct MdsChain<WORKERS, 0, FAST_DIV, CULL> {
+template <int WORKERS, bool FAST_DIV>
+struct MdsChain<WORKERS, 0, FAST_DIV> {
   static __device__ __forceinline__ void run(const MdsCtx&, int&, int&) {}
 };
 
@@ -656,7 +554,7 @@ static inline size_t mds_smem_bytes(int per, int threads, int pt, bool stage_xyz
   return cap * 8 + 16 + (((size_t)per * 2 + 15) & ~(size_t)15) + (stage_xyz ? (size_t)per * 12 : 0);
 }
 
-template <int WORKERS, int PT, int OCC, bool CULL = false>
+template <int WORKERS, int PT, int OCC>
 __global__ void __launch_bounds__(mds_threads(WORKERS), OCC) mds_cluster_kernel(const float* __restrict__ dataset, int n, int m,
                                                                         const float* __restrict__ mean_mst_length, int* __restrict__ idxs,
                                                                         int bs_mask, int bs_log2, int stage_xyz, int msel) {
@@ -699,106 +597,6 @@ __global__ void __launch_bounds__(mds_threads(WORKERS), OCC) mds_cluster_kernel(
   // initial layout: every point of the CTA except the pre-chosen point 0 (MDS.cpp:119-121), then padding; the densities
   // start at the weights of round 1 (the pick is point 0: 0 + w is exact)
   const float x0 = dataset[0], y0 = dataset[1], z0 = dataset[2];
-  if (CULL) {
-    // CULL variant: the CTA's points enter the register layout in Z-order of a 16^3 grid over their bounding box (counting sort in
-    // shared memory), so the 32 points of a warp's register slot are neighbours and the slot's box is small.  Any order of the
-    // layout yields the same picks (tie keys travel with the points); only the skipping rate depends on it.
-    static_assert(!CULL || mds_threads(WORKERS) == 256, "the scan below assumes 256 threads");
-    const int first = (rank == 0) ? 1 : 0;
-    const int nsorted = per > first ? per - first : 0;
-    const size_t off = ((size_t)CAP * 8 + 16 + (((size_t)chunk * 2 + 15) & ~(size_t)15) + (stage_xyz ? (size_t)chunk * 12 : 0) + 15) & ~(size_t)15;
-    int* hist = reinterpret_cast<int*>(dyn + off);
-    unsigned short* order = reinterpret_cast<unsigned short*>(hist + 4096);
-    unsigned* bb = reinterpret_cast<unsigned*>(order + ((chunk + 7) & ~7));
-    int* wsum = reinterpret_cast<int*>(bb + 8);
-    for (int i = tid; i < 4096; i += THREADS) hist[i] = 0;
-    if (tid < 3) bb[tid] = 0xffffffffu;
-    else if (tid < 6) bb[tid] = 0u;
-    __syncthreads();
-    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-    for (int li = tid + first; li < per; li += THREADS) {
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        const float v = sxyz[(size_t)li * xs + a];
-        lo[a] = fminf(lo[a], v);
-        hi[a] = fmaxf(hi[a], v);
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-      }
-      if ((tid & 31) == 0) {
-        atomicMin(&bb[a], float_key(lo[a]));
-        atomicMax(&bb[3 + a], float_key(hi[a]));
-      }
-    }
-    __syncthreads();
-    float bl[3], sc[3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      bl[a] = key_float(bb[a]);
-      sc[a] = 16.f / (key_float(bb[3 + a]) - bl[a] + 1e-20f);
-    }
-    auto cell = [&](int li) {
-      unsigned code = 0;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        int q = (int)((sxyz[(size_t)li * xs + a] - bl[a]) * sc[a]);
-        q = q < 0 ? 0 : (q > 15 ? 15 : q);
-        const unsigned v = (unsigned)q;
-        code |= ((v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6)) << a;
-      }
-      return (int)code;
-    };
-    for (int li = tid + first; li < per; li += THREADS) atomicAdd(&hist[cell(li)], 1);
-    __syncthreads();
-    {  // exclusive scan of the 4096 bins: 16 per thread, warp scans, warp totals
-      int v[16], sum = 0;
-#pragma unroll
-      for (int u = 0; u < 16; u++) {
-        v[u] = hist[tid * 16 + u];
-        sum += v[u];
-      }
-      int inc = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((tid & 31) >= o) inc += up;
-      }
-      if ((tid & 31) == 31) wsum[tid >> 5] = inc;
-      __syncthreads();
-      int base = 0;
-      for (int w = 0; w < (tid >> 5); w++) base += wsum[w];
-      int run = base + inc - sum;
-#pragma unroll
-      for (int u = 0; u < 16; u++) {
-        hist[tid * 16 + u] = run;
-        run += v[u];
-      }
-    }
-    __syncthreads();
-    for (int li = tid + first; li < per; li += THREADS) order[atomicAdd(&hist[cell(li)], 1)] = (unsigned short)li;
-    __syncthreads();
-    for (int e = tid; e < CAP; e += THREADS) {
-      const bool ok = e < nsorted;
-      const int li = ok ? (int)order[e] : 0;
-      const int k = (li << csh) + (int)rank;
-      float w0 = 2e9f;
-      if (ok) {
-        const float* p = sxyz + (size_t)li * xs;
-        const float fac = k < 8192 ? 1.0f : 2.0f;
-        w0 = fast ? mds_add<true>(0.f, fac, p[0], p[1], p[2], x0, y0, z0, t, rcp) : mds_add<false>(0.f, fac, p[0], p[1], p[2], x0, y0, z0, t, rcp);
-      }
-      c.st.t[e] = w0;
-      const unsigned rev = bs_log2 ? (__brev((unsigned)(k & bs_mask)) >> (32 - bs_log2)) : 0u;
-      c.st.k[e] = ok ? ((rev << 21) | (unsigned)k) : 0xffffffffu;
-      if (ok) c.st.loc[li] = (unsigned short)e;
-    }
-  } else
   for (int e = tid; e < CAP; e += THREADS) {
     const int li = e + ((rank == 0) ? 1 : 0);  // local point index; rank 0 skips k = 0
     const int k = (li << csh) + (int)rank;
@@ -844,8 +642,8 @@ __global__ void __launch_bounds__(mds_threads(WORKERS), OCC) mds_cluster_kernel(
       else mds_replay<false>(c, (int)cs * (WORKERS / 32));
     } else if (!idle) {
       int gen = 0;
-      if (fast) MdsChain<WORKERS, PT, true, CULL>::run(c, live, gen);
-      else MdsChain<WORKERS, PT, false, CULL>::run(c, live, gen);
+      if (fast) MdsChain<WORKERS, PT, true>::run(c, live, gen);
+      else MdsChain<WORKERS, PT, false>::run(c, live, gen);
     }
   }
   __syncthreads();
@@ -869,7 +667,7 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float* __restrict
   atomicAdd(&gf[((size_t)b * C + c) * n + idx[(size_t)b * m + j]], g[((size_t)b * C + c) * m + j]);
 }
 
-template <int WORKERS, int PT, int OCC, bool CULL = false>
+template <int WORKERS, int PT, int OCC>
 static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, int* idx, int cs, int bs_mask, int bs_log2, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cs));
@@ -877,7 +675,6 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   const int per = (n + cs - 1) / cs;
   int stage_xyz = mds_smem_bytes(per, WORKERS, PT, true) + sizeof(MdsShared) <= (size_t)(OCC > 1 ? 100 : 220) * 1024 ? 1 : 0;
   size_t smem = mds_smem_bytes(per, WORKERS, PT, stage_xyz != 0);
-  if (CULL) smem = ((smem + 15) & ~(size_t)15) + 4096 * sizeof(int) + 2 * (size_t)((per + 7) & ~7) + 64;  // histogram, order, box keys, warp sums
   const int total_warps = cs * (WORKERS / 32);
   int msel = MDS_POOL / total_warps;
   if (msel > MDS_MAXM) msel = MDS_MAXM;
@@ -886,7 +683,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
     if (v >= 1 && v <= msel) msel = v;
   }
   while (msel & (msel - 1)) msel &= msel - 1;  // a power of two: 1, 2, 4 or 8
-  cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<WORKERS, PT, OCC, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t ea = cudaFuncSetAttribute(mds_cluster_kernel<WORKERS, PT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea != cudaSuccess) return (int)ea;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -897,7 +694,7 @@ static int mds_launch(const float* xyz, int B, int n, int m, const float* mml, i
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<WORKERS, PT, OCC, CULL>, xyz, n, m, mml, idx, bs_mask, bs_log2, stage_xyz, msel);
+  return (int)cudaLaunchKernelEx(&cfg, mds_cluster_kernel<WORKERS, PT, OCC>, xyz, n, m, mml, idx, bs_mask, bs_log2, stage_xyz, msel);
 }
 
 }  // namespace snb
@@ -968,8 +765,6 @@ SNB_API int snb_mds_sample(const float* xyz, int B, int n, int m, const float* m
   else if (per <= 256 * 6) MDS_GO(256, 6, 1);
   else if (per <= 256 * 9) MDS_GO(256, 9, 1);
   else if (per <= 256 * 12) MDS_GO(256, 12, 1);
-  else if (per <= 224 * 21 && getenv("SNB_MDS_CULL") && getenv("SNB_MDS_CULL")[0] == '1')  // experimental, not GPU-validated yet
-    rc = mds_launch<224, 21, 1, true>(xyz, B, n, m, mean_mst_length, idx, cs, bm, lg, s);
   else if (per <= 224 * 21) MDS_GO(224, 21, 1);  // SpareNet's refiner (4608 points per CTA): replay warp beside ONE worker warp
   else if (per <= 512 * 12) MDS_GO(512, 12, 1);
   else if (per <= 512 * 18) MDS_GO(512, 18, 1);

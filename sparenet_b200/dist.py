@@ -17,6 +17,52 @@ def shard_batch(global_batch: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class GradArena:
+    """All gradients of a parameter list in ONE flat buffer per (dtype, device): every p.grad is a 16-byte-aligned view into it, so
+    the gradient all-reduce runs in place on a few large chunks -- no concatenation before and no copy back after the collective
+    (round 1's flat-cat buckets moved ~1.3 GB per step for 330 MB of gradients).  Gradients ACCUMULATE into the views: call zero()
+    at the start of every step instead of zero_grad(set_to_none=True) (which would drop the views)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        groups = {}
+        for p in self.params:
+            groups.setdefault((p.dtype, p.device), []).append(p)
+        self.flats = []
+        for (dt, dev), ps in groups.items():
+            offs, n = [], 0
+            for p in ps:
+                offs.append(n)
+                n += (p.numel() + 3) // 4 * 4                     # keep every view 16-byte aligned for vectorised optimizers
+            flat = torch.zeros(max(n, 4), dtype=dt, device=dev)
+            for p, o in zip(ps, offs):
+                p.grad = flat[o:o + p.numel()].view_as(p)
+            self.flats.append(flat)
+
+    def zero(self):
+        for f in self.flats:
+            f.zero_()
+
+    def allreduce(self, world: int = None, chunk_bytes: int = 128 << 20):
+        """Average over ranks, in place, chunk by chunk (NCCL averages inside the collective; gloo sums and divides)."""
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        if world == 1:
+            return 0
+        avg = dist.get_backend() == "nccl"
+        n_calls = 0
+        for f in self.flats:
+            step = max(1, chunk_bytes // f.element_size())
+            for c in f.split(step):
+                if avg:
+                    dist.all_reduce(c, op=dist.ReduceOp.AVG)
+                else:
+                    dist.all_reduce(c)
+                    c.div_(world)
+                n_calls += 1
+        return n_calls
+
+
 def allreduce_gradients(params, world: int = None, bucket_bytes: int = 256 << 20):
     """Average .grad over ranks in flat buckets (few large NCCL calls: 330 MB of generator gradients per step).
     Parameters whose .grad is None on this rank are skipped consistently (same set on every rank by construction).
@@ -28,6 +74,11 @@ def allreduce_gradients(params, world: int = None, bucket_bytes: int = 256 << 20
         return 0
     avg = dist.get_backend() == "nccl"
     grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    if len({g.dtype for g in grads}) > 1:                         # one pass per dtype: torch.cat would type-promote a mixed bucket
+        return sum(allreduce_gradients([p for p in params if p.grad is not None and p.grad.dtype == dt], world, bucket_bytes)
+                   for dt in sorted({g.dtype for g in grads}, key=str))
     n_calls, bucket, size = 0, [], 0
     for g in grads + [None]:
         if g is not None and (size + g.numel() * g.element_size() <= bucket_bytes or not bucket):

@@ -7,9 +7,8 @@ so reference checkpoints load unchanged.  The 0.4 M-parameter discriminator is 3
 its dense math stays on cuDNN (SURVEY.md 2 #13 -- not a kernel target); what is ours on this side of the GAN step is the renderer
 that feeds it (snb_depthmaps_*, utils/p2i_utils.py).
 
-SpectralNorm differs from the reference only in host mechanics: one power iteration per forward on detached u, v (the
-reference's `.data` updates), sigma = u . (W v) differentiated w.r.t. W, and the normalised weight handed to F.conv2d directly
-instead of being setattr'd onto the wrapped module.
+SpectralNorm keeps the reference's mechanics: one power iteration per forward through `.data` (no autograd edge, no version
+bump), sigma = u . (W v) differentiated w.r.t. W, the normalised weight set as a plain attribute of the wrapped module.
 """
 import torch
 import torch.nn as nn
@@ -40,10 +39,11 @@ class SpectralNorm(nn.Module):  # reference :156-211
     def normalised_weight(self):
         u, v, w = (getattr(self.module, self.name + s) for s in ("_u", "_v", "_bar"))
         w2 = w.view(w.shape[0], -1)
-        with torch.no_grad():
-            for _ in range(self.power_iterations):
-                v.copy_(l2normalize(torch.mv(w2.t(), u)))
-                u.copy_(l2normalize(torch.mv(w2, v)))
+        # like the reference (:171-173) the iterates REPLACE u.data / v.data: an in-place update would invalidate the sigma graph
+        # of an earlier forward that is still waiting for its backward (the D step runs the discriminator twice before backward)
+        for _ in range(self.power_iterations):
+            v.data = l2normalize(torch.mv(w2.data.t(), u.data))
+            u.data = l2normalize(torch.mv(w2.data, v.data))
         sigma = u.dot(w2.mv(v))
         return w / sigma.expand_as(w)
 

@@ -99,7 +99,7 @@ def _pconv(x, W):
     shorter than a TMA box and go through a batched library GEMM."""
     W2 = W.reshape(W.size(0), -1)
     if min(W2.shape) <= 8:
-        return torch.bmm(W2.unsqueeze(0).expand(x.size(0), -1, -1), x)
+        return fused.thin_conv(x, W2)      # a convolution in the reference: TF32 allowed like its cuDNN (nn.Linear layers stay fp32)
     if LIBRARY_GEMM:
         return F.conv1d(x, W2.unsqueeze(-1))
     return fused.conv1x1(x, W2)
@@ -367,13 +367,16 @@ class SpareNetDecode(nn.Module):  # reference :289-391
 
         C1 = sizes[0]
         W1 = self._stack(lambda d: d.conv1.weight).squeeze(-1)                # [P,1026,2] (bias cancels under instance norm)
-        h = torch.matmul(W1, self._grid_t)                                    # [P,1026,pts], batch independent
+        h = fused.thin_conv(self._grid_t.unsqueeze(0), W1)                   # Conv1d(2 -> 1026): [P,1026,pts], batch independent
         var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
         xhat = (h - mean) * torch.rsqrt(var + EPS)
         bns, prm = self._bn_se_params(1)
         A, D = self._bn_se(bns, sty[0][0], sty[0][1], var / (var + EPS), *prm)
         cp = pad8(C1)
-        x = fused.row_affine_act(padc(xhat, cp), padc(A, cp), padc(D, cp), in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D)
+        xhat_p, A_p, D_p = padc(xhat, cp), padc(A, cp), padc(D, cp)
+        x = None
+        if LIBRARY_GEMM:
+            x = fused.row_affine_act(xhat_p, A_p, D_p, in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D) for every sample
         cin = C1
         pro = None                                                            # folded tail of the previous layer, applied inside the next GEMM
         for layer, name in ((2, "conv2"), (3, "conv3")):
@@ -397,7 +400,9 @@ class SpareNetDecode(nn.Module):  # reference :289-391
                 # tcgen05 GEMM per primitive; its epilogue returns the instance statistics, the NEXT GEMM's prologue applies the
                 # resulting scale/shift + ReLU to its operand in shared memory: the activated [P,C,B,512] tensor is never stored
                 if pro is None:
-                    h, m, v = fused.conv1x1(x, Wp, stats_seg=npts)
+                    # layer 1's activation relu(A x_hat + D) is never materialised for the 32 samples: conv2 reads the batch-independent
+                    # x_hat [P,1056,512] and applies the per-sample (A, D) in its prologue
+                    h, m, v = fused.bcast_act_conv(xhat_p, A_p, D_p, Wp)
                 else:
                     h, m, v = fused.act_conv(Wp, pro, stats_seg=npts, h=h)
                 if layer == 2:
@@ -407,7 +412,7 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             cin, cp = cout, cop
         W4 = F.pad(self._stack(lambda d: d.conv4.weight).squeeze(-1), (0, cp - cin))   # [P,3,256]
         b4 = self._stack(lambda d: d.conv4.bias).view(P, 3, 1)
-        out = torch.tanh(torch.bmm(W4, x.view(P, cp, B * npts)) + b4).view(P, 3, B, npts)
+        out = torch.tanh(fused.thin_conv(x.view(P, cp, B * npts), W4) + b4).view(P, 3, B, npts)   # Conv1d(256 -> 3): thin
         return out.permute(2, 1, 0, 3).reshape(B, 3, P * npts).contiguous()   # primitive i owns points [512 i, 512 (i+1))
 
 

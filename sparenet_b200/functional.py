@@ -287,17 +287,19 @@ def p2i_sum_backward(grad_out, points, feat, batch_inds, kernel_kind, radius):
 
 # ----------------------------------------------------------------------------- kNN
 def knn_indices_pruned(x, k):
-    """Same result as knn_indices for wide features: a TF32 library GEMM (X^T X) prunes, snb_knn_pruned re-evaluates the surviving
-    candidates exactly (csrc/knn_prune.cu).  Indices identical to knn_indices (tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force)."""
+    """Same result as knn_indices for wide features: the TF32 Gram matrix X^T X from the tcgen05 GEMM (snb_gemm_tf32: A = the
+    point-major copy, B = the channel-major features) prunes, snb_knn_pruned re-evaluates the surviving candidates exactly
+    (csrc/knn_prune.cu).  Indices identical to knn_indices (tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force)."""
+    from . import gemm
     x = _cuda_f32(x, "x").detach()                       # indices carry no gradient: keep the GEMM out of the autograd graph
     B, C, N = x.shape
     idx = torch.empty(B, N, int(k), dtype=torch.int32, device=x.device)
     lib = _lib.load()
     nbytes = lib.snb_knn_pruned_workspace_bytes(B, N)
     ws = _ws(nbytes, x.device)
-    with torch.cuda.device(x.device), _op("knn", 2):     # the op's time includes the transpose and the library GEMM
+    with torch.cuda.device(x.device), _op("knn", 2):     # the op's time includes the transpose and the Gram GEMM
         xT = x.transpose(1, 2).contiguous()
-        gram = torch.bmm(xT, x)
+        gram, _ = gemm.conv_fwd(x, xT)                   # [B,N,N]: one "weight" per sample = its own points
         check(lib.snb_knn_pruned(ptr(xT), ptr(gram), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn_pruned")
     return idx
 
@@ -320,17 +322,16 @@ def knn_indices(x, k):
     """x: [B, C, N] float32 (channel-major, as the encoder holds it) -> idx [B, N, k] int32."""
     x = _cuda_f32(x, "x")
     B, C, N = x.shape
-    # Wide features: the TF32 Gram matrix prunes, exact fp32 re-evaluation decides (identical indices; parity-tested on B200).  On by
-    # default only where the arithmetic margin over the brute-force kernel is 2x or more (C >= 512) and the GEMM really runs on the
-    # tensor cores (TF32 matmul allowed); SNB_KNN_PRUNE=1 / 0 forces it on (for C >= 64) / off.
+    # Wide features: the TF32 Gram matrix (our tensor-core GEMM) prunes, exact fp32 re-evaluation decides (identical indices;
+    # parity-tested on B200).  On by default from C >= 256, where the brute-force kernel is FP32-issue bound;
+    # SNB_KNN_PRUNE=1 / 0 forces it on (for C >= 64) / off.  Shapes the GEMM does not tile (N % 32, C % 4) take the brute-force kernels.
     force = os.environ.get("SNB_KNN_PRUNE")
-    if (C & 3) == 0 and force != "0" and ((force == "1" and C >= 64) or (C >= 512 and torch.backends.cuda.matmul.allow_tf32)):
-        key = (C, N, int(k))
+    if (C & 3) == 0 and (N & 31) == 0 and force != "0" and ((force == "1" and C >= 64) or C >= 256):
+        key = (C, N, int(k), x.device.index)
         ok = _KNN_PRUNE_CHECKED.get(key)
         if ok is None and not torch.cuda.is_current_stream_capturing():
-            # First use of a shape in this process: both paths once, compared on the device.  The pruning bound assumes a GEMM at
-            # least as accurate as TF32 with fp32 accumulation; a process that lowered the fp32 matmul precision further (e.g.
-            # torch.set_float32_matmul_precision("medium")) would break it, and then the brute-force kernels keep serving -- loudly.
+            # First use of a shape on a device in this process: both paths once, compared on the device; should the indices ever
+            # differ the brute-force kernels keep serving that shape -- loudly.
             a, b = knn_indices_pruned(x, k), _knn_brute(x, k)
             ok = bool(torch.equal(a, b))
             _KNN_PRUNE_CHECKED[key] = ok
@@ -385,3 +386,56 @@ def gridding_reverse_backward(ptcloud, grid, grad_ptcloud, scale):
     with torch.cuda.device(grid.device), _op("gridding_rev_bwd", 1):
         check(_lib.load().snb_gridding_rev_bwd(ptr(ptcloud), ptr(grid), ptr(grad_ptcloud), B, int(scale), ptr(g), stream_ptr()), "gridding_rev_bwd")
     return g
+
+
+# ----------------------------------------------------------------------------- gridding loss / cubic feature sampling (GRNet)
+def gridding_dist_forward(ptcloud, bounds):
+    """Like gridding_forward with eight accumulators per vertex (one per corner role): grid [B,V,8], weights [B,n,8,3], idx [B,n,8]."""
+    ptcloud = _cuda_f32(ptcloud, "ptcloud")
+    B, n, _ = ptcloud.shape
+    lens = [int(bounds[2 * i + 1] - bounds[2 * i] + 1) for i in range(3)]
+    V = lens[0] * lens[1] * lens[2]
+    dev = ptcloud.device
+    grid = torch.empty(B, V, 8, device=dev)
+    w = torch.empty(B, n, 8, 3, device=dev)
+    ix = torch.empty(B, n, 8, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _op("gridding_dist_fwd", 1):
+        check(_lib.load().snb_gridding_dist_fwd(ptr(ptcloud), B, n, *[float(v) for v in bounds], ptr(grid), ptr(w), ptr(ix), stream_ptr()),
+              "gridding_dist_fwd")
+    return grid, w, ix
+
+
+def gridding_dist_backward(weights, indexes, grad_grid):
+    weights, grad_grid, indexes = _cuda_f32(weights, "grid_pt_weights"), _cuda_f32(grad_grid, "grad_grid"), _cuda_i32(indexes, "grid_pt_indexes")
+    B, n = indexes.shape[:2]
+    g = torch.empty(B, n, 3, device=weights.device)
+    with torch.cuda.device(weights.device), _op("gridding_dist_bwd", 1):
+        check(_lib.load().snb_gridding_dist_bwd(ptr(weights), ptr(indexes), ptr(grad_grid), B, n, grad_grid.shape[1], ptr(g), stream_ptr()),
+              "gridding_dist_bwd")
+    return g
+
+
+def cubic_sampling_forward(ptcloud, cubic_features, neighborhood_size):
+    """ptcloud [B,n,3] in grid units, cubic_features [B,C,S,S,S] -> point_features [B,n,(2 ns)^3,C], grid_pt_indexes [B,n,(2 ns)^3]."""
+    ptcloud, cubic_features = _cuda_f32(ptcloud, "ptcloud"), _cuda_f32(cubic_features, "cubic_features")
+    B, n, _ = ptcloud.shape
+    C, S = cubic_features.shape[1], cubic_features.shape[2]
+    V = (2 * int(neighborhood_size)) ** 3
+    dev = ptcloud.device
+    out = torch.empty(B, n, V, C, device=dev)
+    ix = torch.empty(B, n, V, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _op("cubic_sampling_fwd", 2):
+        check(_lib.load().snb_cubic_sampling_fwd(ptr(ptcloud), ptr(cubic_features), B, n, C, S, int(neighborhood_size), ptr(out), ptr(ix), stream_ptr()),
+              "cubic_sampling_fwd")
+    return out, ix
+
+
+def cubic_sampling_backward(grad_point_features, indexes, scale, neighborhood_size):
+    g = _cuda_f32(grad_point_features, "grad_point_features")
+    indexes = _cuda_i32(indexes, "grid_pt_indexes")
+    B, n, V, C = g.shape
+    S = int(scale)
+    gf = torch.empty(B, C, S, S, S, device=g.device)
+    with torch.cuda.device(g.device), _op("cubic_sampling_bwd", 1):
+        check(_lib.load().snb_cubic_sampling_bwd(ptr(g), ptr(indexes), B, n, C, S, int(neighborhood_size), ptr(gf), stream_ptr()), "cubic_sampling_bwd")
+    return gf

@@ -10,6 +10,47 @@ from ._lib import check, ptr, stream_ptr
 from .functional import _op
 
 
+class tf32_matmul:
+    """TF32 for the library GEMMs inside the block (host-side dispatch flag, restored on exit).  Used only where the reference's own
+    arithmetic is a TF32 convolution (the Gram-matrix form of conv3's backward) or where the product merely PRUNES candidates that
+    are re-evaluated exactly (kNN); nn.Linear layers keep fp32 like the reference's."""
+    def __enter__(self):
+        self.old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *a):
+        torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
+class ThinConv(torch.autograd.Function):
+    """y[g] = W x[g] for the THIN 1x1 convolutions (3-8 channels on one side: xyz inputs, xyz outputs, the 2-d lattice), whose rows
+    are shorter than a TMA box of the tensor-core GEMM: batched library GEMM with TF32 allowed in the forward AND in both backward
+    products (the reference runs these layers through cuDNN with TF32 allowed).  W [Co, Ci] or [G, Co, Ci], x [G, Ci, N]."""
+    @staticmethod
+    def forward(ctx, x, W):
+        ctx.save_for_backward(x, W)
+        with tf32_matmul():
+            return torch.matmul(W, x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        gx = gW = None
+        with tf32_matmul():
+            if ctx.needs_input_grad[0]:
+                gx = torch.matmul(W.transpose(-1, -2), gy)
+            if ctx.needs_input_grad[1]:
+                gW = torch.matmul(gy, x.transpose(-1, -2))
+                if W.dim() == 2:
+                    gW = gW.sum(0)
+        return gx, gW
+
+
+def thin_conv(x, W):
+    return ThinConv.apply(x, W)
+
+
 class EdgeReduce(torch.autograd.Function):
     """(a, c [B,C,N], idx [B,N,k] int32) -> umax, umin [B,C,N], S1, S2 [B,C] (float64) of u = a[idx] + c."""
     @staticmethod
@@ -246,10 +287,12 @@ def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, ne
     gx = gW = None
     if need_x:
         M = torch.matmul(Wd.t(), WA).to(dt)                       # [B,Ci,Ci] = W^T diag(a_b) W
-        gx = torch.bmm(M, x)
+        with tf32_matmul():                                       # the reference's arithmetic here is cuDNN's TF32 data gradient
+            gx = torch.bmm(M, x)
         gx += torch.matmul(b, Wd).to(dt).unsqueeze(-1)
     if need_w:
-        G = torch.bmm(x, x.transpose(1, 2)).double()              # [B,Ci,Ci]
+        with tf32_matmul():                                       # ... and its TF32 weight gradient
+            G = torch.bmm(x, x.transpose(1, 2)).double()          # [B,Ci,Ci]
         gW = torch.bmm(WA, G).sum(0) + torch.matmul(b.t(), x.sum(2).double())
     for g, idx in ((gmax, imax), (gmin, imin)):
         if g is None:
@@ -444,6 +487,42 @@ class ActConvRowReduce(torch.autograd.Function):
         gx, gW = conv_row_reduce_backward(x, W2, mean, imax, imin, gmean, gvar, gmax, gmin, True, ctx.needs_input_grad[1])
         gh, gts = pro.backward(gx)
         return (gh, gW.view(ctx.wshape) if gW is not None else None, None, *gts)
+
+
+class BcastActConv(torch.autograd.Function):
+    """y[p, :, b] = W[p] . leaky_relu(A[p,:,b] * xhat[p] + D[p,:,b]) for every sample b, with xhat [P, C, L] SHARED by the samples
+    (the decoders' first layer: the lattice response is batch independent, only the AdaIN.BN.SE scale/shift A, D [P, C, B] differ).
+    The [P, C, B, L] activated tensor is never formed: the GEMM reads xhat (L2 resident) once per sample tile and applies (A, D) in
+    its prologue; the weight gradient does the same.  Returns y [P, Cout, B, L] and its per-(p, c, b) row statistics."""
+    @staticmethod
+    def forward(ctx, xhat, A, D, W, slope):
+        xhat, A, D = xhat.contiguous(), A.contiguous().float(), D.contiguous().float()
+        L, B = xhat.shape[-1], A.shape[-1]
+        y, st = gemm.conv_fwd(xhat, W, scale=A, shift=D, slope=slope, seg=L, stats_seg=L, x_repeat=B)
+        ctx.save_for_backward(xhat, A, D, W)
+        ctx.slope = float(slope)
+        mean, var = st["mean"].reshape(y.shape[:-1]), st["var"].reshape(y.shape[:-1])
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, *_):
+        xhat, A, D, W = ctx.saved_tensors
+        gy = gy.contiguous()
+        L, B = xhat.shape[-1], A.shape[-1]
+        gW = gemm.conv_wgrad(gy, xhat, batched=True, scale=A, shift=D, slope=ctx.slope, seg=L, x_repeat=B) if ctx.needs_input_grad[3] else None
+        gx = gemm.conv_dgrad(gy, W)                                   # [P, C, B, L]: gradient w.r.t. the activated tensor
+        R = A.numel()
+        gh = torch.empty_like(xhat)
+        gsc, gsh = torch.empty_like(A), torch.empty_like(D)
+        with torch.cuda.device(xhat.device), _op("row_affine_act_bwd", 1):
+            check(_lib.load().snb_row_affine_act_bwd(ptr(gx), ptr(xhat), ptr(A), ptr(D), R, L, B, ctx.slope, ptr(gh), ptr(gsc), ptr(gsh),
+                                                     stream_ptr()), "row_affine_act_bwd")
+        return gh, gsc, gsh, gW, None
+
+
+def bcast_act_conv(xhat, A, D, W, slope=0.0):
+    return BcastActConv.apply(xhat, A, D, W, slope)
 
 
 def conv1x1(x, W, stats_seg=None):

@@ -51,9 +51,8 @@ def _weight(W, G, name):
 
 def stat_tiles(N, block_n=0):
     """(number of statistics tiles along N, their width) of a forward call."""
-    t = _lib.load().snb_gemm_tf32_tiles(int(N), int(block_n))
-    bn = block_n if block_n > 0 else (256 if N >= 256 else (N + 63) // 64 * 64)
-    return t, bn // 2
+    lib = _lib.load()
+    return lib.snb_gemm_tf32_tiles(int(N), int(block_n)), lib.snb_gemm_tf32_block_n(int(N), int(block_n)) // 2
 
 
 def _run(desc, dev, what, nbytes=None):
@@ -61,25 +60,31 @@ def _run(desc, dev, what, nbytes=None):
         check(_lib.load().snb_gemm_tf32(ctypes.byref(desc), stream_ptr()), what)
 
 
-def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, minmax=False, store=True):
+def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, minmax=False, store=True, x_repeat=1):
     """y[g] = W . T(x[g]),  T(x) = leaky_relu(scale*x + shift, slope) per (g, channel, segment of `seg` positions) when scale is given.
+    x_repeat = R > 1: x [G, Cin, n] is tiled R times along the position axis (N = R*n output positions; scale/shift still per segment of
+    the long axis) -- the decoder's first layer, whose input is the same lattice response for every sample.
     Returns (y or None, stats) with stats = {} or {"mean","var": [G, Cout, Npos/stats_seg]} (biased variance of every segment of
     `stats_seg` positions of the OUTPUT rows) and, with minmax, {"max","min","imax","imin": [G, Cout]} over all positions."""
-    x, G, Cin, N = _act3(x, "x")
+    x, G, Cin, n_in = _act3(x, "x")
+    N = n_in * int(x_repeat)
     W = _weight(W, G, "W")
     Cout = W.shape[-2]
     if W.shape[-1] != Cin:
         raise SnbValueError(f"weight {tuple(W.shape)} does not match {Cin} input channels")
-    if N % 32 != 0 or Cin % 4 != 0:
-        raise SnbValueError(f"conv_fwd needs positions % 32 == 0 and Cin % 4 == 0 (got {N}, {Cin})")
+    if n_in % 32 != 0 or Cin % 4 != 0:
+        raise SnbValueError(f"conv_fwd needs positions % 32 == 0 and Cin % 4 == 0 (got {n_in}, {Cin})")
     dev = x.device
     d = GemmDesc()
     d.mode, d.G, d.BI, d.M, d.N, d.K = FWD, G, 1, Cout, N, Cin
     d.A, d.lda, d.a_batch_stride = _p(W), W.stride(-2), (W.stride(0) if W.dim() == 3 else 0)
-    d.B, d.ldb, d.b_batch_stride = _p(x), N, Cin * N
+    d.B, d.ldb, d.b_batch_stride = _p(x), n_in, Cin * n_in
+    if x_repeat > 1:
+        d.b_pos_mod = n_in
     y = None
     if store:
-        y = torch.empty((G, Cout) + tuple(x.shape[2:]), device=dev, dtype=torch.float32)
+        yshape = (G, Cout) + ((int(x_repeat),) + tuple(x.shape[2:]) if x_repeat > 1 else tuple(x.shape[2:]))
+        y = torch.empty(yshape, device=dev, dtype=torch.float32)
         d.D, d.ldd, d.d_batch_stride = _p(y), N, Cout * N
     d.store = 1 if store else 0
     keep = [x, W, y]
@@ -141,12 +146,13 @@ def conv_dgrad(gy, W):
     return gx
 
 
-def conv_wgrad(gy, x, batched, scale=None, shift=None, slope=0.0, seg=None):
+def conv_wgrad(gy, x, batched, scale=None, shift=None, slope=0.0, seg=None, x_repeat=1):
     """gW = sum over (batch,) positions of gy . T(x)^T: gy [G, Cout, *pos], x [G, Cin, *pos] -> [Cout, Cin] (batched=False: the
-    batch is reduced) or [G, Cout, Cin] (batched=True: one weight per batch entry).  T as in conv_fwd (the forward's prologue)."""
+    batch is reduced) or [G, Cout, Cin] (batched=True: one weight per batch entry).  T as in conv_fwd (the forward's prologue);
+    x_repeat as in conv_fwd (batched only)."""
     gy, G, Cout, N = _act3(gy, "gy")
     x, G2, Cin, N2 = _act3(x, "x")
-    if G2 != G or N2 != N:
+    if G2 != G or N2 * int(x_repeat) != N or (x_repeat > 1 and not batched):
         raise SnbValueError("gy and x must agree in batch and positions")
     if N % 4 != 0:
         raise SnbValueError("conv_wgrad needs positions % 4 == 0")
@@ -156,7 +162,9 @@ def conv_wgrad(gy, x, batched, scale=None, shift=None, slope=0.0, seg=None):
     d = GemmDesc()
     d.mode, d.G, d.BI, d.M, d.N, d.K = WGRAD, GO, BI, Cout, Cin, N
     d.A, d.lda, d.a_batch_stride = _p(gy), N, Cout * N
-    d.B, d.ldb, d.b_batch_stride = _p(x), N, Cin * N
+    d.B, d.ldb, d.b_batch_stride = _p(x), N2, Cin * N2
+    if x_repeat > 1:
+        d.b_pos_mod = N2
     d.D, d.ldd, d.d_batch_stride = _p(gW), Cin, Cout * Cin
     d.store, d.split = 2, 0                                   # TMA reduce-add into the zeroed gradient; split-K chosen by the library
     keep = [gy, x, gW]

@@ -15,7 +15,9 @@ import torch
 
 
 class GraphedForwardBackward:
-    def __init__(self, loss_fn, params, example_inputs, warmup=3):
+    def __init__(self, loss_fn, params, example_inputs, warmup=3, zero_fn=None):
+        """zero_fn: when the gradients live in a persistent buffer (sparenet_b200.dist.GradArena) they are zeroed by this callable --
+        captured at the head of the graph -- instead of being dropped (p.grad = None) before the capture."""
         self.params = [p for p in params if p.requires_grad]
         self.static_inputs = [torch.empty_like(t, device=self.params[0].device) for t in example_inputs]
         for s, t in zip(self.static_inputs, example_inputs):
@@ -25,14 +27,20 @@ class GraphedForwardBackward:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                for p in self.params:
-                    p.grad = None
+                if zero_fn is not None:
+                    zero_fn()
+                else:
+                    for p in self.params:
+                        p.grad = None
                 loss_fn(*self.static_inputs).backward()
         torch.cuda.current_stream(dev).wait_stream(side)
-        for p in self.params:
-            p.grad = None
+        if zero_fn is None:
+            for p in self.params:
+                p.grad = None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if zero_fn is not None:
+                zero_fn()
             self.static_loss = loss_fn(*self.static_inputs)
             self.static_loss.backward()
 

@@ -48,6 +48,10 @@ def conv_row_reduce(x, W):
     return mean, var, h.amax(-1), h.amin(-1)
 
 
+def thin_conv(x, W):
+    return torch.matmul(W, x)
+
+
 def row_stats_nograd(h):
     return row_stats(h.detach())
 
@@ -60,6 +64,13 @@ def conv1x1(x, W, stats_seg=None):
         return y
     assert stats_seg == y.shape[-1]
     return (y,) + row_stats(y)
+
+
+def bcast_act_conv(xhat, A, D, W, slope=0.0):
+    P, C, L = xhat.shape
+    B = A.shape[-1]
+    x = row_affine_act(xhat, A, D, slope=slope, in_div=B, out_shape=(P, C, B, L))
+    return conv1x1(x, W, stats_seg=L)
 
 
 class Prologue:
@@ -84,5 +95,5 @@ def act_conv_row_reduce(W, pro, h):
 def patch(monkeypatch):
     from sparenet_b200 import fused
     for name in ("edge_reduce", "edge_reduce_sel", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce",
-                 "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce"):
+                 "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce", "bcast_act_conv", "thin_conv"):
         monkeypatch.setattr(fused, name, globals()[name])

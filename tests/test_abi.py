@@ -66,3 +66,36 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, os.path.join(dp, f)
+
+
+def test_integration_snippet_signature_matches_header():
+    """INTEGRATION.md section B / docs/integration_snippet_chamfer.py: the ctypes argument list a maintainer would copy must be the
+    one include/sparenet_b200.h declares (round 1 shipped a 10-argument example for the 12-argument function)."""
+    import importlib.util
+    from sparenet_b200 import _lib
+    spec = importlib.util.spec_from_file_location("integration_snippet_chamfer", os.path.join(ROOT, "docs", "integration_snippet_chamfer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)          # loads the library and sets argtypes; no compute
+    res, args = _lib.SIGNATURES["snb_chamfer_fwd"]
+    assert list(mod._lib.snb_chamfer_fwd.argtypes) == list(args) and mod._lib.snb_chamfer_fwd.restype is res
+    assert len(args) == 12
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    body = open(os.path.join(ROOT, "docs", "integration_snippet_chamfer.py")).read()
+    assert body[body.index("import ctypes"):] in doc, "INTEGRATION.md must quote docs/integration_snippet_chamfer.py verbatim"
+
+
+def test_gemm_desc_struct_matches_header():
+    """The ctypes mirror of snb_gemm_desc must list the header's fields in order."""
+    from sparenet_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "sparenet_b200.h")).read()
+    body = src[src.index("typedef struct snb_gemm_desc {"):src.index("} snb_gemm_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        head, *rest = decl.split(",")
+        names.append(re.findall(r"([A-Za-z_0-9]+)\s*$", head.strip())[0])
+        names += [r.strip().lstrip("*") for r in rest]
+    assert names == [f[0] for f in _lib.GemmDesc._fields_]

@@ -58,3 +58,47 @@ def test_shard_batch_covers_everything():
             assert cuts[0][0] == 0 and cuts[-1][1] == gb
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+
+
+def _arena_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparenet_b200.dist import GradArena, allreduce_gradients, shard_batch
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 17), torch.nn.ReLU(), torch.nn.Linear(17, 3), torch.nn.Linear(3, 1, bias=False))
+    arena = GradArena(net.parameters())
+    views = [p.grad for p in net.parameters()]
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10.0
+    lo, hi = shard_batch(8, rank, world)
+    ok = True
+    for step in range(2):                      # the views must survive a second step (zero() instead of zero_grad(set_to_none))
+        arena.zero()
+        (net(x[lo:hi]).pow(2).sum() / 8.0).backward()
+        ok &= all(p.grad is v for p, v in zip(net.parameters(), views))                       # autograd accumulated IN the arena
+        calls = arena.allreduce(world, chunk_bytes=64)                                         # several in-place collectives
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 17), torch.nn.ReLU(), torch.nn.Linear(17, 3), torch.nn.Linear(3, 1, bias=False))
+        ref.load_state_dict(net.state_dict())
+        (ref(x).pow(2).sum() / 8.0).backward()
+        ok &= all(torch.allclose(a.grad * world, b.grad, rtol=1e-5, atol=1e-6) for a, b in zip(net.parameters(), ref.parameters()))
+    ok &= all(v.data_ptr() % 16 == 0 for v in views)
+    # the flat-bucket path: nothing to reduce must be a no-op, mixed dtypes must not be promoted
+    empty = [torch.nn.Parameter(torch.zeros(3))]
+    ok &= allreduce_gradients(empty, world) == 0
+    a, b = torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(4, dtype=torch.float64))
+    a.grad, b.grad = torch.full((4,), float(rank)), torch.full((4,), float(rank) + 0.25, dtype=torch.float64)
+    allreduce_gradients([a, b], world)
+    ok &= a.grad.dtype == torch.float32 and b.grad.dtype == torch.float64
+    ok &= torch.allclose(a.grad, torch.full((4,), 0.5)) and torch.allclose(b.grad, torch.full((4,), 0.75, dtype=torch.float64))
+    out[rank] = (bool(ok), calls)
+    dist.destroy_process_group()
+
+
+def test_two_rank_grad_arena_allreduce_in_place():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_arena_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        ok, calls = out[rank]
+        assert ok and calls >= 2

@@ -162,6 +162,8 @@ def test_conv_row_reduce_forward_backward(cuda, B, Ci, Co, N):
         ex = (x1.grad.double() - x2.grad).abs().max().item() / x2.grad.abs().max().item()
         ew = (W1.grad.double() - W2.grad).abs().max().item() / W2.grad.abs().max().item()
         print(f"[conv_row_reduce] B={B} {Ci}->{Co} N={N}: grad err/scale x={ex:.2e} W={ew:.2e}")
-        assert ex < 2e-5 and ew < 2e-5
+        # the two Gram-matrix products of the backward run in TF32 by design (they stand for cuDNN's TF32 data / weight gradients):
+        # TF32 bound instead of the fp32 one
+        assert ex < 2e-3 and ew < 2e-3
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

@@ -52,13 +52,39 @@ class _tf32:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.old
 
 
-def _band(a_fp32, a_tf32, ours, what, factor=3.0, floor=2e-3):
+def _band(a_fp32, a_tf32, ours, what, factor=3.0, floor=5e-3):
+    """RMS distance to the reference's fp32 run, against the reference's own TF32-vs-fp32 RMS band.  (The maximum over the ~10^5..10^6
+    coordinates is printed but not asserted: a TF32-sized perturbation of the features flips a few k-nearest-neighbour sets and
+    ReLU / max-pool switches, so single points move by 10-30 % of the cloud's extent between the reference's OWN fp32 and TF32 runs.)"""
     scale = a_fp32.abs().max().item()
-    band = (a_tf32 - a_fp32).abs().max().item()
-    err = (ours - a_fp32).abs().max().item()
-    print(f"[{what}] scale {scale:.3g}: reference TF32-vs-fp32 band {band / scale:.2e}, ours-vs-fp32 {err / scale:.2e}")
-    assert err <= max(factor * band, floor * scale), what
-    return band / scale, err / scale
+    rms = lambda t: t.pow(2).mean().sqrt().item()
+    band, err = rms(a_tf32 - a_fp32) / scale, rms(ours - a_fp32) / scale
+    print(f"[{what}] scale {scale:.3g}: reference TF32-vs-fp32 band rms {band:.2e} (max {(a_tf32 - a_fp32).abs().max().item() / scale:.2e}), "
+          f"ours-vs-fp32 rms {err:.2e} (max {(ours - a_fp32).abs().max().item() / scale:.2e})")
+    assert err <= max(factor * band, floor), what
+    return band, err
+
+
+def test_generator_wiring_exact_in_fp32_with_library_gemm(cuda, monkeypatch):
+    """The fused algebra + point kernels + module wiring with the dense convolutions on fp32 library GEMMs (the LIBRARY_GEMM
+    measurement switch, TF32 off everywhere): agreement with the restatement at fp32 re-association level."""
+    from sparenet_b200.dropin.models import sparenet_generator as M
+    monkeypatch.setattr(M, "LIBRARY_GEMM", True)
+    kw = dict(n_primitives=8, hide_size=256, bottleneck_size=256, num_points=8 * 512)
+    ref = G.SpareNetGenerator(ops=GpuOps, **kw)
+    torch.manual_seed(0)
+    ref.apply(G.init_weights)
+    ref = ref.to(cuda).train()
+    mine = M.SpareNetGenerator(use_SElayer=True, use_AdaIn="share", encode="Residualnet", **kw).to(cuda).train()
+    mine.load_state_dict(ref.state_dict())
+    torch.manual_seed(1)
+    data = {"partial_cloud": (torch.rand(4, 1024, 3, device=cuda) - 0.5)}
+    with _tf32(False):
+        c1, m1, r1, l1 = ref(data)
+        c2, m2, r2, l2 = mine(data)
+    # B=4 batch-norms amplify fp32 re-association noise (float64 CPU test: 1e-13); hold to 1% of the coordinate scale
+    assert torch.allclose(c1, c2, rtol=1e-2, atol=2e-3), (c1 - c2).abs().max()
+    assert abs(l1.item() - l2.item()) <= 1e-2 * abs(l1.item()) + 1e-8
 
 
 def test_generator_matches_restatement(cuda):
@@ -104,19 +130,18 @@ def test_refiner_matches_restatement_given_same_inputs(cuda):
     coarse = (torch.rand(3, 2048, 3, device=cuda) - 0.5) * 0.8
     partial = (torch.rand(3, 3, 512, device=cuda) - 0.5)
     c1, c1t, c2 = (coarse.clone().requires_grad_() for _ in range(3))
+    w = torch.randn(3, 2048, 3, device=cuda)
     with _tf32(False):
         o1, l1 = ref(c1.transpose(1, 2).contiguous(), partial, c1)
-    ref.load_state_dict(sd0)
+        ((o1 * w).sum() + l1).backward()
+    ref.load_state_dict(sd0)          # (in-place: only after the first graph has been used)
+    ref.zero_grad()
     with _tf32(True):
         o1t, _ = ref(c1t.transpose(1, 2).contiguous(), partial, c1t)
+        (o1t * w).sum().backward()
     o2, l2 = mine(c2.transpose(1, 2).contiguous(), partial, c2)
     assert torch.equal(l1, l2)
-    _band(o1, o1t, o2, "refined cloud B=3 N=2048")
-    w = torch.randn_like(o1)
-    with _tf32(False):
-        ((o1 * w).sum() + l1).backward()
-    with _tf32(True):
-        (o1t * w).sum().backward()
+    _band(o1.detach(), o1t.detach(), o2.detach(), "refined cloud B=3 N=2048")
     ((o2 * w).sum() + l2).backward()
     # 7 BatchNorms over a batch of 3 clouds and ReLU / max-pool switches: a TF32-sized perturbation flips a few of them, so the
     # gradient is compared as a relative L2 distance against the same distance between the reference's own TF32 and fp32 runs

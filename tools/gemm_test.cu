@@ -48,6 +48,7 @@ struct Case {
   const char* name;
   int mode, G, BI, M, N, K;
   int lda_pad, a_batched, block_n, store, split, xform, seg, stats, minmax;
+  int bmod;   // > 0: the activation operand holds bmod positions, tiled along the position axis
 };
 
 static const Case CASES[] = {
@@ -71,6 +72,9 @@ static const Case CASES[] = {
     {"wgrad xform G=2 seg=256", 2, 2, 1, 128, 256, 512, 0, 0, 0, 1, 1, 1, 256, 0, 0},
     {"wgrad xform BI=2 seg=K N=160", 2, 1, 2, 128, 160, 256, 0, 0, 0, 1, 1, 1, 256, 0, 0},
     {"wgrad auto split", 2, 1, 8, 256, 128, 2048, 0, 0, 0, 2, 0, 0, 0, 0, 0},
+    {"fwd tiled B (bmod 512) xform seg=512 stats", 0, 2, 1, 136, 2048, 72, 0, 1, 0, 1, 0, 1, 512, 1, 0, 512},
+    {"wgrad tiled B (bmod 256) xform seg=256", 2, 2, 1, 136, 96, 1024, 0, 0, 0, 2, 1, 1, 256, 0, 0, 256},
+    {"wgrad N=1056 auto block_n", 2, 1, 1, 200, 1056, 256, 0, 0, 0, 2, 1, 0, 0, 0, 0, 0},
 };
 static const int NCASES = sizeof(CASES) / sizeof(CASES[0]);
 
@@ -106,8 +110,8 @@ static void setup(Problem& P, const Case& c) {
     P.lda = c.K + c.lda_pad;
     P.a_bs = (long long)c.M * P.lda;
     P.a_elems = (size_t)(c.a_batched ? c.G : 1) * P.a_bs;
-    P.ldb = c.N;
-    P.b_bs = (long long)c.K * c.N;
+    P.ldb = c.bmod > 0 ? c.bmod : c.N;
+    P.b_bs = (long long)c.K * P.ldb;
     P.b_elems = (size_t)c.G * P.b_bs;
     P.cin = c.K;
   } else if (c.mode == 1) {  // A = W [Ga, K rows, M]; B [G, K, N]
@@ -122,15 +126,15 @@ static void setup(Problem& P, const Case& c) {
     P.lda = c.K;
     P.a_bs = (long long)c.M * c.K;
     P.a_elems = (size_t)P.act_batches * P.a_bs;
-    P.ldb = c.K;
-    P.b_bs = (long long)c.N * c.K;
+    P.ldb = c.bmod > 0 ? c.bmod : c.K;
+    P.b_bs = (long long)c.N * P.ldb;
     P.b_elems = (size_t)P.act_batches * P.b_bs;
     P.cin = c.N;
   }
   P.ldd = c.N;
   P.d_bs = (long long)c.M * c.N;
   P.d_elems = (size_t)c.G * P.d_bs;
-  P.bn = (c.block_n > 0 ? c.block_n : (c.N >= 256 ? 256 : (c.N + 63) / 64 * 64)) / 2;   // width of one statistics tile = block_n / 2
+  P.bn = snb_gemm_tf32_block_n(c.N, c.block_n) / 2;   // width of one statistics tile = block_n / 2
   P.nt = snb_gemm_tf32_tiles(c.N, c.block_n);
   P.p_elems = (size_t)c.G * c.M * P.nt;
   const int npos = c.mode == 2 ? c.K : c.N;
@@ -166,7 +170,8 @@ static double ref_elem(const Problem& P, int g, int m, int n, int conv) {
   if (c.mode == 0) {
     const float* A = P.A.data() + (c.a_batched ? (size_t)g * P.a_bs : 0) + (size_t)m * P.lda;
     const float* B = P.B.data() + (size_t)g * P.b_bs;
-    for (int k = 0; k < c.K; ++k) acc += (double)cv(A[k]) * (double)cv(xf(P, B[(size_t)k * P.ldb + n], g, k, n));
+    const int nb = c.bmod > 0 ? n % c.bmod : n;
+    for (int k = 0; k < c.K; ++k) acc += (double)cv(A[k]) * (double)cv(xf(P, B[(size_t)k * P.ldb + nb], g, k, n));
   } else if (c.mode == 1) {
     const float* A = P.A.data() + (c.a_batched ? (size_t)g * P.a_bs : 0);
     const float* B = P.B.data() + (size_t)g * P.b_bs;
@@ -176,7 +181,7 @@ static double ref_elem(const Problem& P, int g, int m, int n, int conv) {
       const int b = g * c.BI + bi;
       const float* A = P.A.data() + (size_t)b * P.a_bs + (size_t)m * P.lda;
       const float* B = P.B.data() + (size_t)b * P.b_bs + (size_t)n * P.ldb;
-      for (int k = 0; k < c.K; ++k) acc += (double)cv(A[k]) * (double)cv(xf(P, B[k], b, n, k));
+      for (int k = 0; k < c.K; ++k) acc += (double)cv(A[k]) * (double)cv(xf(P, B[c.bmod > 0 ? k % c.bmod : k], b, n, k));
     }
   }
   if (c.store == 2) acc += P.D0[((size_t)g * c.M + m) * c.N + n];
@@ -247,6 +252,7 @@ static snb_gemm_desc make_desc(const Problem& P, const Dev& d) {
   g.pmin = d.pmin;
   g.pimax = d.pimax;
   g.pimin = d.pimin;
+  g.b_pos_mod = c.bmod;
   return g;
 }
 
