@@ -192,6 +192,7 @@ def build_gpu(args, dev, rank):
     from sparenet_b200.dropin.cuda.chamfer_distance import ChamferDistance, ChamferDistanceMean
     from sparenet_b200.dropin.models.sparenet_generator import SpareNetGenerator
     from sparenet_b200.dropin.utils.model_init import init_weights  # utils/model_init.py:137-159
+    from sparenet_b200 import functional as F_memo
 
     # Dense 1x1 convolutions run on the repository's own tcgen05 TF32 GEMM (the reference: cuDNN with TF32 allowed, torch's default);
     # nn.Linear layers stay fp32 like the reference's (torch default: matmul TF32 off).  --library-gemm restores round 1's cuDNN/cuBLAS
@@ -239,12 +240,16 @@ def build_gpu(args, dev, rank):
             net.stage_hook = stage_hook
             coarse, middle, refine, loss_mst = net({"partial_cloud": partial})
             torch.cuda.current_stream(dev).wait_stream(side_stream)
-            loss = pending["coarse"] + pending["middle"] + cd_mean(refine, gt).mean() + loss_mst.mean() * 0.1
+            rest = pending["coarse"] + pending["middle"]
         else:
             net.stage_hook = None
             coarse, middle, refine, loss_mst = net({"partial_cloud": partial})
-            loss = cd_mean(coarse, gt).mean() + cd_mean(middle, gt).mean() + cd_mean(refine, gt).mean() + loss_mst.mean() * 0.1
-        d1, _ = cd(refine, gt)
+            rest = cd_mean(coarse, gt).mean() + cd_mean(middle, gt).mean()
+        # the reference evaluates Chamfer(refine, gt) twice (ChamferDistanceMean, then the consistency term,
+        # runners/sparenet_runner.py:87,103): inside this scope the second, identical search reuses the first one's result
+        with F_memo.chamfer_reuse():
+            loss = rest + cd_mean(refine, gt).mean() + loss_mst.mean() * 0.1
+            d1, _ = cd(refine, gt)
         return loss + torch.mean(d1).mean() * 0.5
 
     arena = None
@@ -584,7 +589,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "configs[1]: SpareNet generator + CD loss, synthetic ShapeNet B=32 2048->16384 pts", "local_batch": args.batch,
                        "global_batch": Bg, "n_out": N_OUT, "n_partial": N_PARTIAL, "n_primitives": N_PRIM, "k": 8,
-                       "losses": "3xChamferDistanceMean + 0.1*expansion + 0.5*consistency CD, Adam step", "parallelism": f"dp{world}",
+                       "losses": "3xChamferDistanceMean + 0.1*expansion + 0.5*consistency CD, Adam step; the consistency term reuses the "
+                                 "Chamfer(refine, gt) search of the loss term just before it (explicit functional.chamfer_reuse() scope: "
+                                 "3 searches per step instead of the reference's 4, identical values)", "parallelism": f"dp{world}",
                        "l2": "working set per step (GBs of activations) exceeds the 126 MB L2; no explicit flush", "execution": graph_note,
                        "streams": ("coarse/middle Chamfer losses on a side stream beside the refiner's MDS" if step.overlap["on"] else "single stream")},
             "clocks": clocks, "gpu_launches": launches,

@@ -168,6 +168,18 @@ int snb_row_act_bwd_reduce(const float* gy, const float* h, const float* scale, 
 int snb_row_norm_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, const float* mean,
                          const float* gmean, const float* gvar, long long R, int L, float slope, float* gh, void* stream);
 
+/* Pooled tail: vmax / vmean [R] = max / mean over the row of leaky_relu(scale*h + shift) (first position imax on ties) without
+ * storing the activated row -- the encoder's [max | mean over points] output (models/sparenet_generator.py:234-242).  Backward
+ * in the same two phases as above: _bwd_reduce returns gscale / gshift for gy = gmean/L + [l == imax] gmax, _bwd writes
+ * gh = d*scale + gstat_mean/L + 2 gstat_var (h - mean)/L. */
+int snb_row_act_pool_fwd(const float* h, const float* scale, const float* shift, long long R, int L, float slope,
+                         float* vmax, int* imax, float* vmean, void* stream);
+int snb_row_act_pool_bwd_reduce(const float* h, const float* scale, const float* shift, const float* gmax, const float* gmean,
+                                const int* imax, long long R, int L, float slope, float* gscale, float* gshift, void* stream);
+int snb_row_act_pool_bwd(const float* h, const float* scale, const float* shift, const float* mean, const float* gmax,
+                         const float* gmean, const int* imax, const float* gstat_mean, const float* gstat_var, long long R, int L,
+                         float slope, float* gh, void* stream);
+
 /* ---- TF32 tensor-core GEMM of the 1x1-conv / AdaIN-folding stacks (csrc/gemm_tc.cu: tcgen05.mma + TMEM + TMA) ----------
  * replaces the cuDNN/cuBLAS calls behind nn.Conv1d / nn.Conv2d(kernel_size=1) in models/sparenet_generator.py:146-186,
  * 188-242 (EdgeConv), :593-646 (PointNetRes), :984-991,1044-1062 (GridDecoder) on channel-major activations

@@ -70,6 +70,9 @@ SIGNATURES = {
     "snb_gemm_tf32": (c_int, [ctypes.POINTER(GemmDesc), P]),
     "snb_gemm_tf32_tiles": (c_int, [c_int, c_int]),
     "snb_gemm_tf32_block_n": (c_int, [c_int, c_int]),
+    "snb_row_act_pool_fwd": (c_int, [P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P, P]),
+    "snb_row_act_pool_bwd_reduce": (c_int, [P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P]),
+    "snb_row_act_pool_bwd": (c_int, [P, P, P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P]),
     "snb_gridding_fwd": (c_int, [P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P, P]),
     "snb_gridding_bwd": (c_int, [P, P, P, c_int, c_int, ctypes.c_longlong, P, P]),
     "snb_gridding_rev_fwd": (c_int, [P, c_int, c_int, P, P]),

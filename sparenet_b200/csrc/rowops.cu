@@ -353,6 +353,135 @@ __global__ void __launch_bounds__(ROW_THREADS) row_norm_act_bwd_kernel(const flo
   }
 }
 
+// ---- pooled tail: max and mean over the row of act(scale*h + shift), without materialising the activated row -------------------
+// (the encoder's output, models/sparenet_generator.py:234-242: LeakyReLU(BN(conv5)) -> [max over points | mean over points])
+__global__ void __launch_bounds__(ROW_THREADS) row_act_pool_fwd_kernel(const float* __restrict__ h, const float* __restrict__ scale,
+                                                                        const float* __restrict__ shift, long long R, int L, float slope,
+                                                                        float* __restrict__ vmax, int* __restrict__ imax, float* __restrict__ vmean) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float sc = scale[r], sh = shift[r];
+  const float* __restrict__ p = h + r * L;
+  float best = -INFINITY, sum = 0.f;
+  int bi = 0x7fffffff;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i];
+      const float z0 = act(__fmaf_rn(v.x, sc, sh), slope), z1 = act(__fmaf_rn(v.y, sc, sh), slope);
+      const float z2 = act(__fmaf_rn(v.z, sc, sh), slope), z3 = act(__fmaf_rn(v.w, sc, sh), slope);
+      sum += (z0 + z1) + (z2 + z3);
+      if (z0 > best) { best = z0; bi = 4 * i; }
+      if (z1 > best) { best = z1; bi = 4 * i + 1; }
+      if (z2 > best) { best = z2; bi = 4 * i + 2; }
+      if (z3 > best) { best = z3; bi = 4 * i + 3; }
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) {
+      const float z = act(__fmaf_rn(p[i], sc, sh), slope);
+      sum += z;
+      if (z > best) { best = z; bi = i; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }   // first position on ties
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) {
+    vmax[r] = best;
+    imax[r] = bi;
+    vmean[r] = sum / (float)L;
+  }
+}
+
+// gy[r,l] = gmean[r]/L + (l == imax[r]) gmax[r];  d = gy * act'(scale*h + shift);  gscale = sum_l d*h, gshift = sum_l d
+__global__ void __launch_bounds__(ROW_THREADS) row_act_pool_bwd_reduce_kernel(const float* __restrict__ h, const float* __restrict__ scale,
+                                                                               const float* __restrict__ shift, const float* __restrict__ gmax,
+                                                                               const float* __restrict__ gmean, const int* __restrict__ imax,
+                                                                               long long R, int L, float slope, float* __restrict__ gscale,
+                                                                               float* __restrict__ gshift) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float sc = scale[r], sh = shift[r], gm = gmean[r] / (float)L, gx = gmax[r];
+  const int ix = imax[r];
+  const float* __restrict__ p = h + r * L;
+  float as = 0.f, ab = 0.f;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g = (4 * i + j) == ix ? gm + gx : gm;
+        const float d = __fmaf_rn(e[j], sc, sh) > 0.f ? g : g * slope;
+        as = __fmaf_rn(d, e[j], as);
+        ab += d;
+      }
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) {
+      const float v = p[i];
+      const float g = i == ix ? gm + gx : gm;
+      const float d = __fmaf_rn(v, sc, sh) > 0.f ? g : g * slope;
+      as = __fmaf_rn(d, v, as);
+      ab += d;
+    }
+  }
+  as = warp_sum(as);
+  ab = warp_sum(ab);
+  if (lane == 0) {
+    gscale[r] = as;
+    gshift[r] = ab;
+  }
+}
+
+// gh = d*scale + gmean_stat/L + 2 gvar_stat (h - mean)/L   (the statistics' gradients come back from the closed-form tail)
+__global__ void __launch_bounds__(ROW_THREADS) row_act_pool_bwd_kernel(const float* __restrict__ h, const float* __restrict__ scale,
+                                                                        const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                        const float* __restrict__ gmax, const float* __restrict__ gmean,
+                                                                        const int* __restrict__ imax, const float* __restrict__ gstat_mean,
+                                                                        const float* __restrict__ gstat_var, long long R, int L, float slope,
+                                                                        float* __restrict__ gh) {
+  const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float invL = 1.f / (float)L;
+  const float sc = scale[r], sh = shift[r], gm = gmean[r] * invL, gx = gmax[r], m = mean[r];
+  const float a = gstat_mean[r] * invL, b = 2.f * gstat_var[r] * invL;
+  const int ix = imax[r];
+  const float* __restrict__ p = h + r * L;
+  float* __restrict__ o = gh + r * L;
+  if ((L & 3) == 0) {
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+    float4* __restrict__ o4 = reinterpret_cast<float4*>(o);
+    for (int i = lane; i < (L >> 2); i += 32) {
+      const float4 v = p4[i];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      float w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g = (4 * i + j) == ix ? gm + gx : gm;
+        const float d = __fmaf_rn(e[j], sc, sh) > 0.f ? g : g * slope;
+        w[j] = __fmaf_rn(d, sc, __fmaf_rn(b, e[j] - m, a));
+      }
+      o4[i] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) {
+      const float v = p[i];
+      const float g = i == ix ? gm + gx : gm;
+      const float d = __fmaf_rn(v, sc, sh) > 0.f ? g : g * slope;
+      o[i] = __fmaf_rn(d, sc, __fmaf_rn(b, v - m, a));
+    }
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -434,6 +563,40 @@ SNB_API int snb_row_norm_act_bwd(const float* gy, const float* h, const float* s
   if (R == 0) return SNB_OK;
   if (R > 0x3fffffffLL) return SNB_ELIMIT;
   row_norm_act_bwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, mean, gmean, gvar, R, L, slope, gh);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+// pooled tail (max / mean over the row of act(scale*h + shift)); see the kernels above
+SNB_API int snb_row_act_pool_fwd(const float* h, const float* scale, const float* shift, long long R, int L, float slope, float* vmax, int* imax,
+                                 float* vmean, void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_act_pool_fwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, scale, shift, R, L, slope, vmax, imax, vmean);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_act_pool_bwd_reduce(const float* h, const float* scale, const float* shift, const float* gmax, const float* gmean,
+                                        const int* imax, long long R, int L, float slope, float* gscale, float* gshift, void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_act_pool_bwd_reduce_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, scale, shift, gmax, gmean, imax, R, L, slope, gscale,
+                                                                                        gshift);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_row_act_pool_bwd(const float* h, const float* scale, const float* shift, const float* mean, const float* gmax, const float* gmean,
+                                 const int* imax, const float* gstat_mean, const float* gstat_var, long long R, int L, float slope, float* gh,
+                                 void* stream) {
+  if (R < 0 || L <= 0) return SNB_EINVAL;
+  if (R == 0) return SNB_OK;
+  if (R > 0x3fffffffLL) return SNB_ELIMIT;
+  row_act_pool_bwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(h, scale, shift, mean, gmax, gmean, imax, gstat_mean, gstat_var, R,
+                                                                                 L, slope, gh);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

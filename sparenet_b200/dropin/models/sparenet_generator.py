@@ -189,8 +189,12 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
             mean, var = _bn_from_rows(bn, m_bc, v_bc, L)
             scale = g * torch.rsqrt(var + bn.eps)
             return scale.expand(B, -1), (beta - scale * mean).expand(B, -1)
-        h = fused.row_norm_act(h, tail, (bn.weight, bn.bias), slope=0.2, stats=st5)
-        return torch.cat((h.amax(2), h.mean(2)), 1).view(B, self.output_size)
+        if LIBRARY_GEMM:
+            h = fused.row_norm_act(h, tail, (bn.weight, bn.bias), slope=0.2, stats=st5)
+            return torch.cat((h.amax(2), h.mean(2)), 1).view(B, self.output_size)
+        # [max | mean over the points] of LeakyReLU(BN5(h)) straight from h: the activated [B,2048,N] tensor is never stored
+        pmax, pmean = fused.row_norm_act_pool(h, tail, (bn.weight, bn.bias), slope=0.2, stats=st5)
+        return torch.cat((pmax, pmean), 1).view(B, self.output_size)
 
 
 class PointNetfeat(nn.Module):

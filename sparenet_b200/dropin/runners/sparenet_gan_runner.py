@@ -17,6 +17,7 @@ import random
 
 import torch
 
+from sparenet_b200 import functional as F_
 from sparenet_b200.dropin.cuda.chamfer_distance import ChamferDistance, ChamferDistanceMean
 from sparenet_b200.dropin.cuda.emd import emd_module as emd
 from sparenet_b200.dropin.utils.p2i_utils import N_VIEWS_PREDEFINED
@@ -56,7 +57,8 @@ class sparenetGANStep:
             raise Exception("unknown training metric")
         _loss = coarse_loss + middle_loss + refine_loss + expansion_penalty.mean() * 0.1
         if self.use_consist_loss:
-            dist1, _ = self.chamfer_dist(refine_ptcloud, gt)
+            with F_.chamfer_reuse():      # metric "chamfer": Chamfer(refine, gt) was searched a moment ago -- reuse it (identical values)
+                dist1, _ = self.chamfer_dist(refine_ptcloud, gt)
             _loss = _loss + torch.mean(dist1).mean() * 0.5
         return _loss, refine_ptcloud, middle_ptcloud, coarse_ptcloud, refine_loss, coarse_loss
 

@@ -61,7 +61,25 @@ def _ws(nbytes, device):
 
 # ----------------------------------------------------------------------------- Chamfer
 _CHAMFER_MEMO = {}
+_CHAMFER_REUSE = {"depth": 0}
 CHAMFER_PRUNED = True   # False forces the brute-force kernel (tests compare the two bit for bit)
+
+
+class chamfer_reuse:
+    """Opt-in de-duplication of IDENTICAL Chamfer searches inside the block: the training loss evaluates Chamfer(refine, gt) twice in a
+    row (ChamferDistanceMean, then the consistency term, runners/sparenet_runner.py:87,103).  Within the scope a second
+    chamfer_forward on the very same, unmodified tensors (data pointer, version counter, shape, stream) returns the first search's
+    result instead of repeating the N x M search -- same values, one search less.  Off by default: outside a scope every call
+    searches.  The memo is dropped when the outermost scope exits, so it never pins tensors beyond the loss computation."""
+    def __enter__(self):
+        _CHAMFER_REUSE["depth"] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _CHAMFER_REUSE["depth"] -= 1
+        if _CHAMFER_REUSE["depth"] == 0:
+            _CHAMFER_MEMO.clear()
+        return False
 
 
 def chamfer_forward(xyz1, xyz2):
@@ -71,13 +89,14 @@ def chamfer_forward(xyz1, xyz2):
     B, N, _ = xyz1.shape
     M = xyz2.shape[1]
     dev = xyz1.device
-    # The training loss evaluates Chamfer(refine, gt) twice in a row (ChamferDistanceMean, then the consistency term,
-    # runners/sparenet_runner.py:87,103): a one-entry memo on the very same, unmodified tensors skips the second N x M search.
-    # The entry keeps references to its inputs, so their storage cannot be recycled while it is alive.
+    # Inside a chamfer_reuse() scope a one-entry memo on the very same, unmodified tensors skips a repeated N x M search.  The entry
+    # keeps references to its inputs (their storage cannot be recycled while it is alive) and remembers the outputs' version
+    # counters: an in-place edit of a returned tensor invalidates it.
     c = _CHAMFER_MEMO
+    reuse = _CHAMFER_REUSE["depth"] > 0
     key = (xyz1.data_ptr(), xyz1._version, tuple(xyz1.shape), xyz2.data_ptr(), xyz2._version, tuple(xyz2.shape),
            torch.cuda.current_stream(dev).cuda_stream)
-    if c.get("key") == key:
+    if reuse and c.get("key") == key and all(t._version == v for t, v in zip(c["out"], c["out_versions"])):
         return tuple(t.detach() for t in c["out"])     # fresh aliases: each autograd node owns its output objects
     d1 = torch.empty(B, N, device=dev)
     d2 = torch.empty(B, M, device=dev)
@@ -89,10 +108,12 @@ def chamfer_forward(xyz1, xyz2):
     with torch.cuda.device(dev), _op("chamfer_fwd", 2 if nbytes else 1):
         check(lib.snb_chamfer_fwd(ptr(xyz1), ptr(xyz2), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), ptr(ws), nbytes, stream_ptr()), "chamfer_fwd")
     c.clear()
-    # detached aliases share storage and version counter but not the autograd graph: the inputs carry their history, and the
-    # outputs get the calling autograd.Function's grad_fn attached in place once it returns -- holding either would keep the
-    # previous step's whole graph (and its AccumulateGrad nodes) alive
-    c.update(key=key, keep=(xyz1.detach(), xyz2.detach()), out=(d1.detach(), d2.detach(), i1, i2))
+    if reuse:
+        # detached aliases share storage and version counter but not the autograd graph: the inputs carry their history, and the
+        # outputs get the calling autograd.Function's grad_fn attached in place once it returns -- holding either would keep the
+        # previous step's whole graph (and its AccumulateGrad nodes) alive
+        out = (d1.detach(), d2.detach(), i1, i2)
+        c.update(key=key, keep=(xyz1.detach(), xyz2.detach()), out=out, out_versions=tuple(t._version for t in out))
     return d1, d2, i1, i2
 
 

@@ -14,9 +14,12 @@ class tf32_matmul:
     """TF32 for the library GEMMs inside the block (host-side dispatch flag, restored on exit).  Used only where the reference's own
     arithmetic is a TF32 convolution (the Gram-matrix form of conv3's backward) or where the product merely PRUNES candidates that
     are re-evaluated exactly (kNN); nn.Linear layers keep fp32 like the reference's."""
+    enabled = True      # tests of the fp32 algebra switch this off (tf32_matmul.enabled = False): the blocks then run in fp32
+
     def __enter__(self):
         self.old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
+        if tf32_matmul.enabled:
+            torch.backends.cuda.matmul.allow_tf32 = True
 
     def __exit__(self, *a):
         torch.backends.cuda.matmul.allow_tf32 = self.old
@@ -26,22 +29,31 @@ class tf32_matmul:
 class ThinConv(torch.autograd.Function):
     """y[g] = W x[g] for the THIN 1x1 convolutions (3-8 channels on one side: xyz inputs, xyz outputs, the 2-d lattice), whose rows
     are shorter than a TMA box of the tensor-core GEMM: batched library GEMM with TF32 allowed in the forward AND in both backward
-    products (the reference runs these layers through cuDNN with TF32 allowed).  W [Co, Ci] or [G, Co, Ci], x [G, Ci, N]."""
+    products (the reference runs these layers through cuDNN with TF32 allowed).  W [Co, Ci] or [G, Co, Ci], x [G, Ci, N] (or
+    [1, Ci, N] against a batched W).  Always torch.bmm on an EXPANDED (stride-0) operand: torch.matmul(2-D, 3-D) would first copy x."""
     @staticmethod
     def forward(ctx, x, W):
         ctx.save_for_backward(x, W)
+        G = max(x.shape[0], W.shape[0] if W.dim() == 3 else 1)
+        Wb = W.unsqueeze(0).expand(G, -1, -1) if W.dim() == 2 else W
+        xb = x.expand(G, -1, -1)
         with tf32_matmul():
-            return torch.matmul(W, x)
+            return torch.bmm(Wb, xb)
 
     @staticmethod
     def backward(ctx, gy):
         x, W = ctx.saved_tensors
+        G = gy.shape[0]
+        Wb = W.unsqueeze(0).expand(G, -1, -1) if W.dim() == 2 else W
+        xb = x.expand(G, -1, -1)
         gx = gW = None
         with tf32_matmul():
             if ctx.needs_input_grad[0]:
-                gx = torch.matmul(W.transpose(-1, -2), gy)
+                gx = torch.bmm(Wb.transpose(1, 2), gy)
+                if x.shape[0] != G:
+                    gx = gx.sum(0, keepdim=True)
             if ctx.needs_input_grad[1]:
-                gW = torch.matmul(gy, x.transpose(-1, -2))
+                gW = torch.bmm(gy, xb.transpose(1, 2))
                 if W.dim() == 2:
                     gW = gW.sum(0)
         return gx, gW
@@ -329,6 +341,65 @@ class ConvRowReduce(torch.autograd.Function):
         x, W2, mean, imax, imin = ctx.saved_tensors
         gx, gW = conv_row_reduce_backward(x, W2, mean, imax, imin, gmean, gvar, gmax, gmin, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return gx, (gW.view(ctx.wshape) if gW is not None else None)
+
+
+class RowNormActPool(torch.autograd.Function):
+    """(max over the row, mean over the row) of leaky_relu(scale*h + shift) with (scale, shift) = fn(row statistics, *tensors): the
+    encoder's pooled output WITHOUT storing the activated tensor.  Same two-phase backward as RowNormAct, with the upstream gradient
+    being (gmean/L everywhere) + (gmax at the arg-max position) instead of a full tensor."""
+    @staticmethod
+    def forward(ctx, h, fn, slope, stats, *tensors):
+        h = h.contiguous()
+        L = h.shape[-1]
+        R = h.numel() // L
+        lib = _lib.load()
+        if stats is not None:
+            mean, var = (t.detach().reshape(h.shape[:-1]).contiguous().float() for t in stats)
+        else:
+            mean, var = row_stats_nograd(h)
+        with torch.enable_grad():
+            m_, v_ = mean.requires_grad_(True), var.requires_grad_(True)
+            ts = [t.detach().requires_grad_(t.requires_grad) for t in tensors]
+            scale, shift = fn(m_, v_, *ts)
+        assert scale.shape == mean.shape and shift.shape == mean.shape, "fn must return per-row scale/shift"
+        sc, sh = scale.detach().contiguous().float(), shift.detach().contiguous().float()
+        vmax, vmean = torch.empty_like(sc), torch.empty_like(sc)
+        imax = torch.empty(sc.shape, dtype=torch.int32, device=h.device)
+        with torch.cuda.device(h.device), _op("row_act_pool_fwd", 1, 4 * h.numel()):
+            check(lib.snb_row_act_pool_fwd(ptr(h), ptr(sc), ptr(sh), R, L, float(slope), ptr(vmax), ptr(imax), ptr(vmean), stream_ptr()), "row_act_pool_fwd")
+        ctx.save_for_backward(h, sc, sh, imax)
+        ctx.graph = (m_, v_, ts, scale, shift)
+        ctx.slope = float(slope)
+        return vmax, vmean
+
+    @staticmethod
+    def backward(ctx, gmax, gmean):
+        h, sc, sh, imax = ctx.saved_tensors
+        m_, v_, ts, scale, shift = ctx.graph
+        L = h.shape[-1]
+        R = h.numel() // L
+        lib = _lib.load()
+        gmax = (gmax if gmax is not None else torch.zeros_like(sc)).contiguous().float()
+        gmean = (gmean if gmean is not None else torch.zeros_like(sc)).contiguous().float()
+        gsc, gsh = torch.empty_like(sc), torch.empty_like(sh)
+        with torch.cuda.device(h.device), _op("row_act_pool_bwd_reduce", 1, 4 * h.numel()):
+            check(lib.snb_row_act_pool_bwd_reduce(ptr(h), ptr(sc), ptr(sh), ptr(gmax), ptr(gmean), ptr(imax), R, L, ctx.slope, ptr(gsc), ptr(gsh),
+                                                  stream_ptr()), "row_act_pool_bwd_reduce")
+        wanted = [m_, v_] + [t for t in ts if t.requires_grad]
+        grads = torch.autograd.grad((scale, shift), wanted, (gsc.view_as(scale), gsh.view_as(shift)), allow_unused=True, retain_graph=True)
+        gm = (grads[0] if grads[0] is not None else torch.zeros_like(sc)).contiguous().float()
+        gv = (grads[1] if grads[1] is not None else torch.zeros_like(sc)).contiguous().float()
+        gh = torch.empty_like(h)
+        with torch.cuda.device(h.device), _op("row_act_pool_bwd", 1, 8 * h.numel()):
+            check(lib.snb_row_act_pool_bwd(ptr(h), ptr(sc), ptr(sh), ptr(m_.detach()), ptr(gmax), ptr(gmean), ptr(imax), ptr(gm), ptr(gv), R, L,
+                                           ctx.slope, ptr(gh), stream_ptr()), "row_act_pool_bwd")
+        it = iter(grads[2:])
+        gts = [next(it) if t.requires_grad else None for t in ts]
+        return (gh, None, None, None, *gts)
+
+
+def row_norm_act_pool(h, fn, tensors, slope=0.0, stats=None):
+    return RowNormActPool.apply(h, fn, slope, stats, *tensors)
 
 
 def edge_reduce(a, c, idx):

@@ -42,6 +42,11 @@ def row_norm_act(h, fn, tensors, slope=0.0, stats=None):   # stats (from a GEMM 
     return F.leaky_relu(h * scale.unsqueeze(-1) + shift.unsqueeze(-1), slope)
 
 
+def row_norm_act_pool(h, fn, tensors, slope=0.0, stats=None):
+    y = row_norm_act(h, fn, tensors, slope)
+    return y.amax(-1), y.mean(-1)
+
+
 def conv_row_reduce(x, W):
     h = torch.matmul(W.reshape(W.size(0), -1), x)
     mean, var = row_stats(h)
@@ -95,5 +100,5 @@ def act_conv_row_reduce(W, pro, h):
 def patch(monkeypatch):
     from sparenet_b200 import fused
     for name in ("edge_reduce", "edge_reduce_sel", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce",
-                 "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce", "bcast_act_conv", "thin_conv"):
+                 "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce", "bcast_act_conv", "thin_conv", "row_norm_act_pool"):
         monkeypatch.setattr(fused, name, globals()[name])

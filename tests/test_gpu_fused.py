@@ -163,7 +163,35 @@ def test_conv_row_reduce_forward_backward(cuda, B, Ci, Co, N):
         ew = (W1.grad.double() - W2.grad).abs().max().item() / W2.grad.abs().max().item()
         print(f"[conv_row_reduce] B={B} {Ci}->{Co} N={N}: grad err/scale x={ex:.2e} W={ew:.2e}")
         # the two Gram-matrix products of the backward run in TF32 by design (they stand for cuDNN's TF32 data / weight gradients):
-        # TF32 bound instead of the fp32 one
+        # TF32 bound here; the fp32 algebra itself is covered by the CPU float64 tests
         assert ex < 2e-3 and ew < 2e-3
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,C,L,slope", [(4, 16, 512, 0.2), (3, 8, 2048, 0.0), (2, 5, 333, 0.2)])
+def test_row_norm_act_pool_forward_backward(cuda, B, C, L, slope):
+    """[max | mean over the row] of BN o LeakyReLU without the activated tensor (snb_row_act_pool_*) vs autograd in fp64."""
+    from sparenet_b200 import fused
+    torch.manual_seed(B * 10 + L)
+    h = torch.randn(B, C, L, device=cuda) * 0.7 + 0.3
+    g, beta = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1
+
+    def tail(m_bc, v_bc, g, beta):                              # the encoder's BN5 as one per-channel scale/shift
+        mean = m_bc.mean(0)
+        var = v_bc.mean(0) + ((m_bc - mean) ** 2).mean(0)
+        scale = g * torch.rsqrt(var + 1e-5)
+        return scale.expand(m_bc.size(0), -1), (beta - scale * mean).expand(m_bc.size(0), -1)
+
+    l32 = [t.clone().requires_grad_() for t in (h, g, beta)]
+    l64 = [t.double().requires_grad_() for t in (h, g, beta)]
+    pmax, pmean = fused.row_norm_act_pool(l32[0], tail, tuple(l32[1:]), slope)
+    qmax, qmean = R.row_norm_act_pool(l64[0], tail, tuple(l64[1:]), slope)
+    assert _close(pmax, qmax, 1e-5, 1e-6) and _close(pmean, qmean, 1e-5, 1e-6)
+    w1, w2 = torch.randn_like(pmax), torch.randn_like(pmean)
+    ((pmax * w1).sum() + (pmean * w2).sum()).backward()
+    ((qmax * w1.double()).sum() + (qmean * w2.double()).sum()).backward()
+    for name, a, b in zip(("h", "gamma", "beta"), l32, l64):
+        err = (a.grad.double() - b.grad).abs().max().item() / (b.grad.abs().max().item() + 1e-30)
+        print(f"[row_norm_act_pool] B={B} C={C} L={L} grad {name}: err/scale {err:.2e}")
+        assert err < 2e-5, name

@@ -68,8 +68,10 @@ def _band(a_fp32, a_tf32, ours, what, factor=3.0, floor=5e-3):
 def test_generator_wiring_exact_in_fp32_with_library_gemm(cuda, monkeypatch):
     """The fused algebra + point kernels + module wiring with the dense convolutions on fp32 library GEMMs (the LIBRARY_GEMM
     measurement switch, TF32 off everywhere): agreement with the restatement at fp32 re-association level."""
+    from sparenet_b200 import fused
     from sparenet_b200.dropin.models import sparenet_generator as M
     monkeypatch.setattr(M, "LIBRARY_GEMM", True)
+    monkeypatch.setattr(fused.tf32_matmul, "enabled", False)     # thin convolutions and Gram products in fp32 too
     kw = dict(n_primitives=8, hide_size=256, bottleneck_size=256, num_points=8 * 512)
     ref = G.SpareNetGenerator(ops=GpuOps, **kw)
     torch.manual_seed(0)
@@ -85,6 +87,11 @@ def test_generator_wiring_exact_in_fp32_with_library_gemm(cuda, monkeypatch):
     # B=4 batch-norms amplify fp32 re-association noise (float64 CPU test: 1e-13); hold to 1% of the coordinate scale
     assert torch.allclose(c1, c2, rtol=1e-2, atol=2e-3), (c1 - c2).abs().max()
     assert abs(l1.item() - l2.item()) <= 1e-2 * abs(l1.item()) + 1e-8
+    # running statistics advanced identically (sample a few)
+    b1, b2 = dict(ref.named_buffers()), dict(mine.named_buffers())
+    for k in ("encoder.feat_extractor.bn3.running_var", "decoder.decoder.5.dec.bn2.running_mean", "refine.residual.bn4.running_var",
+              "encoder.bn.running_mean", "decoder.decoder.0.dec.bn1.num_batches_tracked"):
+        assert torch.allclose(b1[k].float(), b2[k].float(), rtol=2e-2, atol=1e-4), k   # fp32 noise through B=4 batch norms
 
 
 def test_generator_matches_restatement(cuda):
@@ -108,13 +115,16 @@ def test_generator_matches_restatement(cuda):
         c1t, _, _, l1t = ref(data)
     with _tf32(False):
         c2, m2, r2, l2 = mine(data)
-    _band(c1, c1t, c2, "coarse cloud, n_primitives=8 hide=256 B=4")
+    # A batch of FOUR samples: the BatchNorms over the batch amplify a 1e-7 perturbation to 1e-2 (see the fp32 test above), so a
+    # TF32-sized one saturates -- the reference's own TF32 run already sits 10 % (max) from its fp32 run.  This case therefore only
+    # guards against gross errors; the calibrated comparison is tests/test_gpu_baseline_config.py at B=32.
+    _band(c1, c1t, c2, "coarse cloud, n_primitives=8 hide=256 B=4", factor=8.0, floor=0.1)
     assert abs(l1.item() - l2.item()) <= max(3 * abs(l1.item() - l1t.item()), 1e-2 * abs(l1.item())) + 1e-8   # MST edges flip across the alpha threshold
     # running statistics advanced identically (sample a few)
     b2 = dict(mine.named_buffers())
     for k in ("encoder.feat_extractor.bn3.running_var", "decoder.decoder.5.dec.bn2.running_mean", "refine.residual.bn4.running_var",
               "encoder.bn.running_mean", "decoder.decoder.0.dec.bn1.num_batches_tracked"):
-        assert torch.allclose(b1[k].float(), b2[k].float(), rtol=3e-2, atol=3e-4), k   # TF32 noise through B=4 batch norms
+        assert torch.allclose(b1[k].float(), b2[k].float(), rtol=1e-1, atol=5e-3), k   # TF32 noise through B=4 batch norms (sanity)
     (r2.mean() + l2).backward()
     assert all(torch.isfinite(p.grad).all() for p in mine.parameters() if p.grad is not None)
 

@@ -128,6 +128,24 @@ def test_chamfer_dropin_modules_autograd(cuda):
     _dropin()
     from cuda.chamfer_dist import ChamferDistance as CDa, ChamferFunction
     from cuda.chamfer_distance import ChamferDistance as CDb, ChamferDistanceMean
+    from sparenet_b200 import functional as F_
+    # the de-duplication of identical searches is opt-in and scoped: identical values, one launch pair less, invalidated by edits
+    xr, yr = torch.rand(2, 512, 3, device=cuda), torch.rand(2, 600, 3, device=cuda)
+    n0 = F_.LAUNCHES["count"]
+    a = F_.chamfer_forward(xr, yr)
+    k1 = F_.LAUNCHES["count"] - n0
+    b = F_.chamfer_forward(xr, yr)
+    assert k1 > 0 and F_.LAUNCHES["count"] - n0 == 2 * k1 and a[0].data_ptr() != b[0].data_ptr()      # no scope: two searches
+    with F_.chamfer_reuse():
+        n1 = F_.LAUNCHES["count"]
+        c = F_.chamfer_forward(xr, yr)
+        per = F_.LAUNCHES["count"] - n1
+        d = F_.chamfer_forward(xr, yr)
+        assert F_.LAUNCHES["count"] - n1 == per and d[0].data_ptr() == c[0].data_ptr() and all(torch.equal(p, q) for p, q in zip(c, d))
+        c[0].mul_(2.0)                                                        # an in-place edit of a returned tensor drops the entry
+        e = F_.chamfer_forward(xr, yr)
+        assert F_.LAUNCHES["count"] - n1 == 2 * per and torch.equal(e[0], a[0])
+    assert not F_._CHAMFER_MEMO
     torch.manual_seed(0)
     x = torch.rand(2, 512, 3, device=cuda, requires_grad=True)
     y = torch.rand(2, 640, 3, device=cuda, requires_grad=True)

@@ -21,6 +21,9 @@ def clean(name):
         f = re.search(r"(direct_copy_kernel_cuda|CUDAFunctor_[a-z]+|[A-Za-z_0-9]+Functor[A-Za-z_0-9]*|[a-z_0-9]+_kernel_cuda|[a-z_0-9]+_kernel_impl|[a-z_0-9]+_kernel(?=[<(])|"
                       r"(Mean|Max|Min|Sum|Norm|Welford)[A-Za-z]*Ops?|func_wrapper_t<[a-z]+, at::native::[A-Za-z]+|[A-Za-z]+Ops)", inner)
         return "at::" + m.group(2) + "<" + (f.group(1)[:60] if f else inner[:60]) + ">"
+    name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    if "gemm_tf32_kernel" in name:
+        return "snb::gemm_tf32_kernel<xform>" if re.search(r"<\(bool\)1>|<true>", name) else "snb::gemm_tf32_kernel<plain>"
     return re.sub(r"<.*", "", name).split("(")[0].strip()
 
 
