@@ -51,10 +51,15 @@ int snb_chamfer_bwd(const float* xyz1, const float* xyz2, int B, int N, int M,
 /* ---- EMD (auction) ---------------------------------------------------------------------------------
  * replaces emd.forward / emd.backward (cuda/emd/emd.cpp:6-28, emd_cuda.cu:228-316).  n == m, n % 1024 == 0,
  * B <= 512 (emd_cuda.cu:236-249 -> SNB_ELIMIT).  The 12 scratch tensors the reference allocates in Python
- * (emd_module.py:43-54) become one caller-owned workspace.  dist = squared distance to the assigned point. */
+ * (emd_module.py:43-54) become one caller-owned workspace.  dist = squared distance to the assigned point.
+ * snb_emd_fwd: N <= 16384 runs the auction over a Morton-ordered box hierarchy of both clouds (a Bid pass only opens boxes whose
+ * bound 3 - dist - min price can still change a bidder's best / second best); larger clouds run the exhaustive Bid.
+ * snb_emd_fwd_scan: always the exhaustive Bid.  Both return the same assignment and distances, bit for bit. */
 size_t snb_emd_workspace_bytes(int B, int N);
 int snb_emd_fwd(const float* xyz1, const float* xyz2, int B, int N, float eps, int iters,
                 float* dist, int* assignment, void* workspace, size_t workspace_bytes, void* stream);
+int snb_emd_fwd_scan(const float* xyz1, const float* xyz2, int B, int N, float eps, int iters,
+                     float* dist, int* assignment, void* workspace, size_t workspace_bytes, void* stream);
 int snb_emd_bwd(const float* xyz1, const float* xyz2, int B, int N, const float* grad_dist,
                 const int* assignment, float* grad_xyz1, void* stream);
 
@@ -179,6 +184,25 @@ int snb_row_act_pool_bwd_reduce(const float* h, const float* scale, const float*
 int snb_row_act_pool_bwd(const float* h, const float* scale, const float* shift, const float* mean, const float* gmax,
                          const float* gmean, const int* imax, const float* gstat_mean, const float* gstat_var, long long R, int L,
                          float slope, float* gh, void* stream);
+
+/* ---- closed-form BatchNorm . SE tail of a dense layer (csrc/tails.cu; models/sparenet_generator.py:593-646, 767-790) -------
+ * (scale, shift) [B,C] of tail(h) = relu(scale*h + shift) from the ROW statistics of the pre-activation h [B,C,L]:
+ * m = row_mean + row_bias ([C], or [B,C] with bias_per_sample), BatchNorm1d over (B, L) from m and row_var (train: batch
+ * statistics, running_* advanced in place with `momentum` and the unbiased factor `unbias` = B*L/(B*L-1), the int64 counter
+ * incremented; eval: running_*), SELayer1D gate = sigmoid(w2 relu(w1 z)) on the squeeze z = BN(m), w1 [H,C], w2 [C,H];
+ * scale = gate*sc, shift = gate*sh + row_bias*scale.  One thread block per call (the data is B*C values).  `save` (fwd -> bwd)
+ * holds snb_bn_se_tail_save_floats floats, `scratch` snb_bn_se_tail_scratch_floats.  bwd: gradients of every input from
+ * (grad_scale, grad_shift); grad_row_bias is [C] or [B,C] like row_bias and may be NULL. */
+size_t snb_bn_se_tail_save_floats(int B, int C, int H);
+size_t snb_bn_se_tail_scratch_floats(int B, int C, int H);
+int snb_bn_se_tail_fwd(const float* row_mean, const float* row_var, const float* row_bias, int bias_per_sample,
+                       const float* gamma, const float* beta, const float* w1, const float* w2, int B, int C, int H,
+                       float eps, int training, float momentum, float unbias, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float* scale, float* shift, float* save, void* stream);
+int snb_bn_se_tail_bwd(const float* grad_scale, const float* grad_shift, const float* row_mean, const float* row_bias,
+                       int bias_per_sample, const float* gamma, const float* w1, const float* w2, int B, int C, int H,
+                       int training, const float* save, float* scratch, float* grad_row_mean, float* grad_row_var,
+                       float* grad_row_bias, float* grad_gamma, float* grad_beta, float* grad_w1, float* grad_w2, void* stream);
 
 /* ---- TF32 tensor-core GEMM of the 1x1-conv / AdaIN-folding stacks (csrc/gemm_tc.cu: tcgen05.mma + TMEM + TMA) ----------
  * replaces the cuDNN/cuBLAS calls behind nn.Conv1d / nn.Conv2d(kernel_size=1) in models/sparenet_generator.py:146-186,

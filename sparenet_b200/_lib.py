@@ -35,6 +35,7 @@ SIGNATURES = {
     "snb_chamfer_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "snb_emd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "snb_emd_fwd": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P, P, c_size_t, P]),
+    "snb_emd_fwd_scan": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P, P, c_size_t, P]),
     "snb_emd_bwd": (c_int, [P, P, c_int, c_int, P, P, P, P]),
     "snb_expansion_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "snb_expansion_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, P, P, P, c_size_t, P]),
@@ -70,6 +71,10 @@ SIGNATURES = {
     "snb_gemm_tf32": (c_int, [ctypes.POINTER(GemmDesc), P]),
     "snb_gemm_tf32_tiles": (c_int, [c_int, c_int]),
     "snb_gemm_tf32_block_n": (c_int, [c_int, c_int]),
+    "snb_bn_se_tail_save_floats": (c_size_t, [c_int, c_int, c_int]),
+    "snb_bn_se_tail_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
+    "snb_bn_se_tail_fwd": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_float, c_float, P, P, P, P, P, P, P]),
+    "snb_bn_se_tail_bwd": (c_int, [P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P]),
     "snb_row_act_pool_fwd": (c_int, [P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P, P]),
     "snb_row_act_pool_bwd_reduce": (c_int, [P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P]),
     "snb_row_act_pool_bwd": (c_int, [P, P, P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P]),

@@ -14,45 +14,9 @@
 //          relative, far more than the fp32 rounding of the bound) does not exceed the running minimum.
 // Ties: candidates compare as (distance, original index), so the lowest index wins regardless of the visiting order.
 #include <math.h>
-#include "common.cuh"
+#include "bvh.cuh"
 
 namespace snb {
-
-constexpr int BVH_MAXN = 16384;
-constexpr int BVH_BUILD_THREADS = 1024;
-constexpr int BVH_LEAF = 32;    // points per cluster
-constexpr int BVH_FAN = 16;     // clusters per super-cluster
-
-struct BvhView {
-  float4* pts;    // [npad32] sorted points, w = original index bits; padding rows hold NaN coordinates
-  float4* box;    // [2*nc]   cluster boxes (lo, hi)
-  float4* sbox;   // [2*ns]   super-cluster boxes
-  int n, nc, ns;
-};
-
-__host__ __device__ inline int bvh_nc(int n) { return (n + BVH_LEAF - 1) / BVH_LEAF; }
-__host__ __device__ inline int bvh_ns(int n) { return (bvh_nc(n) + BVH_FAN - 1) / BVH_FAN; }
-__host__ __device__ inline size_t bvh_cloud_floats4(int n) { return (size_t)bvh_nc(n) * BVH_LEAF + 2 * (size_t)bvh_nc(n) + 2 * (size_t)bvh_ns(n); }
-
-__device__ __forceinline__ BvhView bvh_view(float4* base, int n) {
-  BvhView v;
-  v.n = n;
-  v.nc = bvh_nc(n);
-  v.ns = bvh_ns(n);
-  v.pts = base;
-  v.box = base + (size_t)v.nc * BVH_LEAF;
-  v.sbox = v.box + 2 * (size_t)v.nc;
-  return v;
-}
-
-__device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
-  v &= 0x3ffu;
-  v = (v | (v << 16)) & 0x030000ffu;
-  v = (v | (v << 8)) & 0x0300f00fu;
-  v = (v | (v << 4)) & 0x030c30c3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
-}
 
 __global__ void __launch_bounds__(BVH_BUILD_THREADS) chamfer_bvh_build_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, int N,
                                                                               int M, float4* __restrict__ ws, size_t per_sample_f4) {
@@ -174,13 +138,6 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) chamfer_bvh_build_kernel(co
   }
 }
 
-__device__ __forceinline__ float box_lb(const float4 lo, const float4 hi, float qx, float qy, float qz) {
-  const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f);
-  const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f);
-  const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
-  return (dx * dx + dy * dy + dz * dz) * 0.99999f;  // shrunk: never above the computed distance of any point inside the box
-}
-
 struct Best {
   float d;
   int i;
@@ -259,17 +216,24 @@ size_t chamfer_bvh_workspace_bytes(int B, int N, int M) {
   return (size_t)B * (bvh_cloud_floats4(N) + bvh_cloud_floats4(M)) * sizeof(float4);
 }
 
-int chamfer_bvh_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2, int* idx1, int* idx2, void* workspace,
-                       cudaStream_t s) {
-  const size_t per = bvh_cloud_floats4(N) + bvh_cloud_floats4(M);
+int bvh_build_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float4* ws, size_t per_sample_f4, cudaStream_t s) {
   const int nmax = N > M ? N : M;
   int npad = 1;
   while (npad < nmax) npad <<= 1;
   const size_t smem = (size_t)npad * sizeof(unsigned long long);
   // per device/context and cheap: set before every launch (a process-wide flag would leave the other GPUs of one process without it)
   SNB_CUDA(cudaFuncSetAttribute(chamfer_bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BVH_MAXN * sizeof(unsigned long long))));
-  chamfer_bvh_build_kernel<<<dim3(2, B), BVH_BUILD_THREADS, smem, s>>>(xyz1, xyz2, N, M, (float4*)workspace, per);
+  chamfer_bvh_build_kernel<<<dim3(2, B), BVH_BUILD_THREADS, smem, s>>>(xyz1, xyz2, N, M, ws, per_sample_f4);
   SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+int chamfer_bvh_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2, int* idx1, int* idx2, void* workspace,
+                       cudaStream_t s) {
+  const size_t per = bvh_cloud_floats4(N) + bvh_cloud_floats4(M);
+  const int nmax = N > M ? N : M;
+  const int rc = bvh_build_launch(xyz1, xyz2, B, N, M, (float4*)workspace, per, s);
+  if (rc != SNB_OK) return rc;
   chamfer_bvh_query_kernel<<<dim3((nmax + 127) / 128, B, 2), 128, 0, s>>>(N, M, (float4*)workspace, per, dist1, dist2, idx1, idx2);
   SNB_LAUNCH_CHECK();
   return SNB_OK;

@@ -1,0 +1,238 @@
+// tails.cu -- the closed-form BatchNorm . SE tail of a dense layer as ONE launch per direction, sm_100a.
+//
+// The generator never applies BatchNorm / SE / ReLU to an activation tensor: each dense layer's tail collapses to one
+// (scale, shift) pair per (sample, channel) computed from the ROW statistics of the layer's pre-activation h [B,C,L]
+// (reference models/sparenet_generator.py:593-646: conv -> BatchNorm1d -> SELayer1D -> ReLU of PointNetRes):
+//     m      = row_mean(h) + rb                      rb = the conv bias ([C]) or a per-sample bias ([B,C]): never added to h
+//     mean_c = avg_b m,  var_c = avg_b row_var(h) + avg_b (m - mean_c)^2        (within-row + between-row: no cancellation)
+//     sc_c   = gamma_c * rsqrt(var_c + eps),  sh_c = beta_c - sc_c * mean_c     (BatchNorm, batch statistics in train mode)
+//     z      = m * sc_c + sh_c                        (the SE squeeze: mean over the points of BN(h + rb))
+//     gate   = sigmoid(W2 relu(W1 z))                 (SE excitation, W1 [H,C], W2 [C,H], no biases)
+//     S      = gate * sc_c,   T = gate * sh_c + rb * S                        => tail(h) = relu(S*h + T)
+// As PyTorch glue this is ~37 launches forward and ~48 backward of a few microseconds each (ten such tails per step in the
+// refiner: ~3.4 ms of a 68 ms step); the numbers are tiny (B*C <= 16 K values, 2*B*C*H multiply-adds), so ONE thread block with
+// barriers between the phases does each direction.  Intermediates that cross a phase live in a caller-owned scratch / save
+// buffer (L1/L2 resident; a block barrier orders global memory among the block's threads).
+#include <math.h>
+#include "common.cuh"
+
+namespace snb {
+
+constexpr int TAIL_THREADS = 1024;
+
+__device__ __forceinline__ float tail_rb(const float* __restrict__ rb, int rb_batched, int b, int c, int C) {
+  return rb ? (rb_batched ? rb[b * C + c] : rb[c]) : 0.f;
+}
+
+// save layout (floats): mean[C] inv[C] sc[C] sh[C] z[B*C] gate[B*C] a1[B*H]
+__global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_fwd_kernel(const float* __restrict__ m_bc, const float* __restrict__ v_bc,
+                                                                          const float* __restrict__ rb, int rb_batched, const float* __restrict__ g,
+                                                                          const float* __restrict__ beta, const float* __restrict__ w1,
+                                                                          const float* __restrict__ w2, int B, int C, int H, float eps, int training,
+                                                                          float momentum, float unbias, float* run_mean, float* run_var,
+                                                                          long long* num_batches, float* __restrict__ S, float* __restrict__ T,
+                                                                          float* save) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  float* mean = save;
+  float* inv = mean + C;
+  float* sc = inv + C;
+  float* sh = sc + C;
+  float* z = sh + C;
+  float* gate = z + (size_t)B * C;
+  float* a1 = gate + (size_t)B * C;
+  const float rB = 1.0f / (float)B;
+  // ---- BatchNorm statistics and the per-channel scale / shift ----
+  for (int c = tid; c < C; c += nt) {
+    float mu, var;
+    if (training) {
+      float s = 0.f;
+      for (int b = 0; b < B; b++) s += m_bc[b * C + c] + tail_rb(rb, rb_batched, b, c, C);
+      mu = s * rB;
+      float sd = 0.f, sv = 0.f;
+      for (int b = 0; b < B; b++) {
+        const float d = (m_bc[b * C + c] + tail_rb(rb, rb_batched, b, c, C)) - mu;
+        sd += d * d;
+        sv += v_bc[b * C + c];
+      }
+      var = sv * rB + sd * rB;
+      if (run_mean) {  // nn.BatchNorm bookkeeping: running statistics with the unbiased variance
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mu;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (var * unbias);
+      }
+    } else {
+      mu = run_mean[c];
+      var = run_var[c];
+    }
+    const float iv = rsqrtf(var + eps);
+    const float s_c = g[c] * iv;
+    mean[c] = mu;
+    inv[c] = iv;
+    sc[c] = s_c;
+    sh[c] = beta[c] - s_c * mu;
+  }
+  if (tid == 0 && training && num_batches) *num_batches += 1;
+  __syncthreads();
+  // ---- SE squeeze ----
+  for (int i = tid; i < B * C; i += nt) {
+    const int b = i / C, c = i - b * C;
+    z[i] = (m_bc[i] + tail_rb(rb, rb_batched, b, c, C)) * sc[c] + sh[c];
+  }
+  __syncthreads();
+  // ---- a1 = relu(W1 z): a warp per (sample, hidden unit), lanes over the channels ----
+  for (int o = warp; o < B * H; o += nw) {
+    const int b = o / H, h = o - b * H;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = __fmaf_rn(w1[h * C + c], z[b * C + c], acc);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) a1[o] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  // ---- gate = sigmoid(W2 a1); the folded scale / shift ----
+  for (int i = tid; i < B * C; i += nt) {
+    const int b = i / C, c = i - b * C;
+    float acc = 0.f;
+    for (int h = 0; h < H; h++) acc = __fmaf_rn(w2[c * H + h], a1[b * H + h], acc);
+    const float gt = 1.0f / (1.0f + expf(-acc));
+    gate[i] = gt;
+    const float s_ = gt * sc[c];
+    S[i] = s_;
+    T[i] = gt * sh[c] + tail_rb(rb, rb_batched, b, c, C) * s_;
+  }
+}
+
+// scratch layout (floats): ga2[B*C] gz[B*C] gp1[B*H] gvar[C] gmean[C]
+__global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_bwd_kernel(const float* __restrict__ gS, const float* __restrict__ gT,
+                                                                          const float* __restrict__ m_bc, const float* __restrict__ rb, int rb_batched,
+                                                                          const float* __restrict__ g, const float* __restrict__ w1,
+                                                                          const float* __restrict__ w2, int B, int C, int H, int training,
+                                                                          const float* save, float* scratch, float* __restrict__ gm,
+                                                                          float* __restrict__ gv, float* __restrict__ grb, float* __restrict__ gg,
+                                                                          float* __restrict__ gbeta, float* __restrict__ gw1, float* __restrict__ gw2) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const float* mean = save;
+  const float* inv = mean + C;
+  const float* sc = inv + C;
+  const float* sh = sc + C;
+  const float* z = sh + C;
+  const float* gate = z + (size_t)B * C;
+  const float* a1 = gate + (size_t)B * C;
+  float* ga2 = scratch;
+  float* gz = ga2 + (size_t)B * C;
+  float* gp1 = gz + (size_t)B * C;
+  float* gvar = gp1 + (size_t)B * H;
+  float* gmean = gvar + C;
+  const float rB = 1.0f / (float)B;
+  // ---- through S, T to the gate's pre-activation ----
+  for (int i = tid; i < B * C; i += nt) {
+    const int b = i / C, c = i - b * C;
+    const float gst = gS[i] + gT[i] * tail_rb(rb, rb_batched, b, c, C);
+    const float gt = gate[i];
+    ga2[i] = (gst * sc[c] + gT[i] * sh[c]) * gt * (1.0f - gt);
+  }
+  __syncthreads();
+  // ---- gp1 = (W2^T ga2) masked by the ReLU: a warp per (sample, hidden unit) ----
+  for (int o = warp; o < B * H; o += nw) {
+    const int b = o / H, h = o - b * H;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = __fmaf_rn(w2[c * H + h], ga2[b * C + c], acc);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) gp1[o] = a1[o] > 0.f ? acc : 0.f;
+  }
+  __syncthreads();
+  // ---- the two weight gradients and gz = W1^T gp1 ----
+  for (int i = tid; i < C * H; i += nt) {
+    const int c = i / H, h = i - c * H;     // gw2 [C,H]
+    float acc = 0.f;
+    for (int b = 0; b < B; b++) acc = __fmaf_rn(ga2[b * C + c], a1[b * H + h], acc);
+    gw2[i] = acc;
+    const int h1 = i / C, c1 = i - h1 * C;  // gw1 [H,C]
+    float acc1 = 0.f;
+    for (int b = 0; b < B; b++) acc1 = __fmaf_rn(gp1[b * H + h1], z[b * C + c1], acc1);
+    gw1[i] = acc1;
+  }
+  for (int i = tid; i < B * C; i += nt) {
+    const int b = i / C, c = i - b * C;
+    float acc = 0.f;
+    for (int h = 0; h < H; h++) acc = __fmaf_rn(w1[h * C + c], gp1[b * H + h], acc);
+    gz[i] = acc;
+  }
+  __syncthreads();
+  // ---- per channel: scale / shift gradients -> gamma, beta, batch mean and variance ----
+  for (int c = tid; c < C; c += nt) {
+    float gsc = 0.f, gsh = 0.f;
+    for (int b = 0; b < B; b++) {
+      const int i = b * C + c;
+      const float r_ = tail_rb(rb, rb_batched, b, c, C);
+      const float gst = gS[i] + gT[i] * r_;
+      gsc += gst * gate[i] + gz[i] * (m_bc[i] + r_);
+      gsh += gT[i] * gate[i] + gz[i];
+    }
+    gbeta[c] = gsh;
+    const float gst_c = gsc - gsh * mean[c];
+    gg[c] = gst_c * inv[c];
+    gvar[c] = training ? -0.5f * gst_c * g[c] * inv[c] * inv[c] * inv[c] : 0.f;
+    gmean[c] = training ? -gsh * sc[c] : 0.f;
+  }
+  __syncthreads();
+  // ---- back to the row statistics and the bias ----
+  for (int c = tid; c < C; c += nt) {
+    float grb_c = 0.f;
+    for (int b = 0; b < B; b++) {
+      const int i = b * C + c;
+      const float r_ = tail_rb(rb, rb_batched, b, c, C);
+      const float gm_ = gz[i] * sc[c] + (gmean[c] + gvar[c] * 2.0f * ((m_bc[i] + r_) - mean[c])) * rB;
+      gm[i] = gm_;
+      gv[i] = gvar[c] * rB;
+      const float gr = gm_ + gT[i] * gate[i] * sc[c];   // m = row mean + rb, and T's direct term rb * S
+      if (grb) {
+        if (rb_batched) grb[i] = gr;
+        else grb_c += gr;
+      }
+    }
+    if (grb && !rb_batched) grb[c] = grb_c;
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+SNB_API size_t snb_bn_se_tail_save_floats(int B, int C, int H) {
+  if (B <= 0 || C <= 0 || H <= 0) return 0;
+  return (size_t)4 * C + (size_t)2 * B * C + (size_t)B * H;
+}
+
+SNB_API size_t snb_bn_se_tail_scratch_floats(int B, int C, int H) {
+  if (B <= 0 || C <= 0 || H <= 0) return 0;
+  return (size_t)2 * B * C + (size_t)B * H + (size_t)2 * C;
+}
+
+SNB_API int snb_bn_se_tail_fwd(const float* row_mean, const float* row_var, const float* row_bias, int bias_per_sample, const float* gamma,
+                               const float* beta, const float* w1, const float* w2, int B, int C, int H, float eps, int training, float momentum,
+                               float unbias, float* running_mean, float* running_var, long long* num_batches_tracked, float* scale, float* shift,
+                               float* save, void* stream) {
+  if (B < 0 || C < 0 || H < 0) return SNB_EINVAL;
+  if (B == 0 || C == 0) return SNB_OK;
+  if (H == 0 || (!training && (!running_mean || !running_var))) return SNB_EINVAL;
+  bn_se_tail_fwd_kernel<<<1, TAIL_THREADS, 0, (cudaStream_t)stream>>>(row_mean, row_var, row_bias, bias_per_sample, gamma, beta, w1, w2, B, C, H, eps,
+                                                                      training, momentum, unbias, running_mean, running_var, num_batches_tracked,
+                                                                      scale, shift, save);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_bn_se_tail_bwd(const float* grad_scale, const float* grad_shift, const float* row_mean, const float* row_bias, int bias_per_sample,
+                               const float* gamma, const float* w1, const float* w2, int B, int C, int H, int training, const float* save,
+                               float* scratch, float* grad_row_mean, float* grad_row_var, float* grad_row_bias, float* grad_gamma, float* grad_beta,
+                               float* grad_w1, float* grad_w2, void* stream) {
+  if (B < 0 || C < 0 || H < 0) return SNB_EINVAL;
+  if (B == 0 || C == 0) return SNB_OK;
+  if (H == 0) return SNB_EINVAL;
+  bn_se_tail_bwd_kernel<<<1, TAIL_THREADS, 0, (cudaStream_t)stream>>>(grad_scale, grad_shift, row_mean, row_bias, bias_per_sample, gamma, w1, w2, B, C,
+                                                                      H, training, save, scratch, grad_row_mean, grad_row_var, grad_row_bias,
+                                                                      grad_gamma, grad_beta, grad_w1, grad_w2);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

@@ -90,6 +90,7 @@ def _bn_from_rows(bn, m_bc, v_bc, L):
     return bn.running_mean, bn.running_var
 
 
+FUSED_TAILS = True     # the BatchNorm.SE tails as single launches (csrc/tails.cu); False: the same algebra as PyTorch glue (tests compare)
 LIBRARY_GEMM = False   # measurement switch only (bench.py --library-gemm): route the dense 1x1 convs through cuDNN/cuBLAS like round 1
 
 
@@ -448,7 +449,7 @@ class PointNetRes(nn.Module):  # reference :582-646
         """relu(SE(BN(h + row_bias))) over h [B,C,L] as ONE per-(sample,channel) scale/shift: returns (fn, tensors) for
         fused.row_norm_act / fused.Prologue.  row_bias ([C] conv bias or [B,C]) is never added to the activations: it only shifts
         the statistics and folds into the shift."""
-        def tail(m_bc, v_bc, rb, g, beta, w1, w2):
+        def tail_torch(m_bc, v_bc, rb, g, beta, w1, w2):               # the same closed form as ~37 small PyTorch ops (CPU / fp64 tests)
             m = m_bc + rb
             mean, var = _bn_from_rows(bn, m, v_bc, L)
             inv = torch.rsqrt(var + bn.eps)
@@ -456,6 +457,11 @@ class PointNetRes(nn.Module):  # reference :582-646
             gate = torch.sigmoid(F.linear(torch.relu(F.linear(m * scale + shift, w1)), w2))   # [B,C]: SE squeeze = mean over points of BN(.)
             gs = gate * scale
             return gs, gate * shift + rb * gs
+
+        def tail(m_bc, v_bc, rb, g, beta, w1, w2):
+            if FUSED_TAILS and m_bc.is_cuda and m_bc.dtype == torch.float32:
+                return fused.bn_se_tail(m_bc, v_bc, rb, g, beta, w1, w2, bn, L)   # one launch per direction (csrc/tails.cu)
+            return tail_torch(m_bc, v_bc, rb, g, beta, w1, w2)
         return tail, (row_bias, bn.weight, bn.bias, se.fc[0].weight, se.fc[2].weight)
 
     @classmethod

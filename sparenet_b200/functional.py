@@ -131,7 +131,9 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, g1, g2):
 
 
 # ----------------------------------------------------------------------------- EMD
-def emd_forward(xyz1, xyz2, eps, iters):
+def emd_forward(xyz1, xyz2, eps, iters, exhaustive=False):
+    """exhaustive=True: the Bid pass that evaluates every (bidder, object) pair (snb_emd_fwd_scan) instead of the box-pruned one;
+    identical results, kept for clouds above 16384 points and as the A/B check of the pruning."""
     xyz1, xyz2 = _cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2")
     B, N, _ = xyz1.shape
     dev = xyz1.device
@@ -141,7 +143,8 @@ def emd_forward(xyz1, xyz2, eps, iters):
     nbytes = lib.snb_emd_workspace_bytes(B, N)
     ws = _ws(nbytes, dev)
     with torch.cuda.device(dev), _op("emd_fwd", 1):
-        check(lib.snb_emd_fwd(ptr(xyz1), ptr(xyz2), B, N, float(eps), int(iters), ptr(dist), ptr(ass), ptr(ws), nbytes, stream_ptr()), "emd_fwd")
+        fwd = lib.snb_emd_fwd_scan if exhaustive else lib.snb_emd_fwd
+        check(fwd(ptr(xyz1), ptr(xyz2), B, N, float(eps), int(iters), ptr(dist), ptr(ass), ptr(ws), nbytes, stream_ptr()), "emd_fwd")
     return dist, ass
 
 

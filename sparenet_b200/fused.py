@@ -452,6 +452,56 @@ class Conv1x1(torch.autograd.Function):
         return gx, gW, None
 
 
+class BnSeTail(torch.autograd.Function):
+    """(scale, shift) [B,C] of the folded BatchNorm1d . SELayer1D . ReLU tail from row statistics -- ONE launch per direction
+    (csrc/tails.cu) instead of ~37 + ~48 microsecond-sized PyTorch launches.  m_bc, v_bc [B,C]: row mean / biased row variance of
+    the pre-activation h [B,C,L]; rb: conv bias [C] or per-sample bias [B,C] (only shifts the statistics and folds into the shift);
+    bn: the nn.BatchNorm1d whose running statistics are advanced IN the kernel in train mode; w1 [H,C], w2 [C,H]: the SE layer."""
+    @staticmethod
+    def forward(ctx, m_bc, v_bc, rb, g, beta, w1, w2, bn, L):
+        m_bc, v_bc = m_bc.contiguous().float(), v_bc.contiguous().float()
+        B, C = m_bc.shape
+        H = w1.shape[0]
+        rb, g, beta, w1, w2 = (t.detach().contiguous().float() for t in (rb, g, beta, w1, w2))
+        assert rb.shape in ((C,), (B, C)) and w1.shape == (H, C) and w2.shape == (C, H)
+        dev = m_bc.device
+        lib = _lib.load()
+        S, T = torch.empty(B, C, device=dev), torch.empty(B, C, device=dev)
+        save = torch.empty(lib.snb_bn_se_tail_save_floats(B, C, H), device=dev)
+        training = bool(bn.training)
+        track = training and bn.track_running_stats
+        count = B * L
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if (track or not training) else (None, None, None)
+        with torch.cuda.device(dev), _op("bn_se_tail_fwd", 1):
+            check(lib.snb_bn_se_tail_fwd(ptr(m_bc), ptr(v_bc), ptr(rb), int(rb.dim() == 2), ptr(g), ptr(beta), ptr(w1), ptr(w2), B, C, H, float(bn.eps),
+                                         int(training), float(mom), float(count / max(count - 1, 1)), ptr(rm), ptr(rv),
+                                         ptr(nbt) if track else None, ptr(S), ptr(T), ptr(save), stream_ptr()), "bn_se_tail_fwd")
+        ctx.save_for_backward(m_bc, rb, g, w1, w2, save)
+        ctx.dims = (B, C, H, training)
+        return S, T
+
+    @staticmethod
+    def backward(ctx, gS, gT):
+        m_bc, rb, g, w1, w2, save = ctx.saved_tensors
+        B, C, H, training = ctx.dims
+        dev = m_bc.device
+        lib = _lib.load()
+        gS, gT = gS.contiguous().float(), gT.contiguous().float()
+        gm, gv, grb = torch.empty_like(m_bc), torch.empty_like(m_bc), torch.empty_like(rb)
+        gg, gbeta, gw1, gw2 = torch.empty_like(g), torch.empty_like(g), torch.empty_like(w1), torch.empty_like(w2)
+        scratch = torch.empty(lib.snb_bn_se_tail_scratch_floats(B, C, H), device=dev)
+        with torch.cuda.device(dev), _op("bn_se_tail_bwd", 1):
+            check(lib.snb_bn_se_tail_bwd(ptr(gS), ptr(gT), ptr(m_bc), ptr(rb), int(rb.dim() == 2), ptr(g), ptr(w1), ptr(w2), B, C, H, int(training),
+                                         ptr(save), ptr(scratch), ptr(gm), ptr(gv), ptr(grb), ptr(gg), ptr(gbeta), ptr(gw1), ptr(gw2), stream_ptr()),
+                  "bn_se_tail_bwd")
+        return gm, gv, grb, gg, gbeta, gw1, gw2, None, None
+
+
+def bn_se_tail(m_bc, v_bc, rb, g, beta, w1, w2, bn, L):
+    return BnSeTail.apply(m_bc, v_bc, rb, g, beta, w1, w2, bn, L)
+
+
 class Prologue:
     """The folded normalisation tail of a dense layer, y = leaky_relu(scale*h + shift, slope) with
     (scale, shift) = fn(row_mean(h), row_var(h), *tensors), held as DATA instead of being applied: the next layer's GEMM applies it

@@ -33,7 +33,9 @@ def test_version_and_strerror_without_gpu():
     assert lib.snb_version() >= 100
     assert lib.snb_strerror(0) == b"ok"
     assert b"invalid" in lib.snb_strerror(-1)
-    assert lib.snb_emd_workspace_bytes(32, 8192) == 32 * (8192 * 40 + 64)
+    tree = 2 * (8192 + 2 * 8192 // 32 + 2 * 8192 // 512) * 16     # both clouds: sorted points + leaf boxes + super-boxes (float4)
+    assert lib.snb_emd_workspace_bytes(32, 8192) == 32 * (tree + 8192 * 32 + 8192 // 32 * 4 + 64)
+    assert lib.snb_emd_workspace_bytes(2, 32768) == 2 * (32768 * 40 + 64)            # above 16384 points: exhaustive Bid only
     assert lib.snb_knn_workspace_bytes(2, 128) == 2 * 128 * 128 * 4
 
 

@@ -88,7 +88,9 @@ def test_forward_and_five_step_trajectory_match_the_reference_path(cuda):
         for name, a, b, bb in (("cd(coarse)", c, c_tf32, c_fp32), ("cd(refine)", r, r_tf32, r_fp32)):
             la, lb, lbb = (cd_mean(t.contiguous(), gt).mean().item() for t in (a, b, bb))
             print(f"[B=32 config] {name}: ours {la:.6e}, reference {lb:.6e} (fp32 {lbb:.6e}), rel diff {abs(la - lb) / lb:.2e}")
-            assert abs(la - lb) <= max(3 * abs(lb - lbb), 2e-3 * lb)
+            # both TF32 arithmetics are held against the fp32 value: the tensor core truncates its operands while cuDNN's TF32
+            # kernels round them, so the two can land on opposite sides of it (and their mutual distance counts the band twice)
+            assert abs(la - lbb) <= max(3 * abs(lb - lbb), 2e-3 * lb)
         assert abs(lm.item() - l_tf32.item()) <= max(3 * abs(l_tf32.item() - l_fp32.item()), 1e-2 * abs(l_tf32.item()))
         # ---- 5 Adam steps each, same batch, same initial weights -------------------------------------------------------------------
         ref_losses = [float(ref_step(partial, gt)) for _ in range(5)]

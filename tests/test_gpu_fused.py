@@ -195,3 +195,62 @@ def test_row_norm_act_pool_forward_backward(cuda, B, C, L, slope):
         err = (a.grad.double() - b.grad).abs().max().item() / (b.grad.abs().max().item() + 1e-30)
         print(f"[row_norm_act_pool] B={B} C={C} L={L} grad {name}: err/scale {err:.2e}")
         assert err < 2e-5, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,per_sample,training", [(32, 64, False, True), (32, 512, True, True), (5, 128, False, True),
+                                                     (32, 256, False, False), (3, 48, True, False)])
+def test_bn_se_tail_matches_pytorch_closed_form(cuda, B, C, per_sample, training):
+    """snb_bn_se_tail_fwd/bwd (one launch per direction) against the same closed form written as PyTorch ops
+    (PointNetRes._bn_se_tail's tail_torch): scale/shift, the BatchNorm running statistics and every gradient, fp32 both sides,
+    <= 2e-5 of each tensor's scale (different summation order only)."""
+    import torch.nn as nn
+    from sparenet_b200 import fused
+    from sparenet_b200.dropin.models import sparenet_generator as G
+    torch.manual_seed(C + B)
+    L, H = 4096, max(C // 16, 1)
+    bn_a, bn_b = nn.BatchNorm1d(C).to(cuda), nn.BatchNorm1d(C).to(cuda)
+    for bn in (bn_a, bn_b):
+        bn.train(training)
+        with torch.no_grad():
+            bn.running_mean.copy_(torch.linspace(-0.3, 0.4, C))
+            bn.running_var.copy_(torch.linspace(0.5, 1.5, C))
+    se = G.SELayer1D(C).to(cuda)
+    m0, v0 = torch.randn(B, C, device=cuda), torch.rand(B, C, device=cuda) + 0.1
+    rb0 = torch.randn(B, C, device=cuda) if per_sample else torch.randn(C, device=cuda)
+    g0, b0 = torch.randn(C, device=cuda), torch.randn(C, device=cuda)
+    gS, gT = torch.randn(B, C, device=cuda), torch.randn(B, C, device=cuda)
+
+    def run(fn, bn):
+        leaves = [t.clone().requires_grad_() for t in (m0, v0, rb0, g0, b0, se.fc[0].weight.detach(), se.fc[2].weight.detach())]
+        S, T = fn(bn, *leaves)
+        grads = torch.autograd.grad((S, T), leaves, (gS, gT), allow_unused=True)
+        return S, T, grads
+
+    def ref(bn, m, v, rb, g, beta, w1, w2):
+        mm = m + rb
+        mean, var = G._bn_from_rows(bn, mm, v, L)
+        inv = torch.rsqrt(var + bn.eps)
+        scale, shift = g * inv, beta - g * inv * mean
+        gate = torch.sigmoid(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(mm * scale + shift, w1)), w2))
+        gs = gate * scale
+        return gs, gate * shift + rb * gs
+
+    S1, T1, G1 = run(ref, bn_a)
+    S2, T2, G2 = run(lambda bn, *a: fused.bn_se_tail(*a, bn, L), bn_b)
+    names = ["scale", "shift", "g_mean", "g_var", "g_bias", "g_gamma", "g_beta", "g_w1", "g_w2"]
+    for name, a, b in zip(names, [S1, T1, *G1], [S2, T2, *G2]):
+        if a is None:                       # eval mode: the row variance does not reach the outputs
+            assert b is None or float(b.abs().max()) == 0.0, name
+            continue
+        scale = max(float(a.detach().abs().max()), 1e-6)
+        if name == "g_bias" and not per_sample:
+            # a bias shared by the batch cancels EXACTLY in train mode (it shifts every row mean and the batch mean alike): the
+            # true gradient is 0 and both sides return rounding noise -- judged against the size of the terms that cancel
+            scale = max(scale, float(G1[0].detach().abs().sum(0).max()))
+        err = float((a - b).detach().abs().max()) / scale
+        print(f"[bn_se_tail B={B} C={C} per_sample={per_sample} train={training}] {name}: err/scale {err:.2e}")
+        assert err < 2e-5, name
+    assert torch.allclose(bn_a.running_mean, bn_b.running_mean, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(bn_a.running_var, bn_b.running_var, rtol=1e-6, atol=1e-7)
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked)

@@ -172,7 +172,8 @@ def test_chamfer_dropin_modules_autograd(cuda):
 @pytest.mark.parametrize("B,N,eps,iters,seed,kind", [(2, 1024, 0.005, 50, 4, "iid"), (3, 2048, 0.005, 50, 6, "near"),
                                                      (1, 3072, 0.002, 120, 7, "iid"), (2, 1024, 0.005, 1, 8, "iid"),
                                                      (1, 2048, 0.005, 50, 9, "dups")])
-def test_emd_vs_oracle_bit_exact(cuda, B, N, eps, iters, seed, kind):
+@pytest.mark.parametrize("exhaustive", [False, True])
+def test_emd_vs_oracle_bit_exact(cuda, B, N, eps, iters, seed, kind, exhaustive):
     from sparenet_b200 import functional as F_
     torch.manual_seed(seed)
     y = torch.rand(B, N, 3)
@@ -184,7 +185,7 @@ def test_emd_vs_oracle_bit_exact(cuda, B, N, eps, iters, seed, kind):
         x[:, -256:] = 0
     else:
         x = torch.rand(B, N, 3)
-    dist, ass = F_.emd_forward(x.to(cuda), y.to(cuda), eps, iters)
+    dist, ass = F_.emd_forward(x.to(cuda), y.to(cuda), eps, iters, exhaustive=exhaustive)
     odist, oass = oracle.emd_fwd(x, y, eps, iters)
     assert torch.equal(ass.cpu(), oass)
     assert torch.equal(dist.cpu(), odist)
@@ -240,6 +241,38 @@ def test_emd_full_size_properties(cuda):
     # identical clouds -> identity assignment, zero distance
     d0, a0 = F_.emd_forward(x[:2], x[:2].clone(), 0.005, 5)
     assert (a0 == torch.arange(8192, device=cuda, dtype=torch.int32)).all() and (d0 == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["iid", "blob_vs_shell", "near", "planes", "dups"])
+@pytest.mark.parametrize("N,iters", [(16384, 50), (8192, 50), (2048, 300)])
+def test_emd_pruned_bid_identical_to_exhaustive(cuda, kind, N, iters):
+    """The box-pruned Bid (snb_emd_fwd) against the exhaustive one (snb_emd_fwd_scan, the kernel the oracle pins bit for bit) at
+    sizes the oracle cannot reach: assignments and distances must be the same bits, also when prices pile up (a collapsed
+    prediction against a spread target), on coplanar clouds (degenerate boxes) and with exact ties."""
+    from sparenet_b200 import functional as F_
+    torch.manual_seed(N + iters)
+    B = 8
+    y = torch.rand(B, N, 3, device=cuda) - 0.5
+    if kind == "iid":
+        x = torch.rand(B, N, 3, device=cuda) - 0.5
+    elif kind == "blob_vs_shell":
+        y = torch.nn.functional.normalize(torch.randn(B, N, 3, device=cuda), dim=-1) * 0.5
+        x = 0.02 * torch.randn(B, N, 3, device=cuda)
+    elif kind == "near":
+        x = torch.stack([y[b, torch.randperm(N, device=cuda)] for b in range(B)]) + 0.01 * torch.randn(B, N, 3, device=cuda)
+    elif kind == "planes":
+        x = torch.rand(B, N, 3, device=cuda) - 0.5
+        x[..., 2] = 0.25
+        y[..., 0] = -0.1
+    else:
+        x = torch.rand(B, N, 3, device=cuda) - 0.5
+        y[:, N // 2:] = y[:, :N // 2]
+        x[:, -512:] = 0
+    d_t, a_t = F_.emd_forward(x, y, 0.005, iters)
+    d_s, a_s = F_.emd_forward(x, y, 0.005, iters, exhaustive=True)
+    same = (a_t == a_s).float().mean().item()
+    assert torch.equal(a_t, a_s), f"{kind} N={N}: {same * 100:.4f} % of the assignments agree"
+    assert torch.equal(d_t, d_s)
 
 
 def test_emd_limits_and_dropin(cuda):
