@@ -186,6 +186,32 @@ class ClockSampler:
         return out
 
 
+def _mds_issue_bound(ms_per_launch):
+    """Issue-slot floor of the sampler from the committed ncu --set full capture (profiles/r*_ncu_full_mds_cluster_kernel.csv):
+    warp instructions per launch / (SMs the launch occupied x 4 issue slots per cycle x SM clock)."""
+    import csv
+    import glob
+    caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_mds_cluster_kernel.csv")))
+    if not caps:
+        return None
+    vals = {}
+    for row in csv.reader(open(caps[-1])):
+        if len(row) >= 3:
+            vals[row[0]] = row[2]
+    try:
+        inst = float(vals["smsp__inst_executed.sum"])
+        sms = float(vals.get("launch__grid_size", 128))
+        ghz = float(vals.get("sm__cycles_elapsed.max.per_second", 1.965))
+        busy = float(vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan")) / 100.0
+        cap_ms = float(vals.get("gpu__time_duration.sum", "nan"))
+    except (KeyError, ValueError):
+        return None
+    floor_ms = inst / (sms * 4 * ghz * 1e9) * 1e3
+    return {"warp_instructions_per_launch": inst, "sms_used": sms, "issue_slots_busy_in_capture": busy, "capture_ms": cap_ms,
+            "floor_ms": floor_ms, "frac_of_floor_live": floor_ms / ms_per_launch if ms_per_launch else None,
+            "source": os.path.relpath(caps[-1], ROOT)}
+
+
 def build_gpu(args, dev, rank):
     import sparenet_b200
     sys.path.insert(0, sparenet_b200.dropin_path())
@@ -474,6 +500,7 @@ def run_ours(args):
     # ---- eager pass: per-op CUDA events (roofline of the dominant kernel) and the launch count of our kernels ----------
     F_.LAUNCHES["count"] = 0
     F_.PROFILE = {}
+    F_.FLOPS.clear()
     n_prof = 2
     was_on, step.overlap["on"] = step.overlap["on"], False   # per-op events are only meaningful with every kernel on one stream
     for _ in range(n_prof):
@@ -579,11 +606,28 @@ def run_ours(args):
             "note": "mds_sample is a 16383-round dependent chain (latency bound by construction): the HBM fraction of its compulsory bytes is "
                     "reported as asked; rounds/s is the meaningful figure" if dom == "mds_sample" else "",
             "rounds_per_s": ((N_OUT - 1) / (per_op[dom] * 1e-3)) if dom == "mds_sample" else None,
-            "issue_bound": ({"warp_instructions_per_launch": 4.67e9, "issue_slots_busy": 0.56, "floor_ms_at_128_SMs": 4.7,
-                             "source": "profiles/r1_ncu_full_mds_cluster_kernel.csv"} if dom == "mds_sample" else None),
+            "issue_bound": (_mds_issue_bound(per_op[dom]) if dom == "mds_sample" else None),
             "timing": f"CUDA events around every C-ABI call in an eager pass of {n_prof} steps next to the timed region",
             "hbm_bound_kernels": {k: dict(v, frac=round(v["GB/s"] / hbm_peak, 3)) for k, v in hbm_ops.items()},
             "ops_ms_per_step": {k: round(v, 3) for k, v in sorted(tot_op.items(), key=lambda kv: -kv[1])}}
+    # ---- tensor roofline of the tcgen05 GEMM family (all 1x1-conv products of the step): flops / CUDA-event time of the calls ------
+    gemm_ops = [k for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in prof]
+    roof_tc = None
+    if gemm_ops:
+        g_ms = sum(tot_op[k] for k in gemm_ops)
+        g_fl = sum(F_.FLOPS.get(k, 0) for k in gemm_ops) / n_prof
+        bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1378.4)))
+        ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else None
+        roof_tc = {"kernel": "gemm_tf32_kernel (tcgen05.mma kind::tf32, TMEM accumulators, TMA operands)", "bound": "tensor", "achieved": ach,
+                   "peak": bf16_peak, "unit": "TFLOP/s", "frac": (ach / bf16_peak) if ach else None, "traffic": None,
+                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16, kernel timed inside a long step)" if peaks else "fallback",
+                   "note": "the products are TF32 (fp32 operands): the tensor core's dense TF32 rate is HALF its bf16 rate, so frac_of_tf32_rate "
+                           "is the fraction of what this arithmetic can reach; about half of the calls also apply the previous layer's "
+                           "scale/shift/LeakyReLU to the operand tile in shared memory, which makes those shared-memory-bandwidth bound",
+                   "frac_of_tf32_rate": (ach / (bf16_peak / 2)) if ach else None, "flops_per_step": g_fl, "ms_per_step": g_ms,
+                   "launches_per_step": sum(len(prof[k]) for k in gemm_ops) // n_prof, "share_of_step": g_ms / (ms / args.steps),
+                   "by_arrangement": {k: {"ms_per_step": round(tot_op[k], 3), "TFLOP/s": round(F_.FLOPS.get(k, 0) / n_prof / (tot_op[k] * 1e-3) / 1e12, 1)}
+                                      for k in gemm_ops}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core GEMMs)",
             "data": "synthetic",
@@ -597,7 +641,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(h_partial.numel() + h_gt.numel()) * 4, "d2h_bytes_per_step": 4, "last_loss": last},
-            "roofline": roof}
+            "roofline": roof, "roofline_tensor": roof_tc}
     if world == 1:
         try:
             line["ops_ms_per_batch"] = aux_ops_ms(dev, args.batch)

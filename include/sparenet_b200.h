@@ -167,11 +167,13 @@ int snb_row_stats_minmax(const float* h, long long R, int L, float* mean, float*
                          int* imax, int* imin, void* stream);
 /* Two-phase backward of y = leaky_relu(scale*h + shift) when (scale, shift) depend on h's row statistics (BN o SE o ReLU):
  * _reduce returns gscale[r] = sum_l d*h, gshift[r] = sum_l d with d = gy * act'(scale*h + shift); after the caller has
- * pulled (gscale, gshift) back to (gmean, gvar), row_norm_act_bwd writes gh = d*scale + gmean/L + 2 gvar (h - mean)/L. */
+ * pulled (gscale, gshift) back to (gmean, gvar), row_norm_act_bwd writes gh = d*scale + gmean/L + 2 gvar (h - mean)/L.
+ * gy_row (may be NULL): a per-row constant added to gy on the fly (the W^T b 1^T term of a row-statistics gradient). */
 int snb_row_act_bwd_reduce(const float* gy, const float* h, const float* scale, const float* shift, long long R, int L,
-                           float slope, float* gscale, float* gshift, void* stream);
+                           float slope, float* gscale, float* gshift, const float* gy_row, void* stream);
 int snb_row_norm_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, const float* mean,
-                         const float* gmean, const float* gvar, long long R, int L, float slope, float* gh, void* stream);
+                         const float* gmean, const float* gvar, long long R, int L, float slope, float* gh,
+                         const float* gy_row, void* stream);
 
 /* Pooled tail: vmax / vmean [R] = max / mean over the row of leaky_relu(scale*h + shift) (first position imax on ties) without
  * storing the activated row -- the encoder's [max | mean over points] output (models/sparenet_generator.py:234-242).  Backward

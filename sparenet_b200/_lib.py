@@ -66,8 +66,8 @@ SIGNATURES = {
     "snb_row_affine_act_bwd": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, c_int, c_float, P, P, P, P]),
     "snb_row_minmax": (c_int, [P, ctypes.c_longlong, c_int, P, P, P, P, P]),
     "snb_row_stats_minmax": (c_int, [P, ctypes.c_longlong, c_int, P, P, P, P, P, P, P]),
-    "snb_row_act_bwd_reduce": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P]),
-    "snb_row_norm_act_bwd": (c_int, [P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P]),
+    "snb_row_act_bwd_reduce": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P, P]),
+    "snb_row_norm_act_bwd": (c_int, [P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P]),
     "snb_gemm_tf32": (c_int, [ctypes.POINTER(GemmDesc), P]),
     "snb_gemm_tf32_tiles": (c_int, [c_int, c_int]),
     "snb_gemm_tf32_block_n": (c_int, [c_int, c_int]),

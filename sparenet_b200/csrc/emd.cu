@@ -448,32 +448,7 @@ __device__ unsigned long long g_emd_stats[16];
 template <int G>
 __device__ __forceinline__ void emdt_scan_leaf(const float4* buf, int pos0, int g, float bx, float by, float bz, BidState& st, const int* oid,
                                                int n, int tpu) {
-  if (G > 1) {
-    // sparse rounds are LATENCY bound (a few long passes, one per warp): the lane's 32/G objects are evaluated exactly and
-    // unconditionally -- independent sqrt / fp64 chains that overlap -- instead of a filter pass plus a serial loop over the
-    // flagged ones; the values then go through the same update rule in ascending object order
-    float d[BVH_LEAF / G];
-#pragma unroll
-    for (int i = 0; i < BVH_LEAF / G; i++) {
-      const float4 o = buf[g + G * i];
-      const float sv = sqdist3(__fsub_rn(o.x, bx), __fsub_rn(o.y, by), __fsub_rn(o.z, bz));
-      d[i] = (float)((3.0 - (double)sqrtf(sv)) - (double)o.w);
-    }
-#pragma unroll
-    for (int i = 0; i < BVH_LEAF / G; i++) {
-      const int pos = pos0 + g + G * i;
-      if (d[i] > st.best) {
-        st.better = st.best;
-        st.best = d[i];
-        st.best_i = pos;
-      } else if (d[i] == st.best) {
-        st.better = d[i];
-        if (emdt_tie_key(pos, oid, n, tpu) < emdt_tie_key(st.best_i, oid, n, tpu)) st.best_i = pos;
-      } else if (d[i] > st.better) {
-        st.better = d[i];
-      }
-    }
-  } else {
+  {
     unsigned fl = 0u;
 #pragma unroll
     for (int i = 0; i < BVH_LEAF / G; i++) {
@@ -750,19 +725,21 @@ __global__ void __launch_bounds__(EMDT_THREADS, 1) emd_auction_tree_kernel(const
 
     // ---- Bid.  Dense rounds (a quarter of the bidders or more still unassigned): 32 neighbouring bidders per warp pass, one lane
     //      each.  Sparse rounds: the survivors are far apart in Morton order, the union of the boxes 32 of them open is several
-    //      times what each needs, so a pass takes 8 bidders with 4 lanes each.  Passes differ a lot in length: the warps of the
-    //      cluster draw them from a ticket counter instead of a fixed deal. ----
+    //      times what each needs, and the round lasts as long as its longest pass: 8 bidders with 4 lanes each, or -- when there
+    //      are fewer than 4 bidders per warp of the cluster -- 2 bidders with 16 lanes each.  Passes differ a lot in length: the
+    //      warps of the cluster draw them from a ticket counter instead of a fixed deal. ----
     {
       int* ticket = &w.counter[2 + (it & 1)];
-      const bool dense = (long long)U * 4 >= n;
-      const int pw = dense ? 32 : 8;
+      const int mode = ((long long)U * 4 >= n) ? 0 : (U > 4 * Wn ? 1 : 2);
+      const int pw = mode == 0 ? 32 : (mode == 1 ? 8 : 2);
       for (;;) {
         int p = 0;
         if (lane == 0) p = atomicAdd(ticket, 1);
         p = __shfl_sync(0xffffffffu, p, 0);
         if ((long long)p * pw >= U) break;
-        if (dense) emdt_bid_pass<1>(w, sh, n, nc, ns, U, p * pw, tpu, eps);
-        else emdt_bid_pass<4>(w, sh, n, nc, ns, U, p * pw, tpu, eps);
+        if (mode == 0) emdt_bid_pass<1>(w, sh, n, nc, ns, U, p * pw, tpu, eps);
+        else if (mode == 1) emdt_bid_pass<4>(w, sh, n, nc, ns, U, p * pw, tpu, eps);
+        else emdt_bid_pass<16>(w, sh, n, nc, ns, U, p * pw, tpu, eps);
       }
     }
     const long long tb1 = EMD_CLOCK();

@@ -281,11 +281,12 @@ __global__ void __launch_bounds__(ROW_THREADS) row_stats_minmax_kernel(const flo
 __global__ void __launch_bounds__(ROW_THREADS) row_act_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ h,
                                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                                           long long R, int L, float slope, float* __restrict__ gscale,
-                                                                          float* __restrict__ gshift) {
+                                                                          float* __restrict__ gshift, const float* __restrict__ gy_row) {
   const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
   const float sc = scale[r], sh = shift[r];
+  const float gb = gy_row ? gy_row[r] : 0.f;   // a term of the upstream gradient that is constant along the row
   const float* __restrict__ p = h + r * L;
   const float* __restrict__ q = gy + r * L;
   float as = 0.f, ab = 0.f;
@@ -293,7 +294,9 @@ __global__ void __launch_bounds__(ROW_THREADS) row_act_bwd_reduce_kernel(const f
     const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
     const float4* __restrict__ q4 = reinterpret_cast<const float4*>(q);
     for (int i = lane; i < (L >> 2); i += 32) {
-      const float4 v = p4[i], w = q4[i];
+      const float4 v = p4[i];
+      float4 w = q4[i];
+      w.x += gb; w.y += gb; w.z += gb; w.w += gb;
       const float d0 = __fmaf_rn(v.x, sc, sh) > 0.f ? w.x : w.x * slope;
       const float d1 = __fmaf_rn(v.y, sc, sh) > 0.f ? w.y : w.y * slope;
       const float d2 = __fmaf_rn(v.z, sc, sh) > 0.f ? w.z : w.z * slope;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_act_bwd_reduce_kernel(const f
     }
   } else {
     for (int i = lane; i < L; i += 32) {
-      const float v = p[i], w = q[i];
+      const float v = p[i], w = q[i] + gb;
       const float d = __fmaf_rn(v, sc, sh) > 0.f ? w : w * slope;
       as = __fmaf_rn(d, v, as);
       ab += d;
@@ -321,11 +324,12 @@ __global__ void __launch_bounds__(ROW_THREADS) row_norm_act_bwd_kernel(const flo
                                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                                         const float* __restrict__ mean, const float* __restrict__ gmean,
                                                                         const float* __restrict__ gvar, long long R, int L, float slope,
-                                                                        float* __restrict__ gh) {
+                                                                        float* __restrict__ gh, const float* __restrict__ gy_row) {
   const long long r = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
   const float sc = scale[r], sh = shift[r];
+  const float gb = gy_row ? gy_row[r] : 0.f;
   const float invL = 1.f / (float)L;
   const float a = gmean[r] * invL, b = 2.f * gvar[r] * invL, m = mean[r];
   const float s1 = sc, s0 = sc * slope;
@@ -337,7 +341,9 @@ __global__ void __launch_bounds__(ROW_THREADS) row_norm_act_bwd_kernel(const flo
     const float4* __restrict__ q4 = reinterpret_cast<const float4*>(q);
     float4* __restrict__ g4 = reinterpret_cast<float4*>(g);
     for (int i = lane; i < (L >> 2); i += 32) {
-      const float4 v = p4[i], w = q4[i];
+      const float4 v = p4[i];
+      float4 w = q4[i];
+      w.x += gb; w.y += gb; w.z += gb; w.w += gb;
       float4 o;
       o.x = __fmaf_rn(w.x, __fmaf_rn(v.x, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v.x - m, a));
       o.y = __fmaf_rn(w.y, __fmaf_rn(v.y, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v.y - m, a));
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_norm_act_bwd_kernel(const flo
   } else {
     for (int i = lane; i < L; i += 32) {
       const float v = p[i];
-      g[i] = __fmaf_rn(q[i], __fmaf_rn(v, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v - m, a));
+      g[i] = __fmaf_rn(q[i] + gb, __fmaf_rn(v, sc, sh) > 0.f ? s1 : s0, __fmaf_rn(b, v - m, a));
     }
   }
 }
@@ -548,21 +554,22 @@ SNB_API int snb_row_stats_minmax(const float* h, long long R, int L, float* mean
 }
 
 SNB_API int snb_row_act_bwd_reduce(const float* gy, const float* h, const float* scale, const float* shift, long long R, int L, float slope,
-                                   float* gscale, float* gshift, void* stream) {
+                                   float* gscale, float* gshift, const float* gy_row, void* stream) {
   if (R < 0 || L <= 0) return SNB_EINVAL;
   if (R == 0) return SNB_OK;
   if (R > 0x3fffffffLL) return SNB_ELIMIT;
-  row_act_bwd_reduce_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, R, L, slope, gscale, gshift);
+  row_act_bwd_reduce_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, R, L, slope, gscale, gshift, gy_row);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
 
 SNB_API int snb_row_norm_act_bwd(const float* gy, const float* h, const float* scale, const float* shift, const float* mean,
-                                 const float* gmean, const float* gvar, long long R, int L, float slope, float* gh, void* stream) {
+                                 const float* gmean, const float* gvar, long long R, int L, float slope, float* gh, const float* gy_row,
+                                 void* stream) {
   if (R < 0 || L <= 0) return SNB_EINVAL;
   if (R == 0) return SNB_OK;
   if (R > 0x3fffffffLL) return SNB_ELIMIT;
-  row_norm_act_bwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, mean, gmean, gvar, R, L, slope, gh);
+  row_norm_act_bwd_kernel<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(gy, h, scale, shift, mean, gmean, gvar, R, L, slope, gh, gy_row);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

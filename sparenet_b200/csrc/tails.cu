@@ -9,19 +9,27 @@
 //     z      = m * sc_c + sh_c                        (the SE squeeze: mean over the points of BN(h + rb))
 //     gate   = sigmoid(W2 relu(W1 z))                 (SE excitation, W1 [H,C], W2 [C,H], no biases)
 //     S      = gate * sc_c,   T = gate * sh_c + rb * S                        => tail(h) = relu(S*h + T)
-// As PyTorch glue this is ~37 launches forward and ~48 backward of a few microseconds each (ten such tails per step in the
-// refiner: ~3.4 ms of a 68 ms step); the numbers are tiny (B*C <= 16 K values, 2*B*C*H multiply-adds), so ONE thread block with
-// barriers between the phases does each direction.  Intermediates that cross a phase live in a caller-owned scratch / save
-// buffer (L1/L2 resident; a block barrier orders global memory among the block's threads).
+// As PyTorch glue this is ~37 launches forward and ~48 backward (each ~2 us of kernel + ~2.4 us of launch gap inside the step's CUDA
+// graph: ~360 us per tail, ten tails per step in the refiner).  The data is tiny (B*C <= 16 K values) but the work is a chain of
+// dependent phases, i.e. LATENCY: a first version on ONE thread block took 60-100 us (the two small matrix products alone are
+// ~50 K warp instructions on a single SM).  So one CLUSTER of 8 thread blocks runs each direction: every phase is spread over the
+// 8192 threads / 256 warps of the cluster with all of its loads independent, phases are separated by cluster barriers, and what
+// crosses a barrier goes through the caller's save / scratch buffers in global memory (L2; the barrier's acquire invalidates L1).
 #include <math.h>
 #include "common.cuh"
 
 namespace snb {
 
 constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_CLUSTER = 8;
 
 __device__ __forceinline__ float tail_rb(const float* __restrict__ rb, int rb_batched, int b, int c, int C) {
   return rb ? (rb_batched ? rb[b * C + c] : rb[c]) : 0.f;
+}
+__device__ __forceinline__ float tail_warp_sum(float v) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
 }
 
 // save layout (floats): mean[C] inv[C] sc[C] sh[C] z[B*C] gate[B*C] a1[B*H]
@@ -32,30 +40,34 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_fwd_kernel(const f
                                                                           float momentum, float unbias, float* run_mean, float* run_var,
                                                                           long long* num_batches, float* __restrict__ S, float* __restrict__ T,
                                                                           float* save) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int nt = (int)(cluster_nctarank() * blockDim.x), ct = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+  const int lane = ct & 31, cw = ct >> 5, nw = nt >> 5;
+  const int BC = B * C;
   float* mean = save;
   float* inv = mean + C;
   float* sc = inv + C;
   float* sh = sc + C;
   float* z = sh + C;
-  float* gate = z + (size_t)B * C;
-  float* a1 = gate + (size_t)B * C;
+  float* gate = z + (size_t)BC;
+  float* a1 = gate + (size_t)BC;
   const float rB = 1.0f / (float)B;
-  // ---- BatchNorm statistics and the per-channel scale / shift ----
-  for (int c = tid; c < C; c += nt) {
+  // ---- BatchNorm statistics and the per-channel scale / shift: a warp per channel, lanes over the samples ----
+  for (int c = cw; c < C; c += nw) {
     float mu, var;
     if (training) {
-      float s = 0.f;
-      for (int b = 0; b < B; b++) s += m_bc[b * C + c] + tail_rb(rb, rb_batched, b, c, C);
-      mu = s * rB;
-      float sd = 0.f, sv = 0.f;
-      for (int b = 0; b < B; b++) {
-        const float d = (m_bc[b * C + c] + tail_rb(rb, rb_batched, b, c, C)) - mu;
-        sd += d * d;
+      float sm = 0.f, sv = 0.f;
+      for (int b = lane; b < B; b += 32) {
+        sm += m_bc[b * C + c] + tail_rb(rb, rb_batched, b, c, C);
         sv += v_bc[b * C + c];
       }
-      var = sv * rB + sd * rB;
-      if (run_mean) {  // nn.BatchNorm bookkeeping: running statistics with the unbiased variance
+      mu = tail_warp_sum(sm) * rB;
+      float sd = 0.f;
+      for (int b = lane; b < B; b += 32) {
+        const float d = (m_bc[b * C + c] + tail_rb(rb, rb_batched, b, c, C)) - mu;
+        sd += d * d;
+      }
+      var = tail_warp_sum(sv) * rB + tail_warp_sum(sd) * rB;
+      if (lane == 0 && run_mean) {  // nn.BatchNorm bookkeeping: running statistics with the unbiased variance
         run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mu;
         run_var[c] = (1.f - momentum) * run_var[c] + momentum * (var * unbias);
       }
@@ -63,35 +75,37 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_fwd_kernel(const f
       mu = run_mean[c];
       var = run_var[c];
     }
-    const float iv = rsqrtf(var + eps);
-    const float s_c = g[c] * iv;
-    mean[c] = mu;
-    inv[c] = iv;
-    sc[c] = s_c;
-    sh[c] = beta[c] - s_c * mu;
+    if (lane == 0) {
+      const float iv = rsqrtf(var + eps);
+      const float s_c = g[c] * iv;
+      mean[c] = mu;
+      inv[c] = iv;
+      sc[c] = s_c;
+      sh[c] = beta[c] - s_c * mu;
+    }
   }
-  if (tid == 0 && training && num_batches) *num_batches += 1;
-  __syncthreads();
-  // ---- SE squeeze ----
-  for (int i = tid; i < B * C; i += nt) {
-    const int b = i / C, c = i - b * C;
-    z[i] = (m_bc[i] + tail_rb(rb, rb_batched, b, c, C)) * sc[c] + sh[c];
-  }
-  __syncthreads();
-  // ---- a1 = relu(W1 z): a warp per (sample, hidden unit), lanes over the channels ----
-  for (int o = warp; o < B * H; o += nw) {
+  if (ct == 0 && training && num_batches) *num_batches += 1;
+  cluster_sync_all();
+  // ---- a1 = relu(W1 z), z = m*sc + sh formed on the fly (and stored by the warps of hidden unit 0): a warp per (sample, hidden
+  //      unit), lanes over the channels ----
+  for (int o = cw; o < B * H; o += nw) {
     const int b = o / H, h = o - b * H;
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = __fmaf_rn(w1[h * C + c], z[b * C + c], acc);
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+#pragma unroll 4
+    for (int c = lane; c < C; c += 32) {
+      const float zz = (m_bc[b * C + c] + tail_rb(rb, rb_batched, b, c, C)) * sc[c] + sh[c];
+      if (h == 0) z[b * C + c] = zz;
+      acc = __fmaf_rn(w1[h * C + c], zz, acc);
+    }
+    acc = tail_warp_sum(acc);
     if (lane == 0) a1[o] = fmaxf(acc, 0.f);
   }
-  __syncthreads();
+  cluster_sync_all();
   // ---- gate = sigmoid(W2 a1); the folded scale / shift ----
-  for (int i = tid; i < B * C; i += nt) {
+  for (int i = ct; i < BC; i += nt) {
     const int b = i / C, c = i - b * C;
     float acc = 0.f;
+#pragma unroll 8
     for (int h = 0; h < H; h++) acc = __fmaf_rn(w2[c * H + h], a1[b * H + h], acc);
     const float gt = 1.0f / (1.0f + expf(-acc));
     gate[i] = gt;
@@ -101,7 +115,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_fwd_kernel(const f
   }
 }
 
-// scratch layout (floats): ga2[B*C] gz[B*C] gp1[B*H] gvar[C] gmean[C]
+// scratch layout (floats): ga2[B*C] gz[B*C] p1[B*C] p2[B*C] gp1[B*H]
 __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_bwd_kernel(const float* __restrict__ gS, const float* __restrict__ gT,
                                                                           const float* __restrict__ m_bc, const float* __restrict__ rb, int rb_batched,
                                                                           const float* __restrict__ g, const float* __restrict__ w1,
@@ -109,90 +123,112 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_bwd_kernel(const f
                                                                           const float* save, float* scratch, float* __restrict__ gm,
                                                                           float* __restrict__ gv, float* __restrict__ grb, float* __restrict__ gg,
                                                                           float* __restrict__ gbeta, float* __restrict__ gw1, float* __restrict__ gw2) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int nt = (int)(cluster_nctarank() * blockDim.x), ct = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+  const int lane = ct & 31, cw = ct >> 5, nw = nt >> 5;
+  const int BC = B * C;
   const float* mean = save;
   const float* inv = mean + C;
   const float* sc = inv + C;
   const float* sh = sc + C;
   const float* z = sh + C;
-  const float* gate = z + (size_t)B * C;
-  const float* a1 = gate + (size_t)B * C;
+  const float* gate = z + (size_t)BC;
+  const float* a1 = gate + (size_t)BC;
   float* ga2 = scratch;
-  float* gz = ga2 + (size_t)B * C;
-  float* gp1 = gz + (size_t)B * C;
-  float* gvar = gp1 + (size_t)B * H;
-  float* gmean = gvar + C;
+  float* gz = ga2 + (size_t)BC;
+  float* p1 = gz + (size_t)BC;
+  float* p2 = p1 + (size_t)BC;
+  float* gp1 = p2 + (size_t)BC;
   const float rB = 1.0f / (float)B;
-  // ---- through S, T to the gate's pre-activation ----
-  for (int i = tid; i < B * C; i += nt) {
+  // ---- through S, T to the gate's pre-activation; the direct terms of the per-channel scale / shift gradients ----
+  for (int i = ct; i < BC; i += nt) {
     const int b = i / C, c = i - b * C;
-    const float gst = gS[i] + gT[i] * tail_rb(rb, rb_batched, b, c, C);
-    const float gt = gate[i];
-    ga2[i] = (gst * sc[c] + gT[i] * sh[c]) * gt * (1.0f - gt);
+    const float gt_ = gT[i], ga = gate[i];
+    const float gst = gS[i] + gt_ * tail_rb(rb, rb_batched, b, c, C);
+    ga2[i] = (gst * sc[c] + gt_ * sh[c]) * ga * (1.0f - ga);
+    p1[i] = gst * ga;
+    p2[i] = gt_ * ga;
   }
-  __syncthreads();
-  // ---- gp1 = (W2^T ga2) masked by the ReLU: a warp per (sample, hidden unit) ----
-  for (int o = warp; o < B * H; o += nw) {
+  cluster_sync_all();
+  // ---- gp1 = (W2^T ga2) masked by the ReLU: a warp per (sample, hidden unit), lanes over the channels ----
+  for (int o = cw; o < B * H; o += nw) {
     const int b = o / H, h = o - b * H;
     float acc = 0.f;
+#pragma unroll 4
     for (int c = lane; c < C; c += 32) acc = __fmaf_rn(w2[c * H + h], ga2[b * C + c], acc);
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    acc = tail_warp_sum(acc);
     if (lane == 0) gp1[o] = a1[o] > 0.f ? acc : 0.f;
   }
-  __syncthreads();
-  // ---- the two weight gradients and gz = W1^T gp1 ----
-  for (int i = tid; i < C * H; i += nt) {
+  cluster_sync_all();
+  // ---- the two weight gradients (sums over the samples) and gz = W1^T gp1 with the remaining per-element terms ----
+  for (int i = ct; i < C * H; i += nt) {
     const int c = i / H, h = i - c * H;     // gw2 [C,H]
     float acc = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; b++) acc = __fmaf_rn(ga2[b * C + c], a1[b * H + h], acc);
     gw2[i] = acc;
     const int h1 = i / C, c1 = i - h1 * C;  // gw1 [H,C]
     float acc1 = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; b++) acc1 = __fmaf_rn(gp1[b * H + h1], z[b * C + c1], acc1);
     gw1[i] = acc1;
   }
-  for (int i = tid; i < B * C; i += nt) {
+  for (int i = ct; i < BC; i += nt) {
     const int b = i / C, c = i - b * C;
     float acc = 0.f;
+#pragma unroll 8
     for (int h = 0; h < H; h++) acc = __fmaf_rn(w1[h * C + c], gp1[b * H + h], acc);
     gz[i] = acc;
+    p1[i] += acc * (m_bc[i] + tail_rb(rb, rb_batched, b, c, C));
+    p2[i] += acc;
   }
-  __syncthreads();
-  // ---- per channel: scale / shift gradients -> gamma, beta, batch mean and variance ----
-  for (int c = tid; c < C; c += nt) {
+  cluster_sync_all();
+  // ---- per channel (a warp each, lanes over the samples): scale / shift gradients -> gamma, beta, batch mean and variance, then
+  //      straight back to the row statistics and the bias ----
+  for (int c = cw; c < C; c += nw) {
     float gsc = 0.f, gsh = 0.f;
-    for (int b = 0; b < B; b++) {
-      const int i = b * C + c;
-      const float r_ = tail_rb(rb, rb_batched, b, c, C);
-      const float gst = gS[i] + gT[i] * r_;
-      gsc += gst * gate[i] + gz[i] * (m_bc[i] + r_);
-      gsh += gT[i] * gate[i] + gz[i];
+    for (int b = lane; b < B; b += 32) {
+      gsc += p1[b * C + c];
+      gsh += p2[b * C + c];
     }
-    gbeta[c] = gsh;
-    const float gst_c = gsc - gsh * mean[c];
-    gg[c] = gst_c * inv[c];
-    gvar[c] = training ? -0.5f * gst_c * g[c] * inv[c] * inv[c] * inv[c] : 0.f;
-    gmean[c] = training ? -gsh * sc[c] : 0.f;
-  }
-  __syncthreads();
-  // ---- back to the row statistics and the bias ----
-  for (int c = tid; c < C; c += nt) {
+    gsc = tail_warp_sum(gsc);
+    gsh = tail_warp_sum(gsh);
+    const float mu = mean[c], iv = inv[c], s_c = sc[c];
+    const float gst_c = gsc - gsh * mu;
+    const float gvar = training ? -0.5f * gst_c * g[c] * iv * iv * iv : 0.f;
+    const float gmean = training ? -gsh * s_c : 0.f;
+    if (lane == 0) {
+      gbeta[c] = gsh;
+      gg[c] = gst_c * iv;
+    }
     float grb_c = 0.f;
-    for (int b = 0; b < B; b++) {
+    for (int b = lane; b < B; b += 32) {
       const int i = b * C + c;
       const float r_ = tail_rb(rb, rb_batched, b, c, C);
-      const float gm_ = gz[i] * sc[c] + (gmean[c] + gvar[c] * 2.0f * ((m_bc[i] + r_) - mean[c])) * rB;
+      const float gm_ = gz[i] * s_c + (gmean + gvar * 2.0f * ((m_bc[i] + r_) - mu)) * rB;
       gm[i] = gm_;
-      gv[i] = gvar[c] * rB;
-      const float gr = gm_ + gT[i] * gate[i] * sc[c];   // m = row mean + rb, and T's direct term rb * S
-      if (grb) {
-        if (rb_batched) grb[i] = gr;
-        else grb_c += gr;
-      }
+      gv[i] = gvar * rB;
+      const float gr = gm_ + gT[i] * gate[i] * s_c;   // m = row mean + rb, and T's direct term rb * S
+      if (grb && rb_batched) grb[i] = gr;
+      grb_c += gr;
     }
-    if (grb && !rb_batched) grb[c] = grb_c;
+    grb_c = tail_warp_sum(grb_c);
+    if (grb && !rb_batched && lane == 0) grb[c] = grb_c;
   }
+}
+
+static int tail_launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, cudaStream_t s) {
+  cfg = {};
+  cfg.gridDim = dim3(TAIL_CLUSTER);
+  cfg.blockDim = dim3(TAIL_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = TAIL_CLUSTER;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return 0;
 }
 
 }  // namespace snb
@@ -206,7 +242,7 @@ SNB_API size_t snb_bn_se_tail_save_floats(int B, int C, int H) {
 
 SNB_API size_t snb_bn_se_tail_scratch_floats(int B, int C, int H) {
   if (B <= 0 || C <= 0 || H <= 0) return 0;
-  return (size_t)2 * B * C + (size_t)B * H + (size_t)2 * C;
+  return (size_t)4 * B * C + (size_t)B * H;
 }
 
 SNB_API int snb_bn_se_tail_fwd(const float* row_mean, const float* row_var, const float* row_bias, int bias_per_sample, const float* gamma,
@@ -216,9 +252,11 @@ SNB_API int snb_bn_se_tail_fwd(const float* row_mean, const float* row_var, cons
   if (B < 0 || C < 0 || H < 0) return SNB_EINVAL;
   if (B == 0 || C == 0) return SNB_OK;
   if (H == 0 || (!training && (!running_mean || !running_var))) return SNB_EINVAL;
-  bn_se_tail_fwd_kernel<<<1, TAIL_THREADS, 0, (cudaStream_t)stream>>>(row_mean, row_var, row_bias, bias_per_sample, gamma, beta, w1, w2, B, C, H, eps,
-                                                                      training, momentum, unbias, running_mean, running_var, num_batches_tracked,
-                                                                      scale, shift, save);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  tail_launch_cfg(cfg, at, (cudaStream_t)stream);
+  SNB_CUDA(cudaLaunchKernelEx(&cfg, bn_se_tail_fwd_kernel, row_mean, row_var, row_bias, bias_per_sample, gamma, beta, w1, w2, B, C, H, eps, training,
+                              momentum, unbias, running_mean, running_var, num_batches_tracked, scale, shift, save));
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
@@ -230,9 +268,11 @@ SNB_API int snb_bn_se_tail_bwd(const float* grad_scale, const float* grad_shift,
   if (B < 0 || C < 0 || H < 0) return SNB_EINVAL;
   if (B == 0 || C == 0) return SNB_OK;
   if (H == 0) return SNB_EINVAL;
-  bn_se_tail_bwd_kernel<<<1, TAIL_THREADS, 0, (cudaStream_t)stream>>>(grad_scale, grad_shift, row_mean, row_bias, bias_per_sample, gamma, w1, w2, B, C,
-                                                                      H, training, save, scratch, grad_row_mean, grad_row_var, grad_row_bias,
-                                                                      grad_gamma, grad_beta, grad_w1, grad_w2);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  tail_launch_cfg(cfg, at, (cudaStream_t)stream);
+  SNB_CUDA(cudaLaunchKernelEx(&cfg, bn_se_tail_bwd_kernel, grad_scale, grad_shift, row_mean, row_bias, bias_per_sample, gamma, w1, w2, B, C, H,
+                              training, save, (float*)scratch, grad_row_mean, grad_row_var, grad_row_bias, grad_gamma, grad_beta, grad_w1, grad_w2));
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

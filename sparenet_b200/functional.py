@@ -32,12 +32,14 @@ class SnbValueError(ValueError):
 # ---- instrumentation: kernel-launch counter (bench.py's gpu_launches) and optional per-op CUDA-event timing --------
 LAUNCHES = {"count": 0}
 PROFILE = None  # set to a dict {op: [(start_event, end_event), ...]} by bench.py to time ops on the current stream
+FLOPS = {}      # op -> floating-point operations issued while PROFILE is set (tensor-core GEMMs: 2*M*N*K per product)
 
 
 class _op:
     """Counts the kernels a C-ABI call launches and, when PROFILE is set, brackets it with CUDA events."""
-    def __init__(self, name, launches, nbytes=None):
+    def __init__(self, name, launches, nbytes=None, flops=None):
         self.name, self.launches, self.nbytes = name, launches, nbytes   # nbytes: algorithmic HBM bytes of the call (roofline)
+        self.flops = flops
 
     def __enter__(self):
         LAUNCHES["count"] += self.launches
@@ -51,6 +53,8 @@ class _op:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
             PROFILE.setdefault(self.name, []).append((self.a, b, self.nbytes))
+            if self.flops:
+                FLOPS[self.name] = FLOPS.get(self.name, 0) + self.flops
         return False
 
 

@@ -266,7 +266,7 @@ class RowNormAct(torch.autograd.Function):
         gy = gy.contiguous()
         gsc, gsh = torch.empty_like(sc), torch.empty_like(sh)
         with torch.cuda.device(h.device), _op("row_act_bwd_reduce", 1, 8 * h.numel()):
-            check(lib.snb_row_act_bwd_reduce(ptr(gy), ptr(h), ptr(sc), ptr(sh), R, L, ctx.slope, ptr(gsc), ptr(gsh), stream_ptr()),
+            check(lib.snb_row_act_bwd_reduce(ptr(gy), ptr(h), ptr(sc), ptr(sh), R, L, ctx.slope, ptr(gsc), ptr(gsh), None, stream_ptr()),
                   "row_act_bwd_reduce")
         wanted = [m_, v_] + [t for t in ts if t.requires_grad]
         grads = torch.autograd.grad((scale, shift), wanted, (gsc.view_as(scale), gsh.view_as(shift)), allow_unused=True, retain_graph=True)
@@ -275,18 +275,20 @@ class RowNormAct(torch.autograd.Function):
         gh = torch.empty_like(h)
         with torch.cuda.device(h.device), _op("row_norm_act_bwd", 1, 12 * h.numel()):
             check(lib.snb_row_norm_act_bwd(ptr(gy), ptr(h), ptr(sc), ptr(sh), ptr(m_.detach()), ptr(gm), ptr(gv), R, L, ctx.slope, ptr(gh),
-                                           stream_ptr()), "row_norm_act_bwd")
+                                           None, stream_ptr()), "row_norm_act_bwd")
         it = iter(grads[2:])
         gts = [next(it) if t.requires_grad else None for t in ts]
         return (gh, None, None, None, *gts)
 
 
-def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, need_x=True, need_w=True):
+def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, need_x=True, need_w=True, split_row_term=False):
     """Adjoint of (x [B,Ci,N], W [Co,Ci]) -> per-row mean / biased var / max / min of h = W x WITHOUT h.
     The statistics' gradient is dense in h but affine in it, gh = a*h + b per row (a = 2 gvar/N, b = gmean/N - a*mean), so with
     h = W x:   gx = (W^T diag(a) W) x + W^T b 1^T,   gW = sum_b diag(a_b) W (x_b x_b^T) + b_b (sum_n x_b)^T
     -- Ci x Ci Gram matrices instead of two GEMMs over the [B,Co,N] tensor; the max/min gradients touch one column each.
-    Device-agnostic torch (the small matrices in float64); verified against autograd in tests/."""
+    Device-agnostic torch (the small matrices in float64); verified against autograd in tests/.
+    split_row_term: return (gx without the row-constant term W^T b 1^T, gW, that term as [B,Ci]) so that the consumer can add it on
+    the fly instead of a full-size broadcast add here."""
     B, Ci, N = x.shape
     dt = x.dtype
     z = torch.zeros_like(mean)
@@ -301,7 +303,9 @@ def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, ne
         M = torch.matmul(Wd.t(), WA).to(dt)                       # [B,Ci,Ci] = W^T diag(a_b) W
         with tf32_matmul():                                       # the reference's arithmetic here is cuDNN's TF32 data gradient
             gx = torch.bmm(M, x)
-        gx += torch.matmul(b, Wd).to(dt).unsqueeze(-1)
+        row_term = torch.matmul(b, Wd).to(dt)                      # [B,Ci]
+        if not split_row_term:
+            gx += row_term.unsqueeze(-1)
     if need_w:
         with tf32_matmul():                                       # ... and its TF32 weight gradient
             G = torch.bmm(x, x.transpose(1, 2)).double()          # [B,Ci,Ci]
@@ -314,6 +318,8 @@ def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, ne
             gx.scatter_add_(2, col, (g.unsqueeze(-1) * W).transpose(1, 2))
         if need_w:
             gW += torch.einsum("bc,bic->ci", g.double(), x.gather(2, col).double())
+    if split_row_term:
+        return gx, (gW.to(dt) if gW is not None else None), (row_term if need_x else None)
     return gx, (gW.to(dt) if gW is not None else None)
 
 
@@ -522,18 +528,21 @@ class Prologue:
         self.sc, self.sh = scale.detach().contiguous().float(), shift.detach().contiguous().float()
         self.graph = (m_, v_, ts, scale, shift)
 
-    def backward(self, gy):
-        """gy = gradient w.r.t. the activated tensor -> (gradient w.r.t. h, gradients of `tensors`): the two-phase row backward of
-        RowNormAct (reduce, small graph, one write of gh)."""
+    def backward(self, gy, gy_row=None):
+        """gy (+ gy_row [rows], a term constant along each row, added on the fly) = gradient w.r.t. the activated tensor ->
+        (gradient w.r.t. h, gradients of `tensors`): the two-phase row backward of RowNormAct (reduce, small graph, one write of gh)."""
         h, sc, sh = self.h, self.sc, self.sh
         m_, v_, ts, scale, shift = self.graph
         L = h.shape[-1]
         R = h.numel() // L
         lib = _lib.load()
         gy = gy.contiguous()
+        if gy_row is not None:
+            gy_row = gy_row.reshape(-1).contiguous().float()
+            assert gy_row.numel() == R
         gsc, gsh = torch.empty_like(sc), torch.empty_like(sh)
         with torch.cuda.device(h.device), _op("row_act_bwd_reduce", 1, 8 * h.numel()):
-            check(lib.snb_row_act_bwd_reduce(ptr(gy), ptr(h), ptr(sc), ptr(sh), R, L, self.slope, ptr(gsc), ptr(gsh), stream_ptr()),
+            check(lib.snb_row_act_bwd_reduce(ptr(gy), ptr(h), ptr(sc), ptr(sh), R, L, self.slope, ptr(gsc), ptr(gsh), ptr(gy_row), stream_ptr()),
                   "row_act_bwd_reduce")
         wanted = [m_, v_] + [t for t in ts if t.requires_grad]
         grads = torch.autograd.grad((scale, shift), wanted, (gsc.view_as(scale), gsh.view_as(shift)), allow_unused=True, retain_graph=True)
@@ -542,7 +551,7 @@ class Prologue:
         gh = torch.empty_like(h)
         with torch.cuda.device(h.device), _op("row_norm_act_bwd", 1, 12 * h.numel()):
             check(lib.snb_row_norm_act_bwd(ptr(gy), ptr(h), ptr(sc), ptr(sh), ptr(m_.detach()), ptr(gm), ptr(gv), R, L, self.slope, ptr(gh),
-                                           stream_ptr()), "row_norm_act_bwd")
+                                           ptr(gy_row), stream_ptr()), "row_norm_act_bwd")
         it = iter(grads[2:])
         return gh, [next(it) if t.requires_grad else None for t in ts]
 
@@ -605,8 +614,9 @@ class ActConvRowReduce(torch.autograd.Function):
         W2, mean, imax, imin = ctx.saved_tensors
         pro = ctx.pro
         x = pro.materialise()
-        gx, gW = conv_row_reduce_backward(x, W2, mean, imax, imin, gmean, gvar, gmax, gmin, True, ctx.needs_input_grad[1])
-        gh, gts = pro.backward(gx)
+        gx, gW, row_term = conv_row_reduce_backward(x, W2, mean, imax, imin, gmean, gvar, gmax, gmin, True, ctx.needs_input_grad[1],
+                                                    split_row_term=True)
+        gh, gts = pro.backward(gx, gy_row=row_term)               # the row-constant term is added inside the two row kernels
         return (gh, gW.view(ctx.wshape) if gW is not None else None, None, *gts)
 
 

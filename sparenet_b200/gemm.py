@@ -56,7 +56,8 @@ def stat_tiles(N, block_n=0):
 
 
 def _run(desc, dev, what, nbytes=None):
-    with torch.cuda.device(dev), _op(what, 1, nbytes):
+    flops = 2 * int(desc.G) * int(desc.BI) * int(desc.M) * int(desc.N) * int(desc.K)
+    with torch.cuda.device(dev), _op(what, 1, nbytes, flops):
         check(_lib.load().snb_gemm_tf32(ctypes.byref(desc), stream_ptr()), what)
 
 
