@@ -156,20 +156,33 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         # max_k commutes with the monotone BN.SE.LeakyReLU tail: the sign of gamma picks max or min, inside the kernel
         ustar, S1, S2 = fused.edge_reduce_sel(a, c, idx, (g > 0).detach())
         n = B * N * k
-        if bn.training:
-            mean64 = S1.sum(0) / n
-            var64 = (S2.sum(0) / n - mean64 * mean64).clamp_min(0)
-            mean, var = mean64.to(x.dtype), var64.to(x.dtype)
-            _bn_apply_stats(bn, mean, var, n)
+        if FUSED_TAILS and x.is_cuda and x.dtype == torch.float32:
+            # the same BatchNorm.SE closed form as the refiner's tails (csrc/tails.cu, one launch per direction): the per-sample
+            # row mean / biased row variance of u over (points, neighbours) come from the fp64 sums, the batch statistics are
+            # within-row + between-row variance (no cancellation), the SE squeeze is BN(row mean); no bias in front of this BN
+            m64 = S1 / (N * k)
+            v_bc = (S2 / (N * k) - m64 * m64).clamp_min(0).to(x.dtype)
+            gs, gsh = fused.bn_se_tail(m64.to(x.dtype), v_bc, None, g, bn.bias, se.fc[0].weight, se.fc[2].weight, bn, N * k)
+            out = fused.row_affine_act(ustar, gs, gsh, slope=0.2)
         else:
-            mean, var = bn.running_mean, bn.running_var
-        beta = bn.bias
-        scale = g * torch.rsqrt(var + bn.eps)                      # [Co]
-        shift = beta - scale * mean
-        gate = se.gate((S1 / (N * k)).to(x.dtype) * scale + shift)  # [B,Co] in (0,1): SE squeeze = mean_{N,k} BN(u)
-        out = fused.row_affine_act(ustar, gate * scale, gate * shift, slope=0.2)
+            if bn.training:
+                mean64 = S1.sum(0) / n
+                var64 = (S2.sum(0) / n - mean64 * mean64).clamp_min(0)
+                mean, var = mean64.to(x.dtype), var64.to(x.dtype)
+                _bn_apply_stats(bn, mean, var, n)
+            else:
+                mean, var = bn.running_mean, bn.running_var
+            beta = bn.bias
+            scale = g * torch.rsqrt(var + bn.eps)                      # [Co]
+            shift = beta - scale * mean
+            gate = se.gate((S1 / (N * k)).to(x.dtype) * scale + shift)  # [B,Co] in (0,1): SE squeeze = mean_{N,k} BN(u)
+            out = fused.row_affine_act(ustar, gate * scale, gate * shift, slope=0.2)
         if res is not None:
-            out = out + _pconv(x, res.weight)
+            W2 = res.weight.reshape(res.weight.size(0), -1)
+            if LIBRARY_GEMM or min(W2.shape) <= 8 or not out.is_cuda:
+                out = out + _pconv(x, res.weight)
+            else:
+                out = fused.conv1x1_add_into(out, x, W2)             # the residual conv's epilogue adds into `out`: no add pass
         return out
 
     def forward(self, x):

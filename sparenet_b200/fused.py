@@ -458,6 +458,31 @@ class Conv1x1(torch.autograd.Function):
         return gx, gW, None
 
 
+class Conv1x1AddInto(torch.autograd.Function):
+    """acc += W x, IN PLACE: the GEMM's epilogue reduce-adds its tiles into `acc` (TMA cp.reduce), so a residual branch costs neither
+    a second [G,Cout,N] tensor nor an elementwise add pass (EdgeConvResFeat's `x + resconv(x_prev)`, models/sparenet_generator.py:
+    196-232).  `acc` must be a non-leaf whose producer does not need its own output in backward (row_affine_act does not)."""
+    @staticmethod
+    def forward(ctx, acc, x, W):
+        x = x.contiguous()
+        gemm.conv_fwd(x, W, out=acc)
+        ctx.mark_dirty(acc)
+        ctx.save_for_backward(x, W)
+        return acc
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = g.contiguous()
+        gx = gemm.conv_dgrad(g, W) if ctx.needs_input_grad[1] else None
+        gW = gemm.conv_wgrad(g, x, batched=W.dim() == 3) if ctx.needs_input_grad[2] else None
+        return g, gx, gW
+
+
+def conv1x1_add_into(acc, x, W):
+    return Conv1x1AddInto.apply(acc, x, W)
+
+
 class BnSeTail(torch.autograd.Function):
     """(scale, shift) [B,C] of the folded BatchNorm1d . SELayer1D . ReLU tail from row statistics -- ONE launch per direction
     (csrc/tails.cu) instead of ~37 + ~48 microsecond-sized PyTorch launches.  m_bc, v_bc [B,C]: row mean / biased row variance of
@@ -468,8 +493,9 @@ class BnSeTail(torch.autograd.Function):
         m_bc, v_bc = m_bc.contiguous().float(), v_bc.contiguous().float()
         B, C = m_bc.shape
         H = w1.shape[0]
-        rb, g, beta, w1, w2 = (t.detach().contiguous().float() for t in (rb, g, beta, w1, w2))
-        assert rb.shape in ((C,), (B, C)) and w1.shape == (H, C) and w2.shape == (C, H)
+        g, beta, w1, w2 = (t.detach().contiguous().float() for t in (g, beta, w1, w2))
+        rb = None if rb is None else rb.detach().contiguous().float()
+        assert (rb is None or rb.shape in ((C,), (B, C))) and w1.shape == (H, C) and w2.shape == (C, H)
         dev = m_bc.device
         lib = _lib.load()
         S, T = torch.empty(B, C, device=dev), torch.empty(B, C, device=dev)
@@ -480,25 +506,26 @@ class BnSeTail(torch.autograd.Function):
         mom = bn.momentum if bn.momentum is not None else 0.1
         rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if (track or not training) else (None, None, None)
         with torch.cuda.device(dev), _op("bn_se_tail_fwd", 1):
-            check(lib.snb_bn_se_tail_fwd(ptr(m_bc), ptr(v_bc), ptr(rb), int(rb.dim() == 2), ptr(g), ptr(beta), ptr(w1), ptr(w2), B, C, H, float(bn.eps),
+            check(lib.snb_bn_se_tail_fwd(ptr(m_bc), ptr(v_bc), ptr(rb), int(rb is not None and rb.dim() == 2), ptr(g), ptr(beta), ptr(w1), ptr(w2), B, C, H, float(bn.eps),
                                          int(training), float(mom), float(count / max(count - 1, 1)), ptr(rm), ptr(rv),
                                          ptr(nbt) if track else None, ptr(S), ptr(T), ptr(save), stream_ptr()), "bn_se_tail_fwd")
-        ctx.save_for_backward(m_bc, rb, g, w1, w2, save)
+        ctx.save_for_backward(m_bc, g, w1, w2, save, *(() if rb is None else (rb,)))
         ctx.dims = (B, C, H, training)
         return S, T
 
     @staticmethod
     def backward(ctx, gS, gT):
-        m_bc, rb, g, w1, w2, save = ctx.saved_tensors
+        m_bc, g, w1, w2, save, *rest = ctx.saved_tensors
+        rb = rest[0] if rest else None
         B, C, H, training = ctx.dims
         dev = m_bc.device
         lib = _lib.load()
         gS, gT = gS.contiguous().float(), gT.contiguous().float()
-        gm, gv, grb = torch.empty_like(m_bc), torch.empty_like(m_bc), torch.empty_like(rb)
+        gm, gv, grb = torch.empty_like(m_bc), torch.empty_like(m_bc), (None if rb is None else torch.empty_like(rb))
         gg, gbeta, gw1, gw2 = torch.empty_like(g), torch.empty_like(g), torch.empty_like(w1), torch.empty_like(w2)
         scratch = torch.empty(lib.snb_bn_se_tail_scratch_floats(B, C, H), device=dev)
         with torch.cuda.device(dev), _op("bn_se_tail_bwd", 1):
-            check(lib.snb_bn_se_tail_bwd(ptr(gS), ptr(gT), ptr(m_bc), ptr(rb), int(rb.dim() == 2), ptr(g), ptr(w1), ptr(w2), B, C, H, int(training),
+            check(lib.snb_bn_se_tail_bwd(ptr(gS), ptr(gT), ptr(m_bc), ptr(rb), int(rb is not None and rb.dim() == 2), ptr(g), ptr(w1), ptr(w2), B, C, H, int(training),
                                          ptr(save), ptr(scratch), ptr(gm), ptr(gv), ptr(grb), ptr(gg), ptr(gbeta), ptr(gw1), ptr(gw2), stream_ptr()),
                   "bn_se_tail_bwd")
         return gm, gv, grb, gg, gbeta, gw1, gw2, None, None

@@ -61,10 +61,11 @@ def _run(desc, dev, what, nbytes=None):
         check(_lib.load().snb_gemm_tf32(ctypes.byref(desc), stream_ptr()), what)
 
 
-def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, minmax=False, store=True, x_repeat=1):
+def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, minmax=False, store=True, x_repeat=1, out=None):
     """y[g] = W . T(x[g]),  T(x) = leaky_relu(scale*x + shift, slope) per (g, channel, segment of `seg` positions) when scale is given.
     x_repeat = R > 1: x [G, Cin, n] is tiled R times along the position axis (N = R*n output positions; scale/shift still per segment of
     the long axis) -- the decoder's first layer, whose input is the same lattice response for every sample.
+    out: an existing contiguous [G, Cout, *pos] tensor the product is ADDED to (the epilogue's TMA reduce-add; no statistics then).
     Returns (y or None, stats) with stats = {} or {"mean","var": [G, Cout, Npos/stats_seg]} (biased variance of every segment of
     `stats_seg` positions of the OUTPUT rows) and, with minmax, {"max","min","imax","imin": [G, Cout]} over all positions."""
     x, G, Cin, n_in = _act3(x, "x")
@@ -83,11 +84,21 @@ def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, 
     if x_repeat > 1:
         d.b_pos_mod = n_in
     y = None
-    if store:
+    if out is not None:
+        if stats_seg is not None or minmax or not store:
+            raise SnbValueError("conv_fwd(out=...) accumulates into `out`: no statistics, store must stay on")
+        if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == G * Cout * N and out.shape[1] == Cout):
+            raise SnbValueError(f"out must be a contiguous CUDA float32 [G, {Cout}, *positions] tensor")
+        y = out
+        d.D, d.ldd, d.d_batch_stride = _p(y), N, Cout * N
+        d.store = 2
+    elif store:
         yshape = (G, Cout) + ((int(x_repeat),) + tuple(x.shape[2:]) if x_repeat > 1 else tuple(x.shape[2:]))
         y = torch.empty(yshape, device=dev, dtype=torch.float32)
         d.D, d.ldd, d.d_batch_stride = _p(y), N, Cout * N
-    d.store = 1 if store else 0
+        d.store = 1
+    else:
+        d.store = 0
     keep = [x, W, y]
     if scale is not None:
         seg = N if seg is None else int(seg)

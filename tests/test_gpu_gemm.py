@@ -263,3 +263,27 @@ def test_bcast_act_conv_matches_materialised(cuda):
     (Y * w.double()).sum().backward()
     for n, a, b in zip(("xhat", "A", "D", "W"), l32, l64):
         _grad_close(n, a.grad, b.grad)
+
+
+@pytest.mark.parametrize("G,Cout,Cin,N", [(2, 128, 64, 512), (32, 512, 256, 2048), (3, 256, 256, 96)])
+def test_conv1x1_add_into_matches_separate_add(cuda, G, Cout, Cin, N):
+    """acc += W x through the epilogue's TMA reduce-add (fused.conv1x1_add_into, the EdgeConv residual branch) against
+    acc + conv1x1(x, W): the SAME tensor-core product, so values agree to the fp32 addition (<= 1e-6 of scale); the gradient passes
+    through to acc unchanged and reaches x and W through the usual data / weight gradients."""
+    from sparenet_b200 import fused
+    torch.manual_seed(Cout + N)
+    base = torch.randn(G, Cout, N, device=cuda)
+    x0 = torch.randn(G, Cin, N, device=cuda)
+    W0 = torch.randn(Cout, Cin, device=cuda) / Cin ** 0.5
+    gy = torch.randn(G, Cout, N, device=cuda)
+    outs = []
+    for fusedp in (False, True):
+        b, x, W = base.clone().requires_grad_(), x0.clone().requires_grad_(), W0.clone().requires_grad_()
+        acc = b * 1.0                                   # a non-leaf, like the row_affine_act output it is used on
+        y = fused.conv1x1_add_into(acc, x, W) if fusedp else acc + fused.conv1x1(x, W)
+        y.backward(gy)
+        outs.append((y.detach(), b.grad, x.grad, W.grad))
+    for name, a, c in zip(("y", "g_acc", "g_x", "g_W"), outs[0], outs[1]):
+        err = (a - c).abs().max().item() / max(a.abs().max().item(), 1e-6)
+        print(f"[conv1x1_add_into G={G} {Cin}->{Cout} N={N}] {name}: err/scale {err:.2e}")
+        assert err < 2e-6, name
