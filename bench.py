@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=LOCAL_B, help="local batch per GPU (default: BASELINE config)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="measurement switch: torch.optim.Adam(fused=True) instead of the flat-arena Adam launch")
     ap.add_argument("--no-overlap", action="store_true", help="keep the coarse/middle Chamfer losses on the main stream")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay of forward+backward")
     ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed for the bounded CPU step inside the default run")
@@ -234,7 +235,8 @@ def build_gpu(args, dev, rank):
     net = net.to(dev).train()
     net.decoder.fast_param_grads = True   # stacked-parameter gradients as .grad views: valid here because the step uses
     #                                        sparenet_b200.dist.allreduce_gradients instead of DDP hooks
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9), fused=True)
+    torch_adam = bool(getattr(args, "torch_adam", False))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.9), fused=True) if torch_adam else None
     cd_mean, cd = ChamferDistanceMean(), ChamferDistance()
     B = args.batch
     gp = torch.Generator().manual_seed(1 + 100 * rank)
@@ -278,26 +280,42 @@ def build_gpu(args, dev, rank):
             d1, _ = cd(refine, gt)
         return loss + torch.mean(d1).mean() * 0.5
 
+    # Gradients: autograd assigns fresh tensors every backward (no accumulation launches); GradArena.pack gathers them into ONE flat
+    # buffer with a few multi-tensor copies (captured at the tail of the step's CUDA graph), the all-reduce (N > 1) runs on that
+    # buffer in place, and FlatAdam (torch.optim.Adam's rule, csrc/optim.cu) updates the flat parameter arena in one launch.
+    # --torch-adam: torch.optim.Adam(fused=True) on the separate tensors instead (40 multi-tensor launches), arena only for N > 1.
+    from sparenet_b200.dist import GradArena
     arena = None
-    if world > 1:
-        from sparenet_b200.dist import GradArena
+    if not torch_adam:
+        from sparenet_b200.optim import FlatAdam
+        arena = GradArena(params, own_grads=False)
+        opt_flat = FlatAdam(params, lr=1e-4, betas=(0.0, 0.9), arena=arena)
+    elif world > 1:
         arena = GradArena(params)                   # gradients in one flat buffer: the all-reduce runs in place, no cat / copy-back
 
-    def finish():
-        if arena is not None:
-            arena.allreduce(world)                  # the path's only collective: NCCL all-reduce of the gradients over NVLink
-        opt.step()
+    def finish(packed=False):
+        if torch_adam:
+            if arena is not None:
+                arena.allreduce(world)              # the path's only collective: NCCL all-reduce of the gradients over NVLink
+            opt.step()
+            return
+        if not packed:
+            arena.pack()
+        arena.allreduce(world)
+        opt_flat.step(packed=True)
 
     def step(partial, gt):                          # eager step (warm-up and the per-op event pass)
         loss = loss_fn(partial, gt)
-        if arena is not None:
+        if torch_adam and arena is not None:
             arena.zero()
         else:
-            opt.zero_grad(set_to_none=True)
+            for p in params:
+                p.grad = None
         loss.backward()
         finish()
         return loss
 
+    step.torch_adam = torch_adam
     step.loss_fn, step.finish, step.params, step.overlap, step.arena = loss_fn, finish, params, overlap, arena
     return step, h_partial, h_gt
 
@@ -516,11 +534,14 @@ def run_ours(args):
     if not args.no_graph:
         try:
             from sparenet_b200.graph import GraphedForwardBackward
-            gfb = GraphedForwardBackward(step.loss_fn, step.params, (partial, gt), zero_fn=step.arena.zero if step.arena is not None else None)
+            if step.torch_adam:
+                gfb = GraphedForwardBackward(step.loss_fn, step.params, (partial, gt), zero_fn=step.arena.zero if step.arena is not None else None)
+            else:
+                gfb = GraphedForwardBackward(step.loss_fn, step.params, (partial, gt), post_fn=step.arena.pack)
 
             def run(p, g):
                 loss = gfb(p, g)
-                step.finish()
+                step.finish(*(() if step.torch_adam else (True,)))
                 return loss
             graph_note = "forward+backward replayed as one CUDA graph; Adam (and the gradient all-reduce) outside"
         except Exception as e:  # capture is an optimisation: report and keep measuring the eager step
@@ -637,6 +658,9 @@ def run_ours(args):
                                  "Chamfer(refine, gt) search of the loss term just before it (explicit functional.chamfer_reuse() scope: "
                                  "3 searches per step instead of the reference's 4, identical values)", "parallelism": f"dp{world}",
                        "l2": "working set per step (GBs of activations) exceeds the 126 MB L2; no explicit flush", "execution": graph_note,
+                       "optimizer": ("torch.optim.Adam(fused=True)" if step.torch_adam else
+                                     "Adam(lr 1e-4, betas (0, 0.9)): torch.optim.Adam's update rule as ONE launch over a flat parameter arena "
+                                     "(sparenet_b200.optim.FlatAdam, snb_adam_flat)"),
                        "streams": ("coarse/middle Chamfer losses on a side stream beside the refiner's MDS" if step.overlap["on"] else "single stream")},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

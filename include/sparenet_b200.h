@@ -206,6 +206,13 @@ int snb_bn_se_tail_bwd(const float* grad_scale, const float* grad_shift, const f
                        int training, const float* save, float* scratch, float* grad_row_mean, float* grad_row_var,
                        float* grad_row_bias, float* grad_gamma, float* grad_beta, float* grad_w1, float* grad_w2, void* stream);
 
+/* ---- Adam over a flat parameter arena (csrc/optim.cu) -------------------------------------------------------------------------
+ * One launch for all parameters: param / grad / exp_avg / exp_avg_sq are flat fp32 arrays of n elements (n % 4 == 0, 16-byte
+ * aligned) with the SAME layout (sparenet_b200.dist.GradArena / sparenet_b200.optim.FlatAdam).  torch.optim.Adam's update rule
+ * (no amsgrad, no maximize; weight_decay is the L2 form), `step` = 1, 2, ... is the number of this update. */
+int snb_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* ---- TF32 tensor-core GEMM of the 1x1-conv / AdaIN-folding stacks (csrc/gemm_tc.cu: tcgen05.mma + TMEM + TMA) ----------
  * replaces the cuDNN/cuBLAS calls behind nn.Conv1d / nn.Conv2d(kernel_size=1) in models/sparenet_generator.py:146-186,
  * 188-242 (EdgeConv), :593-646 (PointNetRes), :984-991,1044-1062 (GridDecoder) on channel-major activations

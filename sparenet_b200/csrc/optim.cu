@@ -1,0 +1,57 @@
+// optim.cu -- Adam over one flat parameter arena in ONE launch, sm_100a.
+//
+// The generator has ~800 parameter tensors (32 folding decoders); torch.optim.Adam(fused=True) walks them in 40 multi-tensor
+// launches of 60-320 blocks each and reaches ~2.1 TB/s on the 330 MB of parameters (1.07 ms per step).  With parameters, gradients
+// and both moments living in flat 16-byte-aligned arenas of identical layout (sparenet_b200/dist.py: GradArena; optim.py:
+// FlatAdam) the step is one grid-stride pass of 128-bit accesses: 28 B per parameter at the HBM roofline.
+// Update rule = torch.optim.Adam's (torch/optim/adam.py, _fused_adam; reference runners/sparenet_runner.py builds torch.optim.Adam):
+//   g += wd * p;  m = m + (1 - b1) (g - m);  v = b2 v + (1 - b2) g g;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
+#include <math.h>
+#include "common.cuh"
+
+namespace snb {
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float step_size, float b1c, float b2, float b2c, float eps,
+                                      float rbc2s, float wd) {
+  g = __fmaf_rn(wd, p, g);
+  m = __fmaf_rn(b1c, g - m, m);
+  v = __fmaf_rn(b2, v, b2c * g * g);
+  const float denom = __fmaf_rn(sqrtf(v), rbc2s, eps);
+  p -= step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                         float4* __restrict__ v, size_t n4, float step_size, float b1c, float b2, float b2c,
+                                                         float eps, float rbc2s, float wd) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    const float4 gg = g[i];
+    adam1(pp.x, gg.x, mm.x, vv.x, step_size, b1c, b2, b2c, eps, rbc2s, wd);
+    adam1(pp.y, gg.y, mm.y, vv.y, step_size, b1c, b2, b2c, eps, rbc2s, wd);
+    adam1(pp.z, gg.z, mm.z, vv.z, step_size, b1c, b2, b2c, eps, rbc2s, wd);
+    adam1(pp.w, gg.w, mm.w, vv.w, step_size, b1c, b2, b2c, eps, rbc2s, wd);
+    p[i] = pp;
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+SNB_API int snb_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, void* stream) {
+  if (step < 1 || (n & 3) != 0) return SNB_EINVAL;
+  if (n == 0) return SNB_OK;
+  if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) return SNB_EALIGN;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1), rbc2s = (float)(1.0 / sqrt(bc2));
+  const size_t n4 = n / 4;
+  const size_t want = (n4 + 255) / 256;
+  const unsigned grid = (unsigned)(want < (size_t)kNumSMs * 8 ? want : (size_t)kNumSMs * 8);
+  adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n4,
+                                                          step_size, 1.0f - beta1, beta2, 1.0f - beta2, eps, rbc2s, weight_decay);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

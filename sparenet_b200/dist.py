@@ -23,12 +23,16 @@ class GradArena:
     (round 1's flat-cat buckets moved ~1.3 GB per step for 330 MB of gradients).  Gradients ACCUMULATE into the views: call zero()
     at the start of every step instead of zero_grad(set_to_none=True) (which would drop the views)."""
 
-    def __init__(self, params):
+    def __init__(self, params, own_grads=True):
+        """own_grads=True: every p.grad becomes a view into the arena (gradients ACCUMULATE into it: one add per parameter and
+        backward).  own_grads=False: autograd keeps assigning fresh gradient tensors (no accumulation launches) and pack() gathers
+        them into the arena with a few multi-tensor copies after the backward."""
         self.params = [p for p in params if p.requires_grad]
+        self.own_grads = own_grads
         groups = {}
         for p in self.params:
             groups.setdefault((p.dtype, p.device), []).append(p)
-        self.flats = []
+        self.flats, self.views = [], {}
         for (dt, dev), ps in groups.items():
             offs, n = [], 0
             for p in ps:
@@ -36,8 +40,24 @@ class GradArena:
                 n += (p.numel() + 3) // 4 * 4                     # keep every view 16-byte aligned for vectorised optimizers
             flat = torch.zeros(max(n, 4), dtype=dt, device=dev)
             for p, o in zip(ps, offs):
-                p.grad = flat[o:o + p.numel()].view_as(p)
+                self.views[id(p)] = flat[o:o + p.numel()].view_as(p)
+                if own_grads:
+                    p.grad = self.views[id(p)]
             self.flats.append(flat)
+
+    def pack(self):
+        """own_grads=False: copy the parameters' current .grad tensors into the arena (multi-tensor copies; a parameter without a
+        gradient contributes zeros).  Graph-capturable."""
+        dst, src = [], []
+        for p in self.params:
+            v = self.views[id(p)]
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def zero(self):
         for f in self.flats:

@@ -15,9 +15,10 @@ import torch
 
 
 class GraphedForwardBackward:
-    def __init__(self, loss_fn, params, example_inputs, warmup=3, zero_fn=None):
+    def __init__(self, loss_fn, params, example_inputs, warmup=3, zero_fn=None, post_fn=None):
         """zero_fn: when the gradients live in a persistent buffer (sparenet_b200.dist.GradArena) they are zeroed by this callable --
-        captured at the head of the graph -- instead of being dropped (p.grad = None) before the capture."""
+        captured at the head of the graph -- instead of being dropped (p.grad = None) before the capture.
+        post_fn: captured right after the backward (e.g. GradArena.pack: gather the gradients into the flat arena)."""
         self.params = [p for p in params if p.requires_grad]
         self.static_inputs = [torch.empty_like(t, device=self.params[0].device) for t in example_inputs]
         for s, t in zip(self.static_inputs, example_inputs):
@@ -43,6 +44,8 @@ class GraphedForwardBackward:
                 zero_fn()
             self.static_loss = loss_fn(*self.static_inputs)
             self.static_loss.backward()
+            if post_fn is not None:
+                post_fn()
 
     def __call__(self, *inputs):
         for s, t in zip(self.static_inputs, inputs):

@@ -102,3 +102,24 @@ def test_two_rank_grad_arena_allreduce_in_place():
     for rank in range(world):
         ok, calls = out[rank]
         assert ok and calls >= 2
+
+
+def test_grad_arena_pack_mode_cpu():
+    """GradArena(own_grads=False): autograd keeps assigning fresh gradient tensors; pack() gathers them into the flat buffer (zeros
+    for a parameter without gradient), views stay 16-byte aligned, and a second pack after new gradients overwrites the first."""
+    from sparenet_b200.dist import GradArena
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(*s)) for s in ((5, 3), (7,), (2, 2, 2), (1,))]
+    arena = GradArena(ps, own_grads=False)
+    assert all(p.grad is None for p in ps)
+    for round_ in range(2):
+        for i, p in enumerate(ps):
+            p.grad = None if i == 1 else torch.full_like(p, float(10 * round_ + i + 1))
+        arena.pack()
+        flat = arena.flats[0]
+        for i, p in enumerate(ps):
+            v = arena.views[id(p)]
+            assert (v.data_ptr() - flat.data_ptr()) % 16 == 0
+            want = 0.0 if i == 1 else float(10 * round_ + i + 1)
+            assert torch.equal(v, torch.full_like(p, want))
+    assert flat.numel() == 16 + 8 + 8 + 4      # every view padded to a multiple of 4 elements
