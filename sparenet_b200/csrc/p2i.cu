@@ -166,26 +166,51 @@ __global__ void __launch_bounds__(256) p2i_max_bwd_kernel(const T* __restrict__ 
                                                            const T* __restrict__ feat, int C, int H, int W, size_t total, T radius,
                                                            T* __restrict__ gpoints, T* __restrict__ gfeat, T* __restrict__ gbg) {
   const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= total) return;
+  const bool valid = o < total;                             // no early exit: the warp-wide scan below needs every lane
   const int x = (int)(o % W), y = (int)((o / W) % H), c = (int)((o / ((size_t)W * H)) % C);
-  const T g = gout[o];
-  const int p = ids[o];
-  if (p < 0) {
-    gbg[o] = g;
-    return;
+  const T g = valid ? gout[o] : (T)0;
+  const int p = valid ? ids[o] : -1;
+  const bool hit = p >= 0;
+  if (valid) gbg[o] = hit ? (T)0 : g;
+  // The pixels a point owns are runs along x, i.e. runs of lanes: the three gradient terms are summed over each run with a
+  // segmented warp scan and the LAST lane of a run issues the atomics (the reference issues three per pixel; a footprint of
+  // radius 10 piles ~300 of them onto the same three addresses).
+  T t0 = (T)0, t1 = (T)0, t2 = (T)0;
+  if (hit) {
+    const T py = points[p * 2 + 0], px = points[p * 2 + 1];
+    const T dx = (T)x - px, dy = (T)y - py;
+    const T r = P2I<T>::sqrt_(P2I<T>::fma_(dx, dx, P2I<T>::mul_(dy, dy)));
+    const T w = p2i_weight<T>(r, radius);
+    const T f = feat[(size_t)p * C + c];
+    t0 = g * w;
+    const T wg = g * f;
+    const T rr = r > (T)1e-10 ? r : (T)1e-10;
+    const T k = (T)((double)wg * sin((double)r * P2I_PI / (double)radius) * 0.5 * P2I_PI / (double)radius / (double)rr);
+    t1 = k * dy;
+    t2 = k * dx;
   }
-  gbg[o] = (T)0;
-  const T py = points[p * 2 + 0], px = points[p * 2 + 1];
-  const T dx = (T)x - px, dy = (T)y - py;
-  const T r = P2I<T>::sqrt_(P2I<T>::fma_(dx, dx, P2I<T>::mul_(dy, dy)));
-  const T w = p2i_weight<T>(r, radius);
-  const T f = feat[(size_t)p * C + c];
-  atomicAdd(&gfeat[(size_t)p * C + c], g * w);
-  const T wg = g * f;
-  const T rr = r > (T)1e-10 ? r : (T)1e-10;
-  const T k = (T)((double)wg * sin((double)r * P2I_PI / (double)radius) * 0.5 * P2I_PI / (double)radius / (double)rr);
-  atomicAdd(&gpoints[p * 2 + 0], k * dy);
-  atomicAdd(&gpoints[p * 2 + 1], k * dx);
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int key = hit ? p : -1 - lane;                      // misses never join a run
+  const int prev = __shfl_up_sync(full, key, 1);
+  const bool head = lane == 0 || prev != key;
+  const unsigned heads = __ballot_sync(full, head);
+  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // first lane of this lane's run
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const T a0 = __shfl_up_sync(full, t0, off), a1 = __shfl_up_sync(full, t1, off), a2 = __shfl_up_sync(full, t2, off);
+    if (lane - off >= start) {
+      t0 += a0;
+      t1 += a1;
+      t2 += a2;
+    }
+  }
+  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+  if (hit && tail) {
+    atomicAdd(&gfeat[(size_t)p * C + c], t0);
+    atomicAdd(&gpoints[p * 2 + 0], t1);
+    atomicAdd(&gpoints[p * 2 + 1], t2);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ sum

@@ -75,7 +75,8 @@ def test_row_stats_forward_backward(cuda, shape):
 
 
 @pytest.mark.parametrize("rows,L,in_div,slope", [((4, 6), 512, 1, 0.0), ((3, 5), 2048, 1, 0.2), ((2, 9), 333, 1, 0.0),
-                                                ((3, 4), 512, 5, 0.0), ((2, 3), 100, 4, 0.2)])
+                                                ((3, 4), 512, 5, 0.0), ((2, 3), 100, 4, 0.2), ((2, 7), 128, 3, 0.2), ((3, 3), 256, 32, 0.0),
+                                                ((2, 2), 1024, 6, 0.2), ((1, 5), 640, 4, 0.0)])
 def test_row_affine_act_forward_backward(cuda, rows, L, in_div, slope):
     from sparenet_b200 import fused
     torch.manual_seed(L + in_div)

@@ -17,7 +17,8 @@ fi
 if [[ " ${*:-all} " =~ " all " || " $* " =~ " ncu " ]]; then
   NSTEPS=4 NCU_RANGE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
       python tools/ncu_step.py > gpurun_out/ncu_step.log 2>&1; echo "ncu launches exit $?"
-  for spec in "mds_cluster_kernel:0:mds_cluster_kernel" "gemm_tf32_kernel<\(bool\)0>:20:gemm_tf32_plain" "gemm_tf32_kernel<\(bool\)1>:6:gemm_tf32_prologue" \
+  # gemm_tf32_kernel launches of a step in order: #12 = encoder conv5 forward (plain, 2048^3 x 32), #13 = decoder conv2 forward (prologue)
+  for spec in "mds_cluster_kernel:0:mds_cluster_kernel" "gemm_tf32_kernel:12:gemm_tf32_plain_enc_conv5" "gemm_tf32_kernel:13:gemm_tf32_prologue_dec_conv2" \
               "bn_se_tail_fwd_kernel:4:bn_se_tail_fwd_kernel" "chamfer_bvh_query_kernel:0:chamfer_bvh_query_kernel" "knn_prune_kernel:0:knn_prune_kernel"; do
     IFS=: read -r k skip name <<< "$spec"
     NSTEPS=1 timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$k" -s "$skip" -c 1 -f -o "gpurun_out/full_$name" \

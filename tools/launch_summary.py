@@ -23,7 +23,7 @@ def clean(name):
         return "at::" + m.group(2) + "<" + (f.group(1)[:60] if f else inner[:60]) + ">"
     name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
     if "gemm_tf32_kernel" in name:
-        return "snb::gemm_tf32_kernel<xform>" if re.search(r"<\(bool\)1>|<true>", name) else "snb::gemm_tf32_kernel<plain>"
+        return "snb::gemm_tf32_kernel<xform>" if re.search(r"gemm_tf32_kernel<(\(bool\))?(1|true)>", name) else "snb::gemm_tf32_kernel<plain>"
     return re.sub(r"<.*", "", name).split("(")[0].strip()
 
 
