@@ -187,6 +187,18 @@ class ClockSampler:
         return out
 
 
+def _gemm_traffic():
+    """DRAM bytes of the two captured GEMM launches (profiles/r*_traffic.json) next to their algorithmic bytes."""
+    import glob
+    try:
+        t = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))
+        return {"encoder conv5 forward (plain), 32 x 2048^3": {"dram_bytes": t["gemm_plain"]["bytes"], "algorithmic_bytes": 4 * (2 * 32 * 2048 * 2048 + 2048 * 2048)},
+                "decoders' conv2 forward (prologue, tiled operand), 32 x 544 x 16384 x 1056":
+                    {"dram_bytes": t["gemm_prologue"]["bytes"], "algorithmic_bytes": 4 * 32 * (544 * 16384 + 1056 * 512 + 544 * 1056 + 2 * 1056 * 32)}}
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def _mds_issue_bound(ms_per_launch):
     """Issue-slot floor of the sampler from the committed ncu --set full capture (profiles/r*_ncu_full_mds_cluster_kernel.csv):
     warp instructions per launch / (SMs the launch occupied x 4 issue slots per cycle x SM clock)."""
@@ -618,7 +630,8 @@ def run_ours(args):
     ab = alg_bytes.get(dom)
     traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(dom, {}).get("bytes")
+        import glob
+        traffic = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1])).get(dom, {}).get("bytes")
     except (OSError, ValueError):
         pass
     roof = {"kernel": dom, "bound": "hbm", "achieved": (ab / (per_op[dom] * 1e-3) / 1e9) if ab else None, "peak": hbm_peak, "unit": "GB/s",
@@ -640,7 +653,7 @@ def run_ours(args):
         bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1378.4)))
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else None
         roof_tc = {"kernel": "gemm_tf32_kernel (tcgen05.mma kind::tf32, TMEM accumulators, TMA operands)", "bound": "tensor", "achieved": ach,
-                   "peak": bf16_peak, "unit": "TFLOP/s", "frac": (ach / bf16_peak) if ach else None, "traffic": None,
+                   "peak": bf16_peak, "unit": "TFLOP/s", "frac": (ach / bf16_peak) if ach else None, "traffic": _gemm_traffic(),
                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16, kernel timed inside a long step)" if peaks else "fallback",
                    "note": "the products are TF32 (fp32 operands): the tensor core's dense TF32 rate is HALF its bf16 rate, so frac_of_tf32_rate "
                            "is the fraction of what this arithmetic can reach; about half of the calls also apply the previous layer's "
