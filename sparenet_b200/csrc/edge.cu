@@ -33,55 +33,79 @@ __device__ __forceinline__ double block_sum_double(double v, double* red) {
   return t;  // valid in thread 0
 }
 
+// CHB channel rows per CTA: the k neighbour indices of a point are loaded ONCE and used for CHB rows staged in shared memory (idx is
+// N*k ints per sample = 8x a channel row: with one row per CTA the index reads out of L2 were 70 % of the kernel's traffic).
+template <int CHB>
 __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_fwd_kernel(const float* __restrict__ a, const float* __restrict__ c,
                                                                         const int* __restrict__ idx, int C, int N, int k,
                                                                         float* __restrict__ umax, float* __restrict__ umin,
                                                                         unsigned char* __restrict__ smax, unsigned char* __restrict__ smin,
                                                                         double* __restrict__ S1, double* __restrict__ S2,
                                                                         const unsigned char* __restrict__ sel) {
-  extern __shared__ float arow[];
+  extern __shared__ float arow[];          // [CHB][N]
   __shared__ double red[EDGE_THREADS / 32];
-  const int ch = blockIdx.x, b = blockIdx.y;
-  const size_t row = ((size_t)b * C + ch) * N;
-  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) arow[i] = a[row + i];
+  const int ch0 = blockIdx.x * CHB, b = blockIdx.y;
+  const size_t row0 = ((size_t)b * C + ch0) * N;
+  for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) arow[i] = a[row0 + i];
   __syncthreads();
   const int* __restrict__ ib = idx + (size_t)b * N * k;
-  double s1 = 0.0, s2 = 0.0;
+  double s1[CHB], s2[CHB];
+#pragma unroll
+  for (int q = 0; q < CHB; q++) s1[q] = s2[q] = 0.0;
   for (int i = threadIdx.x; i < N; i += EDGE_THREADS) {
-    const float ci = c[row + i];
-    float mx = -3.4e38f, mn = 3.4e38f, sa = 0.f, sq = 0.f;
-    int ax = 0, an = 0;
+    float mx[CHB], mn[CHB], sa[CHB], sq[CHB];
+    int ax[CHB], an[CHB];
+#pragma unroll
+    for (int q = 0; q < CHB; q++) {
+      mx[q] = -3.4e38f;
+      mn[q] = 3.4e38f;
+      sa[q] = sq[q] = 0.f;
+      ax[q] = an[q] = 0;
+    }
     for (int m = 0; m < k; m++) {
-      const float v = arow[ib[(size_t)i * k + m]];
-      sa += v;
-      sq = __fmaf_rn(v, v, sq);
-      if (v > mx) { mx = v; ax = m; }   // first maximum / minimum wins, like torch.max over dim=-1 on CUDA is free to
-      if (v < mn) { mn = v; an = m; }
+      const int j = ib[(size_t)i * k + m];
+#pragma unroll
+      for (int q = 0; q < CHB; q++) {
+        const float v = arow[q * N + j];
+        sa[q] += v;
+        sq[q] = __fmaf_rn(v, v, sq[q]);
+        if (v > mx[q]) { mx[q] = v; ax[q] = m; }   // first maximum / minimum wins, like torch.max over dim=-1 on CUDA is free to
+        if (v < mn[q]) { mn[q] = v; an[q] = m; }
+      }
     }
-    if (sel) {  // only the extremum the sign of the channel's BatchNorm weight asks for (written to umax / smax)
-      const bool up = sel[ch] != 0;
-      umax[row + i] = (up ? mx : mn) + ci;
-      smax[row + i] = (unsigned char)(up ? ax : an);
-    } else {
-      umax[row + i] = mx + ci;
-      umin[row + i] = mn + ci;
-      smax[row + i] = (unsigned char)ax;
-      smin[row + i] = (unsigned char)an;
+#pragma unroll
+    for (int q = 0; q < CHB; q++) {
+      const size_t row = row0 + (size_t)q * N;
+      const float ci = c[row + i];
+      if (sel) {  // only the extremum the sign of the channel's BatchNorm weight asks for (written to umax / smax)
+        const bool up = sel[ch0 + q] != 0;
+        umax[row + i] = (up ? mx[q] : mn[q]) + ci;
+        smax[row + i] = (unsigned char)(up ? ax[q] : an[q]);
+      } else {
+        umax[row + i] = mx[q] + ci;
+        umin[row + i] = mn[q] + ci;
+        smax[row + i] = (unsigned char)ax[q];
+        smin[row + i] = (unsigned char)an[q];
+      }
+      // sum_m (a_j + c)   and   sum_m (a_j + c)^2 = sum a_j^2 + 2 c sum a_j + k c^2
+      s1[q] += (double)sa[q] + (double)k * (double)ci;
+      s2[q] += (double)sq[q] + 2.0 * (double)ci * (double)sa[q] + (double)k * (double)ci * (double)ci;
     }
-    // sum_m (a_j + c)   and   sum_m (a_j + c)^2 = sum a_j^2 + 2 c sum a_j + k c^2
-    s1 += (double)sa + (double)k * (double)ci;
-    s2 += (double)sq + 2.0 * (double)ci * (double)sa + (double)k * (double)ci * (double)ci;
   }
-  const double t1 = block_sum_double(s1, red);
-  const double t2 = block_sum_double(s2, red);
-  if (threadIdx.x == 0) {
-    S1[(size_t)b * C + ch] = t1;
-    S2[(size_t)b * C + ch] = t2;
+#pragma unroll
+  for (int q = 0; q < CHB; q++) {
+    const double t1 = block_sum_double(s1[q], red);
+    const double t2 = block_sum_double(s2[q], red);
+    if (threadIdx.x == 0) {
+      S1[(size_t)b * C + ch0 + q] = t1;
+      S2[(size_t)b * C + ch0 + q] = t2;
+    }
   }
 }
 
 // adjoint:  gc_i = gmax_i + gmin_i + k gS1 + 2 gS2 (sum_m a_jm + k c_i)
 //           ga_j = sum_{(i,m): idx[i,m] = j} [ gS1 + 2 gS2 (a_j + c_i) + [m = smax_i] gmax_i + [m = smin_i] gmin_i ]
+template <int CHB>
 __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_bwd_kernel(const float* __restrict__ a, const float* __restrict__ c,
                                                                         const int* __restrict__ idx, const unsigned char* __restrict__ smax,
                                                                         const unsigned char* __restrict__ smin, const float* __restrict__ gmax,
@@ -89,41 +113,82 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_bwd_kernel(const flo
                                                                         const double* __restrict__ gS2, int C, int N, int k,
                                                                         float* __restrict__ ga, float* __restrict__ gc) {
   extern __shared__ float sm[];
-  float* arow = sm;
-  float* grow = sm + N;
-  const int ch = blockIdx.x, b = blockIdx.y;
-  const size_t row = ((size_t)b * C + ch) * N;
-  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) {
-    arow[i] = a[row + i];
+  float* arow = sm;                // [CHB][N]
+  float* grow = sm + CHB * N;      // [CHB][N]
+  const int ch0 = blockIdx.x * CHB, b = blockIdx.y;
+  const size_t row0 = ((size_t)b * C + ch0) * N;
+  for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) {
+    arow[i] = a[row0 + i];
     grow[i] = 0.f;
   }
   __syncthreads();
-  const float g1 = (float)gS1[(size_t)b * C + ch];
-  const float g2 = 2.f * (float)gS2[(size_t)b * C + ch];
+  float g1[CHB], g2[CHB];
+#pragma unroll
+  for (int q = 0; q < CHB; q++) {
+    g1[q] = (float)gS1[(size_t)b * C + ch0 + q];
+    g2[q] = 2.f * (float)gS2[(size_t)b * C + ch0 + q];
+  }
   const int* __restrict__ ib = idx + (size_t)b * N * k;
   for (int i = threadIdx.x; i < N; i += EDGE_THREADS) {
-    const float ci = c[row + i];
-    const float gx = gmax[row + i], gn = gmin ? gmin[row + i] : 0.f;   // gmin == nullptr: the selected-extremum form
-    const int ax = smax[row + i], an = gmin ? (int)smin[row + i] : -1;
-    float sa = 0.f;
+    float ci[CHB], gx[CHB], gn[CHB], sa[CHB];
+    int ax[CHB], an[CHB];
+#pragma unroll
+    for (int q = 0; q < CHB; q++) {
+      const size_t r = row0 + (size_t)q * N + i;
+      ci[q] = c[r];
+      gx[q] = gmax[r];
+      gn[q] = gmin ? gmin[r] : 0.f;                 // gmin == nullptr: the selected-extremum form
+      ax[q] = smax[r];
+      an[q] = gmin ? (int)smin[r] : -1;
+      sa[q] = 0.f;
+    }
     for (int m = 0; m < k; m++) {
       const int j = ib[(size_t)i * k + m];
-      const float v = arow[j];
-      sa += v;
-      float g = __fmaf_rn(g2, v + ci, g1);
-      if (m == ax) g += gx;
-      if (m == an) g += gn;
-      atomicAdd(&grow[j], g);
+#pragma unroll
+      for (int q = 0; q < CHB; q++) {
+        const float v = arow[q * N + j];
+        sa[q] += v;
+        float g = __fmaf_rn(g2[q], v + ci[q], g1[q]);
+        if (m == ax[q]) g += gx[q];
+        if (m == an[q]) g += gn[q];
+        atomicAdd(&grow[q * N + j], g);
+      }
     }
-    gc[row + i] = gx + gn + (float)k * g1 + g2 * (sa + (float)k * ci);
+#pragma unroll
+    for (int q = 0; q < CHB; q++)
+      gc[row0 + (size_t)q * N + i] = gx[q] + gn[q] + (float)k * g1[q] + g2[q] * (sa[q] + (float)k * ci[q]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < N; i += EDGE_THREADS) ga[row + i] = grow[i];
+  for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) ga[row0 + i] = grow[i];
 }
 
 }  // namespace snb
 
 using namespace snb;
+
+// channel rows per CTA: 4 when the channel count allows it and the rows fit in shared memory, else 1
+static int edge_chb(int C, int N, int rows_per_channel) { return (C % 4 == 0 && (size_t)N * 4 * rows_per_channel * sizeof(float) <= 160 * 1024) ? 4 : 1; }
+
+template <int CHB>
+static int edge_launch_fwd(const float* a, const float* c, const int* idx, int B, int C, int N, int k, float* umax, float* umin, unsigned char* smax,
+                           unsigned char* smin, double* S1, double* S2, const unsigned char* sel, cudaStream_t s) {
+  const size_t smem = (size_t)N * CHB * sizeof(float);
+  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_fwd_kernel<CHB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_reduce_fwd_kernel<CHB><<<dim3(C / CHB, B), EDGE_THREADS, smem, s>>>(a, c, idx, C, N, k, umax, umin, smax, smin, S1, S2, sel);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+template <int CHB>
+static int edge_launch_bwd(const float* a, const float* c, const int* idx, const unsigned char* smax, const unsigned char* smin, const float* gmax,
+                           const float* gmin, const double* gS1, const double* gS2, int B, int C, int N, int k, float* ga, float* gc,
+                           cudaStream_t s) {
+  const size_t smem = (size_t)N * 2 * CHB * sizeof(float);
+  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_bwd_kernel<CHB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_reduce_bwd_kernel<CHB><<<dim3(C / CHB, B), EDGE_THREADS, smem, s>>>(a, c, idx, smax, smin, gmax, gmin, gS1, gS2, C, N, k, ga, gc);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
 
 static int edge_check(int B, int C, int N, int k) {
   if (B < 0 || C < 0 || N < 0 || k <= 0) return SNB_EINVAL;
@@ -136,12 +201,9 @@ SNB_API int snb_edge_reduce_fwd(const float* a, const float* c, const int* idx, 
   int rc = edge_check(B, C, N, k);
   if (rc) return rc;
   if (B == 0 || C == 0 || N == 0) return SNB_OK;
-  const size_t smem = (size_t)N * sizeof(float);
-  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_reduce_fwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, C, N, k, umax, umin, slot_max, slot_min, S1, S2,
-                                                                                  nullptr);
-  SNB_LAUNCH_CHECK();
-  return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return edge_chb(C, N, 1) == 4 ? edge_launch_fwd<4>(a, c, idx, B, C, N, k, umax, umin, slot_max, slot_min, S1, S2, nullptr, s)
+                                : edge_launch_fwd<1>(a, c, idx, B, C, N, k, umax, umin, slot_max, slot_min, S1, S2, nullptr, s);
 }
 
 SNB_API int snb_edge_reduce_sel_fwd(const float* a, const float* c, const int* idx, const unsigned char* sel_max, int B, int C, int N, int k,
@@ -150,11 +212,9 @@ SNB_API int snb_edge_reduce_sel_fwd(const float* a, const float* c, const int* i
   if (rc) return rc;
   if (!sel_max) return SNB_EINVAL;
   if (B == 0 || C == 0 || N == 0) return SNB_OK;
-  const size_t smem = (size_t)N * sizeof(float);
-  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_reduce_fwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, C, N, k, ustar, nullptr, slot, nullptr, S1, S2, sel_max);
-  SNB_LAUNCH_CHECK();
-  return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return edge_chb(C, N, 1) == 4 ? edge_launch_fwd<4>(a, c, idx, B, C, N, k, ustar, nullptr, slot, nullptr, S1, S2, sel_max, s)
+                                : edge_launch_fwd<1>(a, c, idx, B, C, N, k, ustar, nullptr, slot, nullptr, S1, S2, sel_max, s);
 }
 
 SNB_API int snb_edge_reduce_sel_bwd(const float* a, const float* c, const int* idx, const unsigned char* slot, const float* g_ustar,
@@ -162,12 +222,9 @@ SNB_API int snb_edge_reduce_sel_bwd(const float* a, const float* c, const int* i
   int rc = edge_check(B, C, N, k);
   if (rc) return rc;
   if (B == 0 || C == 0 || N == 0) return SNB_OK;
-  const size_t smem = (size_t)N * 2 * sizeof(float);
-  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_reduce_bwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, slot, nullptr, g_ustar, nullptr, gS1, gS2, C, N, k, ga,
-                                                                                  gc);
-  SNB_LAUNCH_CHECK();
-  return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return edge_chb(C, N, 2) == 4 ? edge_launch_bwd<4>(a, c, idx, slot, nullptr, g_ustar, nullptr, gS1, gS2, B, C, N, k, ga, gc, s)
+                                : edge_launch_bwd<1>(a, c, idx, slot, nullptr, g_ustar, nullptr, gS1, gS2, B, C, N, k, ga, gc, s);
 }
 
 SNB_API int snb_edge_reduce_bwd(const float* a, const float* c, const int* idx, const unsigned char* slot_max, const unsigned char* slot_min,
@@ -176,10 +233,7 @@ SNB_API int snb_edge_reduce_bwd(const float* a, const float* c, const int* idx, 
   int rc = edge_check(B, C, N, k);
   if (rc) return rc;
   if (B == 0 || C == 0 || N == 0) return SNB_OK;
-  const size_t smem = (size_t)N * 2 * sizeof(float);
-  if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_reduce_bwd_kernel<<<dim3(C, B), EDGE_THREADS, smem, (cudaStream_t)stream>>>(a, c, idx, slot_max, slot_min, g_umax, g_umin, gS1, gS2, C, N, k,
-                                                                                  ga, gc);
-  SNB_LAUNCH_CHECK();
-  return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return edge_chb(C, N, 2) == 4 ? edge_launch_bwd<4>(a, c, idx, slot_max, slot_min, g_umax, g_umin, gS1, gS2, B, C, N, k, ga, gc, s)
+                                : edge_launch_bwd<1>(a, c, idx, slot_max, slot_min, g_umax, g_umin, gS1, gS2, B, C, N, k, ga, gc, s);
 }
