@@ -48,13 +48,20 @@ def parse():
                          "(EMD rec loss, 24 depth-map renders, ProjectionD, D step + G step)")
     ap.add_argument("--library-gemm", action="store_true", help="measurement switch: dense 1x1 convs through cuDNN/cuBLAS (round-1 arrangement)")
     ap.add_argument("--batch", type=int, default=LOCAL_B, help="local batch per GPU (default: BASELINE config)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the GLOBAL batch stays 32, each of the N ranks takes 32/N samples")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-adam", action="store_true", help="measurement switch: torch.optim.Adam(fused=True) instead of the flat-arena Adam launch")
     ap.add_argument("--no-overlap", action="store_true", help="keep the coarse/middle Chamfer losses on the main stream")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay of forward+backward")
     ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed for the bounded CPU step inside the default run")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.strong:
+        w_ = int(os.environ.get("WORLD_SIZE", "1"))
+        if LOCAL_B % w_ != 0:
+            raise SystemExit(f"--strong needs the world size to divide {LOCAL_B}")
+        args.batch = LOCAL_B // w_
+    return args
 
 
 def cpu_threads():
@@ -663,7 +670,8 @@ def run_ours(args):
                    "by_arrangement": {k: {"ms_per_step": round(tot_op[k], 3), "TFLOP/s": round(F_.FLOPS.get(k, 0) / n_prof / (tot_op[k] * 1e-3) / 1e12, 1)}
                                       for k in gemm_ops}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core GEMMs)",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f32 (tf32 tensor-core GEMMs)",
             "data": "synthetic",
             "config": {"workload": "configs[1]: SpareNet generator + CD loss, synthetic ShapeNet B=32 2048->16384 pts", "local_batch": args.batch,
                        "global_batch": Bg, "n_out": N_OUT, "n_partial": N_PARTIAL, "n_primitives": N_PRIM, "k": 8,
