@@ -25,6 +25,82 @@ struct ExSmem {
   int xr[512];   // xor of the remaining neighbours' ids
 };
 
+// Everything after Prim, by ONE warp on the shared-memory tree: mean edge length, synchronous leaf peeling, outputs.
+template <int VPL>
+__device__ __forceinline__ void expansion_tail(ExSmem& s, int lane, int P, size_t pbase, int N, int prim, float alpha, float (&esum)[VPL],
+                                               float* __restrict__ dist, int* __restrict__ idx, float* __restrict__ prim_mean) {
+  // mean edge length: the reference's in-place up-sweep (:103-117) is the balanced pairwise tree in index
+  // order.  Levels 1..5 pair neighbouring lanes (xor shuffles), the remaining levels pair register slots.
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      if (o < P) esum[i] = __fadd_rn(esum[i], __shfl_xor_sync(0xffffffffu, esum[i], o));
+    }
+  }
+#pragma unroll
+  for (int st = 1; st < VPL; st <<= 1) {
+#pragma unroll
+    for (int i = 0; i + st < VPL; i += 2 * st) esum[i] = __fadd_rn(esum[i], esum[i + st]);
+  }
+  // for P < 32 the xor tree above summed lanes >= P too; they hold 0 and x+0 == x exactly
+  const float mean_dis = esum[0] / (float)(P - 1);
+  if (lane == 0) prim_mean[prim] = mean_dis;
+  const float thr = mean_dis * alpha;
+
+  // synchronous leaf peeling (:123-146)
+  float dv[VPL];
+  int iv[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    dv[i] = 0.f;
+    iv[i] = -1;
+  }
+  const int ybase = (int)(pbase % (size_t)N);  // index of local vertex 0 inside its sample
+  for (;;) {
+    int peel_u[VPL];
+    bool any_leaf = false;
+#pragma unroll
+    for (int i = 0; i < VPL; i++) {
+      const int v = lane + 32 * i;
+      peel_u[i] = -1;
+      if (v < P && s.cnt[v] == 1) {
+        any_leaf = true;
+        const int u = s.xr[v];
+        const int cu = s.cnt[u];
+        if (cu > 1 || (cu == 1 && v > u)) peel_u[i] = u;
+      }
+    }
+    if (!__any_sync(0xffffffffu, any_leaf)) break;
+    __syncwarp();  // all decisions are taken on the pre-round state
+#pragma unroll
+    for (int i = 0; i < VPL; i++) {
+      const int u = peel_u[i];
+      if (u >= 0) {
+        const int v = lane + 32 * i;
+        const float c = (s.parent[v] == u) ? s.ecost[v] : s.ecost[u];
+        s.cnt[v] = 0;
+        s.xr[v] = 0;
+        atomicSub(&s.cnt[u], 1);
+        atomicXor(&s.xr[u], v);
+        if (c > thr) {
+          dv[i] = c;
+          iv[i] = ybase + u;
+        }
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int v = lane + 32 * i;
+    if (v < P) {
+      dist[pbase + v] = dv[i];
+      idx[pbase + v] = iv[i];
+    }
+  }
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(EX_WARPS * 32) expansion_kernel(const float* __restrict__ xyz, int N, int P, int nprim_total, float alpha,
                                                                   float* __restrict__ dist, int* __restrict__ idx,
@@ -106,75 +182,101 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expansion_kernel(const float* _
     __syncwarp();
   }
 
-  // mean edge length: the reference's in-place up-sweep (:103-117) is the balanced pairwise tree in index
-  // order.  Levels 1..5 pair neighbouring lanes (xor shuffles), the remaining levels pair register slots.
-#pragma unroll
-  for (int i = 0; i < VPL; i++) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      if (o < P) esum[i] = __fadd_rn(esum[i], __shfl_xor_sync(0xffffffffu, esum[i], o));
-    }
-  }
-#pragma unroll
-  for (int st = 1; st < VPL; st <<= 1) {
-#pragma unroll
-    for (int i = 0; i + st < VPL; i += 2 * st) esum[i] = __fadd_rn(esum[i], esum[i + st]);
-  }
-  // for P < 32 the xor tree above summed lanes >= P too; they hold 0 and x+0 == x exactly
-  const float mean_dis = esum[0] / (float)(P - 1);
-  if (lane == 0) prim_mean[prim] = mean_dis;
-  const float thr = mean_dis * alpha;
+  expansion_tail<VPL>(s, lane, P, pbase, N, prim, alpha, esum, dist, idx, prim_mean);
+}
 
-  // synchronous leaf peeling (:123-146)
-  float dv[VPL];
-  int iv[VPL];
-#pragma unroll
-  for (int i = 0; i < VPL; i++) {
-    dv[i] = 0.f;
-    iv[i] = -1;
+// P >= 128: FOUR warps per primitive for the Prim phase.  One warp per primitive leaves 7 warps on an SM (1024 primitives in a batch
+// of 32) with ~530 dependent instructions per round each: 28.6 % of the issue slots.  Here every lane holds P/128 vertices, each
+// warp reduces its arg-min as above, the four results meet in shared memory (double-buffered by round parity: ONE block barrier per
+// round) and every thread takes the minimum -- same distances, same tie rule (larger index), same tree.  Warp 0 then runs the
+// unchanged tail on the shared-memory tree.
+template <int VPW>
+__global__ void __launch_bounds__(128) expansion_kernel_mw(const float* __restrict__ xyz, int N, int P, float alpha, float* __restrict__ dist,
+                                                           int* __restrict__ idx, float* __restrict__ prim_mean) {
+  __shared__ ExSmem s;
+  __shared__ unsigned long long slots[2][4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int prim = blockIdx.x;  // global primitive id = b*(N/P) + y
+  const size_t pbase = (size_t)prim * P;
+  const float* __restrict__ src = xyz + pbase * 3;
+  for (int i = tid; i < P * 3; i += 128) s.xyz[i] = src[i];
+  for (int i = tid; i < P; i += 128) {
+    s.cnt[i] = 0;
+    s.xr[i] = 0;
+    s.parent[i] = -1;
+    s.ecost[i] = 0.f;
   }
-  const int ybase = (int)(pbase % (size_t)N);  // index of local vertex 0 inside its sample
-  for (;;) {
-    int peel_u[VPL];
-    bool any_leaf = false;
+  __syncthreads();
+  float x[VPW], y[VPW], z[VPW], cur[VPW];
+  int cidx[VPW];
+  unsigned vis = 0;  // bit i: vertex tid+128*i already in the tree
 #pragma unroll
-    for (int i = 0; i < VPL; i++) {
-      const int v = lane + 32 * i;
-      peel_u[i] = -1;
-      if (v < P && s.cnt[v] == 1) {
-        any_leaf = true;
-        const int u = s.xr[v];
-        const int cu = s.cnt[u];
-        if (cu > 1 || (cu == 1 && v > u)) peel_u[i] = u;
-      }
-    }
-    if (!__any_sync(0xffffffffu, any_leaf)) break;
-    __syncwarp();  // all decisions are taken on the pre-round state
+  for (int i = 0; i < VPW; i++) {
+    const int v = tid + 128 * i;
+    x[i] = s.xyz[v * 3 + 0];
+    y[i] = s.xyz[v * 3 + 1];
+    z[i] = s.xyz[v * 3 + 2];
+    cur[i] = 1e9f;
+    cidx[i] = 0;
+    if (v == 0) vis |= 1u << i;
+  }
+  int last = 0;
+  for (int r = 0; r < P - 1; r++) {
+    const float xl = s.xyz[last * 3 + 0], yl = s.xyz[last * 3 + 1], zl = s.xyz[last * 3 + 2];
+    float bd = 2e9f;
+    int bi = -1;
 #pragma unroll
-    for (int i = 0; i < VPL; i++) {
-      const int u = peel_u[i];
-      if (u >= 0) {
-        const int v = lane + 32 * i;
-        const float c = (s.parent[v] == u) ? s.ecost[v] : s.ecost[u];
-        s.cnt[v] = 0;
-        s.xr[v] = 0;
-        atomicSub(&s.cnt[u], 1);
-        atomicXor(&s.xr[u], v);
-        if (c > thr) {
-          dv[i] = c;
-          iv[i] = ybase + u;
+    for (int i = 0; i < VPW; i++) {
+      if (!((vis >> i) & 1u)) {
+        const float d = sqrtf(sqdist3(__fsub_rn(x[i], xl), __fsub_rn(y[i], yl), __fsub_rn(z[i], zl)));
+        if (d < cur[i]) {
+          cur[i] = d;
+          cidx[i] = last;
+        }
+        if (cur[i] <= bd) {  // ascending i == ascending index: '<=' lets the larger index win ties
+          bd = cur[i];
+          bi = tid + 128 * i;
         }
       }
     }
-    __syncwarp();
-  }
+    const unsigned mbits = __reduce_min_sync(0xffffffffu, __float_as_uint(bd));
+    const int wl = __reduce_max_sync(0xffffffffu, __float_as_uint(bd) == mbits ? bi : -1);
+    // (distance bits, 0x7fffffff - index): the minimum key is the smallest distance and, among equals, the largest index
+    if (lane == 0) slots[r & 1][warp] = ((unsigned long long)mbits << 32) | (unsigned)(0x7fffffff - wl);
+    __syncthreads();
+    unsigned long long k = slots[r & 1][0];
 #pragma unroll
-  for (int i = 0; i < VPL; i++) {
-    const int v = lane + 32 * i;
-    if (v < P) {
-      dist[pbase + v] = dv[i];
-      idx[pbase + v] = iv[i];
+    for (int q = 1; q < 4; q++) {
+      const unsigned long long o = slots[r & 1][q];
+      k = o < k ? o : k;
     }
+    last = 0x7fffffff - (int)(unsigned)k;
+    if ((last & 127) == tid) {  // owner thread records the tree edge
+      const int slot = last >> 7;
+      int u = 0;
+      float c = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPW; i++)
+        if (i == slot) {
+          u = cidx[i];
+          c = cur[i];
+        }
+      vis |= 1u << slot;
+      s.parent[last] = u;
+      s.ecost[last] = c;
+      atomicAdd(&s.cnt[last], 1);
+      atomicXor(&s.xr[last], u);
+      atomicAdd(&s.cnt[u], 1);
+      atomicXor(&s.xr[u], last);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    constexpr int VPL = VPW * 4;
+    float esum[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; i++) esum[i] = s.ecost[lane + 32 * i];   // cost of the edge that brought vertex lane+32i in (vertex 0: 0)
+    expansion_tail<VPL>(s, lane, P, pbase, N, prim, alpha, esum, dist, idx, prim_mean);
   }
 }
 
@@ -229,14 +331,16 @@ SNB_API int snb_expansion_fwd(const float* xyz, int B, int N, int P, float alpha
   const int grid = (int)((nprim + EX_WARPS - 1) / EX_WARPS);
   const int vpl = P >= 32 ? P / 32 : 1;
 #define EX_LAUNCH(V) expansion_kernel<V><<<grid, EX_WARPS * 32, 0, s>>>(xyz, N, P, (int)nprim, alpha, dist, assignment, prim_mean)
+#define EX_LAUNCH_MW(V) expansion_kernel_mw<V><<<(int)nprim, 128, 0, s>>>(xyz, N, P, alpha, dist, assignment, prim_mean)
   switch (vpl) {
-    case 16: EX_LAUNCH(16); break;
-    case 8: EX_LAUNCH(8); break;
-    case 4: EX_LAUNCH(4); break;
+    case 16: EX_LAUNCH_MW(4); break;   // P = 512, 256, 128: four warps per primitive in the Prim phase
+    case 8: EX_LAUNCH_MW(2); break;
+    case 4: EX_LAUNCH_MW(1); break;
     case 2: EX_LAUNCH(2); break;
     default: EX_LAUNCH(1); break;
   }
 #undef EX_LAUNCH
+#undef EX_LAUNCH_MW
   SNB_LAUNCH_CHECK();
   expansion_mean_kernel<<<(B + 127) / 128, 128, 0, s>>>(prim_mean, B, np, mean_mst_length);
   SNB_LAUNCH_CHECK();
