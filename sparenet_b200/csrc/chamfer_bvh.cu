@@ -14,8 +14,6 @@
 //          relative, far more than the fp32 rounding of the bound) does not exceed the running minimum.
 // Ties: candidates compare as (distance, original index), so the lowest index wins regardless of the visiting order.
 #include <math.h>
-#include <stdlib.h>
-#include <string.h>
 #include "bvh.cuh"
 
 namespace snb {
@@ -212,148 +210,6 @@ __global__ void __launch_bounds__(128) chamfer_bvh_query_kernel(int N, int M, fl
   iout[qid] = best.i;
 }
 
-// ---- warp-cooperative query ------------------------------------------------------------------------------------------------------
-// The thread-per-query traversal above diverges (16.9 of 32 threads active per instruction, every thread walks its own list of
-// boxes).  Here a warp takes 32 queries that are neighbours in Morton order and opens the UNION of the boxes they need; inside an
-// opened leaf every lane evaluates all 32 points, read from a per-warp shared-memory copy of the leaf (one broadcast LDS.128 per
-// point, no divergence), the next marked leaf already in flight.  Every lane first scans its own nearest leaf (the distinct ones
-// of the warp), so the marking pass runs with a tight radius.  Same candidates in a different order: min over (distance, index)
-// does not depend on it, so the bits are the brute-force kernel's.
-constexpr int BVHW_WARPS = 4;
-
-__device__ __forceinline__ void scan_leaf_staged(const float4* buf, float qx, float qy, float qz, Best& best) {
-#pragma unroll 8
-  for (int t = 0; t < BVH_LEAF; t++) {
-    const float4 r = buf[t];
-    const float d = sqdist3(__fsub_rn(r.x, qx), __fsub_rn(r.y, qy), __fsub_rn(r.z, qz));  // NaN padding never compares true
-    const int id = __float_as_int(r.w);
-    if (d < best.d || (d == best.d && id < best.i)) {
-      best.d = d;
-      best.i = id;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(BVHW_WARPS * 32) chamfer_bvh_query_warp_kernel(int N, int M, float4* __restrict__ ws, size_t per_sample_f4,
-                                                                                 float* __restrict__ dist1, float* __restrict__ dist2,
-                                                                                 int* __restrict__ idx1, int* __restrict__ idx2) {
-  __shared__ float4 stage[BVHW_WARPS][2][BVH_LEAF];
-  const int dir = blockIdx.z, b = blockIdx.y;
-  const int nq = dir ? M : N, nr = dir ? N : M;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t0 = (blockIdx.x * BVHW_WARPS + warp) * 32;
-  if (t0 >= nq) return;                                  // whole warps leave together
-  float4* base = ws + (size_t)b * per_sample_f4;
-  const BvhView Qv = bvh_view(base + (dir ? bvh_cloud_floats4(N) : 0), nq);
-  const BvhView R = bvh_view(base + (dir ? 0 : bvh_cloud_floats4(N)), nr);
-  const int t = t0 + lane;
-  const bool act = t < nq;
-  const float4 q = Qv.pts[act ? t : t0];               // idle lanes shadow the first query: they never widen the set of opened boxes
-  const int qid = __float_as_int(q.w);
-  Best best;
-  best.d = __int_as_float(0x7f800000);
-  best.i = 0x7fffffff;
-  // ---- own nearest leaf ----
-  int hl;
-  {
-    float lbmin = 3.4e38f;
-    int smin = 0;
-    for (int s = 0; s < R.ns; s++) {
-      const float lb = box_lb(R.sbox[2 * s], R.sbox[2 * s + 1], q.x, q.y, q.z);
-      if (lb < lbmin) {
-        lbmin = lb;
-        smin = s;
-      }
-    }
-    const int c0 = smin * BVH_FAN, c1 = (c0 + BVH_FAN) < R.nc ? (c0 + BVH_FAN) : R.nc;
-    lbmin = 3.4e38f;
-    hl = c0;
-    for (int c = c0; c < c1; c++) {
-      const float lb = box_lb(R.box[2 * c], R.box[2 * c + 1], q.x, q.y, q.z);
-      if (lb < lbmin) {
-        lbmin = lb;
-        hl = c;
-      }
-    }
-  }
-  constexpr int MAXS = BVH_MAXN / BVH_LEAF / BVH_FAN;   // 32 super-boxes at most: lane s keeps the state of super-box s
-  unsigned hdone = 0u;
-  int bufi = 0;
-  {
-    unsigned pend = 0xffffffffu;
-    int c = __shfl_sync(0xffffffffu, hl, 0);
-    pend &= ~__ballot_sync(0xffffffffu, hl == c);
-    float4 pf = R.pts[(size_t)c * BVH_LEAF + lane];
-    while (c >= 0) {
-      int cn = -1;
-      if (pend) {
-        cn = __shfl_sync(0xffffffffu, hl, __ffs(pend) - 1);
-        pend &= ~__ballot_sync(0xffffffffu, hl == cn);
-      }
-      stage[warp][bufi][lane] = pf;
-      __syncwarp();
-      if (cn >= 0) pf = R.pts[(size_t)cn * BVH_LEAF + lane];
-      scan_leaf_staged(stage[warp][bufi], q.x, q.y, q.z, best);
-      if (lane == c / BVH_FAN) hdone |= 1u << (c % BVH_FAN);
-      bufi ^= 1;
-      c = cn;
-    }
-  }
-  // ---- mark the leaves whose bound can still beat OR TIE some lane's minimum (lane s: the 16-bit mask of super-box s) ----
-  unsigned mym = 0u;
-#pragma unroll 1
-  for (int s = 0; s < R.ns; s++) {
-    const bool need_s = box_lb(R.sbox[2 * s], R.sbox[2 * s + 1], q.x, q.y, q.z) <= best.d;
-    if (!__any_sync(0xffffffffu, need_s)) continue;
-    unsigned m16 = 0u;
-    const int c0 = s * BVH_FAN;
-#pragma unroll 4
-    for (int k = 0; k < BVH_FAN; k++) {
-      const int c = c0 + k;
-      const bool need_c = c < R.nc && box_lb(R.box[2 * c], R.box[2 * c + 1], q.x, q.y, q.z) <= best.d;
-      m16 |= __any_sync(0xffffffffu, need_c) ? (1u << k) : 0u;
-    }
-    if (lane == s) mym = m16 & ~hdone;
-  }
-  static_assert(MAXS <= 32, "one lane per super-box");
-  // ---- walk them; every leaf is tested again right before it is scanned (the radii have shrunk) ----
-  {
-    unsigned smask = __ballot_sync(0xffffffffu, mym != 0u);
-    int cur_s = 0;
-    unsigned cur_m = 0u;
-    auto next_leaf = [&]() -> int {
-      while (cur_m == 0u) {
-        if (smask == 0u) return -1;
-        cur_s = __ffs(smask) - 1;
-        smask &= smask - 1u;
-        cur_m = __shfl_sync(0xffffffffu, mym, cur_s);
-      }
-      const int k = __ffs(cur_m) - 1;
-      cur_m &= cur_m - 1u;
-      return cur_s * BVH_FAN + k;
-    };
-    int c = next_leaf();
-    float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c >= 0) pf = R.pts[(size_t)c * BVH_LEAF + lane];
-    while (c >= 0) {
-      const int cn = next_leaf();
-      stage[warp][bufi][lane] = pf;
-      __syncwarp();
-      if (cn >= 0) pf = R.pts[(size_t)cn * BVH_LEAF + lane];
-      const bool need_c = box_lb(R.box[2 * c], R.box[2 * c + 1], q.x, q.y, q.z) <= best.d;
-      if (__any_sync(0xffffffffu, need_c)) scan_leaf_staged(stage[warp][bufi], q.x, q.y, q.z, best);
-      bufi ^= 1;
-      c = cn;
-    }
-  }
-  if (act) {
-    float* __restrict__ dout = (dir ? dist2 : dist1) + (size_t)b * nq;
-    int* __restrict__ iout = (dir ? idx2 : idx1) + (size_t)b * nq;
-    dout[qid] = best.d;
-    iout[qid] = best.i;
-  }
-}
-
 // host side, called from snb_chamfer_fwd (chamfer.cu)
 size_t chamfer_bvh_workspace_bytes(int B, int N, int M) {
   if (N > BVH_MAXN || M > BVH_MAXN || N < 256 || M < 256) return 0;
@@ -378,16 +234,7 @@ int chamfer_bvh_launch(const float* xyz1, const float* xyz2, int B, int N, int M
   const int nmax = N > M ? N : M;
   const int rc = bvh_build_launch(xyz1, xyz2, B, N, M, (float4*)workspace, per, s);
   if (rc != SNB_OK) return rc;
-  static int warp_query = -1;   // SNB_CHAMFER_QUERY=thread selects the thread-per-query traversal (A/B measurement)
-  if (warp_query < 0) {
-    const char* e = getenv("SNB_CHAMFER_QUERY");
-    warp_query = (e && strcmp(e, "thread") == 0) ? 0 : 1;
-  }
-  if (warp_query)
-    chamfer_bvh_query_warp_kernel<<<dim3((nmax + BVHW_WARPS * 32 - 1) / (BVHW_WARPS * 32), B, 2), BVHW_WARPS * 32, 0, s>>>(
-        N, M, (float4*)workspace, per, dist1, dist2, idx1, idx2);
-  else
-    chamfer_bvh_query_kernel<<<dim3((nmax + 127) / 128, B, 2), 128, 0, s>>>(N, M, (float4*)workspace, per, dist1, dist2, idx1, idx2);
+  chamfer_bvh_query_kernel<<<dim3((nmax + 127) / 128, B, 2), 128, 0, s>>>(N, M, (float4*)workspace, per, dist1, dist2, idx1, idx2);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

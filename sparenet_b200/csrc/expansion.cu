@@ -190,17 +190,18 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expansion_kernel(const float* _
 // warp reduces its arg-min as above, the four results meet in shared memory (double-buffered by round parity: ONE block barrier per
 // round) and every thread takes the minimum -- same distances, same tie rule (larger index), same tree.  Warp 0 then runs the
 // unchanged tail on the shared-memory tree.
-template <int VPW>
-__global__ void __launch_bounds__(128) expansion_kernel_mw(const float* __restrict__ xyz, int N, int P, float alpha, float* __restrict__ dist,
+template <int VPW, int WPP>   // vertices per lane, warps per primitive (VPW * WPP * 32 == P)
+__global__ void __launch_bounds__(WPP * 32) expansion_kernel_mw(const float* __restrict__ xyz, int N, int P, float alpha, float* __restrict__ dist,
                                                            int* __restrict__ idx, float* __restrict__ prim_mean) {
   __shared__ ExSmem s;
-  __shared__ unsigned long long slots[2][4];
+  __shared__ unsigned long long slots[2][WPP];
+  constexpr int T = WPP * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int prim = blockIdx.x;  // global primitive id = b*(N/P) + y
   const size_t pbase = (size_t)prim * P;
   const float* __restrict__ src = xyz + pbase * 3;
-  for (int i = tid; i < P * 3; i += 128) s.xyz[i] = src[i];
-  for (int i = tid; i < P; i += 128) {
+  for (int i = tid; i < P * 3; i += T) s.xyz[i] = src[i];
+  for (int i = tid; i < P; i += T) {
     s.cnt[i] = 0;
     s.xr[i] = 0;
     s.parent[i] = -1;
@@ -209,10 +210,10 @@ __global__ void __launch_bounds__(128) expansion_kernel_mw(const float* __restri
   __syncthreads();
   float x[VPW], y[VPW], z[VPW], cur[VPW];
   int cidx[VPW];
-  unsigned vis = 0;  // bit i: vertex tid+128*i already in the tree
+  unsigned vis = 0;  // bit i: vertex tid+T*i already in the tree
 #pragma unroll
   for (int i = 0; i < VPW; i++) {
-    const int v = tid + 128 * i;
+    const int v = tid + T * i;
     x[i] = s.xyz[v * 3 + 0];
     y[i] = s.xyz[v * 3 + 1];
     z[i] = s.xyz[v * 3 + 2];
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(128) expansion_kernel_mw(const float* __restri
         }
         if (cur[i] <= bd) {  // ascending i == ascending index: '<=' lets the larger index win ties
           bd = cur[i];
-          bi = tid + 128 * i;
+          bi = tid + T * i;
         }
       }
     }
@@ -246,13 +247,13 @@ __global__ void __launch_bounds__(128) expansion_kernel_mw(const float* __restri
     __syncthreads();
     unsigned long long k = slots[r & 1][0];
 #pragma unroll
-    for (int q = 1; q < 4; q++) {
+    for (int q = 1; q < WPP; q++) {
       const unsigned long long o = slots[r & 1][q];
       k = o < k ? o : k;
     }
     last = 0x7fffffff - (int)(unsigned)k;
-    if ((last & 127) == tid) {  // owner thread records the tree edge
-      const int slot = last >> 7;
+    if ((last % T) == tid) {  // owner thread records the tree edge
+      const int slot = last / T;
       int u = 0;
       float c = 0.f;
 #pragma unroll
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(128) expansion_kernel_mw(const float* __restri
   }
   __syncthreads();
   if (warp == 0) {
-    constexpr int VPL = VPW * 4;
+    constexpr int VPL = VPW * WPP;
     float esum[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; i++) esum[i] = s.ecost[lane + 32 * i];   // cost of the edge that brought vertex lane+32i in (vertex 0: 0)
@@ -331,11 +332,11 @@ SNB_API int snb_expansion_fwd(const float* xyz, int B, int N, int P, float alpha
   const int grid = (int)((nprim + EX_WARPS - 1) / EX_WARPS);
   const int vpl = P >= 32 ? P / 32 : 1;
 #define EX_LAUNCH(V) expansion_kernel<V><<<grid, EX_WARPS * 32, 0, s>>>(xyz, N, P, (int)nprim, alpha, dist, assignment, prim_mean)
-#define EX_LAUNCH_MW(V) expansion_kernel_mw<V><<<(int)nprim, 128, 0, s>>>(xyz, N, P, alpha, dist, assignment, prim_mean)
+#define EX_LAUNCH_MW(V, W) expansion_kernel_mw<V, W><<<(int)nprim, W * 32, 0, s>>>(xyz, N, P, alpha, dist, assignment, prim_mean)
   switch (vpl) {
-    case 16: EX_LAUNCH_MW(4); break;   // P = 512, 256, 128: four warps per primitive in the Prim phase
-    case 8: EX_LAUNCH_MW(2); break;
-    case 4: EX_LAUNCH_MW(1); break;
+    case 16: EX_LAUNCH_MW(4, 4); break;   // P = 512, 256, 128: four warps per primitive in the Prim phase (measured at P = 512: 2 warps 0.63 ms, 4 warps 0.53, 8 warps 0.78)
+    case 8: EX_LAUNCH_MW(2, 4); break;
+    case 4: EX_LAUNCH_MW(1, 4); break;
     case 2: EX_LAUNCH(2); break;
     default: EX_LAUNCH(1); break;
   }
