@@ -384,14 +384,17 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             return t if t.size(1) == cp else F.pad(t, (0, 0) * (t.dim() - 2) + (0, cp - t.size(1)))
 
         C1 = sizes[0]
+        cp = pad8(C1)
         W1 = self._stack(lambda d: d.conv1.weight).squeeze(-1)                # [P,1026,2] (bias cancels under instance norm)
-        h = fused.thin_conv(self._grid_t.unsqueeze(0), W1)                   # Conv1d(2 -> 1026): [P,1026,pts], batch independent
+        # the channel padding is applied to the tiny WEIGHT (zero rows), so the padded channels of h, and of x_hat = 0 * rsqrt(eps),
+        # come out as exact zeros without a pad copy of the [P,1056,pts] tensors
+        h = fused.thin_conv(self._grid_t.unsqueeze(0), padc(W1, cp))         # Conv1d(2 -> 1026): [P,1056,pts], batch independent
         var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
-        xhat = (h - mean) * torch.rsqrt(var + EPS)
+        xhat_p = (h - mean) * torch.rsqrt(var + EPS)
+        var = var[:, :C1]
         bns, prm = self._bn_se_params(1)
         A, D = self._bn_se(bns, sty[0][0], sty[0][1], var / (var + EPS), *prm)
-        cp = pad8(C1)
-        xhat_p, A_p, D_p = padc(xhat, cp), padc(A, cp), padc(D, cp)
+        A_p, D_p = padc(A, cp), padc(D, cp)
         x = None
         if LIBRARY_GEMM:
             x = fused.row_affine_act(xhat_p, A_p, D_p, in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D) for every sample
