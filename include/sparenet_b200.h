@@ -206,6 +206,23 @@ int snb_bn_se_tail_bwd(const float* grad_scale, const float* grad_shift, const f
                        int training, const float* save, float* scratch, float* grad_row_mean, float* grad_row_var,
                        float* grad_row_bias, float* grad_gamma, float* grad_beta, float* grad_w1, float* grad_w2, void* stream);
 
+/* ---- the decoders' tail: instance norm -> AdaIN -> BatchNorm1d -> SELayer1D -> ReLU folded to one scale/shift (csrc/tails.cu;
+ * models/sparenet_generator.py:909-1062) for all P primitives at once.  row_mean / row_var [P,Cpad,B]: statistics of the rows
+ * h[p,c,b,:] of the layer's pre-activation (the GEMM epilogue's), style_scale / style_shift [B,C]: the AdaIN weight / bias of the
+ * sample (shared by the primitives), gamma / beta [P,C], w1 [P,H,C], w2 [P,C,H]; scale / shift [P,Cpad,B] (channels >= C: zeros).
+ * Train-mode BatchNorm (batch statistics; they are returned in bn_mean / bn_var [P,C] for the caller's running statistics).  B <= 32.
+ * bwd: gradients of every input; grad_style_* are per-primitive partials [P,B,C] (the caller sums over P). */
+size_t snb_adain_tail_save_floats(int P, int C, int B, int H);
+size_t snb_adain_tail_scratch_floats(int P, int C, int B, int H);
+int snb_adain_tail_fwd(const float* row_mean, const float* row_var, const float* style_scale, const float* style_shift,
+                       const float* gamma, const float* beta, const float* w1, const float* w2, int P, int C, int Cpad, int B,
+                       int H, float eps, float* scale, float* shift, float* save, float* bn_mean, float* bn_var, void* stream);
+int snb_adain_tail_bwd(const float* grad_scale, const float* grad_shift, const float* row_mean, const float* row_var,
+                       const float* style_scale, const float* style_shift, const float* gamma, const float* w1, const float* w2,
+                       int P, int C, int Cpad, int B, int H, float eps, const float* save, float* scratch, float* grad_row_mean,
+                       float* grad_row_var, float* grad_style_scale, float* grad_style_shift, float* grad_gamma, float* grad_beta,
+                       float* grad_w1, float* grad_w2, void* stream);
+
 /* ---- Adam over a flat parameter arena (csrc/optim.cu) -------------------------------------------------------------------------
  * One launch for all parameters: param / grad / exp_avg / exp_avg_sq are flat fp32 arrays of n elements (n % 4 == 0, 16-byte
  * aligned) with the SAME layout (sparenet_b200.dist.GradArena / sparenet_b200.optim.FlatAdam).  torch.optim.Adam's update rule

@@ -71,6 +71,10 @@ SIGNATURES = {
     "snb_gemm_tf32": (c_int, [ctypes.POINTER(GemmDesc), P]),
     "snb_gemm_tf32_tiles": (c_int, [c_int, c_int]),
     "snb_gemm_tf32_block_n": (c_int, [c_int, c_int]),
+    "snb_adain_tail_save_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "snb_adain_tail_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "snb_adain_tail_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),
+    "snb_adain_tail_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, P, P]),
     "snb_adam_flat": (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "snb_bn_se_tail_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "snb_bn_se_tail_scratch_floats": (c_size_t, [c_int, c_int, c_int]),

@@ -276,3 +276,259 @@ SNB_API int snb_bn_se_tail_bwd(const float* grad_scale, const float* grad_shift,
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
+
+// ---- the decoders' tail: instance norm -> AdaIN -> BatchNorm -> SE -> ReLU folded to one scale/shift --------------------------------
+// (reference models/sparenet_generator.py:984-1062: StyleBasedAdaIn / AdaptiveInstanceNorm1d / GridDecoder; all 32 primitives at once)
+// Per primitive p, channel c, sample b, with the row statistics (m, s2) of the pre-activation h[p,c,b,:] and the style (w, t)[b,c]:
+//     r = rsqrt(s2 + eps), v = s2 / (s2 + eps)                        instance norm: x_hat = (h - m) r has mean 0, variance v
+//     mu_c = avg_b t,  q_c = avg_b (w^2 v + t^2) - mu_c^2,  inv = rsqrt(q + eps)          BatchNorm of AdaIN(x_hat) = w x_hat + t
+//     z = gamma inv (t - mu) + beta                                   SE squeeze;  gate = sigmoid(W2 relu(W1 z))
+//     A = gate gamma inv w,  D = gate z          =>   tail(h) = relu(sc h + sh),  sc = A r,  sh = D - sc m
+// One cluster of 4 thread blocks per primitive (128 blocks for the 32 primitives), phases separated by cluster barriers, what
+// crosses a barrier in global scratch.  Channel phases: a warp per channel, lanes = samples (B <= 32).
+namespace snb {
+
+constexpr int ADT_CLUSTER = 4;
+
+// save per primitive (floats): inv[C] mu[C] z[C*B] gate[C*B] a1[H*B]
+__host__ __device__ inline size_t adt_save_floats(int C, int B, int H) { return (size_t)2 * C + (size_t)2 * C * B + (size_t)H * B; }
+// scratch per primitive (floats): ga2[C*B] gz1[C*B] gwt1[C*B] gp1[H*B] ggam_part[C] ginv_part[C]
+__host__ __device__ inline size_t adt_scratch_floats(int C, int B, int H) { return (size_t)3 * C * B + (size_t)H * B + (size_t)2 * C; }
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) adain_tail_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                                                                          const float* __restrict__ wsty, const float* __restrict__ bsty,
+                                                                          const float* __restrict__ gam, const float* __restrict__ bet,
+                                                                          const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cp,
+                                                                          int B, int H, float eps, float* __restrict__ sc, float* __restrict__ sh,
+                                                                          float* save_all, float* __restrict__ bn_mu, float* __restrict__ bn_var) {
+  const int p = blockIdx.x / ADT_CLUSTER;
+  const int nt = ADT_CLUSTER * blockDim.x, ct = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+  const int lane = ct & 31, cw = ct >> 5, nw = nt >> 5;
+  float* save = save_all + (size_t)p * adt_save_floats(C, B, H);
+  float* inv = save;
+  float* mu = inv + C;
+  float* z = mu + C;
+  float* gate = z + (size_t)C * B;
+  float* a1 = gate + (size_t)C * B;
+  const float* __restrict__ mp = mean + (size_t)p * Cp * B;
+  const float* __restrict__ vp = var + (size_t)p * Cp * B;
+  const float* __restrict__ g_ = gam + (size_t)p * C;
+  const float* __restrict__ b_ = bet + (size_t)p * C;
+  const float* __restrict__ w1p = w1 + (size_t)p * H * C;
+  const float* __restrict__ w2p = w2 + (size_t)p * C * H;
+  const float rB = 1.0f / (float)B;
+  const bool on = lane < B;
+  // ---- BatchNorm statistics of AdaIN(x_hat) and the SE squeeze ----
+  for (int c = cw; c < C; c += nw) {
+    const float t = on ? bsty[lane * C + c] : 0.f, w = on ? wsty[lane * C + c] : 0.f;
+    const float s2 = on ? vp[c * B + lane] : 0.f;
+    const float v = s2 / (s2 + eps);
+    const float m_ = tail_warp_sum(t) * rB;
+    const float q = tail_warp_sum(on ? w * w * v + t * t : 0.f) * rB - m_ * m_;
+    const float iv = rsqrtf(q + eps);
+    if (on) z[c * B + lane] = g_[c] * (t - m_) * iv + b_[c];
+    if (lane == 0) {
+      inv[c] = iv;
+      mu[c] = m_;
+      bn_mu[(size_t)p * C + c] = m_;
+      bn_var[(size_t)p * C + c] = q;
+    }
+  }
+  cluster_sync_all();
+  // ---- a1 = relu(W1 z): a warp per hidden unit, lanes = samples ----
+  for (int h = cw; h < H; h += nw) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < C; c++) acc = __fmaf_rn(w1p[h * C + c], on ? z[c * B + lane] : 0.f, acc);
+    if (on) a1[h * B + lane] = fmaxf(acc, 0.f);
+  }
+  cluster_sync_all();
+  // ---- gate and the folded scale / shift (padded channels: zeros) ----
+  for (int i = ct; i < Cp * B; i += nt) {
+    const int c = i / B, b = i - c * B;
+    float s_ = 0.f, h_ = 0.f;
+    if (c < C) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int h = 0; h < H; h++) acc = __fmaf_rn(w2p[c * H + h], a1[h * B + b], acc);
+      const float gt = 1.0f / (1.0f + expf(-acc));
+      gate[c * B + b] = gt;
+      const float s2 = vp[i];
+      const float A = gt * g_[c] * inv[c] * wsty[b * C + c];
+      s_ = A * rsqrtf(s2 + eps);
+      h_ = gt * z[c * B + b] - s_ * mp[i];
+    }
+    sc[(size_t)p * Cp * B + i] = s_;
+    sh[(size_t)p * Cp * B + i] = h_;
+  }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) adain_tail_bwd_kernel(const float* __restrict__ gsc, const float* __restrict__ gsh,
+                                                                          const float* __restrict__ mean, const float* __restrict__ var,
+                                                                          const float* __restrict__ wsty, const float* __restrict__ bsty,
+                                                                          const float* __restrict__ gam, const float* __restrict__ w1,
+                                                                          const float* __restrict__ w2, int C, int Cp, int B, int H, float eps,
+                                                                          const float* save_all, float* scratch_all, float* __restrict__ gmean,
+                                                                          float* __restrict__ gvar, float* __restrict__ gws, float* __restrict__ gbs,
+                                                                          float* __restrict__ ggam, float* __restrict__ gbet, float* __restrict__ gw1,
+                                                                          float* __restrict__ gw2) {
+  const int p = blockIdx.x / ADT_CLUSTER;
+  const int nt = ADT_CLUSTER * blockDim.x, ct = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+  const int lane = ct & 31, cw = ct >> 5, nw = nt >> 5;
+  const float* save = save_all + (size_t)p * adt_save_floats(C, B, H);
+  const float* inv = save;
+  const float* mu = inv + C;
+  const float* z = mu + C;
+  const float* gate = z + (size_t)C * B;
+  const float* a1 = gate + (size_t)C * B;
+  float* scratch = scratch_all + (size_t)p * adt_scratch_floats(C, B, H);
+  float* ga2 = scratch;
+  float* gz1 = ga2 + (size_t)C * B;
+  float* gwt1 = gz1 + (size_t)C * B;
+  float* gp1 = gwt1 + (size_t)C * B;
+  float* ggam_part = gp1 + (size_t)H * B;
+  float* ginv_part = ggam_part + C;
+  const size_t pofs = (size_t)p * Cp * B;
+  const float* __restrict__ g_ = gam + (size_t)p * C;
+  const float* __restrict__ w1p = w1 + (size_t)p * H * C;
+  const float* __restrict__ w2p = w2 + (size_t)p * C * H;
+  const float rB = 1.0f / (float)B;
+  const bool on = lane < B;
+  // ---- through sc, sh to A, D, the instance statistics and the gate's pre-activation (a warp per channel, lanes = samples) ----
+  for (int c = cw; c < Cp; c += nw) {
+    const size_t i = pofs + (size_t)c * B + lane;
+    if (c >= C) {  // padded channel: sc = sh = 0 whatever the statistics
+      if (on) {
+        gmean[i] = 0.f;
+        gvar[i] = 0.f;
+      }
+      continue;
+    }
+    float t_gam = 0.f, t_inv = 0.f;
+    if (on) {
+      const float s2 = var[i], m_ = mean[i], r = rsqrtf(s2 + eps);
+      const float w = wsty[lane * C + c], gt = gate[c * B + lane], zz = z[c * B + lane];
+      const float A = gt * g_[c] * inv[c] * w;
+      const float gD = gsh[i], gsct = gsc[i] - gD * m_;
+      gmean[i] = -gD * (A * r);
+      const float gA = gsct * r;
+      gvar[i] = gsct * A * (-0.5f * r * r * r);                       // through r; the term through v is added in the last phase
+      ga2[c * B + lane] = (gA * g_[c] * inv[c] * w + gD * zz) * gt * (1.0f - gt);
+      gz1[c * B + lane] = gD * gt;
+      gwt1[c * B + lane] = gA * gt * g_[c] * inv[c];
+      t_gam = gA * gt * inv[c] * w;
+      t_inv = gA * gt * g_[c] * w;
+    }
+    t_gam = tail_warp_sum(t_gam);
+    t_inv = tail_warp_sum(t_inv);
+    if (lane == 0) {
+      ggam_part[c] = t_gam;
+      ginv_part[c] = t_inv;
+    }
+  }
+  cluster_sync_all();
+  // ---- gp1 = (W2^T ga2) masked by the ReLU: a warp per hidden unit, lanes = samples ----
+  for (int h = cw; h < H; h += nw) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < C; c++) acc = __fmaf_rn(w2p[c * H + h], on ? ga2[c * B + lane] : 0.f, acc);
+    if (on) gp1[h * B + lane] = a1[h * B + lane] > 0.f ? acc : 0.f;
+  }
+  cluster_sync_all();
+  // ---- per channel: the SE weight gradients, gz, and back through the squeeze and the BatchNorm statistics to the style ----
+  for (int c = cw; c < C; c += nw) {
+    const size_t i = pofs + (size_t)c * B + lane;
+    const float zz = on ? z[c * B + lane] : 0.f, g2 = on ? ga2[c * B + lane] : 0.f;
+    float gz = on ? gz1[c * B + lane] : 0.f;
+    for (int h = 0; h < H; h++) {
+      const float gp = on ? gp1[h * B + lane] : 0.f, a_ = on ? a1[h * B + lane] : 0.f;
+      gz = __fmaf_rn(w1p[h * C + c], gp, gz);
+      const float s1 = tail_warp_sum(gp * zz), s2_ = tail_warp_sum(g2 * a_);
+      if (lane == 0) {
+        gw1[((size_t)p * H + h) * C + c] = s1;
+        gw2[((size_t)p * C + c) * H + h] = s2_;
+      }
+    }
+    const float t = on ? bsty[lane * C + c] : 0.f, w = on ? wsty[lane * C + c] : 0.f;
+    const float s2 = on ? var[i] : 1.f;
+    const float v = s2 / (s2 + eps);
+    const float iv = inv[c], m_ = mu[c], gm_ = g_[c];
+    const float dgam = tail_warp_sum(gz * iv * (t - m_)) + ggam_part[c];
+    const float dinv = tail_warp_sum(gz * gm_ * (t - m_)) + ginv_part[c];
+    const float dbet = tail_warp_sum(gz);
+    const float gq = dinv * (-0.5f * iv * iv * iv);
+    const float dmu = -dbet * gm_ * iv - 2.0f * m_ * gq;
+    if (lane == 0) {
+      ggam[(size_t)p * C + c] = dgam;
+      gbet[(size_t)p * C + c] = dbet;
+    }
+    if (on) {
+      gbs[((size_t)p * B + lane) * C + c] = gz * gm_ * iv + (gq * 2.0f * t + dmu) * rB;
+      gws[((size_t)p * B + lane) * C + c] = gwt1[c * B + lane] + gq * 2.0f * w * v * rB;
+      const float d = s2 + eps;
+      gvar[i] += gq * w * w * rB * (eps / (d * d));                   // v = s2 / (s2 + eps)
+    }
+  }
+}
+
+}  // namespace snb
+
+SNB_API size_t snb_adain_tail_save_floats(int P, int C, int B, int H) {
+  if (P <= 0 || C <= 0 || B <= 0 || H <= 0) return 0;
+  return (size_t)P * adt_save_floats(C, B, H);
+}
+
+SNB_API size_t snb_adain_tail_scratch_floats(int P, int C, int B, int H) {
+  if (P <= 0 || C <= 0 || B <= 0 || H <= 0) return 0;
+  return (size_t)P * adt_scratch_floats(C, B, H);
+}
+
+static int adt_launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int P, cudaStream_t s) {
+  cfg = {};
+  cfg.gridDim = dim3((unsigned)(P * ADT_CLUSTER));
+  cfg.blockDim = dim3(TAIL_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = ADT_CLUSTER;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return 0;
+}
+
+SNB_API int snb_adain_tail_fwd(const float* row_mean, const float* row_var, const float* style_scale, const float* style_shift, const float* gamma,
+                               const float* beta, const float* w1, const float* w2, int P, int C, int Cpad, int B, int H, float eps, float* scale,
+                               float* shift, float* save, float* bn_mean, float* bn_var, void* stream) {
+  if (P < 0 || C < 0 || B < 0 || H < 0 || Cpad < C) return SNB_EINVAL;
+  if (B > 32) return SNB_ELIMIT;
+  if (P == 0 || C == 0 || B == 0) return SNB_OK;
+  if (H == 0) return SNB_EINVAL;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  adt_launch_cfg(cfg, at, P, (cudaStream_t)stream);
+  SNB_CUDA(cudaLaunchKernelEx(&cfg, adain_tail_fwd_kernel, row_mean, row_var, style_scale, style_shift, gamma, beta, w1, w2, C, Cpad, B, H, eps, scale,
+                              shift, save, bn_mean, bn_var));
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_adain_tail_bwd(const float* grad_scale, const float* grad_shift, const float* row_mean, const float* row_var,
+                               const float* style_scale, const float* style_shift, const float* gamma, const float* w1, const float* w2, int P,
+                               int C, int Cpad, int B, int H, float eps, const float* save, float* scratch, float* grad_row_mean,
+                               float* grad_row_var, float* grad_style_scale, float* grad_style_shift, float* grad_gamma, float* grad_beta,
+                               float* grad_w1, float* grad_w2, void* stream) {
+  if (P < 0 || C < 0 || B < 0 || H < 0 || Cpad < C) return SNB_EINVAL;
+  if (B > 32) return SNB_ELIMIT;
+  if (P == 0 || C == 0 || B == 0) return SNB_OK;
+  if (H == 0) return SNB_EINVAL;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  adt_launch_cfg(cfg, at, P, (cudaStream_t)stream);
+  SNB_CUDA(cudaLaunchKernelEx(&cfg, adain_tail_bwd_kernel, grad_scale, grad_shift, row_mean, row_var, style_scale, style_shift, gamma, w1, w2, C, Cpad,
+                              B, H, eps, save, scratch, grad_row_mean, grad_row_var, grad_style_scale, grad_style_shift, grad_gamma, grad_beta,
+                              grad_w1, grad_w2));
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

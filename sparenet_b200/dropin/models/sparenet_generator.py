@@ -409,6 +409,18 @@ class SpareNetDecode(nn.Module):  # reference :289-391
 
             def tail(mean, var, wsty, bsty, gam, bet, w1, w2, bns=bns, cout=cout, cop=cop):
                 """instance norm (row statistics per primitive, channel, sample) + the closed-form AdaIN.BN.SE -> one scale/shift"""
+                if FUSED_TAILS and self.training and mean.is_cuda and mean.dtype == torch.float32 and mean.size(-1) <= 32:
+                    # one launch per direction for the 32 primitives (csrc/tails.cu); the running statistics stay a few foreach ops
+                    sc, sh, mu, q = fused.adain_tail(mean, var, wsty, bsty, gam, bet, w1, w2, EPS)
+                    n = wsty.size(0) * (self.num_points // self.n_primitives)
+                    with torch.no_grad():
+                        rms, rvs = [b.running_mean for b in bns], [b.running_var for b in bns]
+                        torch._foreach_mul_(rms, 1 - MOMENTUM)
+                        torch._foreach_add_(rms, list(mu.unbind(0)), alpha=MOMENTUM)
+                        torch._foreach_mul_(rvs, 1 - MOMENTUM)
+                        torch._foreach_add_(rvs, list((q * (n / max(n - 1, 1))).unbind(0)), alpha=MOMENTUM)
+                        torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
+                    return sc, sh
                 rstd = torch.rsqrt(var + EPS)
                 A, D = self._bn_se(bns, wsty, bsty, (var / (var + EPS))[:, :cout], gam, bet, w1, w2)
                 sc = padc(A, cop) * rstd

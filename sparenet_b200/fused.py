@@ -535,6 +535,56 @@ def bn_se_tail(m_bc, v_bc, rb, g, beta, w1, w2, bn, L):
     return BnSeTail.apply(m_bc, v_bc, rb, g, beta, w1, w2, bn, L)
 
 
+class AdainTail(torch.autograd.Function):
+    """(scale, shift) [P,Cpad,B] of the decoders' folded instance-norm . AdaIN . BatchNorm . SE . ReLU tail from the rows' statistics
+    -- ONE launch per direction for all P primitives (csrc/tails.cu: snb_adain_tail_*), train-mode BatchNorm.  mean, var [P,Cpad,B];
+    wsty, bsty [B,C] (the sample's AdaIN weight / bias); gam, bet [P,C(,1)]; w1 [P,H,C], w2 [P,C,H].  Also returns the BatchNorm batch
+    statistics (mu, q) [P,C], non-differentiable, for the caller's running-statistics bookkeeping."""
+    @staticmethod
+    def forward(ctx, mean, var, wsty, bsty, gam, bet, w1, w2, eps):
+        mean, var = mean.contiguous().float(), var.contiguous().float()
+        P, Cp, B = mean.shape
+        C, H = wsty.shape[1], w1.shape[1]
+        wsty, bsty, w1, w2 = (t.detach().contiguous().float() for t in (wsty, bsty, w1, w2))
+        gshape = gam.shape
+        gam2, bet2 = gam.detach().reshape(P, C).contiguous().float(), bet.detach().reshape(P, C).contiguous().float()
+        assert bsty.shape == (B, C) and w1.shape == (P, H, C) and w2.shape == (P, C, H) and Cp >= C and B <= 32
+        dev = mean.device
+        lib = _lib.load()
+        sc, sh = torch.empty(P, Cp, B, device=dev), torch.empty(P, Cp, B, device=dev)
+        mu, q = torch.empty(P, C, device=dev), torch.empty(P, C, device=dev)
+        save = torch.empty(lib.snb_adain_tail_save_floats(P, C, B, H), device=dev)
+        with torch.cuda.device(dev), _op("adain_tail_fwd", 1):
+            check(lib.snb_adain_tail_fwd(ptr(mean), ptr(var), ptr(wsty), ptr(bsty), ptr(gam2), ptr(bet2), ptr(w1), ptr(w2), P, C, Cp, B, H, float(eps),
+                                         ptr(sc), ptr(sh), ptr(save), ptr(mu), ptr(q), stream_ptr()), "adain_tail_fwd")
+        ctx.save_for_backward(mean, var, wsty, bsty, gam2, w1, w2, save)
+        ctx.meta = (P, C, Cp, B, H, float(eps), gshape)
+        ctx.mark_non_differentiable(mu, q)
+        return sc, sh, mu, q
+
+    @staticmethod
+    def backward(ctx, gsc, gsh, *_):
+        mean, var, wsty, bsty, gam2, w1, w2, save = ctx.saved_tensors
+        P, C, Cp, B, H, eps, gshape = ctx.meta
+        dev = mean.device
+        lib = _lib.load()
+        gsc, gsh = gsc.contiguous().float(), gsh.contiguous().float()
+        gmean, gvar = torch.empty_like(mean), torch.empty_like(var)
+        gws, gbs = torch.empty(P, B, C, device=dev), torch.empty(P, B, C, device=dev)
+        ggam, gbet = torch.empty(P, C, device=dev), torch.empty(P, C, device=dev)
+        gw1, gw2 = torch.empty_like(w1), torch.empty_like(w2)
+        scratch = torch.empty(lib.snb_adain_tail_scratch_floats(P, C, B, H), device=dev)
+        with torch.cuda.device(dev), _op("adain_tail_bwd", 1):
+            check(lib.snb_adain_tail_bwd(ptr(gsc), ptr(gsh), ptr(mean), ptr(var), ptr(wsty), ptr(bsty), ptr(gam2), ptr(w1), ptr(w2), P, C, Cp, B, H, eps,
+                                         ptr(save), ptr(scratch), ptr(gmean), ptr(gvar), ptr(gws), ptr(gbs), ptr(ggam), ptr(gbet), ptr(gw1), ptr(gw2),
+                                         stream_ptr()), "adain_tail_bwd")
+        return gmean, gvar, gws.sum(0), gbs.sum(0), ggam.view(gshape), gbet.view(gshape), gw1, gw2, None
+
+
+def adain_tail(mean, var, wsty, bsty, gam, bet, w1, w2, eps):
+    return AdainTail.apply(mean, var, wsty, bsty, gam, bet, w1, w2, eps)
+
+
 class Prologue:
     """The folded normalisation tail of a dense layer, y = leaky_relu(scale*h + shift, slope) with
     (scale, shift) = fn(row_mean(h), row_var(h), *tensors), held as DATA instead of being applied: the next layer's GEMM applies it

@@ -292,3 +292,48 @@ def test_flat_adam_matches_torch_adam(cuda, own_grads):
     # the parameters live in the arena now: views of one flat buffer, 16-byte aligned
     base = opt.flat_params[0].data_ptr()
     assert all(base <= q.data_ptr() < base + opt.flat_params[0].numel() * 4 and q.data_ptr() % 16 == 0 for q in pb)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,C,Cp,B", [(4, 48, 64, 8), (32, 513, 544, 32), (3, 256, 256, 5), (2, 16, 32, 32)])
+def test_adain_tail_matches_pytorch_closed_form(cuda, P, C, Cp, B):
+    """snb_adain_tail_fwd/bwd (one launch per direction for all primitives) against the same closed form as PyTorch ops -- the
+    decoders' instance-norm . AdaIN . BatchNorm . SE tail of SpareNetDecode (tail() / _bn_se): scale/shift, the BatchNorm batch
+    statistics and all eight gradients, fp32 both sides, <= 3e-5 of each tensor's scale (summation order only)."""
+    from sparenet_b200 import fused
+    torch.manual_seed(P * 100 + C)
+    H, eps = max(C // 16, 1), 1e-5
+    mean0 = torch.randn(P, Cp, B, device=cuda)
+    var0 = torch.rand(P, Cp, B, device=cuda) * 2 + 0.05
+    ws0, bs0 = torch.randn(B, C, device=cuda) * 0.5 + 1.0, torch.randn(B, C, device=cuda) * 0.5
+    gam0, bet0 = torch.randn(P, C, 1, device=cuda) * 0.3 + 1.0, torch.randn(P, C, 1, device=cuda) * 0.3
+    w10, w20 = torch.randn(P, H, C, device=cuda) / C ** 0.5, torch.randn(P, C, H, device=cuda) / H ** 0.5
+    gsc, gsh = torch.randn(P, Cp, B, device=cuda), torch.randn(P, Cp, B, device=cuda)
+
+    def ref(mean, var, wsty, bsty, gam, bet, w1, w2):
+        rstd = torch.rsqrt(var + eps)
+        v = (var / (var + eps))[:, :C]
+        wt, bt = wsty.t().unsqueeze(0), bsty.t().unsqueeze(0)
+        mu = bt.mean(-1, keepdim=True).expand(P, -1, -1)
+        q = (wt * wt * v + bt * bt).mean(-1, keepdim=True) - mu * mu
+        inv = torch.rsqrt(q + eps)
+        squeeze = gam * (bt - mu) * inv + bet
+        gate = torch.sigmoid(torch.bmm(w2, torch.relu(torch.bmm(w1, squeeze))))
+        A = gate * gam * inv * wt
+        D = gate * (gam * inv * (bt - mu) + bet)
+        pad = (0, 0, 0, Cp - C)
+        sc = torch.nn.functional.pad(A, pad) * rstd
+        return sc, torch.nn.functional.pad(D, pad) - sc * mean, mu[:, :, 0], q[:, :, 0]
+
+    outs = []
+    for fn in (ref, lambda *a: fused.adain_tail(*a, eps)):
+        leaves = [t.clone().requires_grad_() for t in (mean0, var0, ws0, bs0, gam0, bet0, w10, w20)]
+        sc, sh, mu, q = fn(*leaves)
+        grads = torch.autograd.grad((sc, sh), leaves, (gsc, gsh))
+        outs.append((sc, sh, mu, q, *grads))
+    names = ["scale", "shift", "bn_mean", "bn_var", "g_mean", "g_var", "g_wsty", "g_bsty", "g_gamma", "g_beta", "g_w1", "g_w2"]
+    for name, a, b in zip(names, *outs):
+        scale = max(float(a.detach().abs().max()), 1e-6)
+        err = float((a - b).detach().abs().max()) / scale
+        print(f"[adain_tail P={P} C={C} Cp={Cp} B={B}] {name}: err/scale {err:.2e}")
+        assert err < 3e-5, name
