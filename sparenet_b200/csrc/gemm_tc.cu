@@ -581,9 +581,23 @@ SNB_API int snb_gemm_tf32(const snb_gemm_desc* d, void* stream) {
   p.kb_total = p.kb_per_batch * BI;
   int split = d->split > 1 ? d->split : 1;
   if (d->mode != MODE_WGRAD) split = 1;
-  if (d->mode == MODE_WGRAD && d->split == 0) {              // auto: fill the 148 SMs
+  if (d->mode == MODE_WGRAD && d->split == 0) {
+    // auto: the persistent grid runs ceil(items / 148) waves of tiles.  Pick the smallest split-K whose last wave is (nearly) full
+    // -- a weight gradient has few output tiles and a very long K (the positions), e.g. 16 tiles x 2048 k-blocks: split 10 gave
+    // 160 items = 2 waves at 54 %, split 9 gives 144 items = one wave at 97 %.  At least 8 k-blocks per item; every split adds one
+    // reduce-add of the (small) output.
     const int tiles = p.mt * p.nt * d->G;
-    split = tiles >= kNumSMs ? 1 : min(p.kb_total / 8 > 0 ? p.kb_total / 8 : 1, (kNumSMs + tiles - 1) / tiles);
+    const int smax = min(kNumSMs, p.kb_total / 8 > 0 ? p.kb_total / 8 : 1);
+    float best = 0.f;
+    for (int s_ = 1; s_ <= smax; ++s_) {
+      const long long items = (long long)tiles * s_;
+      const float eff = (float)items / (float)(((items + kNumSMs - 1) / kNumSMs) * kNumSMs);
+      if (eff > best + 1e-6f) {
+        best = eff;
+        split = s_;
+      }
+      if (eff >= 0.93f) break;
+    }
   }
   if (split > 1 && d->store != 2) return SNB_EINVAL;
   p.split = split;

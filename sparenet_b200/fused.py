@@ -674,12 +674,23 @@ class ActConv(torch.autograd.Function):
 class ActConvRowReduce(torch.autograd.Function):
     """(mean, biased var, max, min) over the positions of W . leaky_relu(scale*h + shift), each [G, Cout], WITHOUT storing the
     product: statistics and extrema come out of the GEMM epilogue (PointNetRes conv3 -> bn3 -> max over points,
-    models/sparenet_generator.py:626-629).  Backward: conv_row_reduce_backward (Gram matrices) on the re-materialised operand."""
+    models/sparenet_generator.py:626-629).  Backward: conv_row_reduce_backward (Gram matrices) on the activated operand.
+    MATERIALISE (default): the activated operand is written once in the forward and kept for the backward (which needs it anyway), and
+    the GEMM runs WITHOUT a prologue -- with Cout / 128 = 8 row tiles per operand tile and only 4 k-blocks, the in-shared-memory
+    transform was repeated 8 times per tile and dominated (524 -> ~360 us per call, and the backward's re-materialisation goes)."""
+    MATERIALISE = True
+
     @staticmethod
     def forward(ctx, h, W, pro, *tensors):
         W2 = W.reshape(W.size(0), -1)
         N = pro.h.shape[-1]
-        _, st = gemm.conv_fwd(pro.h, W2, scale=pro.sc, shift=pro.sh, slope=pro.slope, seg=N, stats_seg=N, minmax=True, store=False)
+        if ActConvRowReduce.MATERIALISE:
+            x = pro.materialise()
+            _, st = gemm.conv_fwd(x, W2, stats_seg=N, minmax=True, store=False)
+            ctx.x = x
+        else:
+            _, st = gemm.conv_fwd(pro.h, W2, scale=pro.sc, shift=pro.sh, slope=pro.slope, seg=N, stats_seg=N, minmax=True, store=False)
+            ctx.x = None
         mean, var = st["mean"].reshape(pro.h.shape[0], -1), st["var"].reshape(pro.h.shape[0], -1)
         ctx.pro = pro
         ctx.save_for_backward(W2, mean, st["imax"], st["imin"])
@@ -690,7 +701,7 @@ class ActConvRowReduce(torch.autograd.Function):
     def backward(ctx, gmean, gvar, gmax, gmin):
         W2, mean, imax, imin = ctx.saved_tensors
         pro = ctx.pro
-        x = pro.materialise()
+        x = ctx.x if ctx.x is not None else pro.materialise()
         gx, gW, row_term = conv_row_reduce_backward(x, W2, mean, imax, imin, gmean, gvar, gmax, gmin, True, ctx.needs_input_grad[1],
                                                     split_row_term=True)
         gh, gts = pro.backward(gx, gy_row=row_term)               # the row-constant term is added inside the two row kernels

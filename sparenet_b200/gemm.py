@@ -55,10 +55,21 @@ def stat_tiles(N, block_n=0):
     return lib.snb_gemm_tf32_tiles(int(N), int(block_n)), lib.snb_gemm_tf32_block_n(int(N), int(block_n)) // 2
 
 
+SHAPE_LOG = None   # development: a list that receives (label, start_event, end_event, flops) per call (tools/gemm_shapes.py)
+
+
 def _run(desc, dev, what, nbytes=None):
     flops = 2 * int(desc.G) * int(desc.BI) * int(desc.M) * int(desc.N) * int(desc.K)
     with torch.cuda.device(dev), _op(what, 1, nbytes, flops):
+        if SHAPE_LOG is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         check(_lib.load().snb_gemm_tf32(ctypes.byref(desc), stream_ptr()), what)
+        if SHAPE_LOG is not None:
+            b.record()
+            label = (f"{what[5:]:5s} G={desc.G:<3d} BI={desc.BI:<3d} M={desc.M:<5d} N={desc.N:<6d} K={desc.K:<6d} "
+                     f"{'prologue' if desc.scale else 'plain   '} store={desc.store} {'stats' if desc.pmean else ''}{' minmax' if desc.pmax else ''}")
+            SHAPE_LOG.append((label, a, b, flops))
 
 
 def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, minmax=False, store=True, x_repeat=1, out=None):
