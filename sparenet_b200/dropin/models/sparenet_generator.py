@@ -90,6 +90,7 @@ def _bn_from_rows(bn, m_bc, v_bc, L):
     return bn.running_mean, bn.running_var
 
 
+MATERIALISE_LAYER1 = True   # decoders' first activation: written once + plain GEMMs (True) or applied in conv2's prologue (False)
 FUSED_TAILS = True     # the BatchNorm.SE tails as single launches (csrc/tails.cu); False: the same algebra as PyTorch glue (tests compare)
 LIBRARY_GEMM = False   # measurement switch only (bench.py --library-gemm): route the dense 1x1 convs through cuDNN/cuBLAS like round 1
 
@@ -432,7 +433,14 @@ class SpareNetDecode(nn.Module):  # reference :289-391
             else:
                 # tcgen05 GEMM per primitive; its epilogue returns the instance statistics, the NEXT GEMM's prologue applies the
                 # resulting scale/shift + ReLU to its operand in shared memory: the activated [P,C,B,512] tensor is never stored
-                if pro is None:
+                if pro is None and MATERIALISE_LAYER1:
+                    # layer 1's activation relu(A x_hat + D) [P,1056,B,pts] written once (2.2 GB) and conv2 run WITHOUT a prologue:
+                    # with 5 row tiles per operand tile the in-shared-memory transform is repeated 5 times in the forward, and the
+                    # weight gradient (K = 16384) runs at half the plain rate with it -- measured 1.68 + 1.96 ms against
+                    # 0.40 + 1.11 + ~1.25 ms (write, plain forward, plain weight gradient)
+                    x1 = fused.row_affine_act(xhat_p, A_p, D_p, in_div=B, out_shape=(P, cp, B, npts))
+                    h, m, v = fused.conv1x1(x1, Wp, stats_seg=npts)
+                elif pro is None:
                     # layer 1's activation relu(A x_hat + D) is never materialised for the 32 samples: conv2 reads the batch-independent
                     # x_hat [P,1056,512] and applies the per-sample (A, D) in its prologue
                     h, m, v = fused.bcast_act_conv(xhat_p, A_p, D_p, Wp)
