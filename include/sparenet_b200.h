@@ -125,8 +125,11 @@ size_t snb_knn_workspace_bytes(int B, int N);
 int snb_knn(const float* x, int B, int C, int N, int k, int* idx, void* workspace, size_t workspace_bytes, void* stream);
 /* The same result (bit-identical indices) for wide features, with a caller-supplied Gram matrix gram [B,N,N] = X^T X from a
  * TF32 library GEMM used as a PRUNING filter and exact fp32 re-evaluation of the surviving candidates (csrc/knn_prune.cu).
- * xT [B,N,C] is the point-major copy of the features.  Parity-tested on B200; timing pending (round 2). */
+ * xT [B,N,C] is the point-major copy of the features.  Parity-tested on B200. */
 size_t snb_knn_pruned_workspace_bytes(int B, int N);
+/* xT [B,N,C] = point-major copy of x [B,C,N] (what snb_knn_pruned and the Gram GEMM read; replaces the tensor permute + copy the
+ * reference's knn() does before calling knn_cuda, models/sparenet_generator.py:866-868). */
+int snb_transpose_cn(const float* x, int B, int C, int N, float* xT, void* stream);
 int snb_knn_pruned(const float* xT, const float* gram, int B, int C, int N, int k, int* idx, void* workspace,
                    size_t workspace_bytes, void* stream);
 

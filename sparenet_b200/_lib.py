@@ -56,6 +56,7 @@ SIGNATURES = {
     "snb_knn": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
     "snb_knn_pruned_workspace_bytes": (c_size_t, [c_int, c_int]),
     "snb_knn_pruned": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
+    "snb_transpose_cn": (c_int, [P, c_int, c_int, c_int, P, P]),
     "snb_edge_reduce_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "snb_edge_reduce_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "snb_edge_reduce_sel_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P]),

@@ -11,6 +11,16 @@
 // Two kernels: (1) a register-tiled 128x128 SIMT distance kernel on the channel-major [B,C,N] layout the
 // encoder already uses (coalesced loads, 8x8 outputs per thread, direct-difference form -- the
 // |a|^2+|b|^2-2ab GEMM form would lose the exact ordering to cancellation); (2) a warp-per-row top-k.
+//
+// The encoder's FIRST layer searches in xyz (C = 3): knn_small_kernel does distance and selection in one launch with the
+// sample's points in shared memory and nothing in HBM but the indices (the two-kernel path wrote and re-read a [B,N,N] matrix:
+// 0.52 ms per step for 134 M three-term distances).  A warp per query: every lane keeps its 64 distances in registers, the
+// k-th smallest of the 32 lane minima is an upper bound of the k-th smallest distance (k distinct points are at or below
+// it), the few entries at or below that bound go to a shared-memory list and k pops of the warp minimum by (d, j) order
+// them -- no per-lane sorted lists (whose insertion path diverges on almost every element when a lane only sees 64).
+// Same arithmetic (d = x_j - x_i, fma in ascending c from 0) and the same (d, j) order as the two-kernel path: identical
+// indices (tests/test_gpu_ops.py::test_knn_small_identical_to_two_kernel_path).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace snb {
@@ -188,6 +198,121 @@ __global__ void __launch_bounds__(256) knn_topk_kernel(const float* __restrict__
   }
 }
 
+// ---- fused distance + selection for narrow features (C <= 4: the xyz layer) --------------------------------------------------------
+constexpr int KS_MAXN = 2048;  // 64 distances per lane
+constexpr int KS_CAP = 96;     // entries at or below the bound (3 per lane); more (many identical points) -> pops over the registers
+constexpr int KS_QPW = 8;      // queries per warp (the CTA stages its sample's points once for 64 queries)
+
+template <int C>
+__global__ void __launch_bounds__(256) knn_small_kernel(const float* __restrict__ x, int N, int k, int* __restrict__ idx) {
+  extern __shared__ __align__(16) float ks_x[];  // [C][N]
+  __shared__ float cd[8][KS_CAP];
+  __shared__ int cj[8][KS_CAP];
+  __shared__ int cnt[8];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ xb = x + (size_t)b * C * N;
+  for (int e = threadIdx.x; e < C * N; e += 256) ks_x[e] = xb[e];
+  __syncthreads();
+  const float INF = __int_as_float(0x7f800000);
+  const int q0 = (blockIdx.x * 8 + warp) * KS_QPW;
+  for (int qq = 0; qq < KS_QPW; qq++) {
+    const int i = q0 + qq;
+    if (i >= N) break;  // warp-uniform
+    float xi[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) xi[c] = ks_x[c * N + i];
+    float v[64];
+    float lm = INF;
+#pragma unroll
+    for (int t = 0; t < 64; t++) {
+      const int j = t * 32 + lane;
+      float acc = INF;
+      if (j < N) {
+        acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const float d = __fsub_rn(ks_x[c * N + j], xi[c]);
+          acc = __fmaf_rn(d, d, acc);
+        }
+      }
+      v[t] = acc;
+      lm = fminf(lm, acc);
+    }
+    // bound: the k-th smallest lane minimum (distances are >= +0: the bit patterns order like the values)
+    unsigned key = __float_as_uint(lm), bound = 0x7f800000u;
+    for (int t = 0; t < k; t++) {
+      bound = __reduce_min_sync(0xffffffffu, key);
+      const unsigned owners = __ballot_sync(0xffffffffu, key == bound);
+      if (lane == __ffs(owners) - 1) key = 0x7f800000u;
+    }
+    const float tau = __uint_as_float(bound);
+    if (lane == 0) cnt[warp] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 64; t++) {
+      if (v[t] <= tau && t * 32 + lane < N) {
+        const int pos = atomicAdd(&cnt[warp], 1);
+        if (pos < KS_CAP) {
+          cd[warp][pos] = v[t];
+          cj[warp][pos] = t * 32 + lane;
+        }
+      }
+    }
+    __syncwarp();
+    const int n = cnt[warp];
+    int* out = idx + ((size_t)b * N + i) * k;
+    if (n <= KS_CAP) {
+      float ed[3];
+      int ej[3];
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int e = lane + 32 * u;
+        ed[u] = e < n ? cd[warp][e] : INF;
+        ej[u] = e < n ? cj[warp][e] : 0x7fffffff;
+      }
+      for (int t = 0; t < k; t++) {
+        float hv = ed[0];
+        int hj = ej[0];
+#pragma unroll
+        for (int u = 1; u < 3; u++)
+          if (ed[u] < hv || (ed[u] == hv && ej[u] < hj)) {
+            hv = ed[u];
+            hj = ej[u];
+          }
+        const unsigned md = __reduce_min_sync(0xffffffffu, __float_as_uint(hv));
+        const int mj = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(hv) == md ? (unsigned)hj : 0x7fffffffu);
+        if (lane == 0) out[t] = mj;
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+          if (ej[u] == mj) {  // indices are unique: one slot of one lane
+            ed[u] = INF;
+            ej[u] = 0x7fffffff;
+          }
+      }
+    } else {
+      // many entries at the bound (duplicated points): k pops straight from the registers
+      for (int t = 0; t < k; t++) {
+        float hv = INF;
+        int hj = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < 64; u++)
+          if (v[u] < hv) {  // ascending j within a lane: strict '<' keeps the smaller index
+            hv = v[u];
+            hj = u * 32 + lane;
+          }
+        const unsigned md = __reduce_min_sync(0xffffffffu, __float_as_uint(hv));
+        const int mj = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(hv) == md ? (unsigned)hj : 0x7fffffffu);
+        if (lane == 0) out[t] = mj;
+#pragma unroll
+        for (int u = 0; u < 64; u++)
+          if (u * 32 + lane == mj) v[u] = INF;
+      }
+    }
+    __syncwarp();  // the lists are reused by the next query
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -204,6 +329,22 @@ SNB_API int snb_knn(const float* x, int B, int C, int N, int k, int* idx, void* 
   if (!workspace || workspace_bytes < snb_knn_workspace_bytes(B, N)) return SNB_EWORKSPACE;
   if (((uintptr_t)workspace & 15) != 0) return SNB_EALIGN;
   cudaStream_t s = (cudaStream_t)stream;
+  // narrow features (the xyz layer): fused distance + selection, nothing but the indices reaches HBM (SNB_KNN_SMALL=0: two-kernel path)
+  if (C <= 4 && N <= KS_MAXN && (size_t)C * N * sizeof(float) <= 40 * 1024) {
+    const char* sw = getenv("SNB_KNN_SMALL");
+    if (!(sw && sw[0] == '0')) {
+      const dim3 grid((unsigned)((N + 8 * KS_QPW - 1) / (8 * KS_QPW)), (unsigned)B);
+      const size_t sm = (size_t)C * N * sizeof(float);
+      switch (C) {
+        case 1: knn_small_kernel<1><<<grid, 256, sm, s>>>(x, N, k, idx); break;
+        case 2: knn_small_kernel<2><<<grid, 256, sm, s>>>(x, N, k, idx); break;
+        case 3: knn_small_kernel<3><<<grid, 256, sm, s>>>(x, N, k, idx); break;
+        default: knn_small_kernel<4><<<grid, 256, sm, s>>>(x, N, k, idx); break;
+      }
+      SNB_LAUNCH_CHECK();
+      return SNB_OK;
+    }
+  }
   float* D = (float*)workspace;
   const int nt = (N + KNN_BT - 1) / KNN_BT;
   knn_dist_kernel<<<dim3(nt, nt, B), 256, 0, s>>>(x, C, N, D);

@@ -25,6 +25,27 @@ namespace snb {
 constexpr int KP_MAXK = 32;
 constexpr int KP_CAND = 96;  // candidate capacity per row (3 per lane)
 
+// point-major copy xT [B,N,C] of the channel-major features x [B,C,N]: 32 x 32 tiles through shared memory, 128-byte rows on both sides
+// (the PyTorch permute-copy ran at ~1.7 TB/s: 0.3 ms per step for the three wide layers)
+__global__ void __launch_bounds__(256) transpose_cn_kernel(const float* __restrict__ x, int C, int N, float* __restrict__ xT) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* __restrict__ xb = x + (size_t)b * C * N;
+  float* __restrict__ tb = xT + (size_t)b * C * N;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int c = c0 + ty + 8 * r, n = n0 + tx;
+    tile[ty + 8 * r][tx] = (c < C && n < N) ? xb[(size_t)c * N + n] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int n = n0 + ty + 8 * r, c = c0 + tx;
+    if (n < N && c < C) tb[(size_t)n * C + c] = tile[tx][ty + 8 * r];
+  }
+}
+
 // squared norms of the points (fp32) and their per-sample maximum (bit pattern; norms are >= 0)
 __global__ void __launch_bounds__(256) knn_norm_kernel(const float* __restrict__ xT, int C, int N, size_t rows, float* __restrict__ nrm,
                                                         unsigned* __restrict__ nmax_bits) {
@@ -68,12 +89,22 @@ __device__ __forceinline__ float knn_exact_dist(const float* __restrict__ xi, co
   return acc;
 }
 
-// warp per query row
+// warp per query row.  Selection without per-lane sorted lists (a lane only sees N/32 entries, so their insertion path ran -- for the
+// whole warp -- on almost every element: 6 000 warp instructions per row, 0.68 ms per layer):
+//   1. every lane computes its approximate distances (kept in registers when N <= 2048: one pass over the Gram row, 128-bit loads all
+//      independent) and their minimum; the k-th smallest of the 32 lane minima, tau0, is an upper bound of the k-th smallest
+//      approximate distance (k distinct entries are at or below it);
+//   2. entries at or below the LOOSE threshold f(tau0), f(t) = t (1 + 2^-10) + 2 eps (monotone, so f(tau0) >= f(kth)), go to a
+//      shared-memory list -- a superset of the candidates, ~a dozen entries;
+//   3. k pops of the warp minimum over the list give the exact k-th smallest approximate distance (duplicates count separately, as
+//      before), the list is filtered by f(kth): the SAME candidate set as the two-pass scan, hence the same indices.
 template <int K>
 __global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict__ xT, const float* __restrict__ gram, const float* __restrict__ nrm,
                                                          const unsigned* __restrict__ nmax_bits, int C, int N, size_t rows, int k,
                                                          int* __restrict__ idx) {
   __shared__ int cand[8][KP_CAND];
+  __shared__ float cval[8][KP_CAND];
+  __shared__ int cnt[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t row = (size_t)blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -82,78 +113,128 @@ __global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict_
   const float* __restrict__ g = gram + row * N;
   const float* __restrict__ nb = nrm + b * N;
   const float ni = nb[i];
-  // ---- pass 1: the k-th smallest approximate distance of the row (per-lane sorted lists, then k pops of the warp minimum) ----
-  float bd[K];
+  const float INF = __int_as_float(0x7f800000);
+  const bool cached = (N & 3) == 0 && N <= 2048;  // 16 x float4 per lane
+  const int n4 = N >> 2;
+  float v[64];
+  float lm = INF;
+  if (cached) {
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(g);
+    const float4* __restrict__ nb4 = reinterpret_cast<const float4*>(nb);
 #pragma unroll
-  for (int t = 0; t < K; t++) bd[t] = __int_as_float(0x7f800000);
-  for (int j = lane; j < N; j += 32) {
-    float v = __fmaf_rn(-2.f, g[j], ni + nb[j]);
-    if (v < bd[K - 1]) {
-      bool ins = false;
-#pragma unroll
-      for (int t = 0; t < K; t++) {
-        if (ins || v < bd[t]) {
-          ins = true;
-          const float tv = bd[t];
-          bd[t] = v;
-          v = tv;
-        }
+    for (int t = 0; t < 16; t++) {
+      const int q = lane + 32 * t;
+      float4 r = make_float4(INF, INF, INF, INF);
+      if (q < n4) {
+        const float4 gg = g4[q], nn = nb4[q];
+        r.x = __fmaf_rn(-2.f, gg.x, ni + nn.x);
+        r.y = __fmaf_rn(-2.f, gg.y, ni + nn.y);
+        r.z = __fmaf_rn(-2.f, gg.z, ni + nn.z);
+        r.w = __fmaf_rn(-2.f, gg.w, ni + nn.w);
       }
+      v[4 * t] = r.x;
+      v[4 * t + 1] = r.y;
+      v[4 * t + 2] = r.z;
+      v[4 * t + 3] = r.w;
+      lm = fminf(lm, fminf(fminf(r.x, r.y), fminf(r.z, r.w)));
     }
+  } else {
+    for (int j = lane; j < N; j += 32) lm = fminf(lm, __fmaf_rn(-2.f, g[j], ni + nb[j]));
   }
-  float kth = 0.f;
+  // ---- tau0: the k-th smallest lane minimum (approximate distances may be slightly negative: order-preserving keys) ----
+  const unsigned KINF = float_key(INF);
+  unsigned key = float_key(lm), kb = KINF;
   for (int t = 0; t < k; t++) {
-    float mv = bd[0];
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) mv = fminf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
-    kth = mv;
-    const unsigned owners = __ballot_sync(0xffffffffu, bd[0] == mv);
-    if (lane == __ffs(owners) - 1) {  // ONE lane pops (equal approximate values in several lanes count separately)
-#pragma unroll
-      for (int u = 0; u + 1 < K; u++) bd[u] = bd[u + 1];
-      bd[K - 1] = __int_as_float(0x7f800000);
-    }
+    kb = __reduce_min_sync(0xffffffffu, key);
+    const unsigned owners = __ballot_sync(0xffffffffu, key == kb);
+    if (lane == __ffs(owners) - 1) key = KINF;
   }
+  const float tau0 = key_float(kb);
   const float nmx = __uint_as_float(nmax_bits[b]);
   // 2^-7.5 |a_i| max|a_j| for the truncated products, 2^-13 (n_i + max n_j) for the fp32 rounding of the norms and the accumulations
   // (also what keeps the rule valid for an all-zero query point, whose first term vanishes)
   const float eps = __fmaf_rn(0.0055242717f * sqrtf(ni), sqrtf(nmx), 0.00012207031f * (ni + nmx));
-  const float thr = __fmaf_rn(fabsf(kth), 0.0009765625f, kth) + 2.f * eps;
-  // ---- pass 2: candidates ----
-  int ncand = 0;
-  for (int j0 = 0; j0 < N; j0 += 32) {
-    const int j = j0 + lane;
-    const bool ok = j < N && __fmaf_rn(-2.f, g[j], ni + nb[j]) <= thr;
-    const unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const int pos = ncand + __popc(m & ((1u << lane) - 1u));
-      if (pos < KP_CAND) cand[warp][pos] = j;
+  const float thr_loose = __fmaf_rn(fabsf(tau0), 0.0009765625f, tau0) + 2.f * eps;
+  // ---- the list: entries at or below the loose threshold ----
+  if (lane == 0) cnt[warp] = 0;
+  __syncwarp();
+  if (cached) {
+#pragma unroll
+    for (int t = 0; t < 64; t++) {
+      if (v[t] <= thr_loose) {  // padding entries are +inf: only reachable when the threshold is +inf, which overflows the list anyway
+        const int j = 4 * (lane + 32 * (t >> 2)) + (t & 3);
+        const int pos = atomicAdd(&cnt[warp], 1);
+        if (pos < KP_CAND && j < N) {
+          cand[warp][pos] = j;
+          cval[warp][pos] = v[t];
+        }
+      }
     }
-    ncand += __popc(m);
+  } else {
+    for (int j = lane; j < N; j += 32) {
+      const float vv = __fmaf_rn(-2.f, g[j], ni + nb[j]);
+      if (vv <= thr_loose) {
+        const int pos = atomicAdd(&cnt[warp], 1);
+        if (pos < KP_CAND) {
+          cand[warp][pos] = j;
+          cval[warp][pos] = vv;
+        }
+      }
+    }
   }
   __syncwarp();
+  const int nlist = cnt[warp];
+  // ---- the exact k-th smallest approximate distance from the list, then the candidates proper ----
+  float cd[3];
+  int cj[3];
+  bool isc[3];
+  int ncand = KP_CAND + 1;  // list overflow (degenerate rows) -> every j evaluated exactly below
+  if (nlist <= KP_CAND) {
+    float ev[3];
+    unsigned ek[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      const int e = lane + 32 * u;
+      ev[u] = e < nlist ? cval[warp][e] : INF;
+      cj[u] = e < nlist ? cand[warp][e] : 0x7fffffff;
+      ek[u] = float_key(ev[u]);
+    }
+    unsigned kk = KINF;
+    for (int t = 0; t < k; t++) {
+      const unsigned lb = min(ek[0], min(ek[1], ek[2]));
+      kk = __reduce_min_sync(0xffffffffu, lb);
+      const unsigned owners = __ballot_sync(0xffffffffu, lb == kk);
+      if (lane == __ffs(owners) - 1) {  // ONE entry pops (equal approximate values count separately)
+        if (ek[0] == kk) ek[0] = KINF;
+        else if (ek[1] == kk) ek[1] = KINF;
+        else ek[2] = KINF;
+      }
+    }
+    const float kth = key_float(kk);
+    const float thr = __fmaf_rn(fabsf(kth), 0.0009765625f, kth) + 2.f * eps;
+    ncand = 0;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      isc[u] = (lane + 32 * u) < nlist && ev[u] <= thr;
+      ncand += __popc(__ballot_sync(0xffffffffu, isc[u]));
+    }
+  }
   // ---- exact distances of the candidates, then the k smallest by (d, j) ----
   const float* __restrict__ xb = xT + b * (size_t)N * C;
   const float* __restrict__ xi = xb + (size_t)i * C;
-  float cd[3];
-  int cj[3];
-#pragma unroll
-  for (int u = 0; u < 3; u++) {
-    cd[u] = __int_as_float(0x7f800000);
-    cj[u] = 0x7fffffff;
-  }
   int* out = idx + row * k;
   if (ncand <= KP_CAND) {
 #pragma unroll
     for (int u = 0; u < 3; u++) {
-      const int e = lane + 32 * u;
-      if (e < ncand) {
-        cj[u] = cand[warp][e];
+      if (isc[u]) {
         cd[u] = knn_exact_dist(xi, xb + (size_t)cj[u] * C, C);
+      } else {
+        cd[u] = INF;
+        cj[u] = 0x7fffffff;
       }
     }
     for (int t = 0; t < k; t++) {
-      // this lane's best remaining candidate
+      // this lane's best remaining candidate, then the warp's by (d, j): exact distances are >= +0, their bits order like the values
       float hv = cd[0];
       int hj = cj[0];
 #pragma unroll
@@ -162,17 +243,8 @@ __global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict_
           hv = cd[u];
           hj = cj[u];
         }
-      float mv = hv;
-      int mj = hj;
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
-        if (ov < mv || (ov == mv && oj < mj)) {
-          mv = ov;
-          mj = oj;
-        }
-      }
+      const unsigned md = __reduce_min_sync(0xffffffffu, __float_as_uint(hv));
+      const int mj = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(hv) == md ? (unsigned)hj : 0x7fffffffu);
       if (lane == 0) out[t] = mj;
 #pragma unroll
       for (int u = 0; u < 3; u++)
@@ -240,6 +312,15 @@ __global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict_
 }  // namespace snb
 
 using namespace snb;
+
+SNB_API int snb_transpose_cn(const float* x, int B, int C, int N, float* xT, void* stream) {
+  if (B < 0 || C <= 0 || N < 0) return SNB_EINVAL;
+  if (B > 65535 || (C + 31) / 32 > 65535) return SNB_ELIMIT;
+  if (B == 0 || N == 0) return SNB_OK;
+  transpose_cn_kernel<<<dim3((unsigned)((N + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(x, C, N, xT);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
 
 // workspace: norms [B,N] floats + per-sample maxima [B] (16-byte aligned pieces)
 SNB_API size_t snb_knn_pruned_workspace_bytes(int B, int N) {

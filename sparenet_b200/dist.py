@@ -44,18 +44,27 @@ class GradArena:
                 if own_grads:
                     p.grad = self.views[id(p)]
             self.flats.append(flat)
+        self._written = set()      # own_grads=False: ids of the parameters whose arena slot pack() has ever copied a gradient into
 
     def pack(self):
         """own_grads=False: copy the parameters' current .grad tensors into the arena (multi-tensor copies; a parameter without a
-        gradient contributes zeros).  Graph-capturable."""
-        dst, src = [], []
+        gradient contributes zeros).  Graph-capturable.  The arena starts as zeros and only pack() writes into it (the all-reduce
+        averages zeros to zeros), so the slot of a parameter that has never had a gradient is still zero: it is cleared only after
+        an earlier pack() copied something there -- the generator has ~100 such parameters (biases that cancel under the instance
+        norm, the unused top-level conv1), which used to cost one fill launch each per step."""
+        dst, src, clear = [], [], []
         for p in self.params:
             v = self.views[id(p)]
             if p.grad is None:
-                v.zero_()
+                if id(p) in self._written:
+                    clear.append(v)
+                    self._written.discard(id(p))
             elif p.grad.data_ptr() != v.data_ptr():
                 dst.append(v)
                 src.append(p.grad)
+                self._written.add(id(p))
+        if clear:
+            torch._foreach_zero_(clear)
         if dst:
             torch._foreach_copy_(dst, src)
 

@@ -338,6 +338,18 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         w2 = self._stack_list([s.fc[2].weight for s in ses])
         return bns, (gam, bet, w1, w2)
 
+    def _adain_running_stats(self, bns, mu, q, B):
+        """Running statistics of the 32 primitives' BatchNorm of one layer from the batch statistics (mu, q) [P,C] of the fused tail:
+        5 multi-tensor launches."""
+        n = B * (self.num_points // self.n_primitives)
+        with torch.no_grad():
+            rms, rvs = [b.running_mean for b in bns], [b.running_var for b in bns]
+            torch._foreach_mul_(rms, 1 - MOMENTUM)
+            torch._foreach_add_(rms, list(mu.unbind(0)), alpha=MOMENTUM)
+            torch._foreach_mul_(rvs, 1 - MOMENTUM)
+            torch._foreach_add_(rvs, list((q * (n / max(n - 1, 1))).unbind(0)), alpha=MOMENTUM)
+            torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
+
     def _bn_se(self, bns, wsty, bsty, v, gam, bet, w1, w2):
         """Closed-form BN statistics + SE gate after AdaIN.  wsty/bsty [B,C] style scale/shift (shared by all
         primitives), v [P,C,B] or [P,C,1] = variance of the instance-normalised activations (= s2/(s2+eps)); the stacked
@@ -390,13 +402,25 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         # the channel padding is applied to the tiny WEIGHT (zero rows), so the padded channels of h, and of x_hat = 0 * rsqrt(eps),
         # come out as exact zeros without a pad copy of the [P,1056,pts] tensors
         h = fused.thin_conv(self._grid_t.unsqueeze(0), padc(W1, cp))         # Conv1d(2 -> 1026): [P,1056,pts], batch independent
-        var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
-        xhat_p = (h - mean) * torch.rsqrt(var + EPS)
-        var = var[:, :C1]
         bns, prm = self._bn_se_params(1)
-        A, D = self._bn_se(bns, sty[0][0], sty[0][1], var / (var + EPS), *prm)
-        A_p, D_p = padc(A, cp), padc(D, cp)
-        x = None
+        x = x1 = None
+        if (FUSED_TAILS and MATERIALISE_LAYER1 and not LIBRARY_GEMM and self.training and h.is_cuda and h.dtype == torch.float32
+                and B <= 32):
+            # layer 1 through the same kernels as layers 2 / 3: row statistics of the lattice response (one launch, with its own
+            # backward), the AdaIN.BN.SE closed form as ONE launch (the statistics are batch independent: broadcast views over the
+            # samples), and relu(sc h + sh) written once for the 32 samples -- x_hat = (h - mean) rstd is never formed (it was ~60
+            # PyTorch launches over 69 MB tensors per step, forward + backward)
+            m1, v1 = fused.row_stats(h)                                       # [P,1056]
+            sc, sh, mu, q = fused.adain_tail(m1.unsqueeze(-1).expand(P, cp, B), v1.unsqueeze(-1).expand(P, cp, B), sty[0][0], sty[0][1],
+                                             *prm, EPS)
+            self._adain_running_stats(bns, mu, q, B)
+            x1 = fused.row_affine_act(h, sc, sh, in_div=B, out_shape=(P, cp, B, npts))
+        else:
+            var, mean = torch.var_mean(h, dim=2, unbiased=False, keepdim=True)
+            xhat_p = (h - mean) * torch.rsqrt(var + EPS)
+            var = var[:, :C1]
+            A, D = self._bn_se(bns, sty[0][0], sty[0][1], var / (var + EPS), *prm)
+            A_p, D_p = padc(A, cp), padc(D, cp)
         if LIBRARY_GEMM:
             x = fused.row_affine_act(xhat_p, A_p, D_p, in_div=B, out_shape=(P, cp, B, npts))   # relu(A x_hat + D) for every sample
         cin = C1
@@ -413,14 +437,7 @@ class SpareNetDecode(nn.Module):  # reference :289-391
                 if FUSED_TAILS and self.training and mean.is_cuda and mean.dtype == torch.float32 and mean.size(-1) <= 32:
                     # one launch per direction for the 32 primitives (csrc/tails.cu); the running statistics stay a few foreach ops
                     sc, sh, mu, q = fused.adain_tail(mean, var, wsty, bsty, gam, bet, w1, w2, EPS)
-                    n = wsty.size(0) * (self.num_points // self.n_primitives)
-                    with torch.no_grad():
-                        rms, rvs = [b.running_mean for b in bns], [b.running_var for b in bns]
-                        torch._foreach_mul_(rms, 1 - MOMENTUM)
-                        torch._foreach_add_(rms, list(mu.unbind(0)), alpha=MOMENTUM)
-                        torch._foreach_mul_(rvs, 1 - MOMENTUM)
-                        torch._foreach_add_(rvs, list((q * (n / max(n - 1, 1))).unbind(0)), alpha=MOMENTUM)
-                        torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
+                    self._adain_running_stats(bns, mu, q, wsty.size(0))
                     return sc, sh
                 rstd = torch.rsqrt(var + EPS)
                 A, D = self._bn_se(bns, wsty, bsty, (var / (var + EPS))[:, :cout], gam, bet, w1, w2)
@@ -438,7 +455,8 @@ class SpareNetDecode(nn.Module):  # reference :289-391
                     # with 5 row tiles per operand tile the in-shared-memory transform is repeated 5 times in the forward, and the
                     # weight gradient (K = 16384) runs at half the plain rate with it -- measured 1.68 + 1.96 ms against
                     # 0.40 + 1.11 + ~1.25 ms (write, plain forward, plain weight gradient)
-                    x1 = fused.row_affine_act(xhat_p, A_p, D_p, in_div=B, out_shape=(P, cp, B, npts))
+                    if x1 is None:
+                        x1 = fused.row_affine_act(xhat_p, A_p, D_p, in_div=B, out_shape=(P, cp, B, npts))
                     h, m, v = fused.conv1x1(x1, Wp, stats_seg=npts)
                 elif pro is None:
                     # layer 1's activation relu(A x_hat + D) is never materialised for the 32 samples: conv2 reads the batch-independent

@@ -326,7 +326,8 @@ def knn_indices_pruned(x, k):
     nbytes = lib.snb_knn_pruned_workspace_bytes(B, N)
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device), _op("knn", 2):     # the op's time includes the transpose and the Gram GEMM
-        xT = x.transpose(1, 2).contiguous()
+        xT = torch.empty(B, N, C, device=x.device, dtype=torch.float32)
+        check(lib.snb_transpose_cn(ptr(x), B, C, N, ptr(xT), stream_ptr()), "transpose_cn")
         gram, _ = gemm.conv_fwd(x, xT)                   # [B,N,N]: one "weight" per sample = its own points
         check(lib.snb_knn_pruned(ptr(xT), ptr(gram), B, C, N, int(k), ptr(idx), ptr(ws), nbytes, stream_ptr()), "knn_pruned")
     return idx

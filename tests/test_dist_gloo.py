@@ -123,3 +123,8 @@ def test_grad_arena_pack_mode_cpu():
             want = 0.0 if i == 1 else float(10 * round_ + i + 1)
             assert torch.equal(v, torch.full_like(p, want))
     assert flat.numel() == 16 + 8 + 8 + 4      # every view padded to a multiple of 4 elements
+    # a parameter that HAD a gradient and then has none: its slot is cleared (once); one that never had any costs nothing
+    ps[0].grad = None
+    arena.pack()
+    assert torch.equal(arena.views[id(ps[0])], torch.zeros_like(ps[0])) and torch.equal(arena.views[id(ps[1])], torch.zeros_like(ps[1]))
+    assert id(ps[0]) not in arena._written and id(ps[1]) not in arena._written and id(ps[2]) in arena._written

@@ -541,7 +541,8 @@ def test_knn_vs_oracle_sets(cuda, B, C, N, k, seed):
     assert same.float().mean().item() > 0.999
 
 
-@pytest.mark.parametrize("B,C,N,k,offset", [(2, 64, 512, 8, 0.0), (3, 256, 2048, 8, 3.0), (2, 512, 1024, 16, 1.0), (1, 128, 320, 8, 0.0)])
+@pytest.mark.parametrize("B,C,N,k,offset", [(2, 64, 512, 8, 0.0), (3, 256, 2048, 8, 3.0), (2, 512, 1024, 16, 1.0), (1, 128, 320, 8, 0.0),
+                                              (1, 64, 4096, 8, 0.5), (2, 256, 2048, 32, 0.0), (2, 64, 96, 32, 0.0)])
 def test_knn_pruned_identical_to_brute_force(cuda, monkeypatch, B, C, N, k, offset):
     """tensor-core Gram matrix as a pruning filter + exact re-evaluation == the brute-force kernel, index for index; `offset` adds
     a common mean to the features (large norms, small distances: the cancellation case the bound has to survive); the last case
@@ -555,6 +556,32 @@ def test_knn_pruned_identical_to_brute_force(cuda, monkeypatch, B, C, N, k, offs
     a = F_.knn_indices_pruned(x, k)                      # Gram matrix from the tcgen05 TF32 GEMM (positions % 32 == 0)
     monkeypatch.setenv("SNB_KNN_PRUNE", "0")             # the reference side is always the brute-force kernels
     assert torch.equal(a, F_.knn_indices(x, k))
+
+
+@pytest.mark.parametrize("B,C,N,k", [(32, 3, 2048, 8), (2, 3, 130, 16), (3, 4, 1000, 8), (2, 3, 40, 32), (2, 2, 2048, 20)])
+def test_knn_small_identical_to_two_kernel_path(cuda, monkeypatch, B, C, N, k):
+    """Fused distance + selection for narrow features (the encoder's xyz layer) == distance matrix + top-k kernels, index for index,
+    including duplicated points (ties by index, list overflow) and a query whose neighbours are all identical."""
+    from sparenet_b200 import functional as F_
+    torch.manual_seed(N + k)
+    x = torch.rand(B, C, N, device=cuda)
+    if N >= 1000:
+        x[:, :, 100:400] = x[:, :, 500:501]               # 300 copies of one point: more ties than the list holds
+        x[:, :, 900:910] = x[:, :, 10:20]
+    a = F_._knn_brute(x, k)
+    monkeypatch.setenv("SNB_KNN_SMALL", "0")
+    assert torch.equal(a, F_._knn_brute(x, k))
+
+
+def test_transpose_cn(cuda):
+    from sparenet_b200 import _lib
+    from sparenet_b200._lib import check, ptr, stream_ptr
+    torch.manual_seed(3)
+    for B, C, N in ((2, 256, 2048), (3, 37, 100), (1, 4, 31)):
+        x = torch.randn(B, C, N, device=cuda)
+        xT = torch.empty(B, N, C, device=cuda)
+        check(_lib.load().snb_transpose_cn(ptr(x), B, C, N, ptr(xT), stream_ptr()), "transpose_cn")
+        assert torch.equal(xT, x.transpose(1, 2).contiguous())
 
 
 def test_knn_cuda_shim(cuda):
