@@ -268,6 +268,13 @@ typedef struct snb_gemm_desc {
 int snb_gemm_tf32(const snb_gemm_desc* desc, void* stream);
 int snb_gemm_tf32_block_n(int N, int block_n);                /* the column-tile width the library uses (block_n = 0: its choice) */
 int snb_gemm_tf32_tiles(int N, int block_n);                  /* statistics tiles along N: 2 per column tile (width block_n/2) */
+/* Merge of the epilogue's per-tile statistics (csrc/rowops.cu), one launch each: tile means / centred second moments
+ * [pairs, tiles_per_segment] of tiles of w positions -> mean and biased variance [pairs] of every segment (pairs = rows x segments);
+ * tile extrema with their positions [rows, T] -> the rows' extrema (first position attaining them). */
+int snb_gemm_stats_merge(const float* pmean, const float* pm2, long long pairs, int tiles_per_segment, int w, float* mean, float* var,
+                         void* stream);
+int snb_gemm_minmax_merge(const float* pmax, const float* pmin, const int* pimax, const int* pimin, long long rows, int T, float* vmax,
+                          float* vmin, int* imax, int* imin, void* stream);
 
 /* ---- Gridding / GriddingReverse (GRNet) --------------------------------------------------------------------
  * replaces gridding.forward / backward / rev_forward / rev_backward (cuda/gridding/gridding_cuda.cpp:43-99,

@@ -208,7 +208,6 @@ __global__ void __launch_bounds__(256) knn_small_kernel(const float* __restrict_
   extern __shared__ __align__(16) float ks_x[];  // [C][N]
   __shared__ float cd[8][KS_CAP];
   __shared__ int cj[8][KS_CAP];
-  __shared__ int cnt[8];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* __restrict__ xb = x + (size_t)b * C * N;
@@ -247,20 +246,24 @@ __global__ void __launch_bounds__(256) knn_small_kernel(const float* __restrict_
       if (lane == __ffs(owners) - 1) key = 0x7f800000u;
     }
     const float tau = __uint_as_float(bound);
-    if (lane == 0) cnt[warp] = 0;
-    __syncwarp();
+    // list positions from ballots (warp-uniform branch, taken for the ~10 of 64 steps that have a hit): a shared-memory atomic per
+    // hit put its round trip on the warp's critical path at every reconvergence point
+    int n = 0;
+    const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int t = 0; t < 64; t++) {
-      if (v[t] <= tau && t * 32 + lane < N) {
-        const int pos = atomicAdd(&cnt[warp], 1);
-        if (pos < KS_CAP) {
+      const bool hit = v[t] <= tau && t * 32 + lane < N;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        const int pos = n + __popc(m & lt);
+        if (hit && pos < KS_CAP) {
           cd[warp][pos] = v[t];
           cj[warp][pos] = t * 32 + lane;
         }
+        n += __popc(m);
       }
     }
     __syncwarp();
-    const int n = cnt[warp];
     int* out = idx + ((size_t)b * N + i) * k;
     if (n <= KS_CAP) {
       float ed[3];

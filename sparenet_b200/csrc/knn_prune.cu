@@ -104,7 +104,6 @@ __global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict_
                                                          int* __restrict__ idx) {
   __shared__ int cand[8][KP_CAND];
   __shared__ float cval[8][KP_CAND];
-  __shared__ int cnt[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t row = (size_t)blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -155,35 +154,41 @@ __global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict_
   // (also what keeps the rule valid for an all-zero query point, whose first term vanishes)
   const float eps = __fmaf_rn(0.0055242717f * sqrtf(ni), sqrtf(nmx), 0.00012207031f * (ni + nmx));
   const float thr_loose = __fmaf_rn(fabsf(tau0), 0.0009765625f, tau0) + 2.f * eps;
-  // ---- the list: entries at or below the loose threshold ----
-  if (lane == 0) cnt[warp] = 0;
-  __syncwarp();
+  // ---- the list: entries at or below the loose threshold (positions from ballots: warp-uniform branch, no shared-memory atomics) ----
+  int nlist = 0;
+  const unsigned lt = (1u << lane) - 1u;
   if (cached) {
 #pragma unroll
     for (int t = 0; t < 64; t++) {
-      if (v[t] <= thr_loose) {  // padding entries are +inf: only reachable when the threshold is +inf, which overflows the list anyway
-        const int j = 4 * (lane + 32 * (t >> 2)) + (t & 3);
-        const int pos = atomicAdd(&cnt[warp], 1);
-        if (pos < KP_CAND && j < N) {
+      const int j = 4 * (lane + 32 * (t >> 2)) + (t & 3);
+      const bool hit = v[t] <= thr_loose;  // padding entries are +inf: only reachable when the threshold is +inf, which overflows the list
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        const int pos = nlist + __popc(m & lt);
+        if (hit && pos < KP_CAND && j < N) {
           cand[warp][pos] = j;
           cval[warp][pos] = v[t];
         }
+        nlist += __popc(m);
       }
     }
   } else {
-    for (int j = lane; j < N; j += 32) {
-      const float vv = __fmaf_rn(-2.f, g[j], ni + nb[j]);
-      if (vv <= thr_loose) {
-        const int pos = atomicAdd(&cnt[warp], 1);
-        if (pos < KP_CAND) {
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      const float vv = j < N ? __fmaf_rn(-2.f, g[j], ni + nb[j]) : INF;
+      const bool hit = j < N && vv <= thr_loose;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        const int pos = nlist + __popc(m & lt);
+        if (hit && pos < KP_CAND) {
           cand[warp][pos] = j;
           cval[warp][pos] = vv;
         }
+        nlist += __popc(m);
       }
     }
   }
   __syncwarp();
-  const int nlist = cnt[warp];
   // ---- the exact k-th smallest approximate distance from the list, then the candidates proper ----
   float cd[3];
   int cj[3];

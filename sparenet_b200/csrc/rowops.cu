@@ -551,6 +551,103 @@ using namespace snb;
 
 static inline unsigned row_grid(long long R) { return (unsigned)((R + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32)); }
 
+// ---- merge of the tensor-core GEMM's per-tile statistics (csrc/gemm_tc.cu epilogue) ------------------------------------------------
+// The epilogue leaves, per output row and tile of `w` positions, the tile mean, the centred second moment and (optionally) the tile's
+// extrema with their positions.  One launch folds them per segment of `tps` tiles -- Chan's pairwise update written for equal tile
+// sizes: mean = avg of tile means, M2 = sum M2_t + w sum (mean_t - mean)^2 (no cancellation) -- and the extrema over ALL tiles of a
+// row (first position attaining them).  This was 7 + 6 microsecond-sized PyTorch launches after every GEMM that returns statistics.
+// A group of `lp` lanes (power of two <= 32) per (row, segment).
+namespace snb {
+__global__ void __launch_bounds__(256) gemm_stats_merge_kernel(const float* __restrict__ pm, const float* __restrict__ p2, long long pairs, int tps,
+                                                                int lp, float w, float inv_seg, float* __restrict__ mean, float* __restrict__ var) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pair = gt / lp;
+  const int sub = (int)(gt % lp);
+  const bool on = pair < pairs;
+  const float* __restrict__ m_ = pm + (on ? pair : 0) * tps;
+  const float* __restrict__ q_ = p2 + (on ? pair : 0) * tps;
+  float s = 0.f, q = 0.f;
+  if (on)
+    for (int t = sub; t < tps; t += lp) {
+      s += m_[t];
+      q += q_[t];
+    }
+  for (int o = lp >> 1; o >= 1; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float mu = s / (float)tps;
+  float d2 = 0.f;
+  if (on)
+    for (int t = sub; t < tps; t += lp) {
+      const float d = m_[t] - mu;
+      d2 = __fmaf_rn(d, d, d2);
+    }
+  for (int o = lp >> 1; o >= 1; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  if (on && sub == 0) {
+    mean[pair] = mu;
+    var[pair] = (q + w * d2) * inv_seg;
+  }
+}
+
+__global__ void __launch_bounds__(256) gemm_minmax_merge_kernel(const float* __restrict__ px, const float* __restrict__ pn, const int* __restrict__ ix,
+                                                                 const int* __restrict__ in_, long long rows, int T, int lp, float* __restrict__ vmax,
+                                                                 float* __restrict__ vmin, int* __restrict__ imax, int* __restrict__ imin) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = gt / lp;
+  const int sub = (int)(gt % lp);
+  const bool on = row < rows;
+  const size_t base = (size_t)(on ? row : 0) * T;
+  float bx = -__int_as_float(0x7f800000), bn = __int_as_float(0x7f800000);
+  int tx = 0x7fffffff, tn = 0x7fffffff;
+  if (on)
+    for (int t = sub; t < T; t += lp) {  // ascending tiles within a lane: strict comparisons keep the first
+      const float a = px[base + t], b = pn[base + t];
+      if (a > bx || tx == 0x7fffffff) { bx = a; tx = t; }
+      if (b < bn || tn == 0x7fffffff) { bn = b; tn = t; }
+    }
+  for (int o = lp >> 1; o >= 1; o >>= 1) {
+    const float ox = __shfl_xor_sync(0xffffffffu, bx, o), on_ = __shfl_xor_sync(0xffffffffu, bn, o);
+    const int otx = __shfl_xor_sync(0xffffffffu, tx, o), otn = __shfl_xor_sync(0xffffffffu, tn, o);
+    if (otx != 0x7fffffff && (tx == 0x7fffffff || ox > bx || (ox == bx && otx < tx))) { bx = ox; tx = otx; }
+    if (otn != 0x7fffffff && (tn == 0x7fffffff || on_ < bn || (on_ == bn && otn < tn))) { bn = on_; tn = otn; }
+  }
+  if (on && sub == 0) {
+    vmax[row] = bx;
+    vmin[row] = bn;
+    imax[row] = ix[base + tx];
+    imin[row] = in_[base + tn];
+  }
+}
+}  // namespace snb
+
+// pm, p2 [pairs, tps] -> mean, var [pairs] (pairs = rows x segments; w = positions per tile, seg = tps * w positions per segment)
+SNB_API int snb_gemm_stats_merge(const float* pmean, const float* pm2, long long pairs, int tps, int w, float* mean, float* var, void* stream) {
+  if (pairs < 0 || tps <= 0 || w <= 0) return SNB_EINVAL;
+  if (pairs == 0) return SNB_OK;
+  int lp = 1;
+  while (lp < tps && lp < 32) lp <<= 1;
+  const long long threads = pairs * lp;
+  snb::gemm_stats_merge_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pmean, pm2, pairs, tps, lp, (float)w,
+                                                                                                 1.0f / ((float)tps * (float)w), mean, var);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+// tile extrema [rows, T] with their positions -> the rows' extrema (first position attaining them)
+SNB_API int snb_gemm_minmax_merge(const float* pmax, const float* pmin, const int* pimax, const int* pimin, long long rows, int T, float* vmax,
+                                  float* vmin, int* imax, int* imin, void* stream) {
+  if (rows < 0 || T <= 0) return SNB_EINVAL;
+  if (rows == 0) return SNB_OK;
+  int lp = 1;
+  while (lp < T && lp < 32) lp <<= 1;
+  const long long threads = rows * lp;
+  snb::gemm_minmax_merge_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pmax, pmin, pimax, pimin, rows, T, lp, vmax, vmin,
+                                                                                                  imax, imin);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
 SNB_API int snb_row_stats(const float* h, long long R, int L, float* mean, float* var, void* stream) {
   if (R < 0 || L <= 0) return SNB_EINVAL;
   if (R == 0) return SNB_OK;

@@ -133,19 +133,22 @@ def conv_fwd(x, W, scale=None, shift=None, slope=0.0, seg=None, stats_seg=None, 
         d.pmax, d.pmin, d.pimax, d.pimin = _p(px), _p(pn), _p(ix), _p(in_)
     _run(d, dev, "gemm_fwd", 4 * (x.numel() + (y.numel() if store else 0)))
     stats = {}
+    lib = _lib.load()
     if stats_seg is not None:
+        # Chan's merge of the tiles of every segment (within-tile + between-tile second moments: no cancellation), one launch
         tps = stats_seg // w                                  # tiles per segment
-        m_t = pm.view(G, Cout, N // stats_seg, tps)
-        mean = m_t.mean(-1)
-        dm = m_t - mean.unsqueeze(-1)
-        m2 = p2.view(G, Cout, N // stats_seg, tps).sum(-1) + float(w) * (dm * dm).sum(-1)   # Chan: within-tile + between-tile
-        stats["mean"], stats["var"] = mean, m2 / float(stats_seg)
+        nseg = N // stats_seg
+        mean, var = (torch.empty(G, Cout, nseg, device=dev, dtype=torch.float32) for _ in range(2))
+        with torch.cuda.device(dev), _op("gemm_stats_merge", 1):
+            check(lib.snb_gemm_stats_merge(_p(pm), _p(p2), G * Cout * nseg, tps, w, _p(mean), _p(var), stream_ptr()), "gemm_stats_merge")
+        stats["mean"], stats["var"] = mean, var
     if minmax:
-        vmax, jx = px.max(-1)
-        vmin, jn = pn.min(-1)
-        stats["max"], stats["min"] = vmax, vmin
-        stats["imax"] = ix.gather(-1, jx.unsqueeze(-1)).squeeze(-1)
-        stats["imin"] = in_.gather(-1, jn.unsqueeze(-1)).squeeze(-1)
+        vmax, vmin = (torch.empty(G, Cout, device=dev, dtype=torch.float32) for _ in range(2))
+        imax, imin = (torch.empty(G, Cout, device=dev, dtype=torch.int32) for _ in range(2))
+        with torch.cuda.device(dev), _op("gemm_stats_merge", 1):
+            check(lib.snb_gemm_minmax_merge(_p(px), _p(pn), _p(ix), _p(in_), G * Cout, T, _p(vmax), _p(vmin), _p(imax), _p(imin), stream_ptr()),
+                  "gemm_minmax_merge")
+        stats["max"], stats["min"], stats["imax"], stats["imin"] = vmax, vmin, imax, imin
     return y, stats
 
 
