@@ -215,6 +215,15 @@ int snb_bn_se_tail_bwd(const float* grad_scale, const float* grad_shift, const f
  * sample (shared by the primitives), gamma / beta [P,C], w1 [P,H,C], w2 [P,C,H]; scale / shift [P,Cpad,B] (channels >= C: zeros).
  * Train-mode BatchNorm (batch statistics; they are returned in bn_mean / bn_var [P,C] for the caller's running statistics).  B <= 32.
  * bwd: gradients of every input; grad_style_* are per-primitive partials [P,B,C] (the caller sums over P). */
+/* The refiner's global feature, conv3 -> bn3 -> max over the points (models/sparenet_generator.py:626-629), from the row statistics and
+ * extrema of h = W3 x alone: glob [B,C] = BN(h* + bias) with h* = row max where gamma > 0, row min otherwise; train mode uses (and
+ * advances the running statistics with) the batch statistics rebuilt from the rows.  save: 2*C floats for the backward. */
+int snb_bn_max_tail_fwd(const float* row_mean, const float* row_var, const float* row_max, const float* row_min, const float* conv_bias,
+                        const float* gamma, const float* beta, int B, int C, float eps, int training, float momentum, float unbias,
+                        float* running_mean, float* running_var, long long* num_batches_tracked, float* glob, float* save, void* stream);
+int snb_bn_max_tail_bwd(const float* grad_glob, const float* row_mean, const float* row_max, const float* row_min, const float* conv_bias,
+                        const float* gamma, const float* save, int B, int C, int training, float* grad_row_mean, float* grad_row_var,
+                        float* grad_row_max, float* grad_row_min, float* grad_gamma, float* grad_beta, float* grad_conv_bias, void* stream);
 size_t snb_adain_tail_save_floats(int P, int C, int B, int H);
 size_t snb_adain_tail_scratch_floats(int P, int C, int B, int H);
 int snb_adain_tail_fwd(const float* row_mean, const float* row_var, const float* style_scale, const float* style_shift,
@@ -268,6 +277,11 @@ typedef struct snb_gemm_desc {
 int snb_gemm_tf32(const snb_gemm_desc* desc, void* stream);
 int snb_gemm_tf32_block_n(int N, int block_n);                /* the column-tile width the library uses (block_n = 0: its choice) */
 int snb_gemm_tf32_tiles(int N, int block_n);                  /* statistics tiles along N: 2 per column tile (width block_n/2) */
+/* Adjoint of the row extrema of h = W x without h (PointNetRes conv3 -> max over the points, models/sparenet_generator.py:626-629):
+ * for every (sample, output channel) with a non-zero gradient on its row max / min, adds g W[co,:] to column imax / imin of gx [B,Ci,N]
+ * and g x[b,:,col] to row co of gW [Co,Ci] (atomic accumulation; gx, gW, gmax, gmin may each be NULL). */
+int snb_conv_extrema_bwd(const float* x, const float* W, const int* imax, const int* imin, const float* gmax, const float* gmin, int B, int Ci,
+                         int Co, int N, float* gx, float* gW, void* stream);
 /* Merge of the epilogue's per-tile statistics (csrc/rowops.cu), one launch each: tile means / centred second moments
  * [pairs, tiles_per_segment] of tiles of w positions -> mean and biased variance [pairs] of every segment (pairs = rows x segments);
  * tile extrema with their positions [rows, T] -> the rows' extrema (first position attaining them). */

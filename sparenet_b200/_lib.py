@@ -71,9 +71,12 @@ SIGNATURES = {
     "snb_row_norm_act_bwd": (c_int, [P, P, P, P, P, P, P, ctypes.c_longlong, c_int, c_float, P, P, P]),
     "snb_gemm_tf32": (c_int, [ctypes.POINTER(GemmDesc), P]),
     "snb_gemm_tf32_tiles": (c_int, [c_int, c_int]),
+    "snb_conv_extrema_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "snb_gemm_stats_merge": (c_int, [P, P, ctypes.c_longlong, c_int, c_int, P, P, P]),
     "snb_gemm_minmax_merge": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, P, P, P, P, P]),
     "snb_gemm_tf32_block_n": (c_int, [c_int, c_int]),
+    "snb_bn_max_tail_fwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_float, c_int, c_float, c_float, P, P, P, P, P, P]),
+    "snb_bn_max_tail_bwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     "snb_adain_tail_save_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "snb_adain_tail_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "snb_adain_tail_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),

@@ -18,6 +18,7 @@
 // Rows whose candidate list overflows fall back to evaluating every j exactly.
 //
 // Inputs: xT [B,N,C] point-major copy of the features (candidate rows are contiguous), gram [B,N,N] from the GEMM.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace snb {
@@ -98,8 +99,8 @@ __device__ __forceinline__ float knn_exact_dist(const float* __restrict__ xi, co
 //      shared-memory list -- a superset of the candidates, ~a dozen entries;
 //   3. k pops of the warp minimum over the list give the exact k-th smallest approximate distance (duplicates count separately, as
 //      before), the list is filtered by f(kth): the SAME candidate set as the two-pass scan, hence the same indices.
-template <int K>
-__global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict__ xT, const float* __restrict__ gram, const float* __restrict__ nrm,
+template <int K, bool CACHE>
+__global__ void __launch_bounds__(256, CACHE ? 2 : 4) knn_prune_kernel(const float* __restrict__ xT, const float* __restrict__ gram, const float* __restrict__ nrm,
                                                          const unsigned* __restrict__ nmax_bits, int C, int N, size_t rows, int k,
                                                          int* __restrict__ idx) {
   __shared__ int cand[8][KP_CAND];
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) knn_prune_kernel(const float* __restrict_
   const float* __restrict__ nb = nrm + b * N;
   const float ni = nb[i];
   const float INF = __int_as_float(0x7f800000);
-  const bool cached = (N & 3) == 0 && N <= 2048;  // 16 x float4 per lane
+  const bool cached = CACHE && (N & 3) == 0 && N <= 2048;  // 16 x float4 per lane
   const int n4 = N >> 2;
   float v[64];
   float lm = INF;
@@ -348,9 +349,19 @@ SNB_API int snb_knn_pruned(const float* xT, const float* gram, int B, int C, int
   knn_norm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(xT, C, N, rows, nrm, nmax);
   SNB_LAUNCH_CHECK();
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (k <= 8) knn_prune_kernel<8><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
-  else if (k <= 16) knn_prune_kernel<16><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
-  else knn_prune_kernel<32><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+  // SNB_KNN_PRUNE_CACHE=0: the approximate distances are recomputed from the Gram row (L1 / L2) for the list pass instead of being
+  // kept in 64 registers per lane -- 64 registers per thread and twice the resident warps (measurement switch)
+  const char* sw = getenv("SNB_KNN_PRUNE_CACHE");
+  const bool cache = !(sw && sw[0] == '0');
+  if (cache) {
+    if (k <= 8) knn_prune_kernel<8, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else if (k <= 16) knn_prune_kernel<16, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else knn_prune_kernel<32, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+  } else {
+    if (k <= 8) knn_prune_kernel<8, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else if (k <= 16) knn_prune_kernel<16, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else knn_prune_kernel<32, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+  }
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -551,6 +551,50 @@ using namespace snb;
 
 static inline unsigned row_grid(long long R) { return (unsigned)((R + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32)); }
 
+// ---- adjoint of the row extrema of h = W x (PointNetRes conv3 -> bn3 -> max over the points) ------------------------------------
+// h [B,Co,N] is never stored; its row max / min sit in column imax / imin [b,co] of x [B,Ci,N].  A gradient g on such an extremum is
+// g W[co,:] on that column of gx and g x[b,:,col] on row co of gW.  One launch for both extrema (entries with g == 0 -- the extremum
+// the sign of the BatchNorm weight did not pick -- are skipped) instead of 2 x (mul, scatter_add_, gather, einsum + dtype copies) on
+// [B,Ci,Co] tensors: ~270 us of PyTorch launches per call.  A block per (8 output channels, sample), threads over the input channels.
+namespace snb {
+__global__ void __launch_bounds__(128) conv_extrema_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const int* __restrict__ imax,
+                                                                const int* __restrict__ imin, const float* __restrict__ gmax,
+                                                                const float* __restrict__ gmin, int Ci, int Co, int N, float* gx, float* gW) {
+  const int b = blockIdx.y;
+  const int co0 = blockIdx.x * 8;
+  const float* __restrict__ xb = x + (size_t)b * Ci * N;
+  float* gxb = gx ? gx + (size_t)b * Ci * N : nullptr;
+  for (int r = 0; r < 8; r++) {
+    const int co = co0 + r;
+    if (co >= Co) break;
+    const size_t e = (size_t)b * Co + co;
+    for (int side = 0; side < 2; side++) {
+      const float* __restrict__ gp = side ? gmin : gmax;
+      if (!gp) continue;
+      const float g = gp[e];
+      if (g == 0.f) continue;
+      const int col = side ? imin[e] : imax[e];
+      for (int ci = threadIdx.x; ci < Ci; ci += blockDim.x) {
+        if (gxb) atomicAdd(&gxb[(size_t)ci * N + col], g * W[(size_t)co * Ci + ci]);
+        if (gW) atomicAdd(&gW[(size_t)co * Ci + ci], g * xb[(size_t)ci * N + col]);
+      }
+    }
+  }
+}
+}  // namespace snb
+
+// gx [B,Ci,N] and gW [Co,Ci] are ACCUMULATED into (atomics); either may be NULL, as may gmax / gmin.
+SNB_API int snb_conv_extrema_bwd(const float* x, const float* W, const int* imax, const int* imin, const float* gmax, const float* gmin, int B, int Ci,
+                                 int Co, int N, float* gx, float* gW, void* stream) {
+  if (B < 0 || Ci <= 0 || Co <= 0 || N <= 0) return SNB_EINVAL;
+  if (B > 65535) return SNB_ELIMIT;
+  if (B == 0 || (!gx && !gW) || (!gmax && !gmin)) return SNB_OK;
+  snb::conv_extrema_bwd_kernel<<<dim3((unsigned)((Co + 7) / 8), (unsigned)B), 128, 0, (cudaStream_t)stream>>>(x, W, imax, imin, gmax, gmin, Ci, Co, N, gx,
+                                                                                                          gW);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
 // ---- merge of the tensor-core GEMM's per-tile statistics (csrc/gemm_tc.cu epilogue) ------------------------------------------------
 // The epilogue leaves, per output row and tile of `w` positions, the tile mean, the centred second moment and (optionally) the tile's
 // extrema with their positions.  One launch folds them per segment of `tps` tiles -- Chan's pairwise update written for equal tile

@@ -568,3 +568,120 @@ SNB_API int snb_adain_tail_bwd(const float* grad_scale, const float* grad_shift,
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
+
+// ---- the refiner's global feature: conv3 -> bn3 -> max over the points, from row statistics and extrema only -------------------------
+// (reference models/sparenet_generator.py:626-629: x = bn3(conv3(x)); x, _ = torch.max(x, 2).)  With h = W3 x kept out of HBM the caller
+// holds, per (sample, channel): the row mean m and biased row variance v of h (without the conv bias), and the row max / min.  BatchNorm
+// is monotone per channel, so max_n BN(h + bias) = BN(h* + bias) with h* = max h where gamma > 0, min h otherwise:
+//     mu = avg_b (m + bias),  q = avg_b v + avg_b (m + bias - mu)^2                      (batch statistics: within + between rows)
+//     glob = (h* + bias - mu) gamma rsqrt(q + eps) + beta
+// A thread per channel loops over the samples (coalesced across the block); forward and backward are one launch each instead of ~25
+// and ~45 PyTorch launches on [B, 1024] tensors.  The conv bias cancels in train mode (its gradient is exactly 0).
+namespace snb {
+
+__global__ void __launch_bounds__(128) bn_max_tail_fwd_kernel(const float* __restrict__ m_bc, const float* __restrict__ v_bc,
+                                                               const float* __restrict__ hmax, const float* __restrict__ hmin,
+                                                               const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int B, int C, float eps, int training, float momentum,
+                                                               float unbias, float* running_mean, float* running_var,
+                                                               long long* num_batches_tracked, float* __restrict__ glob, float* __restrict__ save) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
+  if (c >= C) return;
+  const float bi = bias ? bias[c] : 0.f;
+  float mu, q;
+  if (training) {
+    float s = 0.f, sv = 0.f;
+    for (int b = 0; b < B; b++) {
+      s += m_bc[(size_t)b * C + c] + bi;
+      sv += v_bc[(size_t)b * C + c];
+    }
+    mu = s / (float)B;
+    float d2 = 0.f;
+    for (int b = 0; b < B; b++) {
+      const float d = m_bc[(size_t)b * C + c] + bi - mu;
+      d2 = __fmaf_rn(d, d, d2);
+    }
+    q = (sv + d2) / (float)B;
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * q * unbias;
+    }
+  } else {
+    mu = running_mean[c];
+    q = running_var[c];
+  }
+  const float inv = rsqrtf(q + eps);
+  const float g = gamma[c], sc = g * inv, be = beta[c];
+  const float* __restrict__ hs = g > 0.f ? hmax : hmin;
+  for (int b = 0; b < B; b++) glob[(size_t)b * C + c] = (hs[(size_t)b * C + c] + bi - mu) * sc + be;
+  save[c] = mu;
+  save[C + c] = inv;
+}
+
+__global__ void __launch_bounds__(128) bn_max_tail_bwd_kernel(const float* __restrict__ gglob, const float* __restrict__ m_bc,
+                                                               const float* __restrict__ hmax, const float* __restrict__ hmin,
+                                                               const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                               const float* __restrict__ save, int B, int C, int training, float* __restrict__ gm_bc,
+                                                               float* __restrict__ gv_bc, float* __restrict__ ghmax, float* __restrict__ ghmin,
+                                                               float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ gbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float bi = bias ? bias[c] : 0.f;
+  const float mu = save[c], inv = save[C + c], g = gamma[c], sc = g * inv;
+  const bool up = g > 0.f;
+  const float* __restrict__ hs = up ? hmax : hmin;
+  float sg = 0.f, sgx = 0.f;
+  for (int b = 0; b < B; b++) {
+    const float gg = gglob[(size_t)b * C + c];
+    sg += gg;
+    sgx = __fmaf_rn(gg, hs[(size_t)b * C + c] + bi - mu, sgx);
+  }
+  gbeta[c] = sg;
+  ggamma[c] = sgx * inv;
+  // d glob / d mu = -sc;  d glob / d inv = (h* + bias - mu) gamma  ->  d / d q = . (-1/2) inv^3
+  const float gmu = -sg * sc;
+  const float gq = sgx * g * (-0.5f * inv * inv * inv);
+  const float rB = 1.f / (float)B;
+  for (int b = 0; b < B; b++) {
+    const size_t i = (size_t)b * C + c;
+    const float gh = gglob[i] * sc;
+    ghmax[i] = up ? gh : 0.f;
+    ghmin[i] = up ? 0.f : gh;
+    if (training) {
+      gm_bc[i] = (gmu + 2.f * gq * (m_bc[i] + bi - mu)) * rB;
+      gv_bc[i] = gq * rB;
+    } else {
+      gm_bc[i] = 0.f;
+      gv_bc[i] = 0.f;
+    }
+  }
+  if (gbias) gbias[c] = training ? 0.f : sg * sc;   // train mode: the bias shifts h* and mu alike
+}
+
+}  // namespace snb
+
+SNB_API int snb_bn_max_tail_fwd(const float* row_mean, const float* row_var, const float* row_max, const float* row_min, const float* conv_bias,
+                                const float* gamma, const float* beta, int B, int C, float eps, int training, float momentum, float unbias,
+                                float* running_mean, float* running_var, long long* num_batches_tracked, float* glob, float* save, void* stream) {
+  if (B < 0 || C < 0) return SNB_EINVAL;
+  if (B == 0 || C == 0) return SNB_OK;
+  if (!training && (!running_mean || !running_var)) return SNB_EINVAL;
+  snb::bn_max_tail_fwd_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(row_mean, row_var, row_max, row_min, conv_bias, gamma, beta, B, C, eps,
+                                                                              training, momentum, unbias, running_mean, running_var,
+                                                                              num_batches_tracked, glob, save);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+SNB_API int snb_bn_max_tail_bwd(const float* grad_glob, const float* row_mean, const float* row_max, const float* row_min, const float* conv_bias,
+                                const float* gamma, const float* save, int B, int C, int training, float* grad_row_mean, float* grad_row_var,
+                                float* grad_row_max, float* grad_row_min, float* grad_gamma, float* grad_beta, float* grad_conv_bias, void* stream) {
+  if (B < 0 || C < 0) return SNB_EINVAL;
+  if (B == 0 || C == 0) return SNB_OK;
+  snb::bn_max_tail_bwd_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(grad_glob, row_mean, row_max, row_min, conv_bias, gamma, save, B, C,
+                                                                              training, grad_row_mean, grad_row_var, grad_row_max, grad_row_min,
+                                                                              grad_gamma, grad_beta, grad_conv_bias);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

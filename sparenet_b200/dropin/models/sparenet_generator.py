@@ -556,11 +556,15 @@ class PointNetRes(nn.Module):  # reference :582-646
         # conv3 -> bn3 -> max over points: only row statistics and extrema of h3 = W3 x are needed; the [B,1024,N] product never
         # leaves the tensor memory, its gradient goes through 128x128 Gram matrices (fused.conv_row_reduce_backward)
         m_bc, v_bc, hmax, hmin = fused.act_conv_row_reduce(self.conv3.weight, pro2, h=h2)
-        mean, var = _bn_from_rows(self.bn3, m_bc + self.conv3.bias, v_bc, N)
-        inv = torch.rsqrt(var + self.bn3.eps)
         g3 = self.bn3.weight
-        hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin) + self.conv3.bias   # max_N BN(h3) only needs max/min of h3
-        glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
+        if FUSED_TAILS and m_bc.is_cuda and m_bc.dtype == torch.float32:
+            # max_N BN(h3 + bias) only needs the rows' statistics and extrema: one launch per direction (csrc/tails.cu)
+            glob = fused.bn_max_tail(m_bc, v_bc, hmax, hmin, self.conv3.bias, g3, self.bn3.bias, self.bn3, N)   # [B,1024]
+        else:
+            mean, var = _bn_from_rows(self.bn3, m_bc + self.conv3.bias, v_bc, N)
+            inv = torch.rsqrt(var + self.bn3.eps)
+            hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin) + self.conv3.bias   # max_N BN(h3) only needs max/min of h3
+            glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
         W4 = self.conv4.weight
         pb = F.linear(glob, W4[:, :1024, 0], self.conv4.bias)                 # [B,512]: the broadcast global half of conv4
         h4, m4, v4 = fused.act_conv(W4[:, 1024:, 0], pro1, stats_seg=N, h=h1)  # the pointfeat half of conv4 (strided weight view)

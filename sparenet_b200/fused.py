@@ -310,6 +310,15 @@ def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, ne
         with tf32_matmul():                                       # ... and its TF32 weight gradient
             G = torch.bmm(x, x.transpose(1, 2)).double()          # [B,Ci,Ci]
         gW = torch.bmm(WA, G).sum(0) + torch.matmul(b.t(), x.sum(2).double())
+    if x.is_cuda and dt == torch.float32 and (gmax is not None or gmin is not None) and (need_x or need_w):
+        # both extrema in one launch (csrc/rowops.cu: snb_conv_extrema_bwd), accumulating into gx and the fp32 weight gradient
+        gW32 = gW.to(dt) if need_w else None
+        gmx, gmn = (None if g is None else g.contiguous().float() for g in (gmax, gmin))
+        with torch.cuda.device(x.device), _op("conv_extrema_bwd", 1):
+            check(_lib.load().snb_conv_extrema_bwd(ptr(x), ptr(W.contiguous()), ptr(imax.contiguous()), ptr(imin.contiguous()), ptr(gmx), ptr(gmn),
+                                                   B, Ci, W.shape[0], N, ptr(gx) if need_x else None, ptr(gW32), stream_ptr()), "conv_extrema_bwd")
+        gW = gW32
+        gmax = gmin = None
     for g, idx in ((gmax, imax), (gmin, imin)):
         if g is None:
             continue
@@ -533,6 +542,51 @@ class BnSeTail(torch.autograd.Function):
 
 def bn_se_tail(m_bc, v_bc, rb, g, beta, w1, w2, bn, L):
     return BnSeTail.apply(m_bc, v_bc, rb, g, beta, w1, w2, bn, L)
+
+
+class BnMaxTail(torch.autograd.Function):
+    """glob [B,C] = max over the points of BatchNorm1d(h + bias) from the row statistics and extrema of h alone (PointNetRes conv3 ->
+    bn3 -> max, models/sparenet_generator.py:626-629) -- ONE launch per direction (csrc/tails.cu: snb_bn_max_tail_*) instead of ~25 +
+    ~45 PyTorch launches.  m_bc, v_bc, hmax, hmin [B,C]: row mean / biased row variance / max / min of h [B,C,L] (without the conv
+    bias); bn: the nn.BatchNorm1d (running statistics advanced in the kernel in train mode)."""
+    @staticmethod
+    def forward(ctx, m_bc, v_bc, hmax, hmin, bias, g, beta, bn, L):
+        m_bc, v_bc, hmax, hmin = (t.contiguous().float() for t in (m_bc, v_bc, hmax, hmin))
+        B, C = m_bc.shape
+        bias_, g_, beta_ = (t.detach().contiguous().float() for t in (bias, g, beta))
+        dev = m_bc.device
+        lib = _lib.load()
+        glob = torch.empty(B, C, device=dev)
+        save = torch.empty(2 * C, device=dev)
+        training = bool(bn.training)
+        track = training and bn.track_running_stats
+        count = B * L
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if (track or not training) else (None, None, None)
+        with torch.cuda.device(dev), _op("bn_max_tail_fwd", 1):
+            check(lib.snb_bn_max_tail_fwd(ptr(m_bc), ptr(v_bc), ptr(hmax), ptr(hmin), ptr(bias_), ptr(g_), ptr(beta_), B, C, float(bn.eps),
+                                          int(training), float(mom), float(count / max(count - 1, 1)), ptr(rm), ptr(rv),
+                                          ptr(nbt) if track else None, ptr(glob), ptr(save), stream_ptr()), "bn_max_tail_fwd")
+        ctx.save_for_backward(m_bc, hmax, hmin, bias_, g_, save)
+        ctx.training = training
+        return glob
+
+    @staticmethod
+    def backward(ctx, gglob):
+        m_bc, hmax, hmin, bias_, g_, save = ctx.saved_tensors
+        B, C = m_bc.shape
+        gglob = gglob.contiguous().float()
+        gm, gv, gmax, gmin = (torch.empty_like(m_bc) for _ in range(4))
+        gg, gbeta, gbias = (torch.empty_like(g_) for _ in range(3))
+        with torch.cuda.device(m_bc.device), _op("bn_max_tail_bwd", 1):
+            check(_lib.load().snb_bn_max_tail_bwd(ptr(gglob), ptr(m_bc), ptr(hmax), ptr(hmin), ptr(bias_), ptr(g_), ptr(save), B, C,
+                                                  int(ctx.training), ptr(gm), ptr(gv), ptr(gmax), ptr(gmin), ptr(gg), ptr(gbeta), ptr(gbias),
+                                                  stream_ptr()), "bn_max_tail_bwd")
+        return gm, gv, gmax, gmin, gbias, gg, gbeta, None, None
+
+
+def bn_max_tail(m_bc, v_bc, hmax, hmin, bias, g, beta, bn, L):
+    return BnMaxTail.apply(m_bc, v_bc, hmax, hmin, bias, g, beta, bn, L)
 
 
 class AdainTail(torch.autograd.Function):

@@ -295,7 +295,8 @@ def test_flat_adam_matches_torch_adam(cuda, own_grads):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("P,C,Cp,B", [(4, 48, 64, 8), (32, 513, 544, 32), (3, 256, 256, 5), (2, 16, 32, 32)])
+@pytest.mark.parametrize("P,C,Cp,B", [(4, 48, 64, 8), (32, 513, 544, 32), (3, 256, 256, 5), (2, 16, 32, 32), (4, 1026, 1056, 32),
+                                      (2, 1056, 1056, 4)])
 def test_adain_tail_matches_pytorch_closed_form(cuda, P, C, Cp, B):
     """snb_adain_tail_fwd/bwd (one launch per direction for all primitives) against the same closed form as PyTorch ops -- the
     decoders' instance-norm . AdaIN . BatchNorm . SE tail of SpareNetDecode (tail() / _bn_se): scale/shift, the BatchNorm batch
@@ -337,3 +338,90 @@ def test_adain_tail_matches_pytorch_closed_form(cuda, P, C, Cp, B):
         err = float((a - b).detach().abs().max()) / scale
         print(f"[adain_tail P={P} C={C} Cp={Cp} B={B}] {name}: err/scale {err:.2e}")
         assert err < 3e-5, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,training", [(32, 1024, True), (5, 70, True), (4, 128, False)])
+def test_bn_max_tail_matches_pytorch_closed_form(cuda, B, C, training):
+    """snb_bn_max_tail_fwd/bwd (PointNetRes conv3 -> bn3 -> max over the points from row statistics and extrema, one launch per
+    direction) against the same closed form as PyTorch ops: the global feature, the BatchNorm running statistics and every gradient,
+    fp32 both sides (summation order only); the conv bias has no gradient in train mode (it shifts h* and the batch mean alike)."""
+    from sparenet_b200 import fused
+    torch.manual_seed(B * 1000 + C)
+    L = 4096
+    m0, v0 = torch.randn(B, C, device=cuda), torch.rand(B, C, device=cuda) + 0.1
+    hmax0 = m0 + 3 * v0.sqrt() * (1 + torch.rand(B, C, device=cuda))
+    hmin0 = m0 - 3 * v0.sqrt() * (1 + torch.rand(B, C, device=cuda))
+    bias0, g0, beta0 = torch.randn(C, device=cuda), torch.randn(C, device=cuda), torch.randn(C, device=cuda)
+    gglob = torch.randn(B, C, device=cuda)
+
+    def make_bn():
+        bn = torch.nn.BatchNorm1d(C).to(cuda)
+        with torch.no_grad():
+            bn.running_mean.copy_(torch.linspace(-1, 1, C))
+            bn.running_var.copy_(torch.linspace(0.5, 2, C))
+        return bn.train(training)
+
+    def ref(bn, m_bc, v_bc, hmax, hmin, bias, g, beta):
+        m = m_bc + bias
+        if bn.training:
+            mean = m.mean(0)
+            var = v_bc.mean(0) + ((m - mean) ** 2).mean(0)
+            n = B * L
+            with torch.no_grad():
+                bn.running_mean.mul_(0.9).add_(mean.detach(), alpha=0.1)
+                bn.running_var.mul_(0.9).add_(var.detach() * (n / (n - 1)), alpha=0.1)
+                bn.num_batches_tracked.add_(1)
+        else:
+            mean, var = bn.running_mean, bn.running_var
+        hstar = torch.where((g > 0).view(1, -1), hmax, hmin) + bias
+        return (hstar - mean) * (g * torch.rsqrt(var + bn.eps)) + beta
+
+    outs, bns = [], []
+    for fn in (ref, lambda bn, *a: fused.bn_max_tail(*a, bn, L)):
+        bn = make_bn()
+        leaves = [t.clone().requires_grad_() for t in (m0, v0, hmax0, hmin0, bias0, g0, beta0)]
+        glob = fn(bn, *leaves)
+        grads = torch.autograd.grad(glob, leaves, gglob, allow_unused=True)
+        grads = [torch.zeros_like(t) if gr is None else gr for gr, t in zip(grads, leaves)]
+        outs.append((glob, bn.running_mean.clone(), bn.running_var.clone(), *grads))
+        bns.append(bn)
+    assert int(bns[0].num_batches_tracked) == int(bns[1].num_batches_tracked)
+    names = ["glob", "running_mean", "running_var", "g_m", "g_v", "g_hmax", "g_hmin", "g_bias", "g_gamma", "g_beta"]
+    for name, a, b in zip(names, *outs):
+        scale = max(float(a.detach().abs().max()), 1e-6)
+        err = float((a - b).detach().abs().max()) / scale
+        print(f"[bn_max_tail B={B} C={C} train={training}] {name}: err/scale {err:.2e}")
+        if name == "g_bias" and training:      # exactly 0 in the kernel; autograd's two cancelling sums leave rounding noise
+            assert float(b.abs().max()) == 0.0 and float(a.abs().max()) < 1e-3 * float(outs[0][8].abs().max() + 1)
+        else:
+            assert err < 3e-5, name
+
+
+@pytest.mark.gpu
+def test_conv_row_reduce_backward_extrema_kernel(cuda):
+    """conv_row_reduce_backward on fp32 CUDA tensors (the extrema adjoint through snb_conv_extrema_bwd, one launch for max and min)
+    against the same function in float64 (pure PyTorch path): gx, gW and the row term."""
+    from sparenet_b200 import fused
+    torch.manual_seed(11)
+    B, Ci, Co, N = 3, 64, 200, 512
+    x, W = torch.randn(B, Ci, N, device=cuda), torch.randn(Co, Ci, device=cuda) / 8
+    h = torch.matmul(W.double(), x.double())
+    mean, imax, imin = h.mean(-1), h.argmax(-1).int(), h.argmin(-1).int()
+    gmean, gvar, gmax, gmin = (torch.randn(B, Co, device=cuda) for _ in range(4))
+    up = torch.rand(Co, device=cuda) > 0.5
+    gmax, gmin = gmax * up, gmin * ~up                          # as the BatchNorm sign rule leaves them: one of the two is zero
+    old = fused.tf32_matmul.enabled
+    fused.tf32_matmul.enabled = False
+    try:
+        got = fused.conv_row_reduce_backward(x, W, mean.float(), imax, imin, gmean, gvar, gmax, gmin, split_row_term=True)
+        ref = fused.conv_row_reduce_backward(x.double(), W.double(), mean, imax, imin, gmean.double(), gvar.double(), gmax.double(),
+                                             gmin.double(), split_row_term=True)
+        only_min = fused.conv_row_reduce_backward(x, W, mean.float(), imax, imin, gmean, None, None, gmin)
+        only_min_ref = fused.conv_row_reduce_backward(x.double(), W.double(), mean, imax, imin, gmean.double(), None, None, gmin.double())
+    finally:
+        fused.tf32_matmul.enabled = old
+    for name, a, b in list(zip(("gx", "gW", "row_term"), got, ref)) + list(zip(("gx(min only)", "gW(min only)"), only_min, only_min_ref)):
+        err = float((a.double() - b).abs().max()) / max(float(b.abs().max()), 1e-9)
+        print(f"[conv_extrema_bwd] {name}: err/scale {err:.2e}")
+        assert err < 2e-5, name
