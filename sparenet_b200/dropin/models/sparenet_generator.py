@@ -192,10 +192,15 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         x2 = self._edge_block(x1, self.conv2, self.bn2, self.se2, self.resconv1)
         x3 = self._edge_block(x2, self.conv3, self.bn3, self.se3, self.resconv2)
         x4 = self._edge_block(x3, self.conv4, self.bn4, self.se4, self.resconv3)
-        xcat = torch.cat((x1, x2, x3, x4), dim=1)
         if LIBRARY_GEMM:
-            h, st5 = self.conv5(xcat), None
-        else:                                                        # row statistics of h come out of the GEMM epilogue
+            h, st5 = self.conv5(torch.cat((x1, x2, x3, x4), dim=1)), None
+        elif all(t.size(1) % 32 == 0 for t in (x1, x2, x3, x4)):
+            # row statistics of h come out of the GEMM epilogue; the data gradient is one GEMM per concatenated input (no channel
+            # slices of a [B,2048,N] gradient for the four consumers to copy)
+            h, m5, v5 = fused.cat_conv1x1((x1, x2, x3, x4), self.conv5.weight.squeeze(-1), stats_seg=x1.size(2))
+            st5 = (m5, v5)
+        else:
+            xcat = torch.cat((x1, x2, x3, x4), dim=1)
             h, m5, v5 = fused.conv1x1(xcat, self.conv5.weight.squeeze(-1), stats_seg=xcat.size(2))
             st5 = (m5, v5)
         bn, L = self.bn5, h.size(2)
@@ -584,13 +589,20 @@ class SpareNetRefine(nn.Module):  # reference :530-579
         self.edgeres = False
         self.residual = PointNetRes(use_SElayer=use_SElayer)
 
-    def forward(self, inps, partial, coarse):
+    def forward(self, inps, partial, coarse, _hook=None, _partial_pts=None):
         dist, _, mean_mst_dis = self.expansion(coarse, self.num_points // self.n_primitives, 1.5)
+        if _hook is not None and _hook[0] is not None:
+            # SpareNetGenerator.stage_hook fires HERE, after the expansion penalty is enqueued: work the caller forks onto a side stream
+            # (the cloud's Chamfer loss) then starts behind it.  Forked before it, the Chamfer query's 8192 long-lived blocks filled
+            # every SM and the 1-block expansion_mean launch -- which the sampler waits for -- sat ~0.7 ms in the queue.
+            _hook[0](_hook[1], coarse)
         loss_mst = torch.mean(dist)
         B, _, n_out = inps.shape
         n_in = partial.shape[2]
         base = torch.cat((torch.cat((inps, inps.new_zeros(B, 1, n_out)), 1), torch.cat((partial, partial.new_ones(B, 1, n_in)), 1)), 2)
-        xyz = torch.cat((coarse, partial.transpose(1, 2)), 1).contiguous()    # == base[:, 0:3].transpose(1, 2)
+        # == base[:, 0:3].transpose(1, 2); _partial_pts: the caller's point-major [B,Np,3] copy of `partial` (a contiguous cat instead
+        # of a strided one)
+        xyz = torch.cat((coarse, partial.transpose(1, 2) if _partial_pts is None else _partial_pts), 1).contiguous()
         resampled_idx = MDS_module.minimum_density_sample(xyz.detach(), coarse.shape[1], mean_mst_dis)
         base = MDS_module.gather_operation(base.contiguous(), resampled_idx)
         delta = self.residual(base)
@@ -616,10 +628,10 @@ class SpareNetGenerator(nn.Module):  # reference :12-82
         outs = self.decoder(style, partial)                                   # [B,3,N]
         coarse = outs.transpose(1, 2).contiguous()
         hook = getattr(self, "stage_hook", None)   # optional callable(name, cloud): lets the caller start work on an intermediate
-        if hook is not None:                        # output (e.g. its Chamfer loss on a side stream) while the refiner's sampler runs
-            hook("coarse", coarse)
-        middle, loss_mst = self.refine(outs, partial, coarse)
-        if hook is not None:
-            hook("middle", middle)
-        refine, _ = self.refine(middle.transpose(1, 2).contiguous(), partial, middle)
+        # output (e.g. its Chamfer loss on a side stream) while the refiner's sampler runs; called inside the refiner, right after the
+        # expansion penalty of that cloud has been enqueued
+        pts = data["partial_cloud"]
+        pts = pts.detach() if pts.is_contiguous() else None
+        middle, loss_mst = self.refine(outs, partial, coarse, _hook=(hook, "coarse"), _partial_pts=pts)
+        refine, _ = self.refine(middle.transpose(1, 2).contiguous(), partial, middle, _hook=(hook, "middle"), _partial_pts=pts)
         return coarse, middle, refine, loss_mst

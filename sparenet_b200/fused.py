@@ -43,6 +43,7 @@ class ThinConv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, W = ctx.saved_tensors
+        gy = gy.contiguous()     # a transposed view (the loss hands back [B,N,3]^T) sends cuBLAS to a 4x slower kernel: 6 MB copy instead
         G = gy.shape[0]
         Wb = W.unsqueeze(0).expand(G, -1, -1) if W.dim() == 2 else W
         xb = x.expand(G, -1, -1)
@@ -465,6 +466,40 @@ class Conv1x1(torch.autograd.Function):
         gx = gemm.conv_dgrad(gy, W) if ctx.needs_input_grad[0] else None
         gW = gemm.conv_wgrad(gy, x, batched=W.dim() == 3) if ctx.needs_input_grad[1] else None
         return gx, gW, None
+
+
+class CatConv1x1(torch.autograd.Function):
+    """y = W . cat(xs, dim=1) with the data gradient computed PER INPUT (gx_i = W[:, slice_i]^T gy, one GEMM each, written straight
+    into its own contiguous tensor): autograd's cat backward hands out channel slices of one [G, sum C_i, N] gradient, which every
+    consumer then had to copy to make contiguous (0.39 ms per step for the encoder's conv5 over [x1|x2|x3|x4],
+    models/sparenet_generator.py:234-236).  Forward and weight gradient run on the concatenated operand as before."""
+    @staticmethod
+    def forward(ctx, W, stats_seg, *xs):
+        xcat = torch.cat(xs, dim=1)
+        y, st = gemm.conv_fwd(xcat, W, stats_seg=stats_seg)
+        ctx.save_for_backward(xcat, W)
+        ctx.splits = [int(x.shape[1]) for x in xs]
+        if stats_seg is None:
+            return y
+        mean, var = st["mean"].reshape(y.shape[:-1]), st["var"].reshape(y.shape[:-1])
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, *_):
+        xcat, W = ctx.saved_tensors
+        gy = gy.contiguous()
+        gW = gemm.conv_wgrad(gy, xcat, batched=False) if ctx.needs_input_grad[0] else None
+        gxs, off = [], 0
+        for i, c in enumerate(ctx.splits):
+            gxs.append(gemm.conv_dgrad(gy, W[:, off:off + c]) if ctx.needs_input_grad[2 + i] else None)
+            off += c
+        return (gW, None, *gxs)
+
+
+def cat_conv1x1(xs, W, stats_seg=None):
+    """W [Cout, sum C_i] shared by the batch; every C_i a multiple of 32."""
+    return CatConv1x1.apply(W, stats_seg, *xs)
 
 
 class Conv1x1AddInto(torch.autograd.Function):

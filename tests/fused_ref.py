@@ -71,6 +71,10 @@ def conv1x1(x, W, stats_seg=None):
     return (y,) + row_stats(y)
 
 
+def cat_conv1x1(xs, W, stats_seg=None):
+    return conv1x1(torch.cat(tuple(xs), dim=1), W, stats_seg)
+
+
 def bcast_act_conv(xhat, A, D, W, slope=0.0):
     P, C, L = xhat.shape
     B = A.shape[-1]
@@ -100,5 +104,5 @@ def act_conv_row_reduce(W, pro, h):
 def patch(monkeypatch):
     from sparenet_b200 import fused
     for name in ("edge_reduce", "edge_reduce_sel", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce",
-                 "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce", "bcast_act_conv", "thin_conv", "row_norm_act_pool"):
+                 "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce", "bcast_act_conv", "thin_conv", "row_norm_act_pool", "cat_conv1x1"):
         monkeypatch.setattr(fused, name, globals()[name])
