@@ -32,7 +32,10 @@ __device__ __forceinline__ float tail_warp_sum(float v) {
   return v;
 }
 
-// save layout (floats): mean[C] inv[C] sc[C] sh[C] z[B*C] gate[B*C] a1[B*H]
+// save layout (floats): mean[C] inv[C] sc[C] sh[C] z[B*C] gate[B*C] a1[B*H] w2T[H*C]
+// w2T = W2 transposed, written by the forward's first phase: the gate phase (a thread per (sample, channel), consecutive lanes =
+// consecutive channels) and the backward's W2^T ga2 phase read W2 along the channels, which in its own [C,H] layout is a stride of H
+// floats between lanes -- 32 cache lines per warp load, 131 us per direction for the encoder's C = 1024, H = 64 tail.
 __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_fwd_kernel(const float* __restrict__ m_bc, const float* __restrict__ v_bc,
                                                                           const float* __restrict__ rb, int rb_batched, const float* __restrict__ g,
                                                                           const float* __restrict__ beta, const float* __restrict__ w1,
@@ -50,7 +53,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_fwd_kernel(const f
   float* z = sh + C;
   float* gate = z + (size_t)BC;
   float* a1 = gate + (size_t)BC;
+  float* w2T = a1 + (size_t)B * H;
   const float rB = 1.0f / (float)B;
+  for (int i = ct; i < C * H; i += nt) {
+    const int c = i / H, h = i - c * H;
+    w2T[(size_t)h * C + c] = w2[i];
+  }
   // ---- BatchNorm statistics and the per-channel scale / shift: a warp per channel, lanes over the samples ----
   for (int c = cw; c < C; c += nw) {
     float mu, var;
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_fwd_kernel(const f
     const int b = i / C, c = i - b * C;
     float acc = 0.f;
 #pragma unroll 8
-    for (int h = 0; h < H; h++) acc = __fmaf_rn(w2[c * H + h], a1[b * H + h], acc);
+    for (int h = 0; h < H; h++) acc = __fmaf_rn(w2T[(size_t)h * C + c], a1[b * H + h], acc);
     const float gt = 1.0f / (1.0f + expf(-acc));
     gate[i] = gt;
     const float s_ = gt * sc[c];
@@ -133,6 +141,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_bwd_kernel(const f
   const float* z = sh + C;
   const float* gate = z + (size_t)BC;
   const float* a1 = gate + (size_t)BC;
+  const float* w2T = a1 + (size_t)B * H;
   float* ga2 = scratch;
   float* gz = ga2 + (size_t)BC;
   float* p1 = gz + (size_t)BC;
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bn_se_tail_bwd_kernel(const f
     const int b = o / H, h = o - b * H;
     float acc = 0.f;
 #pragma unroll 4
-    for (int c = lane; c < C; c += 32) acc = __fmaf_rn(w2[c * H + h], ga2[b * C + c], acc);
+    for (int c = lane; c < C; c += 32) acc = __fmaf_rn(w2T[(size_t)h * C + c], ga2[b * C + c], acc);
     acc = tail_warp_sum(acc);
     if (lane == 0) gp1[o] = a1[o] > 0.f ? acc : 0.f;
   }
@@ -237,7 +246,7 @@ using namespace snb;
 
 SNB_API size_t snb_bn_se_tail_save_floats(int B, int C, int H) {
   if (B <= 0 || C <= 0 || H <= 0) return 0;
-  return (size_t)4 * C + (size_t)2 * B * C + (size_t)B * H;
+  return (size_t)4 * C + (size_t)2 * B * C + (size_t)B * H + (size_t)C * H;
 }
 
 SNB_API size_t snb_bn_se_tail_scratch_floats(int B, int C, int H) {
@@ -338,8 +347,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) adain_tail_fwd_kernel(const f
   // ---- a1 = relu(W1 z): a warp per hidden unit, lanes = samples ----
   for (int h = cw; h < H; h += nw) {
     float acc = 0.f;
+    // C dependent steps of one warp: two accumulators and 16 independent loads in flight (the phase is latency, not work)
+    float acc2 = 0.f;
+    int c = 0;
 #pragma unroll 8
-    for (int c = 0; c < C; c++) acc = __fmaf_rn(w1p[h * C + c], on ? z[c * B + lane] : 0.f, acc);
+    for (; c + 1 < C; c += 2) {
+      acc = __fmaf_rn(w1p[h * C + c], on ? z[c * B + lane] : 0.f, acc);
+      acc2 = __fmaf_rn(w1p[h * C + c + 1], on ? z[(c + 1) * B + lane] : 0.f, acc2);
+    }
+    if (c < C) acc = __fmaf_rn(w1p[h * C + c], on ? z[c * B + lane] : 0.f, acc);
+    acc += acc2;
     if (on) a1[h * B + lane] = fmaxf(acc, 0.f);
   }
   cluster_sync_all();
@@ -430,8 +447,15 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) adain_tail_bwd_kernel(const f
   // ---- gp1 = (W2^T ga2) masked by the ReLU: a warp per hidden unit, lanes = samples ----
   for (int h = cw; h < H; h += nw) {
     float acc = 0.f;
+    float acc2 = 0.f;
+    int c = 0;
 #pragma unroll 8
-    for (int c = 0; c < C; c++) acc = __fmaf_rn(w2p[c * H + h], on ? ga2[c * B + lane] : 0.f, acc);
+    for (; c + 1 < C; c += 2) {
+      acc = __fmaf_rn(w2p[c * H + h], on ? ga2[c * B + lane] : 0.f, acc);
+      acc2 = __fmaf_rn(w2p[(c + 1) * H + h], on ? ga2[(c + 1) * B + lane] : 0.f, acc2);
+    }
+    if (c < C) acc = __fmaf_rn(w2p[c * H + h], on ? ga2[c * B + lane] : 0.f, acc);
+    acc += acc2;
     if (on) gp1[h * B + lane] = a1[h * B + lane] > 0.f ? acc : 0.f;
   }
   cluster_sync_all();
