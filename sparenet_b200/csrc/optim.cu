@@ -36,9 +36,57 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float4* __restrict__ p, 
   }
 }
 
+// ---- gather of the step's gradient tensors into the flat arena: ONE launch over a pointer table ---------------------------------------
+// (sparenet_b200.dist.GradArena.pack: autograd hands back ~800 fresh gradient tensors per step; torch._foreach_copy_ moved their
+// 330 MB in 11 multi-tensor launches at ~2.3 TB/s.)  Table entry: {src, dst, n floats, first block}; a block copies 4096 floats.
+struct PackEntry {
+  const float* src;
+  float* dst;
+  long long n;
+  long long first_block;
+};
+constexpr int PACK_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256) multi_copy_kernel(const PackEntry* __restrict__ tab, int ntab) {
+  // binary search: the last entry whose first block is <= this block
+  int lo = 0, hi = ntab - 1;
+  const long long blk = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].first_block <= blk) lo = mid;
+    else hi = mid - 1;
+  }
+  const PackEntry e = tab[lo];
+  const long long off = (blk - e.first_block) * PACK_CHUNK;
+  const long long left = e.n - off;
+  if (left <= 0) return;
+  const int n = left < PACK_CHUNK ? (int)left : PACK_CHUNK;
+  const float* __restrict__ s = e.src + off;
+  float* __restrict__ d = e.dst + off;
+  if (((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += 256) reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(s)[i];
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += 256) d[i] = s[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) d[i] = s[i];
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
+
+// table: ntab entries of {const float* src, float* dst, int64 n, int64 first_block} in DEVICE memory, first_block ascending from 0,
+// entry i owning ceil(n_i / 4096) blocks; total_blocks = their sum.  Contiguous float32 tensors.
+SNB_API int snb_multi_copy(const void* table, int ntab, long long total_blocks, void* stream) {
+  if (ntab < 0 || total_blocks < 0) return SNB_EINVAL;
+  if (ntab == 0 || total_blocks == 0) return SNB_OK;
+  if (!table) return SNB_EINVAL;
+  if (total_blocks > 0x7fffffffLL) return SNB_ELIMIT;
+  multi_copy_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>((const PackEntry*)table, ntab);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
 
 SNB_API int snb_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int step, void* stream) {

@@ -65,3 +65,41 @@ def test_graphed_forward_backward_matches_eager(cuda):
     assert worst < 5e-3, rows[:5]
     loss_g2 = g(partial, gt).item()                          # replay is repeatable
     assert abs(loss_g2 - loss_g) <= 1e-6 * abs(loss_g)
+
+
+@pytest.mark.gpu
+def test_grad_arena_pack_one_launch_eager_and_captured(cuda):
+    """GradArena.pack (own_grads=False) through snb_multi_copy: odd sizes, a 16-byte-misaligned gradient view, several eager calls
+    (alternating pinned pointer tables) and one call captured in a CUDA graph and replayed after the gradients changed in place."""
+    from sparenet_b200.dist import GradArena
+    torch.manual_seed(5)
+    shapes = [(5, 3), (7,), (300, 41), (1,), (4096,), (4097,), (2, 2, 2)]
+    ps = [torch.nn.Parameter(torch.randn(*s, device=cuda)) for s in shapes]
+    arena = GradArena(ps, own_grads=False)
+    big = torch.randn(10000, device=cuda)
+    for round_ in range(3):
+        for i, p in enumerate(ps):
+            p.grad = None if i == 3 else torch.full_like(p, float(10 * round_ + i + 1))
+        ps[1].grad = big[1 + round_:8 + round_]               # a view whose address is not a multiple of 16
+        arena.pack()
+        torch.cuda.synchronize()
+        for i, p in enumerate(ps):
+            want = torch.zeros_like(p) if i == 3 else (big[1 + round_:8 + round_] if i == 1 else torch.full_like(p, float(10 * round_ + i + 1)))
+            assert torch.equal(arena.views[id(p)], want), (round_, i)
+    # captured: static gradient tensors, values change between replays
+    static = [torch.zeros_like(p) for p in ps]
+    for p, g in zip(ps, static):
+        p.grad = g
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        arena.pack()
+    for val in (3.0, -7.5):
+        for g in static:
+            g.fill_(val)
+        arena.pack()                                          # an eager call in between must not disturb the captured table
+        graph.replay()
+        torch.cuda.synchronize()
+        for p in ps:
+            assert torch.equal(arena.views[id(p)], torch.full_like(p, val))
