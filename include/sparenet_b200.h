@@ -241,10 +241,10 @@ int snb_adain_tail_bwd(const float* grad_scale, const float* grad_shift, const f
  * (no amsgrad, no maximize; weight_decay is the L2 form), `step` = 1, 2, ... is the number of this update. */
 int snb_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, void* stream);
-/* Gather of many contiguous float32 tensors into their slots of a flat arena in ONE launch (sparenet_b200.dist.GradArena.pack):
- * `table` = ntab entries {const float* src, float* dst, int64 n, int64 first_block} in device memory, first_block ascending from 0,
- * entry i owning ceil(n_i / 4096) blocks; total_blocks = their sum. */
-int snb_multi_copy(const void* table, int ntab, long long total_blocks, void* stream);
+/* Gather of many contiguous float32 tensors into their slots of a flat arena in ONE launch per 1024 tensors
+ * (sparenet_b200.dist.GradArena.pack): srcs / dsts / ns are HOST arrays of ntab device pointers and element counts; the pointer
+ * table travels as a kernel parameter, so the call is graph-capturable without any host-to-device copy. */
+int snb_multi_copy(const void* const* srcs, void* const* dsts, const long long* ns, int ntab, void* stream);
 
 /* ---- TF32 tensor-core GEMM of the 1x1-conv / AdaIN-folding stacks (csrc/gemm_tc.cu: tcgen05.mma + TMEM + TMA) ----------
  * replaces the cuDNN/cuBLAS calls behind nn.Conv1d / nn.Conv2d(kernel_size=1) in models/sparenet_generator.py:146-186,

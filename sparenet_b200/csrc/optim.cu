@@ -38,31 +38,38 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float4* __restrict__ p, 
 
 // ---- gather of the step's gradient tensors into the flat arena: ONE launch over a pointer table ---------------------------------------
 // (sparenet_b200.dist.GradArena.pack: autograd hands back ~800 fresh gradient tensors per step; torch._foreach_copy_ moved their
-// 330 MB in 11 multi-tensor launches at ~2.3 TB/s.)  Table entry: {src, dst, n floats, first block}; a block copies 4096 floats.
+// 330 MB in 11 multi-tensor launches at ~2.3 TB/s.)  The table travels as a KERNEL PARAMETER (24 B per tensor; CUDA 12.1+ accepts
+// 32 KB of parameters): no device-side table, no host-to-device copy, and under CUDA-graph capture the launch is an ordinary kernel
+// node that carries its table with it.  A block copies 4096 floats.
 struct PackEntry {
   const float* src;
   float* dst;
-  long long n;
-  long long first_block;
+  unsigned n;
+  unsigned first_block;
 };
 constexpr int PACK_CHUNK = 4096;
+constexpr int PACK_MAX = 1024;   // entries per launch (24.6 KB of parameters)
+struct PackTable {
+  PackEntry e[PACK_MAX];
+};
 
-__global__ void __launch_bounds__(256) multi_copy_kernel(const PackEntry* __restrict__ tab, int ntab) {
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ PackTable tab, int ntab) {
   // binary search: the last entry whose first block is <= this block
   int lo = 0, hi = ntab - 1;
-  const long long blk = blockIdx.x;
+  const unsigned blk = blockIdx.x;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (tab[mid].first_block <= blk) lo = mid;
+    if (tab.e[mid].first_block <= blk) lo = mid;
     else hi = mid - 1;
   }
-  const PackEntry e = tab[lo];
-  const long long off = (blk - e.first_block) * PACK_CHUNK;
-  const long long left = e.n - off;
+  const float* __restrict__ s0 = tab.e[lo].src;
+  float* __restrict__ d0 = tab.e[lo].dst;
+  const long long off = (long long)(blk - tab.e[lo].first_block) * PACK_CHUNK;
+  const long long left = (long long)tab.e[lo].n - off;
   if (left <= 0) return;
   const int n = left < PACK_CHUNK ? (int)left : PACK_CHUNK;
-  const float* __restrict__ s = e.src + off;
-  float* __restrict__ d = e.dst + off;
+  const float* __restrict__ s = s0 + off;
+  float* __restrict__ d = d0 + off;
   if (((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0) {
     const int n4 = n >> 2;
     for (int i = threadIdx.x; i < n4; i += 256) reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(s)[i];
@@ -76,18 +83,37 @@ __global__ void __launch_bounds__(256) multi_copy_kernel(const PackEntry* __rest
 
 using namespace snb;
 
-// table: ntab entries of {const float* src, float* dst, int64 n, int64 first_block} in DEVICE memory, first_block ascending from 0,
-// entry i owning ceil(n_i / 4096) blocks; total_blocks = their sum.  Contiguous float32 tensors.
-SNB_API int snb_multi_copy(const void* table, int ntab, long long total_blocks, void* stream) {
-  if (ntab < 0 || total_blocks < 0) return SNB_EINVAL;
-  if (ntab == 0 || total_blocks == 0) return SNB_OK;
-  if (!table) return SNB_EINVAL;
-  if (total_blocks > 0x7fffffffLL) return SNB_ELIMIT;
-  multi_copy_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>((const PackEntry*)table, ntab);
-  SNB_LAUNCH_CHECK();
+// srcs / dsts / ns: HOST arrays of ntab device pointers and element counts (contiguous float32 tensors, each below 2^32 elements).
+SNB_API int snb_multi_copy(const void* const* srcs, void* const* dsts, const long long* ns, int ntab, void* stream) {
+  if (ntab < 0) return SNB_EINVAL;
+  if (ntab == 0) return SNB_OK;
+  if (!srcs || !dsts || !ns) return SNB_EINVAL;
+  static PackTable tab;  // host staging of one launch's parameters (copied by the launch)
+  int i = 0;
+  while (i < ntab) {
+    int m = 0;
+    unsigned long long blk = 0;
+    for (; i < ntab && m < PACK_MAX; i++) {
+      if (ns[i] < 0 || ns[i] > 0xffffffffLL) return SNB_ELIMIT;
+      if (ns[i] == 0) continue;
+      const unsigned long long nb = ((unsigned long long)ns[i] + PACK_CHUNK - 1) / PACK_CHUNK;
+      if (blk + nb > 0x7fffffffULL) break;
+      tab.e[m].src = (const float*)srcs[i];
+      tab.e[m].dst = (float*)dsts[i];
+      tab.e[m].n = (unsigned)ns[i];
+      tab.e[m].first_block = (unsigned)blk;
+      blk += nb;
+      m++;
+    }
+    if (m == 0) {
+      if (i < ntab && ns[i] != 0) return SNB_ELIMIT;   // a single tensor above the grid limit
+      continue;
+    }
+    multi_copy_kernel<<<(unsigned)blk, 256, 0, (cudaStream_t)stream>>>(tab, m);
+    SNB_LAUNCH_CHECK();
+  }
   return SNB_OK;
 }
-
 SNB_API int snb_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int step, void* stream) {
   if (step < 1 || (n & 3) != 0) return SNB_EINVAL;

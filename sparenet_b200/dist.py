@@ -45,17 +45,6 @@ class GradArena:
                     p.grad = self.views[id(p)]
             self.flats.append(flat)
         self._written = set()      # own_grads=False: ids of the parameters whose arena slot pack() has ever copied a gradient into
-        # pointer tables of the one-launch pack (pinned host + device pairs, allocated HERE: nothing may be allocated with cudaHostAlloc
-        # while a stream is capturing).  Two pairs alternate between eager calls (each guarded by an event, so the host side may run
-        # one step ahead); every pack() issued under CUDA-graph capture takes a pair for good, because the graph's upload node re-reads
-        # its pinned table at every replay.
-        self._tabs, self._tab_events, self._tab_turn = [], [None, None], 0
-        devs = {p.device for p in self.params}
-        if not own_grads and len(devs) == 1 and next(iter(devs)).type == "cuda":
-            dev = next(iter(devs))
-            for _ in range(6):
-                self._tabs.append((torch.empty(len(self.params), 4, dtype=torch.int64).pin_memory(),
-                                   torch.empty(len(self.params), 4, dtype=torch.int64, device=dev)))
 
     def pack(self):
         """own_grads=False: copy the parameters' current .grad tensors into the arena (multi-tensor copies; a parameter without a
@@ -84,45 +73,17 @@ class GradArena:
             torch._foreach_copy_(dst, src)
 
     def _pack_one_launch(self, dst, src):
-        """One launch over a pointer table (csrc/optim.cu: snb_multi_copy) instead of ~11 multi-tensor launches.  The table is built on
-        the host, staged in pinned memory and uploaded on the current stream; under CUDA-graph capture the upload is a memcpy node
-        that re-reads the (unchanged) pinned table at every replay, and the captured tensors' addresses are static."""
+        """One launch per 1024 tensors over a pointer table (csrc/optim.cu: snb_multi_copy) instead of ~11 multi-tensor launches.  The
+        table is a kernel parameter: nothing is uploaded, and under CUDA-graph capture the call is an ordinary kernel node (the
+        captured tensors' addresses are static)."""
         import ctypes
         from . import _lib
-        rows, blk = [], 0
-        for v, s in zip(dst, src):
-            n = s.numel()
-            if n == 0:
-                continue
-            rows.append((s.data_ptr(), v.data_ptr(), n, blk))
-            blk += (n + 4095) // 4096
-        if not rows:
-            return
-        capturing = torch.cuda.is_current_stream_capturing()
-        if capturing:
-            if len(self._tabs) <= 2:                       # no table pair left to dedicate to this capture
-                torch._foreach_copy_(dst, src)
-                return
-            host, table = self._tabs.pop()
-        else:
-            if len(self._tabs) < 2:
-                torch._foreach_copy_(dst, src)
-                return
-            turn = self._tab_turn
-            self._tab_turn ^= 1
-            host, table = self._tabs[turn]
-            if self._tab_events[turn] is not None:
-                self._tab_events[turn].synchronize()       # the upload issued two eager calls ago has read this pinned table
-        n = len(rows)
-        host[:n] = torch.tensor(rows, dtype=torch.int64)
-        table[:n].copy_(host[:n], non_blocking=True)
-        if not capturing:
-            ev = torch.cuda.Event()
-            ev.record()
-            self._tab_events[turn] = ev
-        self._pack_keep = list(src)
-        with torch.cuda.device(table.device):
-            _lib.check(_lib.load().snb_multi_copy(ctypes.c_void_p(table.data_ptr()), n, blk, _lib.stream_ptr()), "multi_copy")
+        n = len(dst)
+        srcs = (ctypes.c_void_p * n)(*[s.data_ptr() for s in src])
+        dsts = (ctypes.c_void_p * n)(*[v.data_ptr() for v in dst])
+        ns = (ctypes.c_longlong * n)(*[s.numel() for s in src])
+        with torch.cuda.device(dst[0].device):
+            _lib.check(_lib.load().snb_multi_copy(srcs, dsts, ns, n, _lib.stream_ptr()), "multi_copy")
 
     def zero(self):
         for f in self.flats:
