@@ -152,6 +152,12 @@ int snb_edge_reduce_sel_fwd(const float* a, const float* c, const int* idx, cons
 int snb_edge_reduce_sel_bwd(const float* a, const float* c, const int* idx, const unsigned char* slot,
                             const float* g_ustar, const double* gS1, const double* gS2, int B, int C, int N, int k,
                             float* ga, float* gc, void* stream);
+/* The selected-extremum pair for a and c stored as the two channel halves of ONE [B,2C,N] tensor (the output of a single GEMM with the
+ * stacked weight [W_a ; W_b - W_a]); the backward fills the two halves of ONE [B,2C,N] gradient. */
+int snb_edge_reduce_sel_fwd_stacked(const float* ac, const int* idx, const unsigned char* sel_max, int B, int C, int N, int k,
+                                    float* ustar, unsigned char* slot, double* S1, double* S2, void* stream);
+int snb_edge_reduce_sel_bwd_stacked(const float* ac, const int* idx, const unsigned char* slot, const float* g_ustar, const double* gS1,
+                                    const double* gS2, int B, int C, int N, int k, float* gac, void* stream);
 
 /* ---- row-wise tails of the folded normalisation stacks (models/sparenet_generator.py:618-646,1053-1061) ----
  * h [R,L] contiguous rows.  row_stats: mean / biased variance per row.  row_affine_act:

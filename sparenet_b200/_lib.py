@@ -61,6 +61,8 @@ SIGNATURES = {
     "snb_edge_reduce_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "snb_edge_reduce_sel_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "snb_edge_reduce_sel_bwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "snb_edge_reduce_sel_fwd_stacked": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "snb_edge_reduce_sel_bwd_stacked": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "snb_row_stats": (c_int, [P, ctypes.c_longlong, c_int, P, P, P]),
     "snb_row_stats_bwd": (c_int, [P, P, P, P, ctypes.c_longlong, c_int, P, P]),
     "snb_row_affine_act_fwd": (c_int, [P, P, P, ctypes.c_longlong, c_int, c_int, c_float, P, P]),

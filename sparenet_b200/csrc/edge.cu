@@ -37,7 +37,7 @@ __device__ __forceinline__ double block_sum_double(double v, double* red) {
 // N*k ints per sample = 8x a channel row: with one row per CTA the index reads out of L2 were 70 % of the kernel's traffic).
 template <int CHB>
 __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_fwd_kernel(const float* __restrict__ a, const float* __restrict__ c,
-                                                                        const int* __restrict__ idx, int C, int N, int k,
+                                                                        const int* __restrict__ idx, int C, int N, int k, size_t in_bstride,
                                                                         float* __restrict__ umax, float* __restrict__ umin,
                                                                         unsigned char* __restrict__ smax, unsigned char* __restrict__ smin,
                                                                         double* __restrict__ S1, double* __restrict__ S2,
@@ -45,8 +45,10 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_fwd_kernel(const flo
   extern __shared__ float arow[];          // [CHB][N]
   __shared__ double red[EDGE_THREADS / 32];
   const int ch0 = blockIdx.x * CHB, b = blockIdx.y;
-  const size_t row0 = ((size_t)b * C + ch0) * N;
-  for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) arow[i] = a[row0 + i];
+  const size_t row0 = ((size_t)b * C + ch0) * N;               // outputs: [B,C,N] contiguous
+  const size_t in0 = (size_t)b * in_bstride + (size_t)ch0 * N;  // a, c: batch stride in_bstride (= C*N, or 2*C*N when a and c are the two
+                                                                // channel halves of ONE [B,2C,N] GEMM output)
+  for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) arow[i] = a[in0 + i];
   __syncthreads();
   const int* __restrict__ ib = idx + (size_t)b * N * k;
   double s1[CHB], s2[CHB];
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_fwd_kernel(const flo
 #pragma unroll
     for (int q = 0; q < CHB; q++) {
       const size_t row = row0 + (size_t)q * N;
-      const float ci = c[row + i];
+      const float ci = c[in0 + (size_t)q * N + i];
       if (sel) {  // only the extremum the sign of the channel's BatchNorm weight asks for (written to umax / smax)
         const bool up = sel[ch0 + q] != 0;
         umax[row + i] = (up ? mx[q] : mn[q]) + ci;
@@ -110,15 +112,16 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_bwd_kernel(const flo
                                                                         const int* __restrict__ idx, const unsigned char* __restrict__ smax,
                                                                         const unsigned char* __restrict__ smin, const float* __restrict__ gmax,
                                                                         const float* __restrict__ gmin, const double* __restrict__ gS1,
-                                                                        const double* __restrict__ gS2, int C, int N, int k,
+                                                                        const double* __restrict__ gS2, int C, int N, int k, size_t in_bstride,
                                                                         float* __restrict__ ga, float* __restrict__ gc) {
   extern __shared__ float sm[];
   float* arow = sm;                // [CHB][N]
   float* grow = sm + CHB * N;      // [CHB][N]
   const int ch0 = blockIdx.x * CHB, b = blockIdx.y;
-  const size_t row0 = ((size_t)b * C + ch0) * N;
+  const size_t row0 = ((size_t)b * C + ch0) * N;               // gmax, gmin, slots: [B,C,N] contiguous
+  const size_t in0 = (size_t)b * in_bstride + (size_t)ch0 * N;  // a, c, ga, gc: batch stride in_bstride
   for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) {
-    arow[i] = a[row0 + i];
+    arow[i] = a[in0 + i];
     grow[i] = 0.f;
   }
   __syncthreads();
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_bwd_kernel(const flo
 #pragma unroll
     for (int q = 0; q < CHB; q++) {
       const size_t r = row0 + (size_t)q * N + i;
-      ci[q] = c[r];
+      ci[q] = c[in0 + (size_t)q * N + i];
       gx[q] = gmax[r];
       gn[q] = gmin ? gmin[r] : 0.f;                 // gmin == nullptr: the selected-extremum form
       ax[q] = smax[r];
@@ -156,10 +159,10 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_reduce_bwd_kernel(const flo
     }
 #pragma unroll
     for (int q = 0; q < CHB; q++)
-      gc[row0 + (size_t)q * N + i] = gx[q] + gn[q] + (float)k * g1[q] + g2[q] * (sa[q] + (float)k * ci[q]);
+      gc[in0 + (size_t)q * N + i] = gx[q] + gn[q] + (float)k * g1[q] + g2[q] * (sa[q] + (float)k * ci[q]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) ga[row0 + i] = grow[i];
+  for (int i = threadIdx.x; i < CHB * N; i += EDGE_THREADS) ga[in0 + i] = grow[i];
 }
 
 }  // namespace snb
@@ -171,10 +174,11 @@ static int edge_chb(int C, int N, int rows_per_channel) { return (C % 4 == 0 && 
 
 template <int CHB>
 static int edge_launch_fwd(const float* a, const float* c, const int* idx, int B, int C, int N, int k, float* umax, float* umin, unsigned char* smax,
-                           unsigned char* smin, double* S1, double* S2, const unsigned char* sel, cudaStream_t s) {
+                           unsigned char* smin, double* S1, double* S2, const unsigned char* sel, cudaStream_t s, size_t in_bstride = 0) {
+  if (in_bstride == 0) in_bstride = (size_t)C * N;
   const size_t smem = (size_t)N * CHB * sizeof(float);
   if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_fwd_kernel<CHB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_reduce_fwd_kernel<CHB><<<dim3(C / CHB, B), EDGE_THREADS, smem, s>>>(a, c, idx, C, N, k, umax, umin, smax, smin, S1, S2, sel);
+  edge_reduce_fwd_kernel<CHB><<<dim3(C / CHB, B), EDGE_THREADS, smem, s>>>(a, c, idx, C, N, k, in_bstride, umax, umin, smax, smin, S1, S2, sel);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
@@ -182,10 +186,11 @@ static int edge_launch_fwd(const float* a, const float* c, const int* idx, int B
 template <int CHB>
 static int edge_launch_bwd(const float* a, const float* c, const int* idx, const unsigned char* smax, const unsigned char* smin, const float* gmax,
                            const float* gmin, const double* gS1, const double* gS2, int B, int C, int N, int k, float* ga, float* gc,
-                           cudaStream_t s) {
+                           cudaStream_t s, size_t in_bstride = 0) {
+  if (in_bstride == 0) in_bstride = (size_t)C * N;
   const size_t smem = (size_t)N * 2 * CHB * sizeof(float);
   if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(edge_reduce_bwd_kernel<CHB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_reduce_bwd_kernel<CHB><<<dim3(C / CHB, B), EDGE_THREADS, smem, s>>>(a, c, idx, smax, smin, gmax, gmin, gS1, gS2, C, N, k, ga, gc);
+  edge_reduce_bwd_kernel<CHB><<<dim3(C / CHB, B), EDGE_THREADS, smem, s>>>(a, c, idx, smax, smin, gmax, gmin, gS1, gS2, C, N, k, in_bstride, ga, gc);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
@@ -236,4 +241,33 @@ SNB_API int snb_edge_reduce_bwd(const float* a, const float* c, const int* idx, 
   cudaStream_t s = (cudaStream_t)stream;
   return edge_chb(C, N, 2) == 4 ? edge_launch_bwd<4>(a, c, idx, slot_max, slot_min, g_umax, g_umin, gS1, gS2, B, C, N, k, ga, gc, s)
                                 : edge_launch_bwd<1>(a, c, idx, slot_max, slot_min, g_umax, g_umin, gS1, gS2, B, C, N, k, ga, gc, s);
+}
+
+// The same two calls for a and c living in ONE [B, 2C, N] tensor (channels [0,C) = a, [C,2C) = c: the output of a single GEMM with the
+// stacked weight [W_a ; W_b - W_a]); the backward writes ga and gc into the two halves of ONE [B, 2C, N] gradient, so the data and
+// weight gradients of the pair are single GEMMs too and no elementwise add of two data gradients is left.
+SNB_API int snb_edge_reduce_sel_fwd_stacked(const float* ac, const int* idx, const unsigned char* sel_max, int B, int C, int N, int k, float* ustar,
+                                            unsigned char* slot, double* S1, double* S2, void* stream) {
+  int rc = edge_check(B, C, N, k);
+  if (rc) return rc;
+  if (!sel_max) return SNB_EINVAL;
+  if (B == 0 || C == 0 || N == 0) return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* a = ac;
+  const float* c = ac + (size_t)C * N;
+  const size_t bs = (size_t)2 * C * N;
+  return edge_chb(C, N, 1) == 4 ? edge_launch_fwd<4>(a, c, idx, B, C, N, k, ustar, nullptr, slot, nullptr, S1, S2, sel_max, s, bs)
+                                : edge_launch_fwd<1>(a, c, idx, B, C, N, k, ustar, nullptr, slot, nullptr, S1, S2, sel_max, s, bs);
+}
+
+SNB_API int snb_edge_reduce_sel_bwd_stacked(const float* ac, const int* idx, const unsigned char* slot, const float* g_ustar, const double* gS1,
+                                            const double* gS2, int B, int C, int N, int k, float* gac, void* stream) {
+  int rc = edge_check(B, C, N, k);
+  if (rc) return rc;
+  if (B == 0 || C == 0 || N == 0) return SNB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bs = (size_t)2 * C * N;
+  return edge_chb(C, N, 2) == 4
+             ? edge_launch_bwd<4>(ac, ac + (size_t)C * N, idx, slot, nullptr, g_ustar, nullptr, gS1, gS2, B, C, N, k, gac, gac + (size_t)C * N, s, bs)
+             : edge_launch_bwd<1>(ac, ac + (size_t)C * N, idx, slot, nullptr, g_ustar, nullptr, gS1, gS2, B, C, N, k, gac, gac + (size_t)C * N, s, bs);
 }

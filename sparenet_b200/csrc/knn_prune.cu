@@ -25,7 +25,6 @@ namespace snb {
 
 constexpr int KP_MAXK = 32;
 constexpr int KP_CAND = 96;  // candidate capacity per row (3 per lane)
-constexpr int KP_SPLIT = 32; // candidates per row handed to knn_rank_kernel (one per lane)
 
 // point-major copy xT [B,N,C] of the channel-major features x [B,C,N]: 32 x 32 tiles through shared memory, 128-byte rows on both sides
 // (the PyTorch permute-copy ran at ~1.7 TB/s: 0.3 ms per step for the three wide layers)
@@ -103,7 +102,7 @@ __device__ __forceinline__ float knn_exact_dist(const float* __restrict__ xi, co
 template <int K, bool CACHE>
 __global__ void __launch_bounds__(256, CACHE ? 2 : 4) knn_prune_kernel(const float* __restrict__ xT, const float* __restrict__ gram, const float* __restrict__ nrm,
                                                          const unsigned* __restrict__ nmax_bits, int C, int N, size_t rows, int k,
-                                                         int* __restrict__ idx, int* __restrict__ split_cand, int* __restrict__ split_count) {
+                                                         int* __restrict__ idx) {
   __shared__ int cand[8][KP_CAND];
   __shared__ float cval[8][KP_CAND];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,23 +225,6 @@ __global__ void __launch_bounds__(256, CACHE ? 2 : 4) knn_prune_kernel(const flo
       ncand += __popc(__ballot_sync(0xffffffffu, isc[u]));
     }
   }
-  // ---- split mode: rows with at most 32 candidates (all but degenerate ones) hand their list to knn_rank_kernel, which evaluates the
-  //      exact distances with four times the resident warps (no 64-register distance cache there): the dependent channel chains over
-  //      scattered candidate rows are pure latency (53 % of this kernel's stall samples when done here) ----
-  if (split_cand != nullptr) {
-    if (ncand <= KP_SPLIT) {
-      int pos = 0;
-#pragma unroll
-      for (int u = 0; u < 3; u++) {
-        const unsigned m = __ballot_sync(0xffffffffu, isc[u]);
-        if (isc[u]) split_cand[row * KP_SPLIT + pos + __popc(m & ((1u << lane) - 1u))] = cj[u];
-        pos += __popc(m);
-      }
-      if (lane == 0) split_count[row] = ncand;
-      return;
-    }
-    if (lane == 0) split_count[row] = -1;  // finished here
-  }
   // ---- exact distances of the candidates, then the k smallest by (d, j) ----
   const float* __restrict__ xb = xT + b * (size_t)N * C;
   const float* __restrict__ xi = xb + (size_t)i * C;
@@ -333,37 +315,6 @@ __global__ void __launch_bounds__(256, CACHE ? 2 : 4) knn_prune_kernel(const flo
   }
 }
 
-// second half of the split: a warp per row, a lane per candidate -- exact distance, then the k smallest by (d, j)
-__global__ void __launch_bounds__(256) knn_rank_kernel(const float* __restrict__ xT, const int* __restrict__ split_cand,
-                                                        const int* __restrict__ split_count, int C, int N, size_t rows, int k,
-                                                        int* __restrict__ idx) {
-  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const int n = split_count[row];
-  if (n < 0) return;  // the selection kernel finished this row itself
-  const size_t b = row / N;
-  const float* __restrict__ xb = xT + b * (size_t)N * C;
-  const float* __restrict__ xi = xT + row * C;
-  const float INF = __int_as_float(0x7f800000);
-  float cd = INF;
-  int cj = 0x7fffffff;
-  if (lane < n) {
-    cj = split_cand[row * KP_SPLIT + lane];
-    cd = knn_exact_dist(xi, xb + (size_t)cj * C, C);
-  }
-  int* out = idx + row * k;
-  for (int t = 0; t < k; t++) {
-    const unsigned md = __reduce_min_sync(0xffffffffu, __float_as_uint(cd));
-    const int mj = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(cd) == md ? (unsigned)cj : 0x7fffffffu);
-    if (lane == 0) out[t] = mj;
-    if (cj == mj) {
-      cd = INF;
-      cj = 0x7fffffff;
-    }
-  }
-}
-
 }  // namespace snb
 
 using namespace snb;
@@ -380,8 +331,7 @@ SNB_API int snb_transpose_cn(const float* x, int B, int C, int N, float* xT, voi
 // workspace: norms [B,N] floats + per-sample maxima [B] (16-byte aligned pieces)
 SNB_API size_t snb_knn_pruned_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= 0) return 0;
-  return (((size_t)B * N * sizeof(float) + 15) & ~(size_t)15) + (((size_t)B * sizeof(unsigned) + 15) & ~(size_t)15) +
-         (size_t)B * N * (KP_SPLIT + 1) * sizeof(int);
+  return (((size_t)B * N * sizeof(float) + 15) & ~(size_t)15) + (((size_t)B * sizeof(unsigned) + 15) & ~(size_t)15);
 }
 
 SNB_API int snb_knn_pruned(const float* xT, const float* gram, int B, int C, int N, int k, int* idx, void* workspace, size_t workspace_bytes,
@@ -394,10 +344,6 @@ SNB_API int snb_knn_pruned(const float* xT, const float* gram, int B, int C, int
   cudaStream_t s = (cudaStream_t)stream;
   float* nrm = (float*)workspace;
   unsigned* nmax = (unsigned*)((char*)workspace + (((size_t)B * N * sizeof(float) + 15) & ~(size_t)15));
-  int* split_cand = (int*)((char*)nmax + (((size_t)B * sizeof(unsigned) + 15) & ~(size_t)15));
-  int* split_count = split_cand + (size_t)B * N * KP_SPLIT;
-  const char* sp = getenv("SNB_KNN_PRUNE_SPLIT");   // 0: selection and exact re-ranking in one kernel (measurement switch)
-  if (sp && sp[0] == '0') split_cand = split_count = nullptr;
   SNB_CUDA(cudaMemsetAsync(nmax, 0, sizeof(unsigned) * (size_t)B, s));
   const size_t rows = (size_t)B * N;
   knn_norm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(xT, C, N, rows, nrm, nmax);
@@ -408,18 +354,14 @@ SNB_API int snb_knn_pruned(const float* xT, const float* gram, int B, int C, int
   const char* sw = getenv("SNB_KNN_PRUNE_CACHE");
   const bool cache = !(sw && sw[0] == '0');
   if (cache) {
-    if (k <= 8) knn_prune_kernel<8, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx, split_cand, split_count);
-    else if (k <= 16) knn_prune_kernel<16, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx, split_cand, split_count);
-    else knn_prune_kernel<32, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx, split_cand, split_count);
+    if (k <= 8) knn_prune_kernel<8, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else if (k <= 16) knn_prune_kernel<16, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else knn_prune_kernel<32, true><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
   } else {
-    if (k <= 8) knn_prune_kernel<8, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx, split_cand, split_count);
-    else if (k <= 16) knn_prune_kernel<16, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx, split_cand, split_count);
-    else knn_prune_kernel<32, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx, split_cand, split_count);
+    if (k <= 8) knn_prune_kernel<8, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else if (k <= 16) knn_prune_kernel<16, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
+    else knn_prune_kernel<32, false><<<grid, 256, 0, s>>>(xT, gram, nrm, nmax, C, N, rows, k, idx);
   }
   SNB_LAUNCH_CHECK();
-  if (split_cand != nullptr) {
-    knn_rank_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(xT, split_cand, split_count, C, N, rows, k, idx);
-    SNB_LAUNCH_CHECK();
-  }
   return SNB_OK;
 }

@@ -150,12 +150,13 @@ class EdgeConvResFeat(nn.Module):  # reference :123-242
         W = conv.weight.view(conv.out_channels, 2 * C)
         Wa, Wb = W[:, :C], W[:, C:]
         Co = conv.out_channels
-        a = _pconv(x, Wa)                                          # per-POINT 1x1 convs (k x fewer flops than per edge)
-        c = _pconv(x, Wb - Wa)
+        # per-POINT 1x1 convs (k x fewer flops than per edge): a = W_a x and c = (W_b - W_a) x as ONE product with the stacked weight, so
+        # forward, data gradient and weight gradient are one GEMM each and the two data gradients are never added elementwise
+        ac = _pconv(x, torch.cat((Wa, Wb - Wa), 0))                # [B, 2 Co, N]: channels [0,Co) = a, [Co,2Co) = c
         # u[b,c,i,m] = a[b,c,idx[b,i,m]] + c[b,c,i] is never formed: the fused kernel returns its max/min over m and its moments
         g = bn.weight
         # max_k commutes with the monotone BN.SE.LeakyReLU tail: the sign of gamma picks max or min, inside the kernel
-        ustar, S1, S2 = fused.edge_reduce_sel(a, c, idx, (g > 0).detach())
+        ustar, S1, S2 = fused.edge_reduce_sel_stacked(ac, idx, (g > 0).detach())
         n = B * N * k
         if FUSED_TAILS and x.is_cuda and x.dtype == torch.float32:
             # the same BatchNorm.SE closed form as the refiner's tails (csrc/tails.cu, one launch per direction): the per-sample

@@ -134,6 +134,44 @@ class EdgeReduceSel(torch.autograd.Function):
         return ga, gc, None, None
 
 
+class EdgeReduceSelStacked(torch.autograd.Function):
+    """EdgeReduceSel for a and c stored as the two channel halves of ONE tensor ac [B,2C,N] -- the output of a single GEMM with the
+    stacked weight [W_a ; W_b - W_a].  The backward fills the halves of one [B,2C,N] gradient, so the pair's data and weight gradients
+    are single GEMMs as well and the two data gradients are never added elementwise."""
+    @staticmethod
+    def forward(ctx, ac, idx, sel_max):
+        ac, idx = ac.contiguous(), idx.contiguous()
+        sel = sel_max.to(torch.uint8).contiguous()
+        B, C2, N = ac.shape
+        C = C2 // 2
+        k = idx.shape[2]
+        dev = ac.device
+        ustar = torch.empty(B, C, N, device=dev, dtype=torch.float32)
+        slot = torch.empty(B, C, N, dtype=torch.uint8, device=dev)
+        S1 = torch.empty(B, C, dtype=torch.float64, device=dev)
+        S2 = torch.empty(B, C, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev), _op("edge_reduce_fwd", 1):
+            check(_lib.load().snb_edge_reduce_sel_fwd_stacked(ptr(ac), ptr(idx), ptr(sel), B, C, N, k, ptr(ustar), ptr(slot), ptr(S1), ptr(S2),
+                                                              stream_ptr()), "edge_reduce_sel_fwd_stacked")
+        ctx.save_for_backward(ac, idx, slot)
+        return ustar, S1, S2
+
+    @staticmethod
+    def backward(ctx, gu, gS1, gS2):
+        ac, idx, slot = ctx.saved_tensors
+        B, C2, N = ac.shape
+        C = C2 // 2
+        k = idx.shape[2]
+        gac = torch.empty_like(ac)
+        gu = (gu if gu is not None else torch.zeros(B, C, N, device=ac.device)).contiguous()
+        gS1 = (gS1 if gS1 is not None else torch.zeros(B, C, dtype=torch.float64, device=ac.device)).contiguous()
+        gS2 = (gS2 if gS2 is not None else torch.zeros(B, C, dtype=torch.float64, device=ac.device)).contiguous()
+        with torch.cuda.device(ac.device), _op("edge_reduce_bwd", 1):
+            check(_lib.load().snb_edge_reduce_sel_bwd_stacked(ptr(ac), ptr(idx), ptr(slot), ptr(gu), ptr(gS1), ptr(gS2), B, C, N, k, ptr(gac),
+                                                              stream_ptr()), "edge_reduce_sel_bwd_stacked")
+        return gac, None, None
+
+
 class RowStats(torch.autograd.Function):
     """h [..., L] -> (mean, biased var) over the last dim, shape h.shape[:-1]."""
     @staticmethod
@@ -420,6 +458,10 @@ def row_norm_act_pool(h, fn, tensors, slope=0.0, stats=None):
 
 def edge_reduce(a, c, idx):
     return EdgeReduce.apply(a, c, idx)
+
+
+def edge_reduce_sel_stacked(ac, idx, sel_max):
+    return EdgeReduceSelStacked.apply(ac, idx, sel_max)
 
 
 def edge_reduce_sel(a, c, idx, sel_max):

@@ -18,6 +18,11 @@ def edge_reduce_sel(a, c, idx, sel_max):
     return torch.where(sel_max.view(1, -1, 1), umax, umin), S1, S2
 
 
+def edge_reduce_sel_stacked(ac, idx, sel_max):
+    C = ac.shape[1] // 2
+    return edge_reduce_sel(ac[:, :C], ac[:, C:], idx, sel_max)
+
+
 def row_stats(h):
     var, mean = torch.var_mean(h, dim=-1, unbiased=False)
     return mean, var
@@ -103,6 +108,6 @@ def act_conv_row_reduce(W, pro, h):
 
 def patch(monkeypatch):
     from sparenet_b200 import fused
-    for name in ("edge_reduce", "edge_reduce_sel", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce",
+    for name in ("edge_reduce", "edge_reduce_sel", "edge_reduce_sel_stacked", "row_stats", "row_affine_act", "row_minmax", "row_norm_act", "conv_row_reduce",
                  "row_stats_nograd", "conv1x1", "Prologue", "act_conv", "act_conv_row_reduce", "bcast_act_conv", "thin_conv", "row_norm_act_pool", "cat_conv1x1"):
         monkeypatch.setattr(fused, name, globals()[name])

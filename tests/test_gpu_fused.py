@@ -425,3 +425,25 @@ def test_conv_row_reduce_backward_extrema_kernel(cuda):
         err = float((a.double() - b).abs().max()) / max(float(b.abs().max()), 1e-9)
         print(f"[conv_extrema_bwd] {name}: err/scale {err:.2e}")
         assert err < 2e-5, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,N,k", [(3, 64, 512, 8), (2, 6, 100, 4)])
+def test_edge_reduce_sel_stacked_equals_pair(cuda, B, C, N, k):
+    """a and c as the two channel halves of ONE [B,2C,N] tensor (snb_edge_reduce_sel_*_stacked) == the two-tensor calls, bit for bit:
+    outputs, statistics and the gradients of a and c (which land in the two halves of one gradient tensor)."""
+    from sparenet_b200 import fused
+    torch.manual_seed(C + N)
+    ac = torch.randn(B, 2 * C, N, device=cuda)
+    idx = torch.randint(0, N, (B, N, k), device=cuda, dtype=torch.int32)
+    sel = torch.rand(C, device=cuda) > 0.5
+    gu, g1, g2 = torch.randn(B, C, N, device=cuda), torch.randn(B, C, device=cuda).double(), torch.randn(B, C, device=cuda).double()
+    x1 = ac.clone().requires_grad_()
+    o1 = fused.edge_reduce_sel_stacked(x1, idx, sel)
+    torch.autograd.backward(o1, (gu, g1, g2))
+    a, c = ac[:, :C].clone().requires_grad_(), ac[:, C:].clone().requires_grad_()
+    o2 = fused.edge_reduce_sel(a, c, idx, sel)
+    torch.autograd.backward(o2, (gu, g1, g2))
+    for u, v in zip(o1, o2):
+        assert torch.equal(u, v)
+    assert torch.equal(x1.grad[:, :C], a.grad) and torch.equal(x1.grad[:, C:], c.grad)

@@ -554,13 +554,11 @@ def test_knn_pruned_identical_to_brute_force(cuda, monkeypatch, B, C, N, k, offs
         x[:, :, 200:260] = x[:, :, 100:160]
         x[:, :, 280:] = 0
     a = F_.knn_indices_pruned(x, k)                      # Gram matrix from the tcgen05 TF32 GEMM (positions % 32 == 0)
-    monkeypatch.setenv("SNB_KNN_PRUNE_SPLIT", "0")       # selection + exact re-ranking in one kernel (the default splits them in two)
-    a1 = F_.knn_indices_pruned(x, k)
-    monkeypatch.setenv("SNB_KNN_PRUNE_CACHE", "0")       # ... and without the register cache of the approximate distances
+    monkeypatch.setenv("SNB_KNN_PRUNE_CACHE", "0")       # the variant without the register cache of the approximate distances
     a2 = F_.knn_indices_pruned(x, k)
     monkeypatch.setenv("SNB_KNN_PRUNE", "0")             # the reference side is always the brute-force kernels
     ref = F_.knn_indices(x, k)
-    assert torch.equal(a, ref) and torch.equal(a1, ref) and torch.equal(a2, ref)
+    assert torch.equal(a, ref) and torch.equal(a2, ref)
 
 
 @pytest.mark.parametrize("B,C,N,k", [(32, 3, 2048, 8), (2, 3, 130, 16), (3, 4, 1000, 8), (2, 3, 40, 32), (2, 2, 2048, 20)])
