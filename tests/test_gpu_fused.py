@@ -430,8 +430,9 @@ def test_conv_row_reduce_backward_extrema_kernel(cuda):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,C,N,k", [(3, 64, 512, 8), (2, 6, 100, 4)])
 def test_edge_reduce_sel_stacked_equals_pair(cuda, B, C, N, k):
-    """a and c as the two channel halves of ONE [B,2C,N] tensor (snb_edge_reduce_sel_*_stacked) == the two-tensor calls, bit for bit:
-    outputs, statistics and the gradients of a and c (which land in the two halves of one gradient tensor)."""
+    """a and c as the two channel halves of ONE [B,2C,N] tensor (snb_edge_reduce_sel_*_stacked) == the two-tensor calls: outputs,
+    statistics and gc bit for bit, ga (accumulated with shared-memory atomics in both) to rounding; the gradients land in the two
+    halves of one gradient tensor."""
     from sparenet_b200 import fused
     torch.manual_seed(C + N)
     ac = torch.randn(B, 2 * C, N, device=cuda)
@@ -446,4 +447,5 @@ def test_edge_reduce_sel_stacked_equals_pair(cuda, B, C, N, k):
     torch.autograd.backward(o2, (gu, g1, g2))
     for u, v in zip(o1, o2):
         assert torch.equal(u, v)
-    assert torch.equal(x1.grad[:, :C], a.grad) and torch.equal(x1.grad[:, C:], c.grad)
+    assert torch.equal(x1.grad[:, C:], c.grad)                   # gc: plain stores
+    assert torch.allclose(x1.grad[:, :C], a.grad, rtol=1e-5, atol=1e-5)   # ga: shared-memory atomics, summation order varies run to run
