@@ -325,7 +325,7 @@ def knn_indices_pruned(x, k):
     lib = _lib.load()
     nbytes = lib.snb_knn_pruned_workspace_bytes(B, N)
     ws = _ws(nbytes, x.device)
-    with torch.cuda.device(x.device), _op("knn", 2):     # the op's time includes the transpose and the Gram GEMM
+    with torch.cuda.device(x.device), _op("knn", 3):     # transpose + norms + prune; the op's time includes the Gram GEMM (counted by its own op)
         xT = torch.empty(B, N, C, device=x.device, dtype=torch.float32)
         check(lib.snb_transpose_cn(ptr(x), B, C, N, ptr(xT), stream_ptr()), "transpose_cn")
         gram, _ = gemm.conv_fwd(x, xT)                   # [B,N,N]: one "weight" per sample = its own points
