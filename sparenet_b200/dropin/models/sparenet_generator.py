@@ -61,10 +61,16 @@ def _bn_apply_stats(bn, mean, var_biased, count):
     """Training-mode bookkeeping of nn.BatchNorm (running stats with the unbiased variance, counter)."""
     if bn.training and bn.track_running_stats:
         with torch.no_grad():
-            m = bn.momentum if bn.momentum is not None else MOMENTUM
-            bn.running_mean.mul_(1 - m).add_(mean.detach(), alpha=m)
-            bn.running_var.mul_(1 - m).add_(var_biased.detach() * (count / max(count - 1, 1)), alpha=m)
             bn.num_batches_tracked.add_(1)
+            unb = var_biased.detach() * (count / max(count - 1, 1))
+            if bn.momentum is None:                                  # nn.BatchNorm's cumulative moving average: factor 1 / batches seen
+                f = 1.0 / bn.num_batches_tracked.to(mean.dtype)
+                bn.running_mean.add_((mean.detach() - bn.running_mean) * f)
+                bn.running_var.add_((unb - bn.running_var) * f)
+            else:
+                m = bn.momentum
+                bn.running_mean.mul_(1 - m).add_(mean.detach(), alpha=m)
+                bn.running_var.mul_(1 - m).add_(unb, alpha=m)
 
 
 def _bn_stats(bn, x, dims):
@@ -384,9 +390,24 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         D = gate * (gam * inv * (bt - mu) + bet)
         return A, D
 
+    def _check_norm_settings(self):
+        """The closed forms below (and csrc/tails.cu) are written for the settings the reference constructs its decoders with --
+        BatchNorm1d / AdaptiveInstanceNorm1d eps = 1e-5, momentum = 0.1, running statistics tracked (models/sparenet_generator.py:
+        909-933, 984-1003) -- the same for all primitives.  Anything else would silently change running statistics and eval-mode
+        outputs, so it is refused."""
+        for d in self.decoder:
+            for layer in (1, 2, 3):
+                bn, ad = getattr(d.dec, f"bn{layer}"), getattr(d.dec, f"adain{layer}")
+                if bn.eps != EPS or ad.eps != EPS or bn.momentum != MOMENTUM or not bn.track_running_stats:
+                    raise NotImplementedError(
+                        "sparenet_b200's folded decoder tail serves the reference's normalisation settings only (eps=1e-5, momentum=0.1, "
+                        f"track_running_stats=True); decoder bn{layer}/adain{layer} has eps={bn.eps}/{ad.eps}, momentum={bn.momentum}, "
+                        f"track_running_stats={bn.track_running_stats}")
+
     def forward(self, style, partial_x):
         B, P = style.size(0), self.n_primitives
         npts = self._grid_t.size(1)
+        self._check_norm_settings()
         params = self.mlp(style)                                              # [B, 2*(1026+513+256)]
         sizes = [self.decoder[0].dec.adain1.num_features, self.decoder[0].dec.adain2.num_features, self.decoder[0].dec.adain3.num_features]
         sty, off = [], 0

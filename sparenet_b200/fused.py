@@ -589,6 +589,8 @@ class BnSeTail(torch.autograd.Function):
         training = bool(bn.training)
         track = training and bn.track_running_stats
         count = B * L
+        if bn.momentum is None and training and bn.track_running_stats:
+            raise NotImplementedError("momentum=None (cumulative moving average) is not served by the fused tail kernels")
         mom = bn.momentum if bn.momentum is not None else 0.1
         rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if (track or not training) else (None, None, None)
         with torch.cuda.device(dev), _op("bn_se_tail_fwd", 1):
@@ -638,6 +640,8 @@ class BnMaxTail(torch.autograd.Function):
         training = bool(bn.training)
         track = training and bn.track_running_stats
         count = B * L
+        if bn.momentum is None and training and bn.track_running_stats:
+            raise NotImplementedError("momentum=None (cumulative moving average) is not served by the fused tail kernels")
         mom = bn.momentum if bn.momentum is not None else 0.1
         rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if (track or not training) else (None, None, None)
         with torch.cuda.device(dev), _op("bn_max_tail_fwd", 1):
