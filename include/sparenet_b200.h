@@ -247,6 +247,15 @@ int snb_adain_tail_bwd(const float* grad_scale, const float* grad_shift, const f
  * (no amsgrad, no maximize; weight_decay is the L2 form), `step` = 1, 2, ... is the number of this update. */
 int snb_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, void* stream);
+/* ---- fp32 nn.Linear for small batches (B <= 32 rows, K % 4 == 0): the encoder -> decoder bridge (models/sparenet_generator.py:85-120
+ * SpareNetEncode.linear, :289-330 SpareNetDecode.mlp).  Exact fp32 FMAs like the reference's cuBLAS calls (no tensor cores); x [B,K],
+ * W [O,K] row-major, y [B,O].  workspace: snb_linear_workspace_floats(B,K,O) floats (split-slice partial sums, added in a fixed order).
+ * wgrad: gW [O,K] = gy^T x, gbias [O] (may be NULL). */
+size_t snb_linear_workspace_floats(int B, int K, int O);
+int snb_linear_fwd(const float* x, const float* W, const float* bias, int B, int K, int O, float* y, float* workspace, void* stream);
+int snb_linear_dgrad(const float* gy, const float* W, int B, int K, int O, float* gx, float* workspace, void* stream);
+int snb_linear_wgrad(const float* gy, const float* x, int B, int K, int O, float* gW, float* gbias, void* stream);
+
 /* Gather of many contiguous float32 tensors into their slots of a flat arena in ONE launch per 1024 tensors
  * (sparenet_b200.dist.GradArena.pack): srcs / dsts / ns are HOST arrays of ntab device pointers and element counts; the pointer
  * table travels as a kernel parameter, so the call is graph-capturable without any host-to-device copy. */

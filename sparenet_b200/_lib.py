@@ -84,6 +84,10 @@ SIGNATURES = {
     "snb_adain_tail_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),
     "snb_adain_tail_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, P, P]),
     "snb_adam_flat": (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "snb_linear_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
+    "snb_linear_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
+    "snb_linear_dgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
+    "snb_linear_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
     "snb_multi_copy": (c_int, [P, P, P, c_int, P]),
     "snb_bn_se_tail_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "snb_bn_se_tail_scratch_floats": (c_size_t, [c_int, c_int, c_int]),

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256) p2i_max_bwd_kernel(const T* __restrict__ 
   const int p = valid ? ids[o] : -1;
   const bool hit = p >= 0;
   if (valid) gbg[o] = hit ? (T)0 : g;
+  if (!__any_sync(0xffffffffu, hit)) return;                // a warp of background pixels (most of a sparse view) has nothing to scan
   // The pixels a point owns are runs along x, i.e. runs of lanes: the three gradient terms are summed over each run with a
   // segmented warp scan and the LAST lane of a run issues the atomics (the reference issues three per pixel; a footprint of
   // radius 10 piles ~300 of them onto the same three addresses).

@@ -240,7 +240,9 @@ class SpareNetEncode(nn.Module):  # reference :85-120
         self.relu = nn.ReLU()
 
     def forward(self, x):
-        return self.relu(self.bn(self.linear(self.feat_extractor(x))))
+        feat = self.feat_extractor(x)
+        # nn.Linear in exact fp32 like the reference's, through the small-batch weight-streaming kernels (csrc/linear.cu)
+        return self.relu(self.bn(fused.linear(feat, self.linear.weight, self.linear.bias)))
 
 
 class AdaptiveInstanceNorm1d(nn.Module):  # reference :909-959 (buffers only; the math is folded into SpareNetDecode)
@@ -408,7 +410,9 @@ class SpareNetDecode(nn.Module):  # reference :289-391
         B, P = style.size(0), self.n_primitives
         npts = self._grid_t.size(1)
         self._check_norm_settings()
-        params = self.mlp(style)                                              # [B, 2*(1026+513+256)]
+        # the style MLP (Linear -> ReLU -> Linear, :311-315) in exact fp32 on the small-batch kernels
+        params = fused.linear(torch.relu(fused.linear(style, self.mlp[0].weight, self.mlp[0].bias)), self.mlp[2].weight, self.mlp[2].bias)
+        # [B, 2*(1026+513+256)]
         sizes = [self.decoder[0].dec.adain1.num_features, self.decoder[0].dec.adain2.num_features, self.decoder[0].dec.adain3.num_features]
         sty, off = [], 0
         for nf in sizes:                                                      # assign_adain_params :831-849: [mean(=bias) | std(=weight)]

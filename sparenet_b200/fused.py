@@ -510,6 +510,54 @@ class Conv1x1(torch.autograd.Function):
         return gx, gW, None
 
 
+class SmallBatchLinear(torch.autograd.Function):
+    """y = x W^T + bias for x [B <= 32, K] in exact fp32 (csrc/linear.cu: snb_linear_fwd / _dgrad / _wgrad) -- the three fully connected
+    layers of the encoder -> decoder bridge (models/sparenet_generator.py:85-120, 289-330), which the reference runs as fp32 cuBLAS GEMMs.
+    With 32 rows the product is a stream over the 64 MB weight; the library's tiles reach a tenth of that rate."""
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        x, W = x.contiguous(), W.contiguous()
+        B, K = x.shape
+        O = W.shape[0]
+        lib = _lib.load()
+        y = torch.empty(B, O, device=x.device, dtype=torch.float32)
+        ws = torch.empty(max(lib.snb_linear_workspace_floats(B, K, O), 4), device=x.device, dtype=torch.float32)
+        b_ = None if bias is None else bias.detach().contiguous()
+        with torch.cuda.device(x.device), _op("linear_fwd", 2, 4 * (W.numel() + x.numel() + y.numel())):
+            check(lib.snb_linear_fwd(ptr(x), ptr(W), ptr(b_), B, K, O, ptr(y), ptr(ws), stream_ptr()), "linear_fwd")
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        gy = gy.contiguous()
+        B, K = x.shape
+        O = W.shape[0]
+        lib = _lib.load()
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            ws = torch.empty(max(lib.snb_linear_workspace_floats(B, K, O), 4), device=x.device, dtype=torch.float32)
+            with torch.cuda.device(x.device), _op("linear_dgrad", 2, 4 * (W.numel() + x.numel() + gy.numel())):
+                check(lib.snb_linear_dgrad(ptr(gy), ptr(W), B, K, O, ptr(gx), ptr(ws), stream_ptr()), "linear_dgrad")
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gW = torch.empty_like(W)
+            gb = torch.empty(O, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+            with torch.cuda.device(x.device), _op("linear_wgrad", 1, 4 * (W.numel() + x.numel() + gy.numel())):
+                check(lib.snb_linear_wgrad(ptr(gy), ptr(x), B, K, O, ptr(gW), ptr(gb), stream_ptr()), "linear_wgrad")
+        return gx, gW, gb
+
+
+def linear(x, W, bias=None):
+    """nn.Linear's arithmetic (fp32) for a small batch; shapes the kernels do not serve (more than 32 rows, K % 4, non-CUDA / non-fp32
+    tensors) go to torch.nn.functional.linear, explicitly."""
+    if x.is_cuda and x.dtype == torch.float32 and W.dtype == torch.float32 and x.dim() == 2 and x.shape[0] <= 32 and x.shape[1] % 4 == 0:
+        return SmallBatchLinear.apply(x, W, bias)
+    return torch.nn.functional.linear(x, W, bias)
+
+
 class CatConv1x1(torch.autograd.Function):
     """y = W . cat(xs, dim=1) with the data gradient computed PER INPUT (gx_i = W[:, slice_i]^T gy, one GEMM each, written straight
     into its own contiguous tensor): autograd's cat backward hands out channel slices of one [G, sum C_i, N] gradient, which every

@@ -449,3 +449,28 @@ def test_edge_reduce_sel_stacked_equals_pair(cuda, B, C, N, k):
         assert torch.equal(u, v)
     assert torch.equal(x1.grad[:, C:], c.grad)                   # gc: plain stores
     assert torch.allclose(x1.grad[:, :C], a.grad, rtol=1e-5, atol=1e-5)   # ga: shared-memory atomics, summation order varies run to run
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,K,O,bias", [(32, 4096, 4096, True), (32, 4096, 3590, True), (5, 64, 10, True), (1, 8, 3, False), (17, 520, 300, False)])
+def test_small_batch_linear_matches_float64(cuda, B, K, O, bias):
+    """fused.linear (csrc/linear.cu: exact-fp32 weight-streaming kernels for <= 32 rows) against the float64 product: output and the
+    three gradients within fp32 summation error (and no further from it than torch's own fp32 F.linear)."""
+    from sparenet_b200 import fused
+    torch.manual_seed(B + K + O)
+    x0, W0 = torch.randn(B, K, device=cuda), torch.randn(O, K, device=cuda) / K ** 0.5
+    b0 = torch.randn(O, device=cuda) if bias else None
+    gy = torch.randn(B, O, device=cuda)
+
+    def run(fn, dt):
+        leaves = [t.detach().to(dt).requires_grad_() for t in ([x0, W0] + ([b0] if bias else []))]
+        y = fn(*leaves) if bias else fn(leaves[0], leaves[1], None)
+        return (y,) + torch.autograd.grad(y, leaves, gy.to(dt))
+    ours = run(fused.linear, torch.float32)
+    ref32 = run(torch.nn.functional.linear, torch.float32)
+    ref64 = run(torch.nn.functional.linear, torch.float64)
+    for name, a, r32, r64 in zip(("y", "gx", "gW", "gbias"), ours, ref32, ref64):
+        scale = float(r64.abs().max())
+        err, err32 = float((a.double() - r64).abs().max()) / scale, float((r32.double() - r64).abs().max()) / scale
+        print(f"[linear B={B} K={K} O={O}] {name}: err/scale {err:.2e} (torch fp32: {err32:.2e})")
+        assert err < max(3e-6, 4 * err32), name
