@@ -5,8 +5,9 @@
 // activations.  The reference runs them as fp32 cuBLAS GEMMs (torch.backends.cuda.matmul.allow_tf32 is off by default), and so do we:
 // exact fp32 FMAs, no tensor cores.  With 32 rows the product is a weight STREAM -- every weight is used 32 times -- and the library's
 // 128x64 SIMT tiles reach a tenth of the streaming rate (~100 us forward, ~65 us data gradient per layer).  Here:
-//   forward   y[b,o] = sum_k x[b,k] W[o,k] + bias[o]:   a block owns 32 outputs x one K slice; a thread = (output, 8 of the batch rows), the
-//             weight row streamed with 128-bit loads (the 4 threads of an output share the address), the activation slice in shared memory
+//   forward   y[b,o] = sum_k x[b,k] W[o,k] + bias[o]:   a block owns 128 outputs x one K slice; a thread = (4 outputs, 8 of the batch rows),
+//             the weight rows streamed with 128-bit loads (the 4 threads of an output group share the addresses), the activation slice in
+//             shared memory
 //   dgrad     gx[b,k] = sum_o gy[b,o] W[o,k]:            a block owns 128 inputs x one O slice; a thread = (4 consecutive k, 8 batch rows),
 //             weight rows read as coalesced 128-bit loads, the gradient slice in shared memory
 //   wgrad     gW[o,k] = sum_b gy[b,o] x[b,k], gbias[o] = sum_b gy[b,o]:  64 x 64 output tile per block, 4 x 4 per thread
@@ -16,22 +17,28 @@
 namespace snb {
 
 constexpr int LIN_MAXB = 32;
-constexpr int LIN_FWD_OT = 32;    // outputs per block (forward)
+constexpr int LIN_FWD_OT = 128;   // outputs per block (forward): 32 groups of 4
 constexpr int LIN_FWD_KC = 256;   // activation chunk staged in shared memory (forward): 32 x 256 floats = 32 KB
 constexpr int LIN_DG_KT = 128;    // inputs per block (dgrad)
 constexpr int LIN_DG_OC = 256;    // gradient chunk staged in shared memory (dgrad)
 
-// ---- forward: grid (ceil(O/32), S); block 128 threads; partial[s][b][o] -----------------------------------------------------------
+// ---- forward: grid (ceil(O/128), S); block 128 threads = 32 output groups x 4 batch groups; a thread owns 4 outputs x 8 batch rows, so
+//      the 8 shared-memory vectors of a k step feed 128 FMAs (with one output per thread the kernel was bound by the shared-memory pipe:
+//      8 LDS.128 per 32 FMAs); partial[s][b][o] ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, int B, int K, int O, int kslice,
                                                           float* __restrict__ part) {
   __shared__ __align__(16) float xs[LIN_MAXB][LIN_FWD_KC + 4];   // +16 B per row: the 4 rows a warp reads at once hit different banks
-  const int ol = threadIdx.x >> 2, bq = threadIdx.x & 3;
-  const int o = blockIdx.x * LIN_FWD_OT + ol;
+  const int og = threadIdx.x >> 2, bq = threadIdx.x & 3;
+  const int o0 = blockIdx.x * LIN_FWD_OT + og * 4;
   const int k0 = blockIdx.y * kslice, k1 = min(K, k0 + kslice);
-  const float* __restrict__ wrow = W + (size_t)(o < O ? o : 0) * K;
-  float acc[8];
+  const float* __restrict__ wr[4];
 #pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  for (int j = 0; j < 4; j++) wr[j] = W + (size_t)(o0 + j < O ? o0 + j : 0) * K;
+  float acc[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[j][i] = 0.f;
   for (int kc = k0; kc < k1; kc += LIN_FWD_KC) {
     const int kn = min(LIN_FWD_KC, k1 - kc);   // multiple of 4
     __syncthreads();
@@ -42,26 +49,33 @@ __global__ void __launch_bounds__(128) linear_fwd_kernel(const float* __restrict
       *reinterpret_cast<float4*>(&xs[b][4 * q]) = v;
     }
     __syncthreads();
-    if (o < O) {
-#pragma unroll 4
+    if (o0 < O) {
+#pragma unroll 2
       for (int k = 0; k < kn; k += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(wrow + kc + k);
+        float4 w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = *reinterpret_cast<const float4*>(wr[j] + kc + k);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const float4 xv = *reinterpret_cast<const float4*>(&xs[i * 4 + bq][k]);   // batch row i*4 + bq: adjacent rows within a warp
-          acc[i] = __fmaf_rn(w.x, xv.x, acc[i]);
-          acc[i] = __fmaf_rn(w.y, xv.y, acc[i]);
-          acc[i] = __fmaf_rn(w.z, xv.z, acc[i]);
-          acc[i] = __fmaf_rn(w.w, xv.w, acc[i]);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            acc[j][i] = __fmaf_rn(w[j].x, xv.x, acc[j][i]);
+            acc[j][i] = __fmaf_rn(w[j].y, xv.y, acc[j][i]);
+            acc[j][i] = __fmaf_rn(w[j].z, xv.z, acc[j][i]);
+            acc[j][i] = __fmaf_rn(w[j].w, xv.w, acc[j][i]);
+          }
         }
       }
     }
   }
-  if (o < O) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (o0 + j >= O) continue;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const int b = i * 4 + bq;
-      if (b < B) part[((size_t)blockIdx.y * B + b) * O + o] = acc[i];
+      if (b < B) part[((size_t)blockIdx.y * B + b) * O + o0 + j] = acc[j][i];
     }
   }
 }
@@ -79,7 +93,7 @@ __global__ void __launch_bounds__(256) linear_reduce_kernel(const float* __restr
 // ---- dgrad: grid (ceil(K/128), S); block 128 threads: thread = (4 consecutive k, 8 batch rows); partial[s][b][k] ------------------------
 __global__ void __launch_bounds__(128) linear_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ W, int B, int K, int O, int oslice,
                                                             float* __restrict__ part) {
-  __shared__ float gs[LIN_DG_OC][LIN_MAXB + 1];   // [o][b]: a thread reads 8 consecutive b of one o
+  __shared__ __align__(16) float gs[LIN_DG_OC][LIN_MAXB];   // [o][b]: a thread reads its 8 consecutive b of one o as two 128-bit loads
   const int kq = threadIdx.x >> 2, bq = threadIdx.x & 3;
   const int k = blockIdx.x * LIN_DG_KT + 4 * kq;
   const int o0 = blockIdx.y * oslice, o1 = min(O, o0 + oslice);
@@ -97,16 +111,18 @@ __global__ void __launch_bounds__(128) linear_dgrad_kernel(const float* __restri
     }
     __syncthreads();
     if (k < K) {
-#pragma unroll 4
+      // 16 weight rows in flight per thread: the loop is a stream over W and the loads are its latency
+#pragma unroll 16
       for (int oo = 0; oo < on; oo++) {
         const float4 w = *reinterpret_cast<const float4*>(W + (size_t)(oc + oo) * K + k);
+        const float4 ga = *reinterpret_cast<const float4*>(&gs[oo][bq * 8]), gb = *reinterpret_cast<const float4*>(&gs[oo][bq * 8 + 4]);
+        const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          const float g = gs[oo][bq * 8 + i];
-          acc[i][0] = __fmaf_rn(g, w.x, acc[i][0]);
-          acc[i][1] = __fmaf_rn(g, w.y, acc[i][1]);
-          acc[i][2] = __fmaf_rn(g, w.z, acc[i][2]);
-          acc[i][3] = __fmaf_rn(g, w.w, acc[i][3]);
+          acc[i][0] = __fmaf_rn(g[i], w.x, acc[i][0]);
+          acc[i][1] = __fmaf_rn(g[i], w.y, acc[i][1]);
+          acc[i][2] = __fmaf_rn(g[i], w.z, acc[i][2]);
+          acc[i][3] = __fmaf_rn(g[i], w.w, acc[i][3]);
         }
       }
     }
@@ -168,8 +184,8 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restri
 }
 
 static int lin_splits(int blocks, int len, int chunk) {
-  // enough blocks for ~3 per SM, slices a multiple of `chunk`
-  int s = (3 * kNumSMs + blocks - 1) / blocks;
+  // enough blocks for ~4 per SM, slices a multiple of `chunk`
+  int s = (4 * kNumSMs + blocks - 1) / blocks;
   const int maxs = (len + chunk - 1) / chunk;
   if (s > maxs) s = maxs;
   if (s < 1) s = 1;
