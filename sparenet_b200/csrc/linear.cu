@@ -10,7 +10,7 @@
 //             shared memory
 //   dgrad     gx[b,k] = sum_o gy[b,o] W[o,k]:            a block owns 128 inputs x one O slice; a thread = (4 consecutive k, 8 batch rows),
 //             weight rows read as coalesced 128-bit loads, the gradient slice in shared memory
-//   wgrad     gW[o,k] = sum_b gy[b,o] x[b,k], gbias[o] = sum_b gy[b,o]:  64 x 64 output tile per block, 4 x 4 per thread
+//   wgrad     gW[o,k] = sum_b gy[b,o] x[b,k], gbias[o] = sum_b gy[b,o]:  128 x 128 output tile per block, 8 x 8 per thread
 // Split slices write partial sums to a workspace and a second pass adds them in a FIXED order (deterministic, unlike atomics).
 #include "common.cuh"
 
@@ -111,18 +111,32 @@ __global__ void __launch_bounds__(128) linear_dgrad_kernel(const float* __restri
     }
     __syncthreads();
     if (k < K) {
-      // 16 weight rows in flight per thread: the loop is a stream over W and the loads are its latency
-#pragma unroll 16
-      for (int oo = 0; oo < on; oo++) {
-        const float4 w = *reinterpret_cast<const float4*>(W + (size_t)(oc + oo) * K + k);
-        const float4 ga = *reinterpret_cast<const float4*>(&gs[oo][bq * 8]), gb = *reinterpret_cast<const float4*>(&gs[oo][bq * 8 + 4]);
-        const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      // software pipeline over groups of 8 weight rows: the next group's eight 128-bit loads are in flight while the current group's
+      // 256 FMAs issue (the loop is a stream over W; without the explicit prefetch every group waited out its own load latency)
+      float4 wn[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          acc[i][0] = __fmaf_rn(g[i], w.x, acc[i][0]);
-          acc[i][1] = __fmaf_rn(g[i], w.y, acc[i][1]);
-          acc[i][2] = __fmaf_rn(g[i], w.z, acc[i][2]);
-          acc[i][3] = __fmaf_rn(g[i], w.w, acc[i][3]);
+      for (int u = 0; u < 8; u++) wn[u] = u < on ? *reinterpret_cast<const float4*>(W + (size_t)(oc + u) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int og = 0; og < on; og += 8) {
+        float4 wc[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) wc[u] = wn[u];
+        if (og + 8 < on) {
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+            wn[u] = og + 8 + u < on ? *reinterpret_cast<const float4*>(W + (size_t)(oc + og + 8 + u) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          // rows past the slice hold zeros in shared memory and in wc: they add nothing
+          const float4 ga = *reinterpret_cast<const float4*>(&gs[og + u][bq * 8]), gb = *reinterpret_cast<const float4*>(&gs[og + u][bq * 8 + 4]);
+          const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            acc[i][0] = __fmaf_rn(g[i], wc[u].x, acc[i][0]);
+            acc[i][1] = __fmaf_rn(g[i], wc[u].y, acc[i][1]);
+            acc[i][2] = __fmaf_rn(g[i], wc[u].z, acc[i][2]);
+            acc[i][3] = __fmaf_rn(g[i], wc[u].w, acc[i][3]);
+          }
         }
       }
     }
@@ -136,47 +150,53 @@ __global__ void __launch_bounds__(128) linear_dgrad_kernel(const float* __restri
   }
 }
 
-// ---- wgrad: 64 x 64 tile of gW per block (256 threads, 4 x 4 each); gbias by the blocks of the first k tile -------------------------------
+// ---- wgrad: 128 x 128 tile of gW per block (256 threads, 8 x 8 each: four 128-bit shared-memory loads per 64 FMAs); gbias by the blocks of
+//      the first k tile --------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x, int B, int K, int O,
                                                             float* __restrict__ gW, float* __restrict__ gbias) {
-  __shared__ __align__(16) float gt[LIN_MAXB][64];
-  __shared__ __align__(16) float xt[LIN_MAXB][64];
-  const int o0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
-  for (int e = threadIdx.x; e < LIN_MAXB * 64; e += 256) {
-    const int b = e >> 6, j = e & 63;
+  __shared__ __align__(16) float gt[LIN_MAXB][128];
+  __shared__ __align__(16) float xt[LIN_MAXB][128];
+  const int o0 = blockIdx.y * 128, k0 = blockIdx.x * 128;
+  for (int e = threadIdx.x; e < LIN_MAXB * 128; e += 256) {
+    const int b = e >> 7, j = e & 127;
     gt[b][j] = (b < B && o0 + j < O) ? gy[(size_t)b * O + o0 + j] : 0.f;
     xt[b][j] = (b < B && k0 + j < K) ? x[(size_t)b * K + k0 + j] : 0.f;
   }
   __syncthreads();
-  const int to = (threadIdx.x >> 4) * 4, tk = (threadIdx.x & 15) * 4;
-  float acc[4][4];
+  // thread (ty, tx): outputs o0 + 4 ty + {0..3} and o0 + 64 + 4 ty + {0..3}, inputs k0 + 4 tx + {0..3} and k0 + 64 + 4 tx + {0..3}
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-#pragma unroll 8
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+#pragma unroll 4
   for (int b = 0; b < LIN_MAXB; b++) {
-    const float4 g = *reinterpret_cast<const float4*>(&gt[b][to]);
-    const float4 xv = *reinterpret_cast<const float4*>(&xt[b][tk]);
-    const float gg[4] = {g.x, g.y, g.z, g.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float4 g0 = *reinterpret_cast<const float4*>(&gt[b][4 * ty]), g1 = *reinterpret_cast<const float4*>(&gt[b][64 + 4 * ty]);
+    const float4 x0 = *reinterpret_cast<const float4*>(&xt[b][4 * tx]), x1 = *reinterpret_cast<const float4*>(&xt[b][64 + 4 * tx]);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j] = __fmaf_rn(gg[i], xx[j], acc[i][j]);
+      for (int j = 0; j < 8; j++) acc[i][j] = __fmaf_rn(gg[i], xx[j], acc[i][j]);
   }
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int o = o0 + to + i;
+  for (int i = 0; i < 8; i++) {
+    const int o = o0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
     if (o >= O) continue;
-    if (k0 + tk + 3 < K) {
-      *reinterpret_cast<float4*>(gW + (size_t)o * K + k0 + tk) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (k0 + tk + j < K) gW[(size_t)o * K + k0 + tk + j] = acc[i][j];
+    for (int h = 0; h < 2; h++) {
+      const int kk = k0 + 64 * h + 4 * tx;
+      if (kk + 3 < K) {
+        *reinterpret_cast<float4*>(gW + (size_t)o * K + kk) = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (kk + j < K) gW[(size_t)o * K + kk + j] = acc[i][4 * h + j];
+      }
     }
   }
-  if (gbias != nullptr && blockIdx.x == 0 && threadIdx.x < 64 && o0 + threadIdx.x < O) {
+  if (gbias != nullptr && blockIdx.x == 0 && threadIdx.x < 128 && o0 + threadIdx.x < O) {
     float s = 0.f;
     for (int b = 0; b < B; b++) s += gt[b][threadIdx.x];
     gbias[o0 + threadIdx.x] = s;
@@ -257,7 +277,7 @@ SNB_API int snb_linear_wgrad(const float* gy, const float* x, int B, int K, int 
   if (B < 0 || K <= 0 || O <= 0) return SNB_EINVAL;
   if (B > LIN_MAXB || (K & 3) != 0) return SNB_ELIMIT;
   if (((uintptr_t)gW & 15) != 0) return SNB_EALIGN;
-  linear_wgrad_kernel<<<dim3((unsigned)((K + 63) / 64), (unsigned)((O + 63) / 64)), 256, 0, (cudaStream_t)stream>>>(gy, x, B, K, O, gW, gbias);
+  linear_wgrad_kernel<<<dim3((unsigned)((K + 127) / 128), (unsigned)((O + 127) / 128)), 256, 0, (cudaStream_t)stream>>>(gy, x, B, K, O, gW, gbias);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
