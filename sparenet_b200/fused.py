@@ -523,7 +523,7 @@ class SmallBatchLinear(torch.autograd.Function):
         y = torch.empty(B, O, device=x.device, dtype=torch.float32)
         ws = torch.empty(max(lib.snb_linear_workspace_floats(B, K, O), 4), device=x.device, dtype=torch.float32)
         b_ = None if bias is None else bias.detach().contiguous()
-        with torch.cuda.device(x.device), _op("linear_fwd", 2, 4 * (W.numel() + x.numel() + y.numel())):
+        with torch.cuda.device(x.device), _op("linear_fwd", 2):
             check(lib.snb_linear_fwd(ptr(x), ptr(W), ptr(b_), B, K, O, ptr(y), ptr(ws), stream_ptr()), "linear_fwd")
         ctx.save_for_backward(x, W)
         ctx.has_bias = bias is not None
@@ -540,12 +540,12 @@ class SmallBatchLinear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             ws = torch.empty(max(lib.snb_linear_workspace_floats(B, K, O), 4), device=x.device, dtype=torch.float32)
-            with torch.cuda.device(x.device), _op("linear_dgrad", 2, 4 * (W.numel() + x.numel() + gy.numel())):
+            with torch.cuda.device(x.device), _op("linear_dgrad", 2):
                 check(lib.snb_linear_dgrad(ptr(gy), ptr(W), B, K, O, ptr(gx), ptr(ws), stream_ptr()), "linear_dgrad")
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gW = torch.empty_like(W)
             gb = torch.empty(O, device=x.device, dtype=torch.float32) if ctx.has_bias else None
-            with torch.cuda.device(x.device), _op("linear_wgrad", 1, 4 * (W.numel() + x.numel() + gy.numel())):
+            with torch.cuda.device(x.device), _op("linear_wgrad", 1):
                 check(lib.snb_linear_wgrad(ptr(gy), ptr(x), B, K, O, ptr(gW), ptr(gb), stream_ptr()), "linear_wgrad")
         return gx, gW, gb
 
