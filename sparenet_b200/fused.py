@@ -340,14 +340,21 @@ def conv_row_reduce_backward(x, W, mean, imax, imin, gmean, gvar, gmax, gmin, ne
     gx = gW = None
     if need_x:
         M = torch.matmul(Wd.t(), WA).to(dt)                       # [B,Ci,Ci] = W^T diag(a_b) W
-        with tf32_matmul():                                       # the reference's arithmetic here is cuDNN's TF32 data gradient
-            gx = torch.bmm(M, x)
+        own = x.is_cuda and dt == torch.float32 and x.is_contiguous() and N % 32 == 0 and Ci % 32 == 0 and tf32_matmul.enabled
+        if own:                                                   # one "weight" per sample on the tcgen05 GEMM (TF32 like the reference's
+            gx, _ = gemm.conv_fwd(x, M.contiguous())              # cuDNN data gradient)
+        else:
+            with tf32_matmul():                                   # the reference's arithmetic here is cuDNN's TF32 data gradient
+                gx = torch.bmm(M, x)
         row_term = torch.matmul(b, Wd).to(dt)                      # [B,Ci]
         if not split_row_term:
             gx += row_term.unsqueeze(-1)
     if need_w:
-        with tf32_matmul():                                       # ... and its TF32 weight gradient
-            G = torch.bmm(x, x.transpose(1, 2)).double()          # [B,Ci,Ci]
+        if x.is_cuda and dt == torch.float32 and x.is_contiguous() and N % 32 == 0 and Ci % 32 == 0 and tf32_matmul.enabled:
+            G = gemm.conv_wgrad(x, x, batched=True).double()      # [B,Ci,Ci] = x x^T: the weight-gradient arrangement of the tcgen05 GEMM
+        else:
+            with tf32_matmul():                                   # ... and its TF32 weight gradient
+                G = torch.bmm(x, x.transpose(1, 2)).double()      # [B,Ci,Ci]
         gW = torch.bmm(WA, G).sum(0) + torch.matmul(b.t(), x.sum(2).double())
     if x.is_cuda and dt == torch.float32 and (gmax is not None or gmin is not None) and (need_x or need_w):
         # both extrema in one launch (csrc/rowops.cu: snb_conv_extrema_bwd), accumulating into gx and the fp32 weight gradient
