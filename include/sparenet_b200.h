@@ -247,6 +247,20 @@ int snb_adain_tail_bwd(const float* grad_scale, const float* grad_shift, const f
  * (no amsgrad, no maximize; weight_decay is the L2 form), `step` = 1, 2, ... is the number of this update. */
 int snb_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, void* stream);
+/* ---- 1x1 convolutions with a thin side (<= 8 channels in or out; N % 4 == 0), exact fp32 streaming kernels (csrc/thinconv.cu): the
+ * xyz / lattice input layers and xyz output layers of the generator (models/sparenet_generator.py:146-160, 593-646, 984-991, 1044-1062).
+ * Every operand has its own batch stride in floats (0 = shared by the batch); W is addressed as W[g*w_bs + row*w_rs + col*w_cs], so a data
+ * gradient uses the transposed weight without a copy.
+ *   expand: y [G,Co,N] = W x, x [.,S,N], W rows = output channels, cols = the S thin input channels
+ *   reduce: y [.,S,N]  = W x, x [G,L,N], W rows = the S thin output channels, cols = input channels
+ *   wgrad:  out [G,L,8] (columns >= S zero), out[g][l][s] = sum_n big[g][l,n] small[g][s,n] */
+int snb_thin_expand(const float* x, long long x_bs, const float* W, long long w_bs, int w_rs, int w_cs, int G, int S, int Co, int N, float* y,
+                    void* stream);
+int snb_thin_reduce(const float* x, long long x_bs, const float* W, long long w_bs, int w_rs, int w_cs, int G, int S, int L, int N, float* y,
+                    long long y_bs, void* stream);
+int snb_thin_wgrad(const float* big, long long big_bs, const float* small_, long long small_bs, int G, int S, int L, int N, float* out,
+                   void* stream);
+
 /* ---- fp32 nn.Linear for small batches (B <= 32 rows, K % 4 == 0): the encoder -> decoder bridge (models/sparenet_generator.py:85-120
  * SpareNetEncode.linear, :289-330 SpareNetDecode.mlp).  Exact fp32 FMAs like the reference's cuBLAS calls (no tensor cores); x [B,K],
  * W [O,K] row-major, y [B,O].  workspace: snb_linear_workspace_floats(B,K,O) floats (split-slice partial sums, added in a fixed order).

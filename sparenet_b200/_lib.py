@@ -84,6 +84,9 @@ SIGNATURES = {
     "snb_adain_tail_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),
     "snb_adain_tail_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, P, P]),
     "snb_adam_flat": (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "snb_thin_expand": (c_int, [P, ctypes.c_longlong, P, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "snb_thin_reduce": (c_int, [P, ctypes.c_longlong, P, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, P, ctypes.c_longlong, P]),
+    "snb_thin_wgrad": (c_int, [P, ctypes.c_longlong, P, ctypes.c_longlong, c_int, c_int, c_int, c_int, P, P]),
     "snb_linear_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
     "snb_linear_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
     "snb_linear_dgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),

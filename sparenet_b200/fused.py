@@ -28,13 +28,36 @@ class tf32_matmul:
 
 class ThinConv(torch.autograd.Function):
     """y[g] = W x[g] for the THIN 1x1 convolutions (3-8 channels on one side: xyz inputs, xyz outputs, the 2-d lattice), whose rows
-    are shorter than a TMA box of the tensor-core GEMM: batched library GEMM with TF32 allowed in the forward AND in both backward
-    products (the reference runs these layers through cuDNN with TF32 allowed).  W [Co, Ci] or [G, Co, Ci], x [G, Ci, N] (or
-    [1, Ci, N] against a batched W).  Always torch.bmm on an EXPANDED (stride-0) operand: torch.matmul(2-D, 3-D) would first copy x."""
+    are shorter than a TMA box of the tensor-core GEMM.  W [Co, Ci] or [G, Co, Ci], x [G, Ci, N] (or [1, Ci, N] against a batched W).
+    CUDA fp32 with N % 4 == 0: the exact-fp32 streaming kernels of csrc/thinconv.cu (one pass over the wide tensor per product, forward
+    and both gradients).  Anything else: torch.bmm on an EXPANDED (stride-0) operand, TF32 allowed as in the reference's cuDNN."""
+    USE_KERNELS = True     # measurement switch: False routes everything through the library GEMM
+
+    @staticmethod
+    def _own(x, W):
+        return (ThinConv.USE_KERNELS and x.is_cuda and x.dtype == torch.float32 and W.dtype == torch.float32 and x.dim() == 3
+                and x.shape[2] % 4 == 0 and x.shape[2] > 0 and min(W.shape[-2], W.shape[-1]) <= 8 and W.shape[-1] == x.shape[1])
+
     @staticmethod
     def forward(ctx, x, W):
-        ctx.save_for_backward(x, W)
         G = max(x.shape[0], W.shape[0] if W.dim() == 3 else 1)
+        ctx.own = ThinConv._own(x, W)
+        if ctx.own:
+            x, W = x.contiguous(), W.contiguous()
+            ctx.save_for_backward(x, W)
+            Co, Ci = W.shape[-2], W.shape[-1]
+            N = x.shape[2]
+            x_bs = Ci * N if x.shape[0] == G else 0
+            w_bs = Co * Ci if W.dim() == 3 else 0
+            y = torch.empty(G, Co, N, device=x.device, dtype=torch.float32)
+            lib = _lib.load()
+            with torch.cuda.device(x.device), _op("thin_conv", 1, 4 * (G * Ci * N + y.numel())):
+                if Ci <= 8:
+                    check(lib.snb_thin_expand(ptr(x), x_bs, ptr(W), w_bs, Ci, 1, G, Ci, Co, N, ptr(y), stream_ptr()), "thin_expand")
+                else:
+                    check(lib.snb_thin_reduce(ptr(x), x_bs, ptr(W), w_bs, Ci, 1, G, Co, Ci, N, ptr(y), Co * N, stream_ptr()), "thin_reduce")
+            return y
+        ctx.save_for_backward(x, W)
         Wb = W.unsqueeze(0).expand(G, -1, -1) if W.dim() == 2 else W
         xb = x.expand(G, -1, -1)
         with tf32_matmul():
@@ -45,6 +68,35 @@ class ThinConv(torch.autograd.Function):
         x, W = ctx.saved_tensors
         gy = gy.contiguous()     # a transposed view (the loss hands back [B,N,3]^T) sends cuBLAS to a 4x slower kernel: 6 MB copy instead
         G = gy.shape[0]
+        if ctx.own:
+            Co, Ci = W.shape[-2], W.shape[-1]
+            N = x.shape[2]
+            x_bs = Ci * N if x.shape[0] == G else 0
+            w_bs = Co * Ci if W.dim() == 3 else 0
+            lib = _lib.load()
+            gx = gW = None
+            with torch.cuda.device(x.device):
+                if ctx.needs_input_grad[0]:
+                    gx = torch.empty(G, Ci, N, device=x.device, dtype=torch.float32)
+                    with _op("thin_conv_bwd", 1, 4 * (gy.numel() + gx.numel())):
+                        if Ci <= 8:     # thin input: gx = W^T gy reduces over the Co wide channels
+                            check(lib.snb_thin_reduce(ptr(gy), Co * N, ptr(W), w_bs, 1, Ci, G, Ci, Co, N, ptr(gx), Ci * N, stream_ptr()), "thin_reduce")
+                        else:           # thin output: gx = W^T gy expands the Co thin channels
+                            check(lib.snb_thin_expand(ptr(gy), Co * N, ptr(W), w_bs, 1, Ci, G, Co, Ci, N, ptr(gx), stream_ptr()), "thin_expand")
+                    if x.shape[0] != G:
+                        gx = gx.sum(0, keepdim=True)
+                if ctx.needs_input_grad[1]:
+                    thin_in = Ci <= 8
+                    L, S = (Co, Ci) if thin_in else (Ci, Co)
+                    out = torch.empty(G, L, 8, device=x.device, dtype=torch.float32)
+                    with _op("thin_conv_bwd", 1, 4 * (gy.numel() + G * Ci * N)):
+                        if thin_in:
+                            check(lib.snb_thin_wgrad(ptr(gy), Co * N, ptr(x), x_bs, G, S, L, N, ptr(out), stream_ptr()), "thin_wgrad")
+                        else:
+                            check(lib.snb_thin_wgrad(ptr(x), x_bs, ptr(gy), Co * N, G, S, L, N, ptr(out), stream_ptr()), "thin_wgrad")
+                    gW = out[:, :, :S] if thin_in else out[:, :, :S].transpose(1, 2)      # [G,Co,Ci]
+                    gW = gW.sum(0) if W.dim() == 2 else gW.contiguous()
+            return gx, gW
         Wb = W.unsqueeze(0).expand(G, -1, -1) if W.dim() == 2 else W
         xb = x.expand(G, -1, -1)
         gx = gW = None

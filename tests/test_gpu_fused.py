@@ -474,3 +474,30 @@ def test_small_batch_linear_matches_float64(cuda, B, K, O, bias):
         err, err32 = float((a.double() - r64).abs().max()) / scale, float((r32.double() - r64).abs().max()) / scale
         print(f"[linear B={B} K={K} O={O}] {name}: err/scale {err:.2e} (torch fp32: {err32:.2e})")
         assert err < max(3e-6, 4 * err32), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,Ci,Co,N,wbatched,xbcast", [(32, 3, 512, 2048, False, False), (8, 2, 1056, 512, True, True), (4, 256, 3, 4096, True, False),
+                                                      (3, 4, 64, 1024, False, False), (3, 128, 3, 1024, False, False), (2, 7, 5, 36, False, False)])
+def test_thin_conv_kernels_match_float64(cuda, G, Ci, Co, N, wbatched, xbcast):
+    """fused.thin_conv on csrc/thinconv.cu (expand / reduce / wgrad streaming kernels, exact fp32) against the float64 products: output,
+    data gradient and weight gradient, shared and per-batch weights, batch-broadcast input (the decoders' lattice)."""
+    from sparenet_b200 import fused
+    torch.manual_seed(G * 7 + Ci + Co)
+    x0 = torch.randn(1 if xbcast else G, Ci, N, device=cuda)
+    W0 = torch.randn(*((G, Co, Ci) if wbatched else (Co, Ci)), device=cuda)
+    gy = torch.randn(G, Co, N, device=cuda)
+
+    def ref(x, W):
+        return torch.matmul(W if W.dim() == 3 else W.unsqueeze(0), x)
+
+    outs = []
+    for fn, dt in ((fused.thin_conv, torch.float32), (ref, torch.float64)):
+        x, W = x0.to(dt).requires_grad_(), W0.to(dt).requires_grad_()
+        y = fn(x, W)
+        outs.append((y,) + torch.autograd.grad(y, (x, W), gy.to(dt)))
+    for name, a, b in zip(("y", "gx", "gW"), *outs):
+        assert a.shape == b.shape, (name, a.shape, b.shape)
+        err = float((a.double() - b).abs().max()) / max(float(b.abs().max()), 1e-9)
+        print(f"[thin_conv G={G} Ci={Ci} Co={Co} N={N}] {name}: err/scale {err:.2e}")
+        assert err < 1e-5, name
