@@ -86,49 +86,57 @@ __global__ void __launch_bounds__(256) thin_reduce_kernel(const float* __restric
     if (s < S) *reinterpret_cast<float4*>(yg + (size_t)s * N) = acc[s];
 }
 
-// ---- wgrad: grid (ceil(L/8), G); a block owns 8 wide rows of one batch entry, its 256 threads stride over the positions -----------------
+// ---- wgrad: grid (ceil(L/4), G); a block owns 4 wide rows of one batch entry, its 256 threads stride over the positions.  The thin
+//      channel count is a template parameter (no padded FMAs, ~64 registers: three blocks per SM keep enough loads in flight -- the first
+//      version, 8 rows x 8 padded channels at 200 registers and one block per SM, ran at a quarter of the streaming rate) ----------------
+template <int ST>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict__ big, long long big_bs, const float* __restrict__ small,
                                                           long long small_bs, int S, int L, int N, float* __restrict__ out) {
   // out[g][l][s] (row-major [G, L, THIN_MAXS]; columns >= S are zero)
-  __shared__ float red[8][8 * THIN_MAXS];
-  const int g = blockIdx.y, l0 = blockIdx.x * 8;
+  __shared__ float red[8][4 * THIN_MAXS];
+  const int g = blockIdx.y, l0 = blockIdx.x * 4;
   const float* __restrict__ bg = big + (size_t)g * big_bs;
   const float* __restrict__ sg = small + (size_t)g * small_bs;
-  float acc[8][THIN_MAXS];
+  const float* __restrict__ br[4];
 #pragma unroll
-  for (int r = 0; r < 8; r++)
+  for (int r = 0; r < 4; r++) br[r] = bg + (size_t)min(l0 + r, L - 1) * N;   // rows past L repeat the last one (never stored)
+  float acc[4][ST];
 #pragma unroll
-    for (int s = 0; s < THIN_MAXS; s++) acc[r][s] = 0.f;
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int s = 0; s < ST; s++) acc[r][s] = 0.f;
+#pragma unroll 2
   for (int n = threadIdx.x * 4; n < N; n += 1024) {
-    float4 sv[THIN_MAXS];
+    float4 sv[ST], bv[4];
 #pragma unroll
-    for (int s = 0; s < THIN_MAXS; s++) sv[s] = s < S ? *reinterpret_cast<const float4*>(sg + (size_t)s * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < 4; r++) bv[r] = *reinterpret_cast<const float4*>(br[r] + n);
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      if (l0 + r >= L) break;
-      const float4 b = *reinterpret_cast<const float4*>(bg + (size_t)(l0 + r) * N + n);
+    for (int s = 0; s < ST; s++) sv[s] = s < S ? *reinterpret_cast<const float4*>(sg + (size_t)s * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int s = 0; s < THIN_MAXS; s++)
-        acc[r][s] = __fmaf_rn(b.x, sv[s].x, __fmaf_rn(b.y, sv[s].y, __fmaf_rn(b.z, sv[s].z, __fmaf_rn(b.w, sv[s].w, acc[r][s]))));
-    }
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int s = 0; s < ST; s++)
+        acc[r][s] = __fmaf_rn(bv[r].x, sv[s].x, __fmaf_rn(bv[r].y, sv[s].y, __fmaf_rn(bv[r].z, sv[s].z, __fmaf_rn(bv[r].w, sv[s].w, acc[r][s]))));
   }
   // block reduction: warp shuffles, then the 8 warps through shared memory (fixed order)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int r = 0; r < 8; r++)
+  for (int r = 0; r < 4; r++)
 #pragma unroll
-    for (int s = 0; s < THIN_MAXS; s++) {
+    for (int s = 0; s < ST; s++) {
       float v = acc[r][s];
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) red[warp][r * THIN_MAXS + s] = v;
     }
   __syncthreads();
-  if (threadIdx.x < 8 * THIN_MAXS) {
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+  if (threadIdx.x < 4 * THIN_MAXS) {
     const int r = threadIdx.x / THIN_MAXS, s = threadIdx.x - r * THIN_MAXS;
+    float v = 0.f;
+    if (s < ST) {
+#pragma unroll
+      for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+    }
     if (l0 + r < L) out[((size_t)g * L + l0 + r) * THIN_MAXS + s] = v;
   }
 }
@@ -179,7 +187,12 @@ SNB_API int snb_thin_wgrad(const float* big, long long big_bs, const float* smal
   if (rc) return rc;
   if (G == 0) return SNB_OK;
   if ((((uintptr_t)big | (uintptr_t)small_) & 15) != 0 || (big_bs & 3) != 0 || (small_bs & 3) != 0) return SNB_EALIGN;
-  thin_wgrad_kernel<<<dim3((unsigned)((L + 7) / 8), (unsigned)G), 256, 0, (cudaStream_t)stream>>>(big, big_bs, small_, small_bs, S, L, N, out);
+  const dim3 grid((unsigned)((L + 3) / 4), (unsigned)G);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S <= 2) thin_wgrad_kernel<2><<<grid, 256, 0, st>>>(big, big_bs, small_, small_bs, S, L, N, out);
+  else if (S == 3) thin_wgrad_kernel<3><<<grid, 256, 0, st>>>(big, big_bs, small_, small_bs, S, L, N, out);
+  else if (S == 4) thin_wgrad_kernel<4><<<grid, 256, 0, st>>>(big, big_bs, small_, small_bs, S, L, N, out);
+  else thin_wgrad_kernel<8><<<grid, 256, 0, st>>>(big, big_bs, small_, small_bs, S, L, N, out);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
