@@ -597,7 +597,7 @@ class PointNetRes(nn.Module):  # reference :582-646
             hstar = torch.where((g3 > 0).view(1, -1), hmax, hmin) + self.conv3.bias   # max_N BN(h3) only needs max/min of h3
             glob = (hstar - mean) * (g3 * inv) + self.bn3.bias                    # [B,1024]
         W4 = self.conv4.weight
-        pb = F.linear(glob, W4[:, :1024, 0], self.conv4.bias)                 # [B,512]: the broadcast global half of conv4
+        pb = fused.linear(glob, W4[:, :1024, 0], self.conv4.bias)             # [B,512]: the broadcast global half of conv4 (exact fp32)
         h4, m4, v4 = fused.act_conv(W4[:, 1024:, 0], pro1, stats_seg=N, h=h1)  # the pointfeat half of conv4 (strided weight view)
         pro4 = fused.Prologue(h4, m4, v4, *self._bn_se_tail(self.bn4, self.se4, pb, N))
         h5, m5, v5 = fused.act_conv(self.conv5.weight.squeeze(-1), pro4, stats_seg=N, h=h4)
