@@ -88,7 +88,7 @@ SNB_API int snb_multi_copy(const void* const* srcs, void* const* dsts, const lon
   if (ntab < 0) return SNB_EINVAL;
   if (ntab == 0) return SNB_OK;
   if (!srcs || !dsts || !ns) return SNB_EINVAL;
-  static PackTable tab;  // host staging of one launch's parameters (copied by the launch)
+  PackTable tab;  // host staging of one launch's parameters (24.6 KB on the stack; the launch copies it)
   int i = 0;
   while (i < ntab) {
     int m = 0;
