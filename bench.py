@@ -562,7 +562,7 @@ def run_ours(args):
                 loss = gfb(p, g)
                 step.finish(*(() if step.torch_adam else (True,)))
                 return loss
-            graph_note = "forward+backward replayed as one CUDA graph; Adam (and the gradient all-reduce) outside"
+            graph_note = "forward+backward+gradient pack replayed as one CUDA graph; Adam (and the gradient all-reduce) outside"
         except Exception as e:  # capture is an optimisation: report and keep measuring the eager step
             run = step
             graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
@@ -682,7 +682,9 @@ def run_ours(args):
                        "optimizer": ("torch.optim.Adam(fused=True)" if step.torch_adam else
                                      "Adam(lr 1e-4, betas (0, 0.9)): torch.optim.Adam's update rule as ONE launch over a flat parameter arena "
                                      "(sparenet_b200.optim.FlatAdam, snb_adam_flat)"),
-                       "streams": ("coarse/middle Chamfer losses on a side stream beside the refiner's MDS" if step.overlap["on"] else "single stream")},
+                       "streams": ("coarse/middle Chamfer losses on a low-priority side stream beside the refiner's MDS (forked after the cloud's "
+                                   "expansion penalty is enqueued); the step graph is captured on a high-priority stream"
+                                   if step.overlap["on"] else "single stream")},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(h_partial.numel() + h_gt.numel()) * 4, "d2h_bytes_per_step": 4, "last_loss": last},
