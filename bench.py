@@ -134,8 +134,10 @@ def run_reference(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": min(args.warmup, 1),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": "configs[1]: SpareNet generator + CD loss, B=32 2048->16384 pts (CPU: bounded sample)", "cpu_batch": args.cpu_batch,
-                       "n_out": N_OUT, "n_partial": N_PARTIAL, "n_primitives": N_PRIM},
+            # the workload named exactly as in our arm's line; what was actually timed (a bounded sample of it) is in cpu_baseline.sample
+            "config": {"workload": "configs[1]: SpareNet generator + CD loss, synthetic ShapeNet B=32 2048->16384 pts", "local_batch": LOCAL_B,
+                       "global_batch": LOCAL_B, "n_out": N_OUT, "n_partial": N_PARTIAL, "n_primitives": N_PRIM, "k": 8,
+                       "cpu_sample_batch": args.cpu_batch},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "omp_threads": oracle.num_threads()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
