@@ -179,6 +179,37 @@ def test_unsupported_configurations_raise():
     assert np.allclose(np.array(M.grid_generation(16384, 32)[0], dtype=np.float32), GOLD["grid"])
 
 
+def test_decoder_refuses_non_reference_normalisation_settings():
+    """The folded decoder tail is written for the reference's BatchNorm / AdaIN settings; anything else raises instead of silently
+    producing different running statistics."""
+    from sparenet_b200.dropin.models import sparenet_generator as M
+    dec = M.SpareNetDecode(num_points=4 * 64, n_primitives=4, bottleneck_size=64, use_AdaIn="share", use_SElayer=True)
+    dec._check_norm_settings()
+    dec.decoder[2].dec.bn2.eps = 1e-3
+    with pytest.raises(NotImplementedError):
+        dec._check_norm_settings()
+    dec.decoder[2].dec.bn2.eps = 1e-5
+    dec.decoder[0].dec.bn3.momentum = None
+    with pytest.raises(NotImplementedError):
+        dec._check_norm_settings()
+
+
+def test_bn_bookkeeping_matches_nn_batchnorm_including_cumulative_average():
+    """_bn_apply_stats (running statistics from externally computed batch statistics) == nn.BatchNorm1d's own bookkeeping, for a
+    momentum and for momentum=None (cumulative moving average)."""
+    from sparenet_b200.dropin.models.sparenet_generator import _bn_apply_stats
+    torch.manual_seed(0)
+    for momentum in (0.1, 0.3, None):
+        ref, ours = torch.nn.BatchNorm1d(6, momentum=momentum).train(), torch.nn.BatchNorm1d(6, momentum=momentum).train()
+        for _ in range(3):
+            x = torch.randn(5, 6, 7) * 2 + 1
+            ref(x)
+            var, mean = torch.var_mean(x, dim=(0, 2), unbiased=False)
+            _bn_apply_stats(ours, mean, var, 5 * 7)
+        assert torch.allclose(ours.running_mean, ref.running_mean, atol=1e-6) and torch.allclose(ours.running_var, ref.running_var, atol=1e-6)
+        assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == 3
+
+
 def test_stacked_parameter_gradients_are_views_of_one_buffer():
     """_StackParams: the forward equals torch.stack; the backward hands each parameter its slice of the stacked gradient as .grad
     (accumulating when a gradient already exists), exactly what torch.stack + AccumulateGrad would leave behind."""
