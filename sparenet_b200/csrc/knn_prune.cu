@@ -2,9 +2,11 @@
 //
 // Parity: tests/test_gpu_ops.py::test_knn_pruned_identical_to_brute_force (identical indices incl. the large-norm cancellation case
 // and duplicated / all-zero points); the rule was also checked on the CPU on the encoder's real features
-// (tests/perf/knn_prune_study.py: ~11 candidates per row survive for k = 8).  Timed on B200 (B=32, N=2048, k=8): C=256 1.10 ms,
-// C=512 1.97 ms per layer including the Gram GEMM (brute-force kernels: 1.45 ms per 256 channels); sparenet_b200.functional.knn_indices
-// uses it for C >= 256 (SNB_KNN_PRUNE=1 / 0 forces it on / off), the Gram matrix comes from snb_gemm_tf32.
+// (tests/perf/knn_prune_study.py: ~11 candidates per row survive for k = 8).  Timed on B200 inside the step (B=32, N=2048, k=8, CUPTI):
+// per layer 0.43 ms (C=256) / 0.59 ms (C=512) for the selection + exact re-ranking below, plus 0.16 / 0.25 ms of Gram GEMM, 0.05 ms of
+// norms and 0.03 / 0.05 ms for the point-major copy (the first version of this file: 0.68 / 0.82 ms for the kernel alone; the
+// brute-force kernels: 1.45 ms per 256 channels); sparenet_b200.functional.knn_indices uses it for C >= 256 (SNB_KNN_PRUNE=1 / 0
+// forces it on / off), the Gram matrix comes from snb_gemm_tf32.
 //
 // Same contract and the SAME BITS as snb_knn (knn.cu): for every point the k points with the smallest
 //     d(i,j) = sum_c (x[c,j] - x[c,i])^2,  accumulated with FMAs in ascending c, fp32,
