@@ -8,7 +8,7 @@ sys.path to import those modules under the reference's own names.
 """
 import os
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 
 def dropin_path():

@@ -1,7 +1,7 @@
 // abi.cu -- version / error-text entry points of the C ABI (include/sparenet_b200.h).
 #include "common.cuh"
 
-SNB_API int snb_version(void) { return 100; }  // 0.1.0
+SNB_API int snb_version(void) { return 200; }  // 0.2.0: round 2 (tcgen05 GEMM, tails, thin / linear / kNN kernels, multi-tensor copy)
 
 SNB_API const char* snb_strerror(int code) {
   switch (code) {
